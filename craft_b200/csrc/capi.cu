@@ -1,0 +1,406 @@
+// craft_b200 -- C ABI (include/craft_b200.h): argument checking, TMA tensor-map construction and
+// kernel launches.  No torch, no global mutable state besides the thread-local error string.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+
+#include "../../include/craft_b200.h"
+#include "attn_pv.cuh"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "pointwise.cuh"
+#include "scores.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return -1;
+}
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("%s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+cb::Grid2 make_grid(int H, int W) {
+  cb::Grid2 g;
+  g.H = H;
+  g.W = W;
+  g.Wp = W + 2;
+  g.Mp = H * (W + 2);
+  return g;
+}
+
+// ---- cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed) ------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 map over a row-major [rows, ld] matrix, box = [box_rows, 64 cols], 128B swizzle.
+int make_map_2d(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld,
+                int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16) return fail("tensor map: base/stride not 16B aligned");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(2d) failed: %d", static_cast<int>(r));
+  return 0;
+}
+// 3-D bf16 map over token rows viewed as [H][W][C] with row pitch Wp: box = [8][8][64].
+int make_map_3d_keys(CUtensorMap* m, const void* base, const cb::Grid2& g, int C) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(g.W), static_cast<cuuint64_t>(g.H)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(g.Wp) * C * 2};
+  cuuint32_t box[3] = {64, 8, 8};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(3d) failed: %d", static_cast<int>(r));
+  return 0;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// number of key splits so that tiles*split fills whole waves as evenly as possible
+int pick_split(int base_ctas, int max_split) {
+  const int sms = sm_count();
+  int best = 1;
+  double best_eff = 0;
+  for (int s = 1; s <= max_split; ++s) {
+    const int ctas = base_ctas * s;
+    const int waves = (ctas + sms - 1) / sms;
+    const double eff = static_cast<double>(ctas) / (static_cast<double>(waves) * sms);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+  }
+  return best;
+}
+
+template <int BN, int EPI>
+int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const cb::GemmParams& p, cudaStream_t st) {
+  using S = cb::GemmSmem<BN>;
+  static bool attr_set = false;
+  auto kern = cb::shift_gemm_kernel<BN, EPI>;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal) != cudaSuccess)
+      return fail("gemm: cannot set dynamic smem %d", S::kTotal);
+    attr_set = true;
+  }
+  dim3 grid((p.M + cb::kGemmBM - 1) / cb::kGemmBM, p.Npad / BN);
+  kern<<<grid, cb::kGemmThreads, S::kTotal, st>>>(ta, tb, p);
+  return check_launch("shift_gemm");
+}
+
+template <int EPI>
+int launch_gemm_bn(int BN, const CUtensorMap& ta, const CUtensorMap& tb, const cb::GemmParams& p, cudaStream_t st) {
+  switch (BN) {
+    case 32: return launch_gemm_t<32, EPI>(ta, tb, p, st);
+    case 64: return launch_gemm_t<64, EPI>(ta, tb, p, st);
+    case 128: return launch_gemm_t<128, EPI>(ta, tb, p, st);
+    case 256: return launch_gemm_t<256, EPI>(ta, tb, p, st);
+  }
+  return fail("gemm: unsupported BN %d", BN);
+}
+
+}  // namespace
+
+extern "C" {
+
+int craft_b200_abi_version(void) { return CRAFT_B200_ABI_VERSION; }
+const char* craft_b200_last_error(void) { return g_err; }
+
+int craft_b200_device_info(int* out3) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail("no CUDA device");
+  cudaDeviceGetAttribute(&out3[0], cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&out3[1], cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&out3[2], cudaDevAttrComputeCapabilityMinor, dev);
+  return 0;
+}
+
+int craft_pack_tokens(const float* src, int C, int H, int W, int mode, void* out_b, int ldb, int colb,
+                      float* out_f, int ldf, int colf, void* stream) {
+  cb::Grid2 g = make_grid(H, W);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid(H * ((g.Wp + 31) / 32));
+  auto* ob = static_cast<__nv_bfloat16*>(out_b);
+  if (C == 128) cb::pack_tokens_kernel<128><<<grid, 256, 0, st>>>(src, g, mode, ob, ldb, colb, out_f, ldf, colf);
+  else if (C == 256) cb::pack_tokens_kernel<256><<<grid, 256, 0, st>>>(src, g, mode, ob, ldb, colb, out_f, ldf, colf);
+  else return fail("pack_tokens: C must be 128 or 256 (got %d)", C);
+  return check_launch("pack_tokens");
+}
+
+int craft_unpack_tokens(const void* src, int is_bf16, int ld, int col, int C, int H, int W, float* dst,
+                        void* stream) {
+  cb::Grid2 g = make_grid(H, W);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid(H * ((W + 31) / 32), (C + 31) / 32);
+  if (is_bf16)
+    cb::unpack_tokens_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), ld, col, C, g, dst);
+  else
+    cb::unpack_tokens_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(src), ld, col, C, g, dst);
+  return check_launch("unpack_tokens");
+}
+
+int craft_shift_gemm(const craft_gemm_args* a, void* stream) {
+  if (!a || !a->A || !a->B) return fail("gemm: null operand");
+  if (a->K <= 0 || a->K % 64) return fail("gemm: K=%d must be a positive multiple of 64", a->K);
+  if (a->T < 1 || a->T > CRAFT_MAX_TAPS) return fail("gemm: T=%d out of range", a->T);
+  if (a->Npad % a->BN) return fail("gemm: Npad=%d not a multiple of BN=%d", a->Npad, a->BN);
+  if (a->a_koff % 64 || a->b_koff % 64) return fail("gemm: koff must be multiples of 64");
+  if (a->a_koff + a->K > a->lda || a->b_koff + a->K > a->ldb_) return fail("gemm: K range exceeds operand width");
+  if (a->b_rows < a->T * a->Npad) return fail("gemm: B has %d rows, needs %d", a->b_rows, a->T * a->Npad);
+  if (a->out_bf16 && ((a->ldo_b % 8) || (a->colo_b % 8))) return fail("gemm: bf16 output ld/col must be multiples of 8");
+  if (a->out_f32 && ((a->ldo_f % 4) || (a->colo_f % 4))) return fail("gemm: f32 output ld/col must be multiples of 4");
+  CUtensorMap ta, tb;
+  if (make_map_2d(&ta, a->A, a->a_rows, a->lda, a->lda, cb::kGemmBM)) return -1;
+  if (make_map_2d(&tb, a->B, a->b_rows, a->ldb_, a->ldb_, a->BN)) return -1;
+  cb::GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = a->M; p.Npad = a->Npad; p.K = a->K; p.T = a->T;
+  p.a_koff = a->a_koff; p.b_koff = a->b_koff;
+  for (int t = 0; t < a->T; ++t) p.tap_off[t] = a->tap_off[t];
+  if (a->H > 0) { p.Wp = a->W + 2; p.W = a->W; p.H = a->H; } else { p.Wp = 0; p.W = 0; p.H = 0; }
+  p.alpha = a->alpha; p.act = a->act; p.bias = a->bias;
+  p.out_b = static_cast<__nv_bfloat16*>(a->out_bf16); p.ldb = a->ldo_b; p.colb = a->colo_b;
+  p.out_f = a->out_f32; p.ldf = a->ldo_f; p.colf = a->colo_f;
+  p.aux_f0 = a->aux0; p.aux_f1 = a->aux1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (a->epilogue) {
+    case cb::EPI_STORE: return launch_gemm_bn<cb::EPI_STORE>(a->BN, ta, tb, p, st);
+    case cb::EPI_GRU_ZR:
+      if (a->Npad != 256 || !a->aux0 || !a->aux1 || !a->out_bf16) return fail("gemm: gru_zr needs Npad=256, Z, Hm, out");
+      if (a->BN > 128) return fail("gemm: gru_zr needs BN <= 128");
+      return launch_gemm_bn<cb::EPI_GRU_ZR>(a->BN, ta, tb, p, st);
+    case cb::EPI_GRU_Q:
+      if (a->Npad != 128 || !a->aux0 || !a->aux1 || !a->out_bf16) return fail("gemm: gru_q needs Npad=128, Z, Hm, out");
+      return launch_gemm_bn<cb::EPI_GRU_Q>(a->BN, ta, tb, p, st);
+    case cb::EPI_MOTION:
+      if (a->Npad != 128 || !a->aux1 || !a->out_bf16) return fail("gemm: motion needs Npad=128, flow, out");
+      return launch_gemm_bn<cb::EPI_MOTION>(a->BN, ta, tb, p, st);
+  }
+  return fail("gemm: unknown epilogue %d", a->epilogue);
+}
+
+int craft_scores_auto_ksplit(int H, int W) {
+  cb::Grid2 g = make_grid(H, W);
+  const int nqt = (g.Mp + 127) / 128;
+  const int nkt = ((H + 7) / 8) * ((W + 7) / 8);
+  int s = pick_split(nqt, 12);
+  if (s > nkt) s = nkt;
+  return s < 1 ? 1 : s;
+}
+int craft_pv_auto_ksplit(int H, int W, int M) {
+  cb::Grid2 g = make_grid(H, W);
+  const int nqt = (g.Mp + 127) / 128;
+  int s = pick_split(nqt * M, 6);
+  const int nkt = (g.Mp + 127) / 128;
+  if (s > nkt) s = nkt;
+  return s < 1 ? 1 : s;
+}
+
+}  // extern "C" (pause)
+static int scores_common(const craft_scores_args* a, int mode, void* stream) {
+  if (!a || !a->Q || !a->K) return fail("scores: null operand");
+  if (a->C != a->M * a->d || a->C % 64 || a->C > 256) return fail("scores: bad C/M/d = %d/%d/%d", a->C, a->M, a->d);
+  if (!(a->M == 1 || a->M == 2 || a->M == 4)) return fail("scores: M must be 1, 2 or 4");
+  if (a->d % 16 || (a->d < 64 && 64 % a->d)) return fail("scores: d=%d unsupported", a->d);
+  if (a->pos_table && (2 * a->R + 1) * (2 * a->R + 1) > 225) return fail("scores: pos radius too large");
+  cb::Grid2 g = make_grid(a->H, a->W);
+  CUtensorMap tq, tk;
+  if (make_map_2d(&tq, a->Q, g.Mp, a->C, a->C, 128)) return -1;
+  if (make_map_3d_keys(&tk, a->K, g, a->C)) return -1;
+  cb::ScoreParams p;
+  memset(&p, 0, sizeof(p));
+  p.g = g; p.C = a->C; p.M = a->M; p.d = a->d; p.scale = a->scale; p.w_pos = a->w_pos;
+  p.pos_table = a->pos_table; p.R = a->R; p.clip = a->clip; p.run_flag = a->run_flag;
+  p.nkt_y = (a->H + 7) / 8; p.nkt_x = (a->W + 7) / 8;
+  p.ksplit = a->ksplit > 0 ? a->ksplit : craft_scores_auto_ksplit(a->H, a->W);
+  p.w_agg = a->w_agg; p.stat_sum = a->stat_sum; p.stat_max = a->stat_max;
+  int h = a->H, w = a->W;
+  for (int l = 0; l < 4; ++l) {
+    p.lvl[l] = a->lvl[l]; p.hl[l] = h; p.wl[l] = w;
+    h /= 2; w /= 2;
+  }
+  p.lse_part = static_cast<float2*>(a->lse_part);
+  const int atoms = a->C / 64;
+  const int smem = 1024 + atoms * 128 * 128 + cb::kScKStages * atoms * 64 * 128 + 2048;
+  dim3 grid((g.Mp + 127) / 128, p.ksplit);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mode == cb::SC_CORR) {
+    if (!a->stat_sum || !a->stat_max || !a->lvl[1] || !a->lvl[2] || !a->lvl[3]) return fail("corr_build: missing outputs");
+    auto kern = cb::scores_kernel<cb::SC_CORR>;
+    static bool set = false;
+    if (!set) { if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return fail("scores: smem attr"); set = true; }
+    kern<<<grid, cb::kScThreads, smem, st>>>(tq, tk, p);
+    return check_launch("corr_build");
+  } else {
+    if (!a->lse_part || !a->lse2 || !a->stat_max) return fail("attn_lse: missing outputs");
+    auto kern = cb::scores_kernel<cb::SC_LSE>;
+    static bool set = false;
+    if (!set) { if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return fail("scores: smem attr"); set = true; }
+    kern<<<grid, cb::kScThreads, smem, st>>>(tq, tk, p);
+    if (check_launch("attn_lse")) return -1;
+    const int n = a->M * g.Mp;
+    cb::lse_merge_kernel<<<(n + 255) / 256, 256, 0, st>>>(p.lse_part, p.ksplit, a->M, g.Mp, a->lse2);
+    return check_launch("lse_merge");
+  }
+}
+
+extern "C" {
+int craft_corr_build(const craft_scores_args* a, void* stream) { return scores_common(a, cb::SC_CORR, stream); }
+int craft_attn_lse(const craft_scores_args* a, void* stream) { return scores_common(a, cb::SC_LSE, stream); }
+
+int craft_corr_stats_finalize(const double* stat_sum, double n, float* mean_rstd, void* stream) {
+  cb::corr_stats_finalize_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(stat_sum, n, mean_rstd);
+  return check_launch("corr_stats_finalize");
+}
+int craft_clip_gate(const float* stat_max, float attn_clip, float* clip, int* flag, void* stream) {
+  cb::clip_gate_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(stat_max, attn_clip, clip, flag);
+  return check_launch("clip_gate");
+}
+
+}  // extern "C" (pause)
+template <int D, int F, int BK, int KS, int VS>
+static int launch_pv(const craft_pv_args* a, const cb::Grid2& g, cudaStream_t st) {
+  using S = cb::PvSmem<D, F, BK, KS, VS>;
+  CUtensorMap tq, tk, tv;
+  if (make_map_2d(&tq, a->Q, g.Mp, a->C, a->C, 128)) return -1;
+  if (make_map_2d(&tk, a->K, g.Mp, a->C, a->C, BK)) return -1;
+  if (make_map_2d(&tv, a->Vt, static_cast<long long>(a->M) * F, g.Mp, a->ldv, F)) return -1;
+  cb::PvParams p;
+  memset(&p, 0, sizeof(p));
+  p.g = g; p.M = a->M; p.ksplit = a->ksplit; p.scale = a->scale; p.w_pos = a->w_pos;
+  p.pos_table = a->pos_table; p.R = a->R; p.clip = a->clip; p.lse2 = a->lse2; p.out = a->out;
+  p.nkeys = g.Mp;
+  auto kern = cb::attn_pv_kernel<D, F, BK, KS, VS>;
+  static bool set = false;
+  if (!set) { if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal) != cudaSuccess) return fail("pv: smem attr %d", S::kTotal); set = true; }
+  dim3 grid((g.Mp + 127) / 128, a->M, a->ksplit);
+  kern<<<grid, cb::kPvThreads, S::kTotal, st>>>(tq, tk, tv, p);
+  return check_launch("attn_pv");
+}
+
+extern "C" {
+int craft_attn_pv(const craft_pv_args* a, void* stream) {
+  if (!a || !a->Q || !a->K || !a->Vt || !a->out || !a->lse2 || !a->clip) return fail("attn_pv: null operand");
+  if (a->C != a->M * a->d) return fail("attn_pv: C != M*d");
+  if (a->ksplit < 1) return fail("attn_pv: ksplit must be >= 1");
+  if (a->pos_table && (2 * a->R + 1) * (2 * a->R + 1) > 225) return fail("attn_pv: pos radius too large");
+  cb::Grid2 g = make_grid(a->H, a->W);
+  if (a->ldv < g.Mp || a->ldv % 8) return fail("attn_pv: ldv=%d must be >= Mp and a multiple of 8", a->ldv);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a->d == 32 && a->F == 128) return launch_pv<32, 128, 128, 2, 2>(a, g, st);
+  if (a->d == 64 && a->F == 256) return launch_pv<64, 256, 64, 3, 3>(a, g, st);
+  if (a->d == 128 && a->F == 128) return launch_pv<128, 128, 64, 3, 3>(a, g, st);
+  if (a->d == 64 && a->F == 128) return launch_pv<64, 128, 128, 2, 2>(a, g, st);
+  return fail("attn_pv: unsupported (d=%d, F=%d)", a->d, a->F);
+}
+
+int craft_modes_finalize(const float* O, int nsum, int M, int F, const float* w_score, const float* b_score,
+                         const float* coeff, int gma, const void* x_bf16, int ldx, int colx,
+                         const float* x_f32, int ldxf, int colxf, int H, int W, void* out_bf16, int ldb,
+                         int colb, float* out_f32, int ldf, int colf, void* stream) {
+  cb::Grid2 g = make_grid(H, W);
+  if (M < 1 || M > 4) return fail("modes_finalize: M out of range");
+  if (!x_bf16 && !x_f32) return fail("modes_finalize: need the skip input");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long mode_stride = static_cast<long long>(g.Mp) * F;
+  const long long part_stride = mode_stride * M;
+  dim3 grid((g.Mp + 7) / 8);
+  auto* xb = static_cast<const __nv_bfloat16*>(x_bf16);
+  auto* ob = static_cast<__nv_bfloat16*>(out_bf16);
+  if (F == 128)
+    cb::modes_finalize_kernel<128><<<grid, 256, 0, st>>>(O, nsum, part_stride, M, mode_stride, w_score, b_score, coeff, gma, xb, ldx, colx, x_f32, ldxf, colxf, g, ob, ldb, colb, out_f32, ldf, colf);
+  else if (F == 256)
+    cb::modes_finalize_kernel<256><<<grid, 256, 0, st>>>(O, nsum, part_stride, M, mode_stride, w_score, b_score, coeff, gma, xb, ldx, colx, x_f32, ldxf, colxf, g, ob, ldb, colb, out_f32, ldf, colf);
+  else return fail("modes_finalize: F must be 128 or 256");
+  return check_launch("modes_finalize");
+}
+
+int craft_corr_lookup(const float* const* lvl, int H, int W, const float* coords, const float* mean_rstd,
+                      void* out_bf16, int ldb, float* out_nchw, int first_level, void* stream) {
+  cb::Grid2 g = make_grid(H, W);
+  cb::LookupParams p;
+  memset(&p, 0, sizeof(p));
+  int h = H, w = W;
+  for (int l = 0; l < 4; ++l) {
+    p.lvl[l] = lvl[l]; p.hl[l] = h; p.wl[l] = w; p.qstride[l] = static_cast<long long>(h) * w;
+    if (l >= first_level && !lvl[l]) return fail("corr_lookup: level %d missing", l);
+    h /= 2; w /= 2;
+  }
+  p.coords = coords; p.stats = mean_rstd; p.out_b = static_cast<__nv_bfloat16*>(out_bf16); p.ldb = ldb;
+  p.out_nchw = out_nchw; p.first_level = first_level;
+  cb::corr_lookup_kernel<<<(g.Mp + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g);
+  return check_launch("corr_lookup");
+}
+
+int craft_convf1(const float* flow, const float* wt, const float* bias, int H, int W, void* out_bf16, int ldo,
+                 int colo, void* stream) {
+  cb::Grid2 g = make_grid(H, W);
+  dim3 grid(H * ((W + 15) / 16), 2);
+  cb::convf1_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(flow, wt, bias, g, static_cast<__nv_bfloat16*>(out_bf16), ldo, colo);
+  return check_launch("convf1");
+}
+
+int craft_flow_update(float* coords1, float* flow, const float* delta, int ldd, int H, int W, void* stream) {
+  cb::Grid2 g = make_grid(H, W);
+  cb::flow_update_kernel<<<(g.Mp + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(coords1, flow, delta, ldd, g);
+  return check_launch("flow_update");
+}
+int craft_init_coords(float* coords1, const float* flow_init, int H, int W, void* stream) {
+  cb::Grid2 g = make_grid(H, W);
+  cb::init_coords_kernel<<<(g.Mp + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(coords1, flow_init, g);
+  return check_launch("init_coords");
+}
+
+int craft_upsample_flow(const void* mask, int mask_is_bf16, int ldm, const float* flow, int H, int W,
+                        float* out, void* stream) {
+  cb::Grid2 g = make_grid(H, W);
+  dim3 grid((H * W + 3) / 4);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mask_is_bf16)
+    cb::upsample_flow_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(mask), ldm, flow, g, out);
+  else
+    cb::upsample_flow_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(mask), ldm, flow, g, out);
+  return check_launch("upsample_flow");
+}
+
+}  // extern "C"

@@ -1,0 +1,377 @@
+// craft_b200 -- HBM-bound kernels of the hot path (coalesced, vectorised, warp-shuffle reductions).
+//
+// Geometry ("padded-flat token grid"): a feature map of h x w tokens is stored
+// token-major as rows p = y * Wp + x with Wp = w + 2; the two cells x in {w, w+1} of every grid
+// row are halo cells that always hold zeros, so a conv tap (dy,dx), |dx| <= 2, is the row offset
+// dy*Wp + dx (gemm.cuh).  Mp = h * Wp rows.
+#pragma once
+#include "common.cuh"
+
+namespace cb {
+
+struct Grid2 {
+  int H, W, Wp, Mp;
+};
+
+// -------------------------------------------------------------------------------------------
+// pack_tokens: NCHW fp32 -> token-major rows, with optional per-token LayerNorm / activation.
+//   reference: SETransInputFeatEncoder.forward core/setrans.py:791-795 (transpose + LayerNorm,
+//   eps 1e-12, no affine; pos_code_weight = 0 for pos_code_type 'bias'), and the tanh / relu
+//   split of cnet features core/network.py:209-211.
+// mode: 0 copy, 1 layer-norm over C, 2 tanh, 3 relu
+// Block = 256 threads handles 32 consecutive tokens of one grid row, all C channels.
+// -------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) pack_tokens_kernel(const float* __restrict__ src, Grid2 g,
+                                                          int mode, __nv_bfloat16* __restrict__ out_b,
+                                                          int ldb, int colb, float* __restrict__ out_f,
+                                                          int ldf, int colf) {
+  __shared__ float tile[C][33];
+  const int tiles_per_row = (g.Wp + 31) / 32;
+  const int y = blockIdx.x / tiles_per_row;
+  const int x0 = (blockIdx.x - y * tiles_per_row) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 warps
+  // coalesced read along x for each channel
+  for (int c = ty; c < C; c += 8) {
+    const int x = x0 + tx;
+    tile[c][tx] = (x < g.W) ? __ldg(src + (static_cast<size_t>(c) * g.H + y) * g.W + x) : 0.0f;
+  }
+  __syncthreads();
+  // each warp owns 4 tokens; lanes stride channels
+  for (int t = ty * 4; t < ty * 4 + 4; ++t) {
+    const int x = x0 + t;
+    if (x >= g.Wp) break;
+    const size_t p = static_cast<size_t>(y) * g.Wp + x;
+    const bool halo = x >= g.W;
+    float mean = 0.f, rstd = 1.f;
+    if (mode == 1 && !halo) {
+      float s = 0.f;
+      for (int c = tx; c < C; c += 32) s += tile[c][t];
+      mean = warp_sum(s) * (1.0f / C);
+      float v = 0.f;
+      for (int c = tx; c < C; c += 32) {
+        const float d = tile[c][t] - mean;
+        v += d * d;
+      }
+      rstd = rsqrtf(warp_sum(v) * (1.0f / C) + 1e-12f);
+    }
+    for (int c = tx; c < C; c += 32) {
+      float v = tile[c][t];
+      if (halo) v = 0.f;
+      else if (mode == 1) v = (v - mean) * rstd;
+      else if (mode == 2) v = tanhf(v);
+      else if (mode == 3) v = fmaxf(v, 0.f);
+      if (out_b) out_b[p * ldb + colb + c] = __float2bfloat16_rn(v);
+      if (out_f) out_f[p * ldf + colf + c] = v;
+    }
+  }
+}
+
+// unpack_tokens: token-major rows (bf16 or f32) -> NCHW fp32.
+template <typename T>
+__global__ void __launch_bounds__(256) unpack_tokens_kernel(const T* __restrict__ src, int ld, int col,
+                                                            int C, Grid2 g, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int tiles_per_row = (g.W + 31) / 32;
+  const int y = blockIdx.x / tiles_per_row;
+  const int x0 = (blockIdx.x - y * tiles_per_row) * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int t = ty; t < 32; t += 8) {
+    const int x = x0 + t;
+    const int c = c0 + tx;
+    float v = 0.f;
+    if (x < g.W && c < C) v = static_cast<float>(src[(static_cast<size_t>(y) * g.Wp + x) * ld + col + c]);
+    tile[t][tx] = v;
+  }
+  __syncthreads();
+  for (int cc = ty; cc < 32; cc += 8) {
+    const int c = c0 + cc;
+    const int x = x0 + tx;
+    if (c < C && x < g.W) dst[(static_cast<size_t>(c) * g.H + y) * g.W + x] = tile[tx][cc];
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// corr_lookup: radius-r bilinear window lookup over the 4-level pyramid with the global
+// layer-norm applied as a deferred affine.
+//   reference: CorrBlock.__call__ core/corr.py:47-71, bilinear_sampler core/utils/utils.py:65-79
+//   (grid_sample bilinear, zeros padding, align_corners=True), global LN core/corr.py:200-204.
+// Output channel = l*(2r+1)^2 + i*(2r+1) + j with x-offset = i - r, y-offset = j - r.
+// lookup(LN(v)) = rstd * (lookup(v) - mean * sum_of_inbounds_weights)  (LN is affine, pooling
+// and bilinear sampling are linear).  stats = {mean, rstd}; pass {0,1} for no normalisation.
+// One warp per query token.  R = 4 -> 10x10 cells per level.
+// -------------------------------------------------------------------------------------------
+struct LookupParams {
+  const float* lvl[4];   // level l volume: [Mq(query rows, padded-flat)][h_l * w_l]  (lvl[0] may be null if on-demand)
+  int hl[4], wl[4];
+  long long qstride[4];  // elements between consecutive query rows
+  const float* coords;   // [Mp, 2] (x, y) padded-flat
+  const float* stats;    // device {mean, rstd}
+  __nv_bfloat16* out_b;  // [Mp, ldb] token-major (cols >= 4*81 left untouched)
+  int ldb;
+  float* out_nchw;       // [324, H, W] or nullptr
+  int first_level;       // levels < first_level are skipped (handled by the on-demand kernel)
+};
+
+__global__ void __launch_bounds__(256) corr_lookup_kernel(LookupParams p, Grid2 g) {
+  constexpr int R = 4, D = 2 * R + 1, WN = D + 1;   // 9 taps, 10 cells
+  __shared__ float win[8][WN * WN + 4];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 8 + wib;   // padded-flat query index
+  if (q >= g.Mp) return;
+  const int qy = q / g.Wp, qx = q - qy * g.Wp;
+  if (qx >= g.W) return;                // halo token: leave zeros
+  const float cx = p.coords[2 * q], cy = p.coords[2 * q + 1];
+  const float mean = p.stats[0], rstd = p.stats[1];
+  float* wv = win[wib];
+  for (int l = p.first_level; l < 4; ++l) {
+    const float inv = 1.0f / static_cast<float>(1 << l);
+    const float px = cx * inv, py = cy * inv;
+    const float fx0 = floorf(px), fy0 = floorf(py);
+    const float ax = px - fx0, ay = py - fy0;
+    const int x0 = static_cast<int>(fx0) - R, y0 = static_cast<int>(fy0) - R;
+    const int hl = p.hl[l], wl = p.wl[l];
+    const float* vol = p.lvl[l] + static_cast<long long>(q) * p.qstride[l];
+    __syncwarp();
+    for (int e = lane; e < WN * WN; e += 32) {
+      const int r = e / WN, c = e - r * WN;
+      const int yy = y0 + r, xx = x0 + c;
+      float v = 0.f;
+      if (yy >= 0 && yy < hl && xx >= 0 && xx < wl) v = __ldg(vol + yy * wl + xx) - mean;
+      wv[e] = v;   // (value - mean) inside bounds, 0 outside == deferred-LN numerator
+    }
+    __syncwarp();
+    for (int e = lane; e < D * D; e += 32) {
+      const int i = e / D, j = e - i * D;   // i: x offset index, j: y offset index
+      const float v00 = wv[j * WN + i], v01 = wv[j * WN + i + 1];
+      const float v10 = wv[(j + 1) * WN + i], v11 = wv[(j + 1) * WN + i + 1];
+      const float top = v00 + ax * (v01 - v00);
+      const float bot = v10 + ax * (v11 - v10);
+      const float val = (top + ay * (bot - top)) * rstd;
+      const int ch = l * D * D + e;
+      if (p.out_b) p.out_b[static_cast<size_t>(q) * p.ldb + ch] = __float2bfloat16_rn(val);
+      if (p.out_nchw) p.out_nchw[(static_cast<size_t>(ch) * g.H + qy) * g.W + qx] = val;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// upsample_flow: convex 8x upsampling.
+//   reference: CRAFT.upsample_flow core/network.py:151-162.  mask channel = k*64 + sy*8 + sx,
+//   k = 3x3 neighbour (row-major, zero padded), softmax over k, output pixel (8y+sy, 8x+sx).
+// mask: token-major [Mp, ldm] (already scaled by 0.25 by the mask head), flow: [Mp, 2] f32.
+// Block = 256 threads = 4 tokens x 64 sub-pixels.
+// -------------------------------------------------------------------------------------------
+template <typename TM>
+__global__ void __launch_bounds__(256) upsample_flow_kernel(const TM* __restrict__ mask, int ldm,
+                                                            const float* __restrict__ flow, Grid2 g,
+                                                            float* __restrict__ out /*[2,8H,8W]*/) {
+  const int sub = threadIdx.x & 63;
+  const int tok = blockIdx.x * 4 + (threadIdx.x >> 6);   // index over real tokens (y*W + x)
+  if (tok >= g.H * g.W) return;
+  const int y = tok / g.W, x = tok - y * g.W;
+  const size_t p = static_cast<size_t>(y) * g.Wp + x;
+  float m[9];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    m[k] = static_cast<float>(mask[p * ldm + k * 64 + sub]);
+    mx = fmaxf(mx, m[k]);
+  }
+  float den = 0.f, ox = 0.f, oy = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const int dy = k / 3 - 1, dx = k % 3 - 1;
+    const int yy = y + dy, xx = x + dx;
+    const float e = __expf(m[k] - mx);
+    den += e;
+    if (yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) {
+      const size_t pn = static_cast<size_t>(yy) * g.Wp + xx;
+      ox += e * flow[2 * pn];
+      oy += e * flow[2 * pn + 1];
+    }
+  }
+  const float s = 8.0f / den;
+  const int sy = sub >> 3, sx = sub & 7;
+  const size_t HW8 = static_cast<size_t>(8 * g.H) * (8 * g.W);
+  const size_t o = static_cast<size_t>(8 * y + sy) * (8 * g.W) + 8 * x + sx;
+  out[o] = ox * s;
+  out[HW8 + o] = oy * s;
+}
+
+// -------------------------------------------------------------------------------------------
+// convf1: 7x7 conv 2 -> 128 + ReLU on the flow field (K = 98: too thin for a tensor-core tile).
+//   reference: BasicMotionEncoder.convf1 core/update.py:75,82.
+// weights wt: [98][128] f32 (tap-major: (c*49 + ky*7 + kx), cout), bias [128].
+// Block: 128 threads (= cout), 16 consecutive tokens of one grid row.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) convf1_kernel(const float* __restrict__ flow /*[Mp,2]*/,
+                                                     const float* __restrict__ wt,
+                                                     const float* __restrict__ bias, Grid2 g,
+                                                     __nv_bfloat16* __restrict__ out, int ldo, int colo) {
+  constexpr int TX = 8;     // tokens per thread; block covers 16 tokens x 64 couts (gridDim.y = 2)
+  __shared__ float in[2][7][16 + 6];
+  __shared__ float ws[98 * 64];
+  const int tiles_per_row = (g.W + 15) / 16;
+  const int y = blockIdx.x / tiles_per_row;
+  const int xb = (blockIdx.x - y * tiles_per_row) * 16;
+  const int co = blockIdx.y * 64 + (threadIdx.x & 63);
+  const int tg = threadIdx.x >> 6;
+  const int x0 = xb + tg * TX;
+  for (int i = threadIdx.x; i < 98 * 64; i += 128) ws[i] = wt[(i >> 6) * 128 + blockIdx.y * 64 + (i & 63)];
+  for (int i = threadIdx.x; i < 2 * 7 * 22; i += 128) {
+    const int c = i / (7 * 22);
+    const int r = (i / 22) % 7;
+    const int cx = i % 22;
+    const int yy = y + r - 3, xx = xb + cx - 3;
+    float v = 0.f;
+    if (yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) v = flow[(static_cast<size_t>(yy) * g.Wp + xx) * 2 + c];
+    in[c][r][cx] = v;
+  }
+  __syncthreads();
+  float acc[TX];
+  const float b = bias[co];
+#pragma unroll
+  for (int t = 0; t < TX; ++t) acc[t] = b;
+  for (int c = 0; c < 2; ++c)
+    for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        const float w = ws[(c * 49 + ky * 7 + kx) * 64 + (threadIdx.x & 63)];
+#pragma unroll
+        for (int t = 0; t < TX; ++t) acc[t] += w * in[c][ky][tg * TX + t + kx];
+      }
+  for (int t = 0; t < TX; ++t) {
+    const int x = x0 + t;
+    if (x < g.W)
+      out[(static_cast<size_t>(y) * g.Wp + x) * ldo + colo + co] = __float2bfloat16_rn(fmaxf(acc[t], 0.f));
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// flow_update: coords1 += delta ; flow = coords1 - coords0 (coords0 is the token's own (x,y)).
+//   reference: core/network.py:236,247.  delta: [Mp, ldd] f32 (cols 0,1).  Halo rows stay zero.
+// -------------------------------------------------------------------------------------------
+__global__ void flow_update_kernel(float* __restrict__ coords1, float* __restrict__ flow,
+                                   const float* __restrict__ delta, int ldd, Grid2 g) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g.Mp) return;
+  const int y = p / g.Wp, x = p - y * g.Wp;
+  if (x >= g.W) return;
+  float cx = coords1[2 * p], cy = coords1[2 * p + 1];
+  if (delta) {
+    cx += delta[static_cast<size_t>(p) * ldd];
+    cy += delta[static_cast<size_t>(p) * ldd + 1];
+    coords1[2 * p] = cx;
+    coords1[2 * p + 1] = cy;
+  }
+  flow[2 * p] = cx - static_cast<float>(x);
+  flow[2 * p + 1] = cy - static_cast<float>(y);
+}
+
+// init_coords: coords1 = grid (+ flow_init NCHW [2,H,W]); reference core/network.py:142-149,221-222.
+__global__ void init_coords_kernel(float* __restrict__ coords1, const float* __restrict__ flow_init,
+                                   Grid2 g) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g.Mp) return;
+  const int y = p / g.Wp, x = p - y * g.Wp;
+  float cx = 0.f, cy = 0.f;
+  if (x < g.W) {
+    cx = static_cast<float>(x);
+    cy = static_cast<float>(y);
+    if (flow_init) {
+      cx += flow_init[static_cast<size_t>(y) * g.W + x];
+      cy += flow_init[static_cast<size_t>(g.H) * g.W + static_cast<size_t>(y) * g.W + x];
+    }
+  }
+  coords1[2 * p] = cx;
+  coords1[2 * p + 1] = cy;
+}
+
+// -------------------------------------------------------------------------------------------
+// modes_finalize: collapse M per-mode aggregated features into one, add the input skip and
+// LayerNorm.   reference: ExpandedFeatTrans.forward core/setrans.py:395-407 with
+// LearnedSoftAggregate (num_feat = F) core/setrans.py:289-300:
+//     s_m = <w, O_m> + b ; p = softmax_m(s) ; agg = sum_m p_m O_m ; y = LN(coeff * x + agg)
+// GMA variant (core/gma.py:140): M = 1, y = x + gamma * O  (no LN) -- `gma` != 0.
+// O: [M][Mp][F] f32.  x: token-major bf16 (ldx, colx).  One warp per token.
+// -------------------------------------------------------------------------------------------
+template <int F>
+__global__ void __launch_bounds__(256) modes_finalize_kernel(
+    const float* __restrict__ O, int nsum, long long part_stride, int M, long long mode_stride,
+    const float* __restrict__ w_score,
+    const float* __restrict__ b_score, const float* __restrict__ coeff, int gma,
+    const __nv_bfloat16* __restrict__ xb, int ldx, int colx, const float* __restrict__ xf, int ldxf,
+    int colxf, Grid2 g, __nv_bfloat16* __restrict__ out_b, int ldb, int colb,
+    float* __restrict__ out_f, int ldf, int colf) {
+  constexpr int PER = F / 32;
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (p >= g.Mp) return;
+  const int y = p / g.Wp, x = p - y * g.Wp;
+  if (x >= g.W) return;
+  float o[4][PER];
+  float sc[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    sc[m] = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < PER; ++e) o[m][e] = 0.f;
+    if (m < M) {
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < PER; ++e) {
+        const int f = lane + 32 * e;
+        float acc = 0.f;
+        for (int sp = 0; sp < nsum; ++sp)
+          acc += O[sp * part_stride + m * mode_stride + static_cast<long long>(p) * F + f];
+        o[m][e] = acc;
+        if (!gma) s += acc * __ldg(w_score + f);
+      }
+      sc[m] = gma ? 0.f : warp_sum(s) + b_score[0];
+    }
+  }
+  const float mx = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
+  float den = 0.f;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    sc[m] = (m < M) ? __expf(sc[m] - mx) : 0.f;
+    den += sc[m];
+  }
+  const float c = coeff[0];
+  float yv[PER];
+  float s1 = 0.f;
+#pragma unroll
+  for (int e = 0; e < PER; ++e) {
+    const int f = lane + 32 * e;
+    float agg = 0.f;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) agg += sc[m] * o[m][e];
+    agg /= den;
+    const float xin = xf ? xf[static_cast<size_t>(p) * ldxf + colxf + f]
+                         : __bfloat162float(xb[static_cast<size_t>(p) * ldx + colx + f]);
+    yv[e] = gma ? (xin + c * agg) : (c * xin + agg);
+    s1 += yv[e];
+  }
+  if (!gma) {
+    const float mean = warp_sum(s1) * (1.0f / F);
+    float s2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+      const float d = yv[e] - mean;
+      s2 += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(s2) * (1.0f / F) + 1e-12f);
+#pragma unroll
+    for (int e = 0; e < PER; ++e) yv[e] = (yv[e] - mean) * rstd;
+  }
+#pragma unroll
+  for (int e = 0; e < PER; ++e) {
+    const int f = lane + 32 * e;
+    if (out_b) out_b[static_cast<size_t>(p) * ldb + colb + f] = __float2bfloat16_rn(yv[e]);
+    if (out_f) out_f[static_cast<size_t>(p) * ldf + colf + f] = yv[e];
+  }
+}
+
+}  // namespace cb

@@ -1,0 +1,149 @@
+/* craft_b200 -- C ABI of the B200-native CRAFT hot path (libcraft_b200.so).
+ *
+ * Every entry point takes plain device pointers, sizes and a cudaStream_t (as void*); no torch
+ * types cross this boundary.  All return 0 on success or a negative code; the message is
+ * available from craft_b200_last_error().  Pointers are device pointers unless noted.
+ *
+ * Layout convention ("padded-flat token grid"): a feature map of h x w
+ * tokens is stored token-major with rows p = y*(w+2) + x; the two trailing cells of every grid
+ * row are zero halo cells.  Mp = h*(w+2).  bf16 buffers are row-major [Mp, ld].
+ *
+ * Each function names the reference code it replaces (paths relative to askerlee/craft).
+ */
+#ifndef CRAFT_B200_H_
+#define CRAFT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRAFT_B200_ABI_VERSION 1
+#define CRAFT_MAX_TAPS 49
+
+int craft_b200_abi_version(void);
+const char* craft_b200_last_error(void);
+/* device properties the host uses for grid sizing: [0]=sm count, [1]=cc major, [2]=cc minor */
+int craft_b200_device_info(int* out3);
+
+/* ---- layout ------------------------------------------------------------------------------ */
+/* NCHW f32 -> token rows.  mode: 0 copy, 1 LayerNorm over C (eps 1e-12, no affine), 2 tanh,
+ * 3 relu.  C in {128, 256}.  Replaces SETransInputFeatEncoder.forward
+ * core/setrans.py:791-795 (mode 1) and the tanh/relu split core/network.py:209-211.       */
+int craft_pack_tokens(const float* src_nchw, int C, int H, int W, int mode, void* out_bf16,
+                      int ldb, int colb, float* out_f32, int ldf, int colf, void* stream);
+/* token rows (bf16 if is_bf16 else f32) -> NCHW f32 */
+int craft_unpack_tokens(const void* src, int is_bf16, int ld, int col, int C, int H, int W,
+                        float* dst_nchw, void* stream);
+
+/* ---- tcgen05 shift-GEMM -------------------------------------------------------------------
+ * D[m,n] = sum_t sum_k A[m + tap_off[t], a_koff + k] * B[t*Npad + n, b_koff + k]
+ * Replaces every nn.Linear / nn.Conv2d on the hot path: query/key projections
+ * core/setrans.py:507-508, first_linear :373, BasicMotionEncoder core/update.py:80-86,
+ * SepConvGRU :49-64, FlowHead :16, mask head :124-127,161.                                 */
+typedef struct craft_gemm_args {
+  const void* A;      /* bf16 [a_rows, lda]                                                  */
+  int a_rows, lda, a_koff;
+  const void* B;      /* bf16 [T*Npad, ldb_]                                                  */
+  int b_rows, ldb_, b_koff;
+  int M, Npad, K, T;
+  int BN;             /* CTA tile width: 32, 64, 128 or 256 (Npad % BN == 0)                 */
+  int tap_off[CRAFT_MAX_TAPS];
+  int H, W;           /* >0: rows are a padded-flat grid, halo rows are not written; 0: plain */
+  int epilogue;       /* 0 store, 1 gru_zr, 2 gru_q, 3 motion                                 */
+  float alpha;
+  int act;            /* 0 none, 1 relu                                                       */
+  const float* bias;  /* [Npad] or NULL                                                       */
+  void* out_bf16;     /* row-major, may be NULL                                               */
+  int ldo_b, colo_b;
+  float* out_f32;
+  int ldo_f, colo_f;
+  float* aux0;        /* gru: Z [M,128]                                                       */
+  float* aux1;        /* gru: Hm [M,128]; motion: flow [M,2]                                  */
+} craft_gemm_args;
+int craft_shift_gemm(const craft_gemm_args* a, void* stream);
+
+/* ---- scores: correlation volume build + attention LSE ------------------------------------ */
+typedef struct craft_scores_args {
+  const void* Q;      /* bf16 [Mp, C] projected queries (token rows)                          */
+  const void* K;      /* bf16 [Mp, C] projected keys                                          */
+  int C, M, d;        /* channels, modes, per-mode dim (C == M*d)                             */
+  int H, W;
+  float scale;        /* 1/sqrt(d)                                                            */
+  float w_pos;        /* pos_code_weight                                                      */
+  const float* pos_table;   /* [(2R+1)^2] or NULL                                             */
+  int R;
+  const float* clip;  /* device scalar: +inf or attn_clip                                     */
+  const int* run_flag;/* NULL, or device int: kernel is a no-op when *run_flag == 0           */
+  int ksplit;         /* 0 = auto                                                             */
+  /* corr build */
+  float w_agg;        /* attn_softaggr.feat2score.weight                                      */
+  double* stat_sum;   /* [2] sum, sum of squares (must be zeroed by the caller)               */
+  float* stat_max;    /* [1] running max of raw scaled scores (caller initialises to -inf)    */
+  float* lvl[4];      /* pyramid volumes [Mp][h_l*w_l]; lvl[0] may be NULL                    */
+  /* lse */
+  void* lse_part;     /* float2 [ksplit][M][Mp] scratch                                       */
+  float* lse2;        /* [M][Mp] out                                                          */
+} craft_scores_args;
+/* TransCorrBlock.update core/corr.py:148-207 (+ CorrBlock.__init__ :16-45 with M=1).         */
+int craft_corr_build(const craft_scores_args* a, void* stream);
+/* softmax statistics of CrossAttFeatTrans.forward core/setrans.py:514-553 / gma.Attention.   */
+int craft_attn_lse(const craft_scores_args* a, void* stream);
+/* grid heuristics (host-side): key splits chosen so the grid fills whole waves of SMs         */
+int craft_scores_auto_ksplit(int H, int W);
+int craft_pv_auto_ksplit(int H, int W, int M);
+/* {sum,sumsq} -> {mean,rstd} (F.layer_norm, core/corr.py:200-204); n = number of elements.   */
+int craft_corr_stats_finalize(const double* stat_sum, double n, float* mean_rstd, void* stream);
+/* clip = (max > attn_clip) ? attn_clip : +inf ; flag = hit (core/setrans.py:527-529).        */
+int craft_clip_gate(const float* stat_max, float attn_clip, float* clip, int* flag, void* stream);
+
+/* ---- flash P.V ---------------------------------------------------------------------------- */
+typedef struct craft_pv_args {
+  const void* Q;      /* bf16 [Mp, C]                                                          */
+  const void* K;      /* bf16 [Mp, C]                                                          */
+  const void* Vt;     /* bf16 [M*F, ldv]  (V transposed: keys contiguous)                      */
+  int ldv;
+  int C, M, d, F;
+  int H, W;
+  float scale, w_pos;
+  const float* pos_table;
+  int R;
+  const float* clip;
+  const float* lse2;  /* [M][Mp]                                                               */
+  float* out;         /* f32 [ksplit][M][Mp][F]                                                */
+  int ksplit;
+} craft_pv_args;
+/* ExpandedFeatTrans.forward core/setrans.py:373-383, gma.Aggregate.forward core/gma.py:131-134 */
+int craft_attn_pv(const craft_pv_args* a, void* stream);
+
+/* mode soft-pooling + input skip + LayerNorm (core/setrans.py:395-407, :289-300);
+ * gma != 0: y = x + gamma*O (core/gma.py:140).  O: [nsum][M][Mp][F] partials are summed.      */
+int craft_modes_finalize(const float* O, int nsum, int M, int F, const float* w_score,
+                         const float* b_score, const float* coeff, int gma, const void* x_bf16,
+                         int ldx, int colx, const float* x_f32, int ldxf, int colxf, int H, int W,
+                         void* out_bf16, int ldb, int colb, float* out_f32, int ldf, int colf,
+                         void* stream);
+
+/* ---- correlation lookup (CorrBlock.__call__ core/corr.py:47-71) --------------------------- */
+int craft_corr_lookup(const float* const* lvl /*host array of 4 device ptrs*/, int H, int W,
+                      const float* coords /*[Mp,2]*/, const float* mean_rstd, void* out_bf16,
+                      int ldb, float* out_nchw, int first_level, void* stream);
+
+/* ---- small HBM-bound pieces ---------------------------------------------------------------- */
+/* BasicMotionEncoder.convf1 (7x7, 2->128) + ReLU, core/update.py:75,82. wt [98][128], bias[128] */
+int craft_convf1(const float* flow, const float* wt, const float* bias, int H, int W, void* out_bf16,
+                 int ldo, int colo, void* stream);
+/* coords1 += delta; flow = coords1 - coords0 (core/network.py:236,247). delta may be NULL.     */
+int craft_flow_update(float* coords1, float* flow, const float* delta, int ldd, int H, int W,
+                      void* stream);
+/* coords1 = grid (+ flow_init NCHW) (core/network.py:142-149,221-222)                          */
+int craft_init_coords(float* coords1, const float* flow_init_nchw, int H, int W, void* stream);
+/* convex 8x upsampling (CRAFT.upsample_flow core/network.py:151-162). mask rows [Mp, ldm].      */
+int craft_upsample_flow(const void* mask, int mask_is_bf16, int ldm, const float* flow, int H, int W,
+                        float* out_nchw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRAFT_B200_H_ */

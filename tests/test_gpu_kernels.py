@@ -1,0 +1,306 @@
+"""Kernel-level parity on the GPU: every C-ABI entry point against the oracle restatement
+(oracle/restate.py, plain torch fp32) on identical, bf16-representable inputs."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from craft_b200 import ops                      # noqa: E402
+from craft_b200.ops import TokenGrid            # noqa: E402
+from oracle import restate as R                 # noqa: E402
+
+DEV = "cuda"
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).float()
+
+
+def rows_from_nchw(x, grid, cols=None, col0=0, dtype=torch.bfloat16):
+    """[C,H,W] -> padded-flat token rows (host-side reference packer)."""
+    Cc = x.shape[0]
+    buf = torch.zeros((grid.H, grid.Wp, cols or Cc), dtype=torch.float32, device=x.device)
+    buf[:, : grid.W, col0:col0 + Cc] = x.permute(1, 2, 0)
+    return buf.reshape(grid.Mp, -1).to(dtype).contiguous()
+
+
+def nchw_from_rows(buf, grid, Cc, col0=0):
+    return buf.float().reshape(grid.H, grid.Wp, -1)[:, : grid.W, col0:col0 + Cc].permute(2, 0, 1).contiguous()
+
+
+@pytest.mark.parametrize("BN,Npad,K,M", [(128, 128, 64, 128), (128, 256, 256, 300), (64, 192, 128, 1000),
+                                         (32, 32, 320, 129), (256, 512, 512, 777)])
+def test_gemm_plain(BN, Npad, K, M):
+    g = torch.Generator(device=DEV).manual_seed(BN + K)
+    A = bf16r(torch.randn((M, K), device=DEV, generator=g))
+    B = bf16r(torch.randn((Npad, K), device=DEV, generator=g) * 0.1)
+    bias = torch.randn((Npad,), device=DEV, generator=g)
+    out_b = torch.zeros((M, Npad), dtype=torch.bfloat16, device=DEV)
+    out_f = torch.zeros((M, Npad), dtype=torch.float32, device=DEV)
+    ops.shift_gemm(A.to(torch.bfloat16), B.to(torch.bfloat16), M=M, Npad=Npad, K=K, BN=BN, bias=bias, act=1,
+                   alpha=0.5, out_b=out_b, out_f=out_f)
+    torch.cuda.synchronize()
+    ref = torch.relu(0.5 * (A @ B.t()) + bias)
+    assert torch.allclose(out_f, ref, atol=2e-3, rtol=1e-3), (out_f - ref).abs().max()
+    assert torch.allclose(out_b.float(), ref, atol=3e-2, rtol=1e-2)
+
+
+@pytest.mark.parametrize("kh,kw,Cin,Cout,BN", [(3, 3, 64, 128, 128), (1, 5, 128, 64, 64), (5, 1, 192, 256, 128),
+                                               (1, 1, 384, 256, 256), (3, 3, 256, 32, 32)])
+def test_gemm_conv(kh, kw, Cin, Cout, BN):
+    grid = TokenGrid(13, 21)
+    g = torch.Generator(device=DEV).manual_seed(kh * 10 + kw)
+    x = bf16r(torch.randn((Cin, grid.H, grid.W), device=DEV, generator=g))
+    w = bf16r(torch.randn((Cout, Cin, kh, kw), device=DEV, generator=g) * 0.05)
+    b = torch.randn((Cout,), device=DEV, generator=g)
+    X = rows_from_nchw(x, grid)
+    Wp = ops.pack_conv_weight(w)
+    out = grid.zeros(Cout, dtype=torch.float32)
+    ops.shift_gemm(X, Wp, M=grid.Mp, Npad=Cout, K=Wp.shape[1], BN=BN, taps=ops.conv_taps(kh, kw, grid), grid=grid,
+                   bias=b, act=0, out_f=out)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x[None], w, b, padding=(kh // 2, kw // 2))[0]
+    got = nchw_from_rows(out, grid, Cout)
+    assert torch.allclose(got, ref, atol=3e-3, rtol=1e-3), (got - ref).abs().max()
+    # halo rows must stay untouched (zero)
+    assert out.reshape(grid.H, grid.Wp, -1)[:, grid.W:].abs().max() == 0
+
+
+def test_gemm_gru_epilogues():
+    grid = TokenGrid(10, 18)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    h = torch.tanh(torch.randn((128, grid.H, grid.W), device=DEV, generator=g))
+    x = bf16r(torch.randn((384, grid.H, grid.W), device=DEV, generator=g))
+    P = {}
+    for n in "zrq":
+        P["conv%s1.weight" % n] = bf16r(torch.randn((128, 512, 1, 5), device=DEV, generator=g) * 0.03)
+        P["conv%s1.bias" % n] = torch.randn((128,), device=DEV, generator=g) * 0.1
+    # X buffer: [h | x | rh]
+    X = grid.zeros(640)
+    X[:, :512] = rows_from_nchw(torch.cat([h, x], 0), grid)
+    Hm = rows_from_nchw(h, grid, dtype=torch.float32)
+    Z = grid.zeros(128, dtype=torch.float32)
+    Wzr = ops.pack_conv_weight(torch.cat([P["convz1.weight"], P["convr1.weight"]], 0))
+    bzr = torch.cat([P["convz1.bias"], P["convr1.bias"]]).contiguous()
+    perm = list(range(128, 512)) + list(range(0, 128))       # q conv sees [x | r*h]
+    Wq = ops.pack_conv_weight(P["convq1.weight"], cin_perm=perm)
+    taps = ops.conv_taps(1, 5, grid)
+    hb = bf16r(h)
+    ops.shift_gemm(X, Wzr, M=grid.Mp, Npad=256, K=512, BN=128, taps=taps, grid=grid, epilogue=ops.EPI_GRU_ZR,
+                   bias=bzr, out_b=X, colb=512, aux0=Z, aux1=Hm)
+    ops.shift_gemm(X, Wq, M=grid.Mp, Npad=128, K=512, BN=64, taps=taps, a_koff=128, grid=grid,
+                   epilogue=ops.EPI_GRU_Q, bias=P["convq1.bias"].contiguous(), out_b=X, colb=0, aux0=Z, aux1=Hm)
+    torch.cuda.synchronize()
+    hx = torch.cat([hb, x], 0)[None]
+    z = torch.sigmoid(F.conv2d(hx, P["convz1.weight"], P["convz1.bias"], padding=(0, 2)))
+    r = torch.sigmoid(F.conv2d(hx, P["convr1.weight"], P["convr1.bias"], padding=(0, 2)))
+    rh = bf16r(r * h[None])
+    q = torch.tanh(F.conv2d(torch.cat([rh, x[None]], 1), P["convq1.weight"], P["convq1.bias"], padding=(0, 2)))
+    ref = ((1 - z) * h[None] + z * q)[0]
+    got = nchw_from_rows(Hm, grid, 128)
+    assert torch.allclose(got, ref, atol=5e-3), (got - ref).abs().max()
+    got_b = nchw_from_rows(X, grid, 128)
+    assert torch.allclose(got_b, ref, atol=2e-2)
+
+
+@pytest.mark.parametrize("Cc,mode", [(256, 1), (128, 2), (128, 3), (256, 0)])
+def test_pack_unpack(Cc, mode):
+    grid = TokenGrid(11, 37)
+    x = torch.randn((Cc, grid.H, grid.W), device=DEV) * 3 + 0.5
+    ob = grid.zeros(Cc + 64)
+    of = grid.zeros(Cc, dtype=torch.float32)
+    ops.pack_tokens(x, grid, mode, out_b=ob, colb=64, out_f=of)
+    back = ops.unpack_tokens(of, 0, Cc, grid)
+    back_b = ops.unpack_tokens(ob, 64, Cc, grid)
+    torch.cuda.synchronize()
+    if mode == 1:
+        ref = R.encode_tokens(x[None])[0].t().reshape(Cc, grid.H, grid.W)
+    elif mode == 2:
+        ref = torch.tanh(x)
+    elif mode == 3:
+        ref = torch.relu(x)
+    else:
+        ref = x
+    assert torch.allclose(back, ref, atol=1e-5, rtol=1e-5), (back - ref).abs().max()
+    assert torch.allclose(back_b, ref, atol=3e-2, rtol=1e-2)
+    assert of.reshape(grid.H, grid.Wp, -1)[:, grid.W:].abs().max() == 0
+
+
+@pytest.mark.parametrize("H,W", [(16, 24), (17, 22)])
+def test_corr_lookup(H, W):
+    grid = TokenGrid(H, W)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    vol = torch.randn((1, grid.U, H, W), device=DEV, generator=g) * 2 + 0.7
+    mean, rstd = 0.3, 1.7
+    normed = (vol - mean) * rstd
+    pyr_ref = R.corr_pyramid(normed)
+    coords = R.coords_grid(1, H, W, DEV) + torch.randn((1, 2, H, W), device=DEV, generator=g) * 4
+    ref = R.corr_lookup(pyr_ref, coords)[0]
+    # device layout: query rows are padded-flat
+    pyr_raw = R.corr_pyramid(vol)
+    levels = []
+    for lv in pyr_raw:
+        hl, wl = lv.shape[-2:]
+        buf = torch.zeros((grid.H, grid.Wp, hl * wl), device=DEV)
+        buf[:, :W] = lv.reshape(H, W, hl * wl)
+        levels.append(buf.reshape(grid.Mp, hl * wl).contiguous())
+    cbuf = rows_from_nchw(coords[0], grid, dtype=torch.float32)
+    stats = torch.tensor([mean, rstd], device=DEV)
+    out_b = grid.zeros(384)
+    out_n = torch.zeros((324, H, W), device=DEV)
+    ops.corr_lookup(levels, grid, cbuf, stats, out_b=out_b, out_nchw=out_n)
+    torch.cuda.synchronize()
+    assert torch.allclose(out_n, ref, atol=2e-4, rtol=1e-4), (out_n - ref).abs().max()
+    got_b = nchw_from_rows(out_b, grid, 324)
+    assert torch.allclose(got_b, ref, atol=5e-2, rtol=1e-2)
+
+
+def test_upsample_and_small_kernels():
+    grid = TokenGrid(9, 14)
+    g = torch.Generator(device=DEV).manual_seed(4)
+    flow = torch.randn((1, 2, grid.H, grid.W), device=DEV, generator=g) * 3
+    mask = torch.randn((1, 576, grid.H, grid.W), device=DEV, generator=g)
+    ref = R.upsample_flow(flow, mask)[0]
+    fb = rows_from_nchw(flow[0], grid, dtype=torch.float32)
+    mb = rows_from_nchw(mask[0], grid, dtype=torch.float32)
+    out = ops.upsample_flow(mb, fb, grid)
+    torch.cuda.synchronize()
+    assert torch.allclose(out, ref, atol=1e-4, rtol=1e-4), (out - ref).abs().max()
+    # convf1
+    w = torch.randn((128, 2, 7, 7), device=DEV, generator=g) * 0.1
+    b = torch.randn((128,), device=DEV, generator=g)
+    wt = w.permute(1, 2, 3, 0).reshape(98, 128).contiguous()
+    ob = grid.zeros(128)
+    ops.convf1(fb, wt, b, grid, ob)
+    torch.cuda.synchronize()
+    ref2 = torch.relu(F.conv2d(flow, w, b, padding=3))[0]
+    got2 = nchw_from_rows(ob, grid, 128)
+    assert torch.allclose(got2, ref2, atol=3e-2, rtol=1e-2), (got2 - ref2).abs().max()
+    # coords init / update
+    c1 = grid.zeros(2, dtype=torch.float32)
+    fl = grid.zeros(2, dtype=torch.float32)
+    finit = torch.randn((2, grid.H, grid.W), device=DEV, generator=g)
+    ops.init_coords(c1, finit, grid)
+    delta = grid.zeros(32, dtype=torch.float32)
+    delta[:, :2] = 0.25
+    ops.flow_update(c1, fl, delta, grid)
+    torch.cuda.synchronize()
+    got = nchw_from_rows(fl, grid, 2)
+    assert torch.allclose(got, finit + 0.25, atol=1e-5)
+
+
+def _rand_qk(grid, Cc, g, scale=1.0):
+    q = bf16r(torch.randn((Cc, grid.H, grid.W), device=DEV, generator=g) * scale)
+    k = bf16r(torch.randn((Cc, grid.H, grid.W), device=DEV, generator=g) * scale)
+    return q, k
+
+
+def _scores_ref(q, k, M, table, w_pos, clipv):
+    Cc, H, W = q.shape
+    d = Cc // M
+    qq = q.reshape(M, d, H * W).transpose(1, 2)
+    kk = k.reshape(M, d, H * W).transpose(1, 2)
+    s = qq @ kk.transpose(1, 2) / math.sqrt(d)
+    gmax = s.max()
+    s = s.clamp(-clipv, clipv)
+    if table is not None:
+        s = s + w_pos * R.sliding_pos_bias(table, H, W)[None]
+    return s, gmax
+
+
+@pytest.mark.parametrize("H,W,M,d,clipv", [(16, 24, 4, 64, float("inf")), (13, 22, 4, 64, 2.0), (8, 16, 1, 256, float("inf")),
+                                           (16, 16, 2, 64, float("inf"))])
+def test_corr_build(H, W, M, d, clipv):
+    grid = TokenGrid(H, W)
+    g = torch.Generator(device=DEV).manual_seed(11)
+    q, k = _rand_qk(grid, M * d, g, 0.6)
+    table = torch.randn((15, 15), device=DEV, generator=g) if M > 1 else None
+    w_agg, w_pos = 0.13, 0.5
+    s, gmax = _scores_ref(q, k, M, table, w_pos, clipv)
+    if M > 1:
+        # soft aggregation is shift-invariant to the shared bias, so this matches the reference order
+        p = torch.softmax(s * w_agg, dim=0)
+        raw = (s * p).sum(0)
+    else:
+        raw = s[0]
+    vol = raw.reshape(1, grid.U, H, W)
+    pyr = R.corr_pyramid(vol)
+    Q, K = rows_from_nchw(q, grid), rows_from_nchw(k, grid)
+    shapes = grid.level_shapes()
+    levels = [torch.full((grid.Mp, h * w), float("nan"), device=DEV) for (h, w) in shapes]
+    stat_sum = torch.zeros(2, dtype=torch.float64, device=DEV)
+    stat_max = torch.full((1,), -float("inf"), device=DEV)
+    clip = torch.tensor([clipv], device=DEV)
+    ops.corr_build(Q, K, grid, M=M, d=d, w_agg=w_agg, w_pos=w_pos, pos_table=table, R=7, clip=clip,
+                   stat_sum=stat_sum, stat_max=stat_max, levels=levels)
+    mr = torch.zeros(2, device=DEV)
+    ops.corr_stats_finalize(stat_sum, grid.U * grid.U, mr)
+    torch.cuda.synchronize()
+    assert abs(stat_max.item() - gmax.item()) < 1e-3
+    n = grid.U * grid.U
+    assert abs(stat_sum[0].item() / n - raw.mean().item()) < 1e-4
+    assert abs(mr[0].item() - raw.mean().item()) < 1e-4
+    rstd_ref = 1.0 / math.sqrt(raw.var(unbiased=False).item() + 1e-12)
+    assert abs(mr[1].item() - rstd_ref) < 1e-3 * rstd_ref
+    for l, ((h, w), lv) in enumerate(zip(shapes, levels)):
+        got = lv.reshape(grid.H, grid.Wp, h * w)[:, :W].reshape(grid.U, h, w)
+        ref = pyr[l].reshape(grid.U, h, w)
+        assert torch.allclose(got, ref, atol=2e-3, rtol=1e-3), (l, (got - ref).abs().max())
+
+
+@pytest.mark.parametrize("H,W,M,d,F_", [(16, 24, 4, 32, 128), (13, 22, 4, 64, 256), (12, 20, 1, 128, 128)])
+def test_attn_lse_pv_finalize(H, W, M, d, F_):
+    grid = TokenGrid(H, W)
+    g = torch.Generator(device=DEV).manual_seed(21)
+    q, k = _rand_qk(grid, M * d, g, 0.7)
+    table = torch.randn((15, 15), device=DEV, generator=g) if M > 1 else None
+    w_pos = 1.0
+    clipv = float("inf")
+    s, gmax = _scores_ref(q, k, M, table, w_pos, clipv)
+    P = torch.softmax(s, dim=-1)                                    # [M,U,U]
+    v = bf16r(torch.randn((M, grid.U, F_), device=DEV, generator=g))
+    O_ref = P @ v                                                   # [M,U,F]
+    Q, K = rows_from_nchw(q, grid), rows_from_nchw(k, grid)
+    ldv = ((grid.Mp + 63) // 64) * 64
+    Vt = torch.zeros((M * F_, ldv), dtype=torch.bfloat16, device=DEV)
+    vt_grid = torch.zeros((M * F_, grid.H, grid.Wp), device=DEV)
+    vt_grid[:, :, :W] = v.permute(0, 2, 1).reshape(M * F_, H, W)
+    Vt[:, : grid.Mp] = vt_grid.reshape(M * F_, grid.Mp).to(torch.bfloat16)
+    ks = ops.scores_auto_ksplit(grid)
+    lse_part = torch.zeros((ks, M, grid.Mp, 2), device=DEV)
+    lse2 = torch.zeros((M, grid.Mp), device=DEV)
+    stat_max = torch.full((1,), -float("inf"), device=DEV)
+    clip = torch.tensor([clipv], device=DEV)
+    ops.attn_lse(Q, K, grid, M=M, d=d, w_pos=w_pos, pos_table=table, R=7, clip=clip, stat_max=stat_max,
+                 lse_part=lse_part, lse2=lse2, ksplit=ks)
+    torch.cuda.synchronize()
+    lse_ref = torch.logsumexp(s, dim=-1) * math.log2(math.e)        # [M,U]
+    got = lse2.reshape(M, grid.H, grid.Wp)[:, :, :W].reshape(M, grid.U)
+    assert torch.allclose(got, lse_ref, atol=2e-3, rtol=1e-4), (got - lse_ref).abs().max()
+    assert abs(stat_max.item() - gmax.item()) < 1e-3
+    kp = 2
+    out = torch.full((kp, M, grid.Mp, F_), float("nan"), device=DEV)
+    ops.attn_pv(Q, K, Vt, grid, M=M, d=d, F=F_, w_pos=w_pos, pos_table=table, R=7, clip=clip, lse2=lse2,
+                out=out, ksplit=kp)
+    torch.cuda.synchronize()
+    O = out.sum(0).reshape(M, grid.H, grid.Wp, F_)[:, :, :W].reshape(M, grid.U, F_)
+    assert torch.allclose(O, O_ref, atol=2e-2, rtol=2e-2), (O - O_ref).abs().max()
+    # finalize (setrans flavour) against the restatement fed with the kernel's own O
+    if M > 1:
+        w_sc = torch.randn((1, F_), device=DEV, generator=g) * 0.1
+        b_sc = torch.randn((1,), device=DEV, generator=g)
+        coeff = torch.tensor([0.8], device=DEV)
+        x = bf16r(torch.randn((grid.U, F_), device=DEV, generator=g))
+        xb = torch.zeros((grid.H, grid.Wp, F_), device=DEV)
+        xb[:, :W] = x.reshape(H, W, F_)
+        xb = xb.reshape(grid.Mp, F_).to(torch.bfloat16)
+        yf = grid.zeros(F_, dtype=torch.float32)
+        ops.modes_finalize(out, kp, M, F_, grid, w_score=w_sc, b_score=b_sc, coeff=coeff, x_b=xb, out_f=yf)
+        torch.cuda.synchronize()
+        agg = R.soft_aggregate_feat(O[None], w_sc, b_sc)[0]
+        ref = F.layer_norm(0.8 * x + agg, (F_,), eps=1e-12)
+        gy = yf.reshape(grid.H, grid.Wp, F_)[:, :W].reshape(grid.U, F_)
+        assert torch.allclose(gy, ref, atol=1e-3, rtol=1e-3), (gy - ref).abs().max()
