@@ -186,7 +186,8 @@ int craft_shift_gemm(const craft_gemm_args* a, void* stream) {
   if (a->Npad % a->BN) return fail("gemm: Npad=%d not a multiple of BN=%d", a->Npad, a->BN);
   if (a->a_koff % 64 || a->b_koff % 64) return fail("gemm: koff must be multiples of 64");
   if (a->a_koff + a->K > a->lda || a->b_koff + a->K > a->ldb_) return fail("gemm: K range exceeds operand width");
-  if (a->b_rows < a->T * a->Npad) return fail("gemm: B has %d rows, needs %d", a->b_rows, a->T * a->Npad);
+  // T == 1: B rows beyond b_rows are zero-filled by TMA (used for V^T = W X^T with a padded ld)
+  if (a->T > 1 && a->b_rows < a->T * a->Npad) return fail("gemm: B has %d rows, needs %d", a->b_rows, a->T * a->Npad);
   if (a->out_bf16 && ((a->ldo_b % 8) || (a->colo_b % 8))) return fail("gemm: bf16 output ld/col must be multiples of 8");
   if (a->out_f32 && ((a->ldo_f % 4) || (a->colo_f % 4))) return fail("gemm: f32 output ld/col must be multiples of 4");
   CUtensorMap ta, tb;

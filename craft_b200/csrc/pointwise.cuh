@@ -18,7 +18,7 @@ struct Grid2 {
 //   reference: SETransInputFeatEncoder.forward core/setrans.py:791-795 (transpose + LayerNorm,
 //   eps 1e-12, no affine; pos_code_weight = 0 for pos_code_type 'bias'), and the tanh / relu
 //   split of cnet features core/network.py:209-211.
-// mode: 0 copy, 1 layer-norm over C, 2 tanh, 3 relu
+// mode: 0 copy, 1 layer-norm over C, 2 tanh, 3 relu, 4 relu followed by layer-norm
 // Block = 256 threads handles 32 consecutive tokens of one grid row, all C channels.
 // -------------------------------------------------------------------------------------------
 template <int C>
@@ -34,8 +34,11 @@ __global__ void __launch_bounds__(256) pack_tokens_kernel(const float* __restric
   // coalesced read along x for each channel
   for (int c = ty; c < C; c += 8) {
     const int x = x0 + tx;
-    tile[c][tx] = (x < g.W) ? __ldg(src + (static_cast<size_t>(c) * g.H + y) * g.W + x) : 0.0f;
+    float v = (x < g.W) ? __ldg(src + (static_cast<size_t>(c) * g.H + y) * g.W + x) : 0.0f;
+    if (mode == 4) v = fmaxf(v, 0.0f);
+    tile[c][tx] = v;
   }
+  if (mode == 4) mode = 1;   // relu then LayerNorm (intra-frame attention input, network.py:211,214)
   __syncthreads();
   // each warp owns 4 tokens; lanes stride channels
   for (int t = ty * 4; t < ty * 4 + 4; ++t) {

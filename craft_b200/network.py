@@ -1,0 +1,218 @@
+"""CRAFT model with the reference's constructor, parameter names and forward() contract
+(core/network.py:26-267), running its dense per-pixel path on the sm_100a kernels.
+
+    CRAFT(args).forward(image1, image2, iters=12, flow_init=None, upsample=True, test_mode=0)
+
+Drop-in notes: `args` is the same argparse.Namespace the reference drivers
+build, and it is mutated the same way (corr_levels, corr_multiplier, *_trans_config, dropout);
+`network.RAFTER` is the alias evaluate.py installs for old checkpoints.  fnet / cnet stay stock
+PyTorch (outside the named hot path).  Forward-only in this round.
+"""
+import torch
+import torch.nn as nn
+
+from . import hotpath as hp
+from . import ops
+from .corr import CorrBlock, TransCorrBlock
+from .extractor import BasicEncoder
+from .gma import Attention
+from .ops import TokenGrid
+from .setrans import SETransConfig, SelfAttVisPosTrans, get_workspace, _require_inference
+from .update import GMAUpdateBlock
+from .utils.utils import coords_grid, print0, upflow8
+
+
+class CRAFT(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.hidden_dim = hdim = 128
+        self.context_dim = cdim = 128
+        args.corr_levels = 4
+        if "dropout" not in self.args:
+            self.args.dropout = 0
+        if args.corr_radius == -1:
+            args.corr_radius = 4
+
+        if args.craft:
+            c = self.inter_trans_config = SETransConfig()
+            c.update_config(args)
+            c.in_feat_dim = c.feat_dim = 256
+            c.max_pos_size = 160
+            c.out_attn_scores_only = True
+            c.attn_diag_cycles = 1000
+            c.num_modes = args.inter_num_modes
+            c.tie_qk_scheme = "shared"
+            c.qk_have_bias = args.inter_qk_have_bias
+            c.pos_code_type = args.inter_pos_code_type
+            c.pos_code_weight = args.inter_pos_code_weight
+            self.args.inter_trans_config = c
+            self.corr_fn = TransCorrBlock(c, radius=self.args.corr_radius, do_corr_global_norm=True)
+
+        self.fnet = BasicEncoder(output_dim=256, norm_fn="instance", dropout=args.dropout)
+        self.cnet = BasicEncoder(output_dim=hdim + cdim, norm_fn="batch", dropout=args.dropout)
+
+        if args.f2trans != "none":
+            c = self.f2_trans_config = SETransConfig()
+            c.update_config(args)
+            c.in_feat_dim = c.feat_dim = 256
+            c.has_input_skip = True
+            c.has_FFN = False
+            c.attn_mask_radius = args.f2_attn_mask_radius
+            c.tie_qk_scheme = None
+            c.qk_have_bias = False
+            c.out_attn_probs_only = False
+            c.attn_diag_cycles = 1000
+            c.num_modes = args.f2_num_modes
+            c.pos_code_type = args.intra_pos_code_type
+            c.pos_code_weight = args.f2_pos_code_weight
+            self.f2_trans = SelfAttVisPosTrans(c, "F2 transformer")
+            self.args.f2_trans_config = c
+            if args.f1trans != "none":
+                raise NotImplementedError("--f1 shared/private (two-way correlation) is an ablation outside the "
+                                          "hot path; the shipped checkpoints use f1trans='none'")
+            self.f1_trans = None
+            args.corr_multiplier = 1
+        else:
+            # network.py leaves corr_multiplier unset here; BasicMotionEncoder needs it
+            if not hasattr(args, "corr_multiplier"):
+                args.corr_multiplier = 1
+
+        if args.use_setrans:
+            c = self.intra_trans_config = SETransConfig()
+            c.update_config(args)
+            c.in_feat_dim = c.feat_dim = 128
+            c.has_FFN = False
+            c.has_input_skip = True
+            c.attn_mask_radius = -1
+            c.tie_qk_scheme = None
+            c.qk_have_bias = False
+            c.out_attn_probs_only = True
+            c.attn_diag_cycles = 1000
+            c.num_modes = args.intra_num_modes
+            c.pos_code_type = args.intra_pos_code_type
+            c.pos_code_weight = args.intra_pos_code_weight
+            self.att = SelfAttVisPosTrans(c, "Intra-frame attention")
+            self.args.intra_trans_config = c
+        else:
+            self.att = Attention(args=self.args, dim=cdim, heads=self.args.num_heads, max_pos_size=160, dim_head=cdim)
+
+        self.update_block = GMAUpdateBlock(self.args, hidden_dim=hdim)
+        self.call_counter = 0
+        self.materialize_level0 = True
+
+    def freeze_bn(self):
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.eval()
+
+    def initialize_flow(self, img):
+        N, _, H, W = img.shape
+        c = coords_grid(N, H // 8, W // 8, device=img.device)
+        return c, c.clone()
+
+    def upsample_flow(self, flow, mask):
+        """[N,2,h,w], [N,576,h,w] -> [N,2,8h,8w] (core/network.py:151-162), via the upsample kernel."""
+        N, _, h, w = flow.shape
+        g = TokenGrid(h, w)
+        out = torch.empty((N, 2, 8 * h, 8 * w), dtype=torch.float32, device=flow.device)
+        fr = torch.zeros((g.Mp, 2), dtype=torch.float32, device=flow.device)
+        mr = torch.zeros((g.Mp, 576), dtype=torch.float32, device=flow.device)
+        for b in range(N):
+            fr.view(g.H, g.Wp, 2)[:, :g.W] = flow[b].permute(1, 2, 0)
+            mr.view(g.H, g.Wp, 576)[:, :g.W] = mask[b].permute(1, 2, 0)
+            ops.upsample_flow(mr, fr, g, out=out[b])
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    def _encoders(self, image1, image2):
+        image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
+        image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
+        amp = bool(getattr(self.args, "mixed_precision", False))
+        with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+            fmap1, fmap2 = self.fnet([image1, image2])
+            cnet_feat = self.cnet(image1)
+        return fmap1.float().contiguous(), fmap2.float().contiguous(), cnet_feat.float().contiguous()
+
+    def _prepare_pair(self, ws, fmap1, fmap2, cnet_feat, flow_init):
+        """Everything that happens once per pair (core/network.py:179-228) on one batch element."""
+        g = ws.grid
+        a = self.args
+        if a.f2trans != "none":
+            att2 = self.f2_trans.attend(ws, fmap2, ws.T2, ws.Q2, ws.K2, ws.lse2_f2, ws.clip_f2, slot=1)
+            self.f2_trans.setrans.out_trans.run(ws, att2, ws.T2, 0, out_b=ws.T2f)
+            second_is_tokens = True
+        else:
+            second_is_tokens = False
+        if a.craft:
+            ops.pack_tokens(fmap1, g, ops.PACK_LN, out_b=ws.T1)
+            if not second_is_tokens:
+                ops.pack_tokens(fmap2, g, ops.PACK_LN, out_b=ws.T2f)
+            # f2_trans already ends in the same affine-free LayerNorm the correlation encoder applies
+            # (core/setrans.py:407 then :794): LN(LN(x)) == LN(x) up to eps = 1e-12.
+            self.corr_fn.build_rows(ws, ws.T1, ws.T2f)
+        else:
+            ops.pack_tokens(fmap1, g, ops.PACK_COPY, out_b=ws.Qc)
+            if second_is_tokens:
+                ws.Kc.copy_(ws.T2f)
+            else:
+                ops.pack_tokens(fmap2, g, ops.PACK_COPY, out_b=ws.Kc)
+            hp.build_correlation(ws, ws.Qc, ws.Kc, M=1, d=256, w_agg=0.0, table=None, w_pos=0.0, global_norm=False)
+        net, inp = cnet_feat[:128], cnet_feat[128:]
+        ops.pack_tokens(net.contiguous(), g, ops.PACK_TANH, out_b=ws.X, colb=0, out_f=ws.Hm)
+        ops.pack_tokens(inp.contiguous(), g, ops.PACK_RELU, out_b=ws.X, colb=128)
+        if a.use_setrans:
+            att = self.att.attend(ws, inp.contiguous(), ws.Ta, ws.Qa, ws.Ka, ws.lse2_att, ws.clip_att, slot=2,
+                                  pack_mode=ops.PACK_RELU_LN)
+        else:
+            ops.pack_tokens(inp.contiguous(), g, ops.PACK_RELU, out_b=ws.Ta)
+            att = self.att.attend(ws, ws.Ta, ws.Qa, ws.Ka, ws.lse2_att, ws.clip_att)
+        ops.init_coords(ws.coords1, flow_init, g)
+        ops.flow_update(ws.coords1, ws.flow, None, g)
+        return att
+
+    def forward(self, image1, image2, iters=12, flow_init=None, upsample=True, test_mode=0):
+        """Estimate optical flow between a pair of frames (same contract as core/network.py:164-267)."""
+        _require_inference(self.update_block.encoder.convc1.weight)
+        if not image1.is_cuda:
+            raise RuntimeError("craft_b200.CRAFT runs on a CUDA (sm_100a) device only; there is no CPU path")
+        B, _, H, W = image1.shape
+        if H % 8 or W % 8:
+            raise ValueError("image sides must be multiples of 8 (use InputPadder, as the reference drivers do)")
+        fmap1, fmap2, cnet_feat = self._encoders(image1.float(), image2.float())
+        g = TokenGrid(H // 8, W // 8)
+        ws = get_workspace(g, image1.device, self.materialize_level0)
+        dev = image1.device
+        flow_lo = torch.empty((B, 2, g.H, g.W), dtype=torch.float32, device=dev)
+        n_up = iters if test_mode != 1 else 1
+        flow_ups = [torch.empty((B, 2, H, W), dtype=torch.float32, device=dev) for _ in range(n_up)]
+        corr_fn = self.corr_fn if self.args.craft else _PlainLookup(self.args.corr_radius)
+        for b in range(B):
+            fi = flow_init[b].float().contiguous() if flow_init is not None else None
+            att = self._prepare_pair(ws, fmap1[b], fmap2[b], cnet_feat[b], fi)
+            for itr in range(iters):
+                corr_fn.lookup_rows(ws, ws.coords1, out_b=ws.CORR)
+                self.update_block.step(ws, att)
+                ops.flow_update(ws.coords1, ws.flow, ws.DELTA, g)
+                # the reference upsamples after every iteration (core/network.py:250-260)
+                dst = flow_ups[itr if test_mode != 1 else 0][b]
+                ops.upsample_flow(ws.MASK, ws.flow, g, out=dst)
+            ops.unpack_tokens(ws.flow, 0, 2, g, out=flow_lo[b])
+        self.call_counter += 1
+        if test_mode == 1:
+            return flow_lo, flow_ups[0]
+        if test_mode == 2:
+            return flow_lo, flow_ups
+        return flow_ups
+
+
+class _PlainLookup:
+    """Lookup on a pyramid built by hotpath.build_correlation(M=1) (non-craft CorrBlock path)."""
+
+    def __init__(self, radius):
+        self.radius, self.num_levels = radius, 4
+
+    lookup_rows = CorrBlock.lookup_rows
+
+
+RAFTER = CRAFT   # back-compat alias used by evaluate.py:17-19 when unpickling old checkpoints

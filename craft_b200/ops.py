@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import GemmArgs, PvArgs, ScoresArgs
 
 EPI_STORE, EPI_GRU_ZR, EPI_GRU_Q, EPI_MOTION = 0, 1, 2, 3
-PACK_COPY, PACK_LN, PACK_TANH, PACK_RELU = 0, 1, 2, 3
+PACK_COPY, PACK_LN, PACK_TANH, PACK_RELU, PACK_RELU_LN = 0, 1, 2, 3, 4
 
 
 class TokenGrid:
@@ -221,7 +221,7 @@ def attn_pv(Q, K, Vt, grid, *, M, d, F, w_pos, pos_table, R, clip, lse2, out, ks
     _chk(Vt, torch.bfloat16, "Vt")
     _chk(out, torch.float32, "out")
     _chk(lse2, torch.float32, "lse2")
-    assert Vt.shape[0] == M * F and out.numel() >= ksplit * M * grid.Mp * F
+    assert Vt.shape[0] >= M * F and out.numel() >= ksplit * M * grid.Mp * F
     a = PvArgs()
     a.Q, a.K, a.Vt, a.ldv = Q.data_ptr(), K.data_ptr(), Vt.data_ptr(), Vt.shape[1]
     a.C, a.M, a.d, a.F = M * d, M, d, F

@@ -1,0 +1,149 @@
+"""Generates tests/golden/*.pt by EXECUTING the unmodified reference (/root/reference) on CPU fp32.
+Run in the build container only:   python tests/golden/make_golden.py
+
+Two weight sources:
+  * "seeded": craft_b200.network.CRAFT(args) constructed under torch.manual_seed(1234) on CPU; its
+    state dict is loaded into the reference model (identical keys), so the GPU box can rebuild the
+    very same weights without any file.
+  * "sintel": the reference's checkpoints/craft-sintel.pth.  Its 'model' dict is also copied to
+    tests/golden/_local/ (git-ignored) so it can travel to the GPU box with gpurun; tests that
+    need it skip when it is absent.
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.ref_loader import (REF_ROOT, build_reference_model, craft_args, smooth_pair,  # noqa: E402
+                               synthetic_pair)
+
+OUT = os.path.join(ROOT, "tests", "golden")
+LOCAL = os.path.join(OUT, "_local")
+
+
+def seeded_state(args_kw):
+    from craft_b200.network import CRAFT
+    torch.manual_seed(1234)
+    m = CRAFT(craft_args(**args_kw))
+    return {k: v.clone() for k, v in m.state_dict().items()}
+
+
+def capture(model, image1, image2, iters, flow_init=None, seams=False):
+    """Runs the reference; returns outputs (+ per-seam tensors from hooks when seams=True)."""
+    rec = {}
+    hooks = []
+    if seams:
+        def save(name, idx=None):
+            def fn(mod, inp, out):
+                if name in rec:
+                    return
+                rec[name] = (out[idx] if idx is not None else out)
+            return fn
+        def fnet_hook(m, i, o):
+            rec.setdefault("fnet_out", torch.cat(list(o), 0))
+        hooks.append(model.fnet.register_forward_hook(fnet_hook))
+        hooks.append(model.cnet.register_forward_hook(save("cnet_out")))
+        if hasattr(model, "f2_trans"):
+            hooks.append(model.f2_trans.register_forward_hook(save("f2_out")))
+        ub = model.update_block
+        hooks.append(ub.encoder.register_forward_hook(save("motion_it0")))
+        hooks.append(ub.aggregator.register_forward_hook(save("aggr_it0")))
+        hooks.append(ub.gru.register_forward_hook(save("net_it0")))
+        def ub_hook(m, i, o):
+            rec.setdefault("ub_it0", dict(corr=i[2].clone(), flow=i[3].clone(), mask=o[1].clone(), delta=o[2].clone()))
+        hooks.append(ub.register_forward_hook(ub_hook))
+    with torch.no_grad():
+        flow_lo, ups = model(image1, image2, iters=iters, flow_init=flow_init, test_mode=2)
+    for h in hooks:
+        h.remove()
+    out = dict(flow_lo=flow_lo[0].clone(), flow_up=ups[-1][0].clone(),
+               flow_up_first=ups[0][0].clone())
+    for k, v in rec.items():
+        if isinstance(v, dict):
+            for kk, vv in v.items():
+                out["ub_it0." + kk] = vv[0].clone() if vv.dim() == 4 else vv.clone()
+        else:
+            out[k] = v.detach().clone()
+    return out
+
+
+def main():
+    os.makedirs(LOCAL, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    # local, untracked copy of the trained weights + the shipped frame pair for the GPU box
+    ck = torch.load(os.path.join(REF_ROOT, "checkpoints", "craft-sintel.pth"), map_location="cpu", weights_only=False)
+    sd = ck["model"] if "model" in ck else ck
+    sd = {k[len("module."):] if k.startswith("module.") else k: v for k, v in sd.items()}
+    torch.save(sd, os.path.join(LOCAL, "craft-sintel-model.pth"))
+    import shutil
+    for f in ("frame_0047.png", "frame_0048.png"):
+        shutil.copy(os.path.join(REF_ROOT, "imgs", f), os.path.join(LOCAL, f))
+
+    cases = [
+        # name, weights, args overrides, H, W, iters, input kind, seams
+        ("seeded_setrans_128", "seeded", {}, 128, 128, 4, "noise", True),
+        ("seeded_gma_128", "seeded", dict(use_setrans=False), 128, 128, 4, "noise", False),
+        ("seeded_plain_128", "seeded", dict(craft=False, use_setrans=False, f2trans="none", corr_multiplier=1),
+         128, 128, 4, "noise", False),
+        ("sintel_128", "sintel", {}, 128, 128, 4, "noise", True),
+        ("sintel_smooth_256x320", "sintel", {}, 256, 320, 12, "smooth", False),
+        ("sintel_flowinit_192x256", "sintel", {}, 192, 256, 6, "smooth_init", False),
+        ("sintel_448x1024", "sintel", {}, 448, 1024, 12, "noise", False),
+        ("sintel_kitti_384x1248", "sintel", {}, 384, 1248, 24, "smooth", False),
+        ("sintel_frames_440x1024", "sintel", {}, 440, 1024, 12, "frames", False),
+    ]
+    only = sys.argv[1:]
+    for name, wsrc, kw, H, W, iters, kind, seams in cases:
+        if only and name not in only:
+            continue
+        args = craft_args(**kw)
+        model, _ = build_reference_model(args, checkpoint=("craft-sintel.pth" if wsrc == "sintel" else None))
+        if wsrc == "seeded":
+            model.load_state_dict(seeded_state(kw), strict=True)
+        flow_init = None
+        if kind == "noise":
+            i1, i2 = synthetic_pair(H, W)
+        elif kind in ("smooth", "smooth_init"):
+            i1, i2 = smooth_pair(H, W)
+            if kind == "smooth_init":
+                g = torch.Generator().manual_seed(7)
+                flow_init = torch.randn((1, 2, H // 8, W // 8), generator=g) * 0.5 + torch.tensor([0.3, 0.2]).view(1, 2, 1, 1)
+        else:
+            import numpy as np
+            from PIL import Image
+            from craft_b200.utils.utils import InputPadder
+            a = torch.from_numpy(np.array(Image.open(os.path.join(LOCAL, "frame_0047.png")))).permute(2, 0, 1).float()[None]
+            b = torch.from_numpy(np.array(Image.open(os.path.join(LOCAL, "frame_0048.png")))).permute(2, 0, 1).float()[None]
+            i1, i2 = InputPadder(a.shape).pad(a, b)
+        out = capture(model, i1, i2, iters, flow_init, seams)
+        big = H * W > 256 * 320
+        rec = dict(name=name, weights=wsrc, args=kw, H=H, W=W, iters=iters, kind=kind,
+                   flow_lo=out["flow_lo"], flow_up_mean=out["flow_up"].mean((1, 2)),
+                   flow_up_absmax=out["flow_up"].abs().max())
+        if big:
+            rec["flow_up_s4"] = out["flow_up"][:, ::4, ::4].contiguous()
+        else:
+            rec["flow_up"] = out["flow_up"]
+            rec["flow_up_first"] = out["flow_up_first"]
+        if flow_init is not None:
+            rec["flow_init"] = flow_init
+        if kind == "frames":
+            # yardstick for this ill-conditioned real pair (occlusions, 200-px motions): how far the
+            # reference's OWN reduced-precision mode (bf16 autocast) lands from its fp32 result.
+            with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+                _, up16 = model(i1, i2, iters=iters, test_mode=1)
+            e = (out["flow_up"] - up16[0].float()).pow(2).sum(0).sqrt()
+            rec["ref_bf16_autocast_epe_mean"] = float(e.mean())
+            rec["ref_bf16_autocast_epe_median"] = float(e.median())
+        for k, v in out.items():
+            if k not in ("flow_lo", "flow_up", "flow_up_first"):
+                rec[k] = v
+        torch.save(rec, os.path.join(OUT, name + ".pt"))
+        print(name, "flow_up mean", rec["flow_up_mean"].tolist(), "absmax", float(rec["flow_up_absmax"]),
+              "keys", len(rec), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,143 @@
+"""End-to-end and per-seam parity of craft_b200.network.CRAFT against golden outputs of the
+executed reference (tests/golden/*.pt, produced by tests/golden/make_golden.py on CPU fp32).
+
+Tolerance: the hot path computes in bf16 with fp32 accumulation, so the bound is north_star's
+bf16 figure: mean end-point error <= 1e-2 px on the full-resolution flow."""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+LOCAL = os.path.join(GOLD, "_local")
+EPE_TOL = 1e-2
+
+from oracle.ref_loader import craft_args, smooth_pair, synthetic_pair   # noqa: E402 (pure torch helpers)
+
+
+def _report(name, **kv):
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "e2e_parity.jsonl"), "a") as f:
+        f.write(json.dumps(dict(case=name, **kv)) + "\n")
+
+
+def _model(rec):
+    from craft_b200.network import CRAFT
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(1234)
+    m = CRAFT(craft_args(**rec["args"]))
+    if rec["weights"] == "sintel":
+        path = os.path.join(LOCAL, "craft-sintel-model.pth")
+        if not os.path.isfile(path):
+            pytest.skip("trained weights not present (tests/golden/_local is not tracked)")
+        m.load_state_dict(torch.load(path, map_location="cpu"), strict=True)
+    return m.cuda().eval()
+
+
+def _inputs(rec):
+    H, W, kind = rec["H"], rec["W"], rec["kind"]
+    if kind == "noise":
+        return synthetic_pair(H, W)
+    if kind in ("smooth", "smooth_init"):
+        return smooth_pair(H, W)
+    import numpy as np
+    from PIL import Image
+    from craft_b200.utils.utils import InputPadder
+    p0 = os.path.join(LOCAL, "frame_0047.png")
+    if not os.path.isfile(p0):
+        pytest.skip("frame pair not present")
+    a = torch.from_numpy(np.array(Image.open(p0))).permute(2, 0, 1).float()[None]
+    b = torch.from_numpy(np.array(Image.open(os.path.join(LOCAL, "frame_0048.png")))).permute(2, 0, 1).float()[None]
+    return InputPadder(a.shape).pad(a, b)
+
+
+def _epe(a, b):
+    return (a - b).pow(2).sum(0).sqrt().mean().item()
+
+
+CASES = ["seeded_setrans_128", "seeded_gma_128", "seeded_plain_128", "sintel_128", "sintel_smooth_256x320",
+         "sintel_flowinit_192x256", "sintel_448x1024", "sintel_kitti_384x1248", "sintel_frames_440x1024"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_flow_matches_reference(name):
+    rec = torch.load(os.path.join(GOLD, name + ".pt"), map_location="cpu")
+    model = _model(rec)
+    i1, i2 = _inputs(rec)
+    fi = rec.get("flow_init")
+    with torch.no_grad():
+        flow_lo, flow_up = model(i1.cuda(), i2.cuda(), iters=rec["iters"],
+                                 flow_init=fi.cuda() if fi is not None else None, test_mode=1)
+    torch.cuda.synchronize()
+    flow_lo, flow_up = flow_lo[0].cpu(), flow_up[0].cpu()
+    assert torch.isfinite(flow_up).all()
+    epe_lo = _epe(flow_lo, rec["flow_lo"])
+    if "flow_up" in rec:
+        err = (flow_up - rec["flow_up"]).pow(2).sum(0).sqrt()
+    else:
+        err = (flow_up[:, ::4, ::4] - rec["flow_up_s4"]).pow(2).sum(0).sqrt()
+    epe_up, epe_med = err.mean().item(), err.median().item()
+    _report(name, epe_up=epe_up, epe_median=epe_med, epe_lo_x8=8 * epe_lo, mean_flow=flow_up.mean((1, 2)).tolist(),
+            ref_mean_flow=rec["flow_up_mean"].tolist(), ref_bf16_autocast_epe=rec.get("ref_bf16_autocast_epe_mean"))
+    if "ref_bf16_autocast_epe_mean" in rec:
+        # ill-conditioned real pair: the mean is dominated by a few chaotic (occluded) regions where
+        # even the reference's own bf16-autocast run is 0.58 px away from its fp32 run.  Bound the
+        # median by the bf16 tolerance and the mean by the reference's own reduced-precision spread.
+        assert epe_med <= EPE_TOL and epe_up <= rec["ref_bf16_autocast_epe_mean"], (epe_up, epe_med)
+        return
+    assert epe_up <= EPE_TOL, "EPE %.5f px vs reference (1/8-res EPE x8 = %.5f)" % (epe_up, 8 * epe_lo)
+
+
+@pytest.mark.parametrize("name", ["seeded_setrans_128", "sintel_128"])
+def test_seams_match_reference(name):
+    """Feed the reference's encoder outputs and compare every hot-path seam after one iteration."""
+    from craft_b200 import ops
+    from craft_b200.ops import TokenGrid
+    from craft_b200.setrans import get_workspace
+    rec = torch.load(os.path.join(GOLD, name + ".pt"), map_location="cpu")
+    model = _model(rec)
+    fn, cn = rec["fnet_out"].cuda(), rec["cnet_out"].cuda()
+    model._encoders = lambda a, b: (fn[0:1].contiguous(), fn[1:2].contiguous(), cn.contiguous())
+    i1, i2 = _inputs(rec)
+    with torch.no_grad():
+        model(i1.cuda(), i2.cuda(), iters=1, test_mode=1)
+    torch.cuda.synchronize()
+    g = TokenGrid(rec["H"] // 8, rec["W"] // 8)
+    ws = get_workspace(g, torch.device("cuda", 0), True)
+
+    def rows(buf, c0, c1):
+        return buf.float().view(g.H, g.Wp, -1)[:, :g.W, c0:c1].permute(2, 0, 1).cpu()
+
+    got = {
+        "f2_out": None,
+        "ub_it0.corr": rows(ws.CORR, 0, 324),
+        "motion_it0": rows(ws.X, 256, 384),
+        "aggr_it0": rows(ws.X, 384, 512),
+        "net_it0": rows(ws.Hm, 0, 128),
+        "ub_it0.delta": rows(ws.DELTA, 0, 2),
+        "ub_it0.mask": rows(ws.MASK, 0, 576),
+    }
+    # f2_trans output: tokens after the transformer == LN'ed features the correlation encoder sees
+    f2 = rec["f2_out"][0]
+    f2_tok = torch.nn.functional.layer_norm(f2.reshape(256, -1).t(), (256,), eps=1e-12).t().reshape(f2.shape)
+    got["f2_out"] = rows(ws.T2f, 0, 256)
+    refs = dict(rec)
+    refs["f2_out"] = f2_tok
+    refs["aggr_it0"] = rec["aggr_it0"][0].t().reshape(128, g.H, g.W)
+    refs["motion_it0"] = rec["motion_it0"][0]
+    refs["net_it0"] = rec["net_it0"][0]
+    tol = {"f2_out": 0.06, "ub_it0.corr": 0.08, "motion_it0": 0.06, "aggr_it0": 0.08, "net_it0": 0.03,
+           "ub_it0.delta": 0.03, "ub_it0.mask": 0.15}
+    errs = {}
+    for k, v in got.items():
+        r = refs[k]
+        errs[k] = dict(max_abs=(v - r).abs().max().item(), mean_abs=(v - r).abs().mean().item(),
+                       ref_absmax=r.abs().max().item())
+    _report(name + ":seams", **errs)
+    for k, e in errs.items():
+        assert e["mean_abs"] <= tol[k] * max(1.0, 0.1 * e["ref_absmax"]), (k, e)
