@@ -20,6 +20,7 @@ class GemmArgs(C.Structure):
     _fields_ = [
         ("A", C.c_void_p), ("a_rows", C.c_int), ("lda", C.c_int), ("a_koff", C.c_int),
         ("B", C.c_void_p), ("b_rows", C.c_int), ("ldb_", C.c_int), ("b_koff", C.c_int),
+        ("b_blocked", C.c_int), ("b_H", C.c_int), ("b_W", C.c_int),
         ("M", C.c_int), ("Npad", C.c_int), ("K", C.c_int), ("T", C.c_int),
         ("BN", C.c_int),
         ("tap_off", C.c_int * MAX_TAPS),
@@ -67,6 +68,7 @@ _vp, _i, _f, _d = C.c_void_p, C.c_int, C.c_float, C.c_double
 SIGNATURES = {
     "craft_b200_abi_version": (_i, []),
     "craft_b200_last_error": (C.c_char_p, []),
+    "craft_b200_launch_count": (C.c_longlong, []),
     "craft_b200_device_info": (_i, [C.POINTER(_i)]),
     "craft_pack_tokens": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp]),
     "craft_unpack_tokens": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
@@ -75,6 +77,7 @@ SIGNATURES = {
     "craft_attn_lse": (_i, [C.POINTER(ScoresArgs), _vp]),
     "craft_scores_auto_ksplit": (_i, [_i, _i]),
     "craft_pv_auto_ksplit": (_i, [_i, _i, _i]),
+    "craft_pv_block_keys": (_i, [_i, _i]),
     "craft_corr_stats_finalize": (_i, [_vp, _d, _vp, _vp]),
     "craft_clip_gate": (_i, [_vp, _f, _vp, _vp, _vp]),
     "craft_attn_pv": (_i, [C.POINTER(PvArgs), _vp]),

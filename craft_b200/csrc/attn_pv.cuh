@@ -8,19 +8,21 @@
 //
 // The row log-sum-exp is known up front (scores.cuh SC_LSE), so no online rescaling is needed:
 // every key tile contributes an exact, final slice of P.  One CTA = (128 queries, one mode, one
-// key split).  Pipeline per key tile j:
+// key split).  Keys are visited in spatial blocks of 8 x (BK/8) tokens (3-D TMA box), so that the
+// positional-bias window (|dy|,|dx| <= R) touches only the few blocks around the query and every
+// other block takes the 3-instruction fast path.  V^T arrives in the same block order
+// (gemm.cuh b_blocked).  Pipeline per key tile j:
 //     MMA warp : S[j&1] = Q K_j^T                     (tcgen05, accumulator in TMEM)
-//     softmax  : P[j&1] = exp2(...) as bf16 -> smem    (two 128-thread groups alternate tiles)
+//     softmax  : P[j&1] = exp2(...) as bf16 -> smem    (4 groups of 4 warps: tile parity x column half)
 //     MMA warp : O += P[j&1] V_j                       (A = P from smem, B = V^T tile from TMA)
-// S(j+1) is issued before PV(j) so the tensor pipe never waits for the softmax group.
-// V is consumed as V^T ([M*F, keys], keys contiguous) so that every operand is K-major.
+// S(j+1) is issued before PV(j) so the tensor pipe never waits for the softmax groups.
 #pragma once
 #include "common.cuh"
 #include "pointwise.cuh"
 
 namespace cb {
 
-constexpr int kPvThreads = 320;
+constexpr int kPvThreads = 64 + 512;   // TMA warp, MMA warp, 16 softmax warps
 
 struct PvParams {
   Grid2 g;
@@ -33,7 +35,7 @@ struct PvParams {
   const float* clip;       // device scalar (+inf or attn_clip)
   const float* lse2;       // [M][Mp] log2-domain log-sum-exp
   float* out;              // [ksplit][M][Mp][F] f32 partial sums
-  int nkeys;               // number of key rows to visit (Mp)
+  int nkt, nbx;            // key tiles (blocks) in total / per block-row
 };
 
 template <int D, int F, int BK, int KS, int VS>
@@ -51,6 +53,8 @@ __global__ void __launch_bounds__(kPvThreads, 1)
 attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ PvParams p) {
   using S = PvSmem<D, F, BK, KS, VS>;
+  constexpr int BW = BK / 8;             // block width in tokens (block height is 8)
+  constexpr int HALF = BK / 2;           // columns per softmax thread
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -65,8 +69,8 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t* v_full = k_empty + KS;
   uint64_t* v_empty = v_full + VS;
   uint64_t* s_full = v_empty + VS;     // [2]
-  uint64_t* s_empty = s_full + 2;      // [2] count 128
-  uint64_t* p_full = s_empty + 2;      // [2] count 128
+  uint64_t* s_empty = s_full + 2;      // [2] count 256
+  uint64_t* p_full = s_empty + 2;      // [2] count 256
   uint64_t* p_empty = p_full + 2;      // [2]
   uint64_t* o_full = p_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
@@ -75,9 +79,8 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int q0 = blockIdx.x * 128;
   const int mode = blockIdx.y;
-  const int nkt = (p.nkeys + BK - 1) / BK;
-  const int kt_begin = static_cast<int>((static_cast<long long>(nkt) * blockIdx.z) / p.ksplit);
-  const int kt_end = static_cast<int>((static_cast<long long>(nkt) * (blockIdx.z + 1)) / p.ksplit);
+  const int kt_begin = static_cast<int>((static_cast<long long>(p.nkt) * blockIdx.z) / p.ksplit);
+  const int kt_end = static_cast<int>((static_cast<long long>(p.nkt) * (blockIdx.z + 1)) / p.ksplit);
   const int ntiles = kt_end - kt_begin;
   const int ch0 = mode * D;               // first channel of this mode in the Q/K rows
   const int qk_col = (ch0 >> 6) << 6;     // TMA column of the 64-channel atom holding it
@@ -93,8 +96,8 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     for (int s = 0; s < VS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_full[b], 1);
-      mbar_init(&s_empty[b], 128);
-      mbar_init(&p_full[b], 128);
+      mbar_init(&s_empty[b], 256);
+      mbar_init(&p_full[b], 256);
       mbar_init(&p_empty[b], 1);
     }
     mbar_init(o_full, 1);
@@ -103,7 +106,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (p.pos_table) {
     const int n = (2 * p.R + 1) * (2 * p.R + 1);
     for (int i = threadIdx.x; i < n; i += blockDim.x)
-      s_table[i] = p.pos_table[i] * p.w_pos * 1.4426950408889634f;   // pre-scaled to log2 domain
+      s_table[i] = p.pos_table[i] * p.w_pos * 1.4426950408889634f;   // pre-scaled to the log2 domain
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -121,16 +124,17 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         int ks = 0, vs = 0;
         uint32_t kph = 0, vph = 0;
         for (int i = 0; i < ntiles; ++i) {
-          const int k0 = (kt_begin + i) * BK;
+          const int kt = kt_begin + i;
+          const int by = kt / p.nbx, bx = kt - by * p.nbx;
           mbar_wait(&k_empty[ks], kph ^ 1u);
           mbar_arrive_expect_tx(&k_full[ks], S::kKBytes);
           for (int a = 0; a < S::kQAtoms; ++a)
-            tma_load_2d(sK + ks * S::kKBytes + a * BK * 128, &tmK, &k_full[ks], qk_col + a * 64, k0);
+            tma_load_3d(sK + ks * S::kKBytes + a * BK * 128, &tmK, &k_full[ks], qk_col + a * 64, bx * BW, by * 8);
           if (++ks == KS) { ks = 0; kph ^= 1u; }
           mbar_wait(&v_empty[vs], vph ^ 1u);
           mbar_arrive_expect_tx(&v_full[vs], S::kVBytes);
           for (int a = 0; a < BK / 64; ++a)
-            tma_load_2d(sV + vs * S::kVBytes + a * F * 128, &tmV, &v_full[vs], k0 + a * 64, mode * F);
+            tma_load_2d(sV + vs * S::kVBytes + a * F * 128, &tmV, &v_full[vs], kt * BK + a * 64, mode * F);
           if (++vs == VS) { vs = 0; vph ^= 1u; }
         }
       }
@@ -190,57 +194,66 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
     } else {
       // ------------------------------------ softmax groups ----------------------------------
-      const int sg = (warp - 2) >> 2;
+      // warp w (2..17): tile parity sg = ((w-2)>>2)&1, column half ch = (w-2)>>3, TMEM lane quadrant w&3
+      const int sg = ((warp - 2) >> 2) & 1;
+      const int ch = (warp - 2) >> 3;
       const int lane_grp = warp & 3;
       const int row = lane_grp * 32 + (threadIdx.x & 31);
       const int q = q0 + row;
       const int qy = q / p.g.Wp, qx = q - qy * p.g.Wp;
       const float clipv = *p.clip;
+      const bool clamped = clipv < INFINITY;
       const float lse = (q < p.g.Mp) ? p.lse2[static_cast<size_t>(mode) * p.g.Mp + q] : 0.f;
       const float sc2 = p.scale * 1.4426950408889634f;
       const float clip2 = clipv * 1.4426950408889634f;
       const uint32_t tlane = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16);
       const int R = p.R, TD = 2 * R + 1;
-      // query rows covered by this CTA (for the tile-level "near the diagonal" test)
-      const int qy_lo = q0 / p.g.Wp, qy_hi = (q0 + 127) / p.g.Wp;
+      const bool has_bias = p.pos_table != nullptr;
 
       for (int j = sg; j < ntiles; j += 2) {
         const uint32_t use = static_cast<uint32_t>(j >> 1);
-        const int k0 = (kt_begin + j) * BK;
-        const int ky_lo = k0 / p.g.Wp, ky_hi = (k0 + BK - 1) / p.g.Wp;
-        const bool near = p.pos_table && (ky_hi >= qy_lo - R) && (ky_lo <= qy_hi + R);
+        const int kt = kt_begin + j;
+        const int by = kt / p.nbx, bx = kt - by * p.nbx;
+        // this thread's half block: block rows [ch*4, ch*4+4), all BW columns
+        const int iy0 = by * 8 + ch * 4 - qy + R;       // table row of the first block row
+        const int ix0 = bx * BW - qx + R;               // table column of the first block column
+        const bool near = has_bias && (iy0 + 3 >= 0) && (iy0 <= 2 * R) && (ix0 + BW - 1 >= 0) && (ix0 <= 2 * R);
         mbar_wait(&s_full[sg], use & 1u);
         mbar_wait(&p_empty[sg], (use & 1u) ^ 1u);
         tc_fence_after();
         __syncwarp();
         uint8_t* pbuf = sP + sg * S::kPBytes;
-#pragma unroll 1
-        for (int c = 0; c < BK; c += 32) {
+#pragma unroll
+        for (int c = 0; c < HALF; c += 32) {
           uint32_t raw[32];
-          tmem_ld32(tlane + sg * BK + c, raw);
+          tmem_ld32(tlane + sg * BK + ch * HALF + c, raw);
           tmem_ld_wait();
-          if (c + 32 >= BK) {      // S buffer fully read -> MMA warp may overwrite it
+          if (c + 32 >= HALF) {      // this thread's share of the S buffer is read
             tc_fence_before();
             mbar_arrive(&s_empty[sg]);
           }
           float x[32];
+          if (!clamped) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float s = __uint_as_float(raw[e]) * sc2;
-            x[e] = fminf(fmaxf(s, -clip2), clip2) - lse;
+            for (int e = 0; e < 32; ++e) x[e] = fmaf(__uint_as_float(raw[e]), sc2, -lse);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              x[e] = fminf(fmaxf(__uint_as_float(raw[e]) * sc2, -clip2), clip2) - lse;
           }
           if (near) {
-            int k = k0 + c;
-            int ky = k / p.g.Wp, kx = k - ky * p.g.Wp;
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
-              const int dy = ky - qy, dx = kx - qx;
-              if (dy >= -R && dy <= R && dx >= -R && dx <= R) x[e] += s_table[(dy + R) * TD + dx + R];
-              if (++kx == p.g.Wp) { kx = 0; ++ky; }
+              const int col = c + e;                       // column inside this half: row-major (4 x BW)
+              const int iy = iy0 + col / BW, ix = ix0 + col % BW;
+              if (static_cast<unsigned>(iy) <= static_cast<unsigned>(2 * R) &&
+                  static_cast<unsigned>(ix) <= static_cast<unsigned>(2 * R))
+                x[e] += s_table[iy * TD + ix];
             }
           }
-          const int atom = c >> 6;
-          const int chunk0 = (c & 63) >> 3;
+          const int kcol = ch * HALF + c;                  // key column inside the tile
+          const int atom = kcol >> 6;
+          const int chunk0 = (kcol & 63) >> 3;
 #pragma unroll
           for (int v4 = 0; v4 < 4; ++v4) {
             uint4 u;
@@ -256,19 +269,20 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
 
       // ------------------------------------ O epilogue --------------------------------------
-      // both groups split the F columns in halves
+      // the four groups split the F columns in quarters
       mbar_wait(o_full, 0);
       tc_fence_after();
       __syncwarp();
       float* dst = p.out + ((static_cast<size_t>(blockIdx.z) * p.M + mode) * p.g.Mp + q) * F;
-      constexpr int kHalf = F / 2;
-#pragma unroll 1
-      for (int c = sg * kHalf; c < (sg + 1) * kHalf; c += 32) {
+      constexpr int kQuarter = F / 4;
+      const int c_begin = (sg * 2 + ch) * kQuarter;
+#pragma unroll
+      for (int c = 0; c < kQuarter; c += 32) {
         uint32_t raw[32];
-        tmem_ld32(tlane + kTmemO + c, raw);
+        tmem_ld32(tlane + kTmemO + c_begin + c, raw);
         tmem_ld_wait();
         if (q < p.g.Mp) {
-          float4* d4 = reinterpret_cast<float4*>(dst + c);
+          float4* d4 = reinterpret_cast<float4*>(dst + c_begin + c);
 #pragma unroll
           for (int e = 0; e < 8; ++e)
             d4[e] = make_float4(__uint_as_float(raw[4 * e]), __uint_as_float(raw[4 * e + 1]),
@@ -281,11 +295,11 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // empty key range: this split contributes zeros
     if (warp >= 2) {
       const int row = (warp & 3) * 32 + (threadIdx.x & 31);
-      const int sg = (warp - 2) >> 2;
+      const int part = (((warp - 2) >> 2) & 1) * 2 + ((warp - 2) >> 3);
       const int q = q0 + row;
       if (q < p.g.Mp) {
         float* dst = p.out + ((static_cast<size_t>(blockIdx.z) * p.M + mode) * p.g.Mp + q) * F;
-        for (int c = sg * (F / 2); c < (sg + 1) * (F / 2); ++c) dst[c] = 0.f;
+        for (int c = part * (F / 4); c < (part + 1) * (F / 4); ++c) dst[c] = 0.f;
       }
     }
   }

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cmath>
+#include <atomic>
 
 #include "../../include/craft_b200.h"
 #include "attn_pv.cuh"
@@ -17,6 +18,7 @@
 namespace {
 
 thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};   // kernels launched by this library (bench.py's gpu_launches)
 
 int fail(const char* fmt, ...) {
   va_list ap;
@@ -28,6 +30,7 @@ int fail(const char* fmt, ...) {
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail("%s: %s", what, cudaGetErrorString(e));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
 
@@ -73,13 +76,13 @@ int make_map_2d(CUtensorMap* m, const void* base, long long rows, long long cols
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(2d) failed: %d", static_cast<int>(r));
   return 0;
 }
-// 3-D bf16 map over token rows viewed as [H][W][C] with row pitch Wp: box = [8][8][64].
-int make_map_3d_keys(CUtensorMap* m, const void* base, const cb::Grid2& g, int C) {
+// 3-D bf16 map over token rows viewed as [H][W][C] with row pitch Wp: box = [8][bw][64].
+int make_map_3d_keys(CUtensorMap* m, const void* base, const cb::Grid2& g, int C, int bw = 8) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail("cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(g.W), static_cast<cuuint64_t>(g.H)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(g.Wp) * C * 2};
-  cuuint32_t box[3] = {64, 8, 8};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(bw), 8};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -145,6 +148,7 @@ extern "C" {
 
 int craft_b200_abi_version(void) { return CRAFT_B200_ABI_VERSION; }
 const char* craft_b200_last_error(void) { return g_err; }
+long long craft_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int craft_b200_device_info(int* out3) {
   int dev = 0;
@@ -192,9 +196,20 @@ int craft_shift_gemm(const craft_gemm_args* a, void* stream) {
   if (a->out_f32 && ((a->ldo_f % 4) || (a->colo_f % 4))) return fail("gemm: f32 output ld/col must be multiples of 4");
   CUtensorMap ta, tb;
   if (make_map_2d(&ta, a->A, a->a_rows, a->lda, a->lda, cb::kGemmBM)) return -1;
-  if (make_map_2d(&tb, a->B, a->b_rows, a->ldb_, a->ldb_, a->BN)) return -1;
   cb::GemmParams p;
   memset(&p, 0, sizeof(p));
+  if (a->b_blocked) {
+    if (a->T != 1 || (a->BN != 64 && a->BN != 128)) return fail("gemm: blocked B needs T=1 and BN in {64,128}");
+    cb::Grid2 bg = make_grid(a->b_H, a->b_W);
+    if (a->b_rows < bg.Mp) return fail("gemm: blocked B has %d rows, grid needs %d", a->b_rows, bg.Mp);
+    const int bw = a->BN / 8;
+    p.b_blocked = 1;
+    p.b_nbx = (a->b_W + bw - 1) / bw;
+    if (a->Npad != p.b_nbx * ((a->b_H + 7) / 8) * a->BN) return fail("gemm: blocked B: Npad must be nblocks*BN");
+    if (make_map_3d_keys(&tb, a->B, bg, a->ldb_, bw)) return -1;
+  } else {
+    if (make_map_2d(&tb, a->B, a->b_rows, a->ldb_, a->ldb_, a->BN)) return -1;
+  }
   p.M = a->M; p.Npad = a->Npad; p.K = a->K; p.T = a->T;
   p.a_koff = a->a_koff; p.b_koff = a->b_koff;
   for (int t = 0; t < a->T; ++t) p.tap_off[t] = a->tap_off[t];
@@ -228,11 +243,18 @@ int craft_scores_auto_ksplit(int H, int W) {
   if (s > nkt) s = nkt;
   return s < 1 ? 1 : s;
 }
+int craft_pv_block_keys(int d, int F) {
+  if (d == 32 && F == 128) return 128;
+  if (d == 64 && F == 256) return 64;
+  if (d == 128 && F == 128) return 64;
+  if (d == 64 && F == 128) return 128;
+  return 0;
+}
 int craft_pv_auto_ksplit(int H, int W, int M) {
   cb::Grid2 g = make_grid(H, W);
   const int nqt = (g.Mp + 127) / 128;
-  int s = pick_split(nqt * M, 6);
-  const int nkt = (g.Mp + 127) / 128;
+  int s = pick_split(nqt * M, 4);
+  const int nkt = ((H + 7) / 8) * ((W + 15) / 16);
   if (s > nkt) s = nkt;
   return s < 1 ? 1 : s;
 }
@@ -304,13 +326,17 @@ static int launch_pv(const craft_pv_args* a, const cb::Grid2& g, cudaStream_t st
   using S = cb::PvSmem<D, F, BK, KS, VS>;
   CUtensorMap tq, tk, tv;
   if (make_map_2d(&tq, a->Q, g.Mp, a->C, a->C, 128)) return -1;
-  if (make_map_2d(&tk, a->K, g.Mp, a->C, a->C, BK)) return -1;
-  if (make_map_2d(&tv, a->Vt, static_cast<long long>(a->M) * F, g.Mp, a->ldv, F)) return -1;
+  constexpr int BW = BK / 8;
+  const int nbx = (g.W + BW - 1) / BW;
+  const int nkt = nbx * ((g.H + 7) / 8);
+  if (a->ldv < nkt * BK) return fail("attn_pv: ldv=%d must cover %d blocked keys", a->ldv, nkt * BK);
+  if (make_map_3d_keys(&tk, a->K, g, a->C, BW)) return -1;
+  if (make_map_2d(&tv, a->Vt, static_cast<long long>(a->M) * F, static_cast<long long>(nkt) * BK, a->ldv, F)) return -1;
   cb::PvParams p;
   memset(&p, 0, sizeof(p));
   p.g = g; p.M = a->M; p.ksplit = a->ksplit; p.scale = a->scale; p.w_pos = a->w_pos;
   p.pos_table = a->pos_table; p.R = a->R; p.clip = a->clip; p.lse2 = a->lse2; p.out = a->out;
-  p.nkeys = g.Mp;
+  p.nkt = nkt; p.nbx = nbx;
   auto kern = cb::attn_pv_kernel<D, F, BK, KS, VS>;
   static bool set = false;
   if (!set) { if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal) != cudaSuccess) return fail("pv: smem attr %d", S::kTotal); set = true; }
@@ -326,7 +352,7 @@ int craft_attn_pv(const craft_pv_args* a, void* stream) {
   if (a->ksplit < 1) return fail("attn_pv: ksplit must be >= 1");
   if (a->pos_table && (2 * a->R + 1) * (2 * a->R + 1) > 225) return fail("attn_pv: pos radius too large");
   cb::Grid2 g = make_grid(a->H, a->W);
-  if (a->ldv < g.Mp || a->ldv % 8) return fail("attn_pv: ldv=%d must be >= Mp and a multiple of 8", a->ldv);
+  if (a->ldv % 8) return fail("attn_pv: ldv=%d must be a multiple of 8", a->ldv);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (a->d == 32 && a->F == 128) return launch_pv<32, 128, 128, 2, 2>(a, g, st);
   if (a->d == 64 && a->F == 256) return launch_pv<64, 256, 64, 3, 3>(a, g, st);

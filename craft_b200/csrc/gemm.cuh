@@ -35,6 +35,10 @@ struct GemmParams {
   int T;        // number of taps
   int a_koff;   // first A column used
   int b_koff;   // first B column used
+  // b_blocked != 0: B rows are tokens of a padded-flat grid and the n-th tile of BN rows is the
+  // 8 x (BN/8) spatial block (by, bx) = (n / b_nbx, n % b_nbx), fetched with a 3-D TMA box (tmB is
+  // then a [H][W][C] map).  Used to emit V^T with keys in the block order attn_pv consumes.
+  int b_blocked, b_nbx;
   int tap_off[kMaxTaps];
   // row validity: Wp > 0 => row m is a real token iff (m % Wp) < W and (m / Wp) < H;
   //               Wp == 0 => every m < M is valid.
@@ -110,7 +114,12 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint8_t* sb = sa + S::kABytes;
         mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
         tma_load_2d(sa, &tmA, &full_bar[stage], p.a_koff + kc * kGemmBK, m0 + p.tap_off[t]);
-        tma_load_2d(sb, &tmB, &full_bar[stage], p.b_koff + kc * kGemmBK, t * p.Npad + n0);
+        if (p.b_blocked) {
+          const int by = static_cast<int>(blockIdx.y) / p.b_nbx, bx = static_cast<int>(blockIdx.y) - by * p.b_nbx;
+          tma_load_3d(sb, &tmB, &full_bar[stage], p.b_koff + kc * kGemmBK, bx * (BN / 8), by * 8);
+        } else {
+          tma_load_2d(sb, &tmB, &full_bar[stage], p.b_koff + kc * kGemmBK, t * p.Npad + n0);
+        }
         if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
       }
     }

@@ -46,7 +46,7 @@ class Workspace:
         self.device = device
         z = lambda cols, dt=torch.bfloat16: torch.zeros((g.Mp, cols), dtype=dt, device=device)
         f32 = torch.float32
-        self.ldv = ((g.Mp + 127) // 128) * 128
+        self.ldv = (((g.H + 7) // 8) * 8) * (((g.W + 15) // 16) * 16)     # keys in 8x16 (or 8x8) block order
         # --- feature tokens / projections
         self.T1 = z(256); self.T2 = z(256); self.T2f = z(256)
         self.Qc = z(256); self.Kc = z(256)                     # corr_fn projections
@@ -136,7 +136,9 @@ def value_aggregate(ws, Q, K, X, x_koff, W1p, *, M, d, F, table, w_pos, clip, ls
     V^T = W1 X^T (tcgen05 GEMM) -> flash P.V per mode -> mode soft-pool + skip + LayerNorm."""
     g = ws.grid
     C_in = W1p.shape[1]
-    ops.shift_gemm(W1p, X, M=M * F, Npad=ws.ldv, K=C_in, BN=128, b_koff=x_koff, out_b=ws.Vt)
+    BK = ops.pv_block_keys(d, F)
+    ops.shift_gemm(W1p, X, M=M * F, Npad=ops.blocked_keys(g, BK), K=C_in, BN=BK, b_koff=x_koff, out_b=ws.Vt,
+                   b_block_grid=g)
     ks = ws.pv_split(M)
     O = ws.opart(ks, M, F)
     ops.attn_pv(Q, K, ws.Vt, g, M=M, d=d, F=F, w_pos=w_pos, pos_table=table, R=7, clip=clip, lse2=lse2,

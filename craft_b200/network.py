@@ -8,6 +8,8 @@ build, and it is mutated the same way (corr_levels, corr_multiplier, *_trans_con
 `network.RAFTER` is the alias evaluate.py installs for old checkpoints.  fnet / cnet stay stock
 PyTorch (outside the named hot path).  Forward-only in this round.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -100,6 +102,14 @@ class CRAFT(nn.Module):
         self.update_block = GMAUpdateBlock(self.args, hidden_dim=hdim)
         self.call_counter = 0
         self.materialize_level0 = True
+        # Inference calls are captured into one CUDA graph per (shape, iters, test_mode) and replayed:
+        # the ~250 launches of a forward then cost no host time.  Set False (or CRAFT_B200_NO_GRAPH=1)
+        # to launch eagerly.
+        self.use_cuda_graph = os.environ.get("CRAFT_B200_NO_GRAPH", "0") != "1"
+        # fnet / cnet are outside the hot path; TF32 convolutions there cost ~6e-3 max abs error on
+        # features of magnitude 20 and are 2.5x faster than strict fp32 (profiles/README.md).
+        self.encoder_tf32 = True
+        self._graphs = {}
 
     def freeze_bn(self):
         for m in self.modules():
@@ -129,7 +139,9 @@ class CRAFT(nn.Module):
         image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
         image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
         amp = bool(getattr(self.args, "mixed_precision", False))
-        with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+        with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark,
+                                        deterministic=False, allow_tf32=self.encoder_tf32), \
+                torch.autocast("cuda", dtype=torch.float16, enabled=amp):
             fmap1, fmap2 = self.fnet([image1, image2])
             cnet_feat = self.cnet(image1)
         return fmap1.float().contiguous(), fmap2.float().contiguous(), cnet_feat.float().contiguous()
@@ -179,6 +191,54 @@ class CRAFT(nn.Module):
         B, _, H, W = image1.shape
         if H % 8 or W % 8:
             raise ValueError("image sides must be multiples of 8 (use InputPadder, as the reference drivers do)")
+        if self.use_cuda_graph and not self.training and not torch.cuda.is_current_stream_capturing() \
+                and "SAVECORR" not in os.environ:
+            return self._forward_graphed(image1, image2, iters, flow_init, test_mode)
+        return self._forward_impl(image1, image2, iters, flow_init, test_mode)
+
+    def _weights_signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters()) + \
+            tuple((b.data_ptr(), b._version) for b in self.buffers())
+
+    def _forward_graphed(self, image1, image2, iters, flow_init, test_mode):
+        key = (image1.device.index, tuple(image1.shape), int(iters), int(test_mode), flow_init is not None,
+               self.materialize_level0, self.encoder_tf32)
+        sig = self._weights_signature()
+        ent = self._graphs.get(key)
+        if ent is None or ent["sig"] != sig:
+            ent = dict(sig=sig)
+            ent["i1"] = image1.float().clone()
+            ent["i2"] = image2.float().clone()
+            ent["fi"] = flow_init.float().clone() if flow_init is not None else None
+            side = torch.cuda.Stream(device=image1.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):      # lazy init (cuDNN autotune, workspaces, packed weights) outside capture
+                    self._forward_impl(ent["i1"], ent["i2"], iters, ent["fi"], test_mode)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(image1.device)
+            g = torch.cuda.CUDAGraph()
+            from . import _lib
+            n0 = _lib.load().craft_b200_launch_count()
+            with torch.cuda.graph(g):
+                ent["out"] = self._forward_impl(ent["i1"], ent["i2"], iters, ent["fi"], test_mode)
+            ent["graph"] = g
+            ent["launches"] = _lib.load().craft_b200_launch_count() - n0   # craft_b200 kernels per replay
+            self._graphs[key] = ent
+        ent["i1"].copy_(image1)
+        ent["i2"].copy_(image2)
+        if flow_init is not None:
+            ent["fi"].copy_(flow_init)
+        ent["graph"].replay()
+        self.launches_last_forward = ent["launches"]
+        out = ent["out"]
+        # hand out copies: the graph's output buffers are overwritten by the next replay
+        if isinstance(out, tuple):
+            return tuple([t.clone() for t in o] if isinstance(o, list) else o.clone() for o in out)
+        return [t.clone() for t in out]
+
+    def _forward_impl(self, image1, image2, iters, flow_init, test_mode):
+        B, _, H, W = image1.shape
         fmap1, fmap2, cnet_feat = self._encoders(image1.float(), image2.float())
         g = TokenGrid(H // 8, W // 8)
         ws = get_workspace(g, image1.device, self.materialize_level0)

@@ -90,7 +90,9 @@ def unpack_tokens(buf, col, Cc, grid, out=None):
 # shift-GEMM
 # ------------------------------------------------------------------------------------------------
 def shift_gemm(A, Bw, *, M, Npad, K, BN, taps=(0,), a_koff=0, b_koff=0, grid=None, epilogue=EPI_STORE,
-               alpha=1.0, act=0, bias=None, out_b=None, colb=0, out_f=None, colf=0, aux0=None, aux1=None):
+               alpha=1.0, act=0, bias=None, out_b=None, colb=0, out_f=None, colf=0, aux0=None, aux1=None,
+               b_block_grid=None):
+    """b_block_grid: B rows are the tokens of that grid and n-tile j is its j-th 8 x BN/8 spatial block."""
     _chk(A, torch.bfloat16, "A")
     _chk(Bw, torch.bfloat16, "B")
     _chk(bias, torch.float32, "bias")
@@ -102,6 +104,8 @@ def shift_gemm(A, Bw, *, M, Npad, K, BN, taps=(0,), a_koff=0, b_koff=0, grid=Non
     a.A, a.a_rows, a.lda, a.a_koff = A.data_ptr(), A.shape[0], A.shape[1], a_koff
     a.B, a.b_rows, a.ldb_, a.b_koff = Bw.data_ptr(), Bw.shape[0], Bw.shape[1], b_koff
     a.M, a.Npad, a.K, a.T, a.BN = M, Npad, K, len(taps), BN
+    if b_block_grid is not None:
+        a.b_blocked, a.b_H, a.b_W = 1, b_block_grid.H, b_block_grid.W
     for i, t in enumerate(taps):
         a.tap_off[i] = int(t)
     a.H, a.W = (grid.H, grid.W) if grid is not None else (0, 0)
@@ -162,6 +166,19 @@ def scores_auto_ksplit(grid):
 
 def pv_auto_ksplit(grid, M):
     return _lib.load().craft_pv_auto_ksplit(grid.H, grid.W, M)
+
+
+def pv_block_keys(d, F):
+    bk = _lib.load().craft_pv_block_keys(d, F)
+    if bk <= 0:
+        raise _lib.CraftB200Error("attn_pv: unsupported (d=%d, F=%d)" % (d, F))
+    return bk
+
+
+def blocked_keys(grid, BK):
+    """Number of key columns of a V^T matrix in 8 x BK/8 block order."""
+    bw = BK // 8
+    return ((grid.H + 7) // 8) * ((grid.W + bw - 1) // bw) * BK
 
 
 def _scores_args(Q, K, grid, M, d, w_pos, pos_table, R, clip, run_flag, ksplit):

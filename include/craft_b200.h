@@ -24,6 +24,8 @@ extern "C" {
 
 int craft_b200_abi_version(void);
 const char* craft_b200_last_error(void);
+/* number of kernels this library has launched so far in this process (host-side counter) */
+long long craft_b200_launch_count(void);
 /* device properties the host uses for grid sizing: [0]=sm count, [1]=cc major, [2]=cc minor */
 int craft_b200_device_info(int* out3);
 
@@ -47,6 +49,8 @@ typedef struct craft_gemm_args {
   int a_rows, lda, a_koff;
   const void* B;      /* bf16 [T*Npad, ldb_]                                                  */
   int b_rows, ldb_, b_koff;
+  int b_blocked;      /* !=0: B rows are grid tokens (b_H x b_W); n-tile j = 8 x BN/8 spatial block */
+  int b_H, b_W;
   int M, Npad, K, T;
   int BN;             /* CTA tile width: 32, 64, 128 or 256 (Npad % BN == 0)                 */
   int tap_off[CRAFT_MAX_TAPS];
@@ -93,6 +97,9 @@ int craft_attn_lse(const craft_scores_args* a, void* stream);
 /* grid heuristics (host-side): key splits chosen so the grid fills whole waves of SMs         */
 int craft_scores_auto_ksplit(int H, int W);
 int craft_pv_auto_ksplit(int H, int W, int M);
+/* keys per tile (8 x BK/8 spatial block) the P.V kernel uses for (d, F); V^T must be laid out in
+ * that block order: column = block*BK + (y%8)*(BK/8) + x%(BK/8) (craft_shift_gemm b_blocked). */
+int craft_pv_block_keys(int d, int F);
 /* {sum,sumsq} -> {mean,rstd} (F.layer_norm, core/corr.py:200-204); n = number of elements.   */
 int craft_corr_stats_finalize(const double* stat_sum, double n, float* mean_rstd, void* stream);
 /* clip = (max > attn_clip) ? attn_clip : +inf ; flag = hit (core/setrans.py:527-529).        */
@@ -102,7 +109,7 @@ int craft_clip_gate(const float* stat_max, float attn_clip, float* clip, int* fl
 typedef struct craft_pv_args {
   const void* Q;      /* bf16 [Mp, C]                                                          */
   const void* K;      /* bf16 [Mp, C]                                                          */
-  const void* Vt;     /* bf16 [M*F, ldv]  (V transposed: keys contiguous)                      */
+  const void* Vt;     /* bf16 [M*F, ldv]  (V transposed, keys in 8 x BK/8 block order)         */
   int ldv;
   int C, M, d, F;
   int H, W;

@@ -1,0 +1,70 @@
+"""Launch one hot-path kernel a few times on realistic buffers (448x1024 grid) so that
+`ncu --set full -k regex:<name>` can capture it without profiling a whole forward.
+usage: python profiles/kernel_only.py {pv|pv_f2|corr|lse|gru_zr|gru_q|lookup|heads} [reps]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from bench import H, ITERS, W, _pairs, _state_dict  # noqa: E402
+from craft_b200 import hotpath as hp, ops  # noqa: E402
+from craft_b200.ops import TokenGrid  # noqa: E402
+from craft_b200.setrans import get_workspace  # noqa: E402
+
+
+def main(which, reps):
+    dev = torch.device("cuda", 0)
+    model, _ = _state_dict()
+    model = model.to(dev).eval()
+    a, b = _pairs(1, dev)[0]
+    with torch.no_grad():
+        model(a, b, iters=1, test_mode=1)       # fills every workspace buffer with realistic data
+        torch.cuda.synchronize()
+        g = TokenGrid(H // 8, W // 8)
+        ws = get_workspace(g, dev, True)
+        ub = model.update_block
+        uw = ub.weights(g)
+        att_tbl = model.att.vispos_encoder.table()
+        f2_tbl = model.f2_trans.vispos_encoder.table()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def run():
+            if which == "pv":
+                ks = ws.pv_split(4)
+                ops.attn_pv(ws.Qa, ws.Ka, ws.Vt, g, M=4, d=32, F=128, w_pos=1.0, pos_table=att_tbl, R=7,
+                            clip=ws.clip_att, lse2=ws.lse2_att, out=ws.opart(ks, 4, 128), ksplit=ks)
+            elif which == "pv_f2":
+                ks = ws.pv_split(4)
+                ops.attn_pv(ws.Q2, ws.K2, ws.Vt, g, M=4, d=64, F=256, w_pos=0.5, pos_table=f2_tbl, R=7,
+                            clip=ws.clip_f2, lse2=ws.lse2_f2, out=ws.opart(ks, 4, 256), ksplit=ks)
+            elif which == "corr":
+                ws.stat_sum.zero_()
+                ops.corr_build(ws.Qc, ws.Kc, g, M=4, d=64, w_agg=0.1285, w_pos=0.5, pos_table=f2_tbl, R=7,
+                               clip=ws.inf_clip, stat_sum=ws.stat_sum[0], stat_max=ws.stat_max[0:1], levels=ws.levels,
+                               ksplit=ws.ks_sc)
+            elif which == "lse":
+                ops.attn_lse(ws.Qa, ws.Ka, g, M=4, d=32, w_pos=1.0, pos_table=att_tbl, R=7, clip=ws.inf_clip,
+                             stat_max=ws.stat_max[2:3], lse_part=ws.lse_part, lse2=ws.lse2_att, ksplit=ws.ks_sc)
+            elif which in ("gru_zr", "gru_q"):
+                hp.sep_conv_gru(ws, uw)
+            elif which == "lookup":
+                ops.corr_lookup(ws.levels, g, ws.coords1, ws.mean_rstd, out_b=ws.CORR)
+            elif which == "heads":
+                hp.heads(ws, uw)
+            else:
+                raise SystemExit("unknown kernel " + which)
+
+        run()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        print("%s: %.2f us per call (avg of %d)" % (which, 1000 * e0.elapsed_time(e1) / reps, reps))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 5)

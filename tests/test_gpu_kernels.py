@@ -264,11 +264,14 @@ def test_attn_lse_pv_finalize(H, W, M, d, F_):
     v = bf16r(torch.randn((M, grid.U, F_), device=DEV, generator=g))
     O_ref = P @ v                                                   # [M,U,F]
     Q, K = rows_from_nchw(q, grid), rows_from_nchw(k, grid)
-    ldv = ((grid.Mp + 63) // 64) * 64
-    Vt = torch.zeros((M * F_, ldv), dtype=torch.bfloat16, device=DEV)
-    vt_grid = torch.zeros((M * F_, grid.H, grid.Wp), device=DEV)
-    vt_grid[:, :, :W] = v.permute(0, 2, 1).reshape(M * F_, H, W)
-    Vt[:, : grid.Mp] = vt_grid.reshape(M * F_, grid.Mp).to(torch.bfloat16)
+    # V^T in the kernel's key-block order: column = block*BK + (y%8)*BW + x%BW
+    BK = ops.pv_block_keys(d, F_)
+    BW = BK // 8
+    nby, nbx = (H + 7) // 8, (W + BW - 1) // BW
+    ldv = nby * nbx * BK
+    vt_pad = torch.zeros((M * F_, nby * 8, nbx * BW), device=DEV)
+    vt_pad[:, :H, :W] = v.permute(0, 2, 1).reshape(M * F_, H, W)
+    Vt = vt_pad.reshape(M * F_, nby, 8, nbx, BW).permute(0, 1, 3, 2, 4).reshape(M * F_, ldv).to(torch.bfloat16).contiguous()
     ks = ops.scores_auto_ksplit(grid)
     lse_part = torch.zeros((ks, M, grid.Mp, 2), device=DEV)
     lse2 = torch.zeros((M, grid.Mp), device=DEV)
