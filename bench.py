@@ -200,6 +200,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.ncu:
+        with torch.no_grad():
+            for i in range(max(args.warmup, 3)):
+                step(i)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+            step(0)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+        return
     sampler = ClockSampler(local) if rank == 0 else None
     with torch.no_grad():
         for i in range(args.warmup):
@@ -307,6 +317,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu", action="store_true",
+                    help="profiling helper: warm up, then run ONE step inside a cudaProfilerStart/Stop range and exit "
+                         "(use with `ncu --profile-from-start off ...`); prints no bench line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -367,6 +367,7 @@ int craft_modes_finalize(const float* O, int nsum, int M, int F, const float* w_
                          int colb, float* out_f32, int ldf, int colf, void* stream) {
   cb::Grid2 g = make_grid(H, W);
   if (M < 1 || M > 4) return fail("modes_finalize: M out of range");
+  if (nsum < 1 || nsum > 4) return fail("modes_finalize: nsum must be in [1,4]");
   if (!x_bf16 && !x_f32) return fail("modes_finalize: need the skip input");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long mode_stride = static_cast<long long>(g.Mp) * F;

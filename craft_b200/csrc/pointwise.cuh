@@ -326,9 +326,12 @@ __global__ void __launch_bounds__(256) modes_finalize_kernel(
 #pragma unroll
       for (int e = 0; e < PER; ++e) {
         const int f = lane + 32 * e;
-        float acc = 0.f;
-        for (int sp = 0; sp < nsum; ++sp)
-          acc += O[sp * part_stride + m * mode_stride + static_cast<long long>(p) * F + f];
+        // up to 4 key-split partials, loaded as independent requests (nsum <= 4, checked by the host)
+        const float* src = O + m * mode_stride + static_cast<long long>(p) * F + f;
+        float part[4];
+#pragma unroll
+        for (int sp = 0; sp < 4; ++sp) part[sp] = (sp < nsum) ? __ldg(src + sp * part_stride) : 0.f;
+        const float acc = (part[0] + part[1]) + (part[2] + part[3]);
         o[m][e] = acc;
         if (!gma) s += acc * __ldg(w_score + f);
       }
