@@ -22,7 +22,7 @@ class GemmArgs(C.Structure):
         ("B", C.c_void_p), ("b_rows", C.c_int), ("ldb_", C.c_int), ("b_koff", C.c_int),
         ("b_blocked", C.c_int), ("b_H", C.c_int), ("b_W", C.c_int),
         ("M", C.c_int), ("Npad", C.c_int), ("K", C.c_int), ("T", C.c_int),
-        ("BN", C.c_int),
+        ("BN", C.c_int), ("cluster", C.c_int), ("stages", C.c_int),
         ("tap_off", C.c_int * MAX_TAPS),
         ("H", C.c_int), ("W", C.c_int),
         ("epilogue", C.c_int),

@@ -116,28 +116,51 @@ int pick_split(int base_ctas, int max_split) {
   return best;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CL>
 int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const cb::GemmParams& p, cudaStream_t st) {
   using S = cb::GemmSmem<BN>;
   static bool attr_set = false;
-  auto kern = cb::shift_gemm_kernel<BN, EPI>;
+  auto kern = cb::shift_gemm_kernel<BN, EPI, CL>;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal) != cudaSuccess)
       return fail("gemm: cannot set dynamic smem %d", S::kTotal);
     attr_set = true;
   }
-  dim3 grid((p.M + cb::kGemmBM - 1) / cb::kGemmBM, p.Npad / BN);
-  kern<<<grid, cb::kGemmThreads, S::kTotal, st>>>(ta, tb, p);
+  const int mtiles = (p.M + cb::kGemmBM - 1) / cb::kGemmBM;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(((mtiles + CL - 1) / CL) * CL, p.Npad / BN, 1);   // M tiles padded to whole clusters
+  cfg.blockDim = dim3(cb::kGemmThreads, 1, 1);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+  if (e != cudaSuccess) return fail("shift_gemm launch: %s", cudaGetErrorString(e));
   return check_launch("shift_gemm");
 }
 
+template <int BN, int EPI>
+int launch_gemm_cl(int CL, const CUtensorMap& ta, const CUtensorMap& tb, const cb::GemmParams& p, cudaStream_t st) {
+  if constexpr (BN >= 32) {
+    if (CL == 4) return launch_gemm_t<BN, EPI, 4>(ta, tb, p, st);
+  }
+  if (CL == 2) return launch_gemm_t<BN, EPI, 2>(ta, tb, p, st);
+  return launch_gemm_t<BN, EPI, 1>(ta, tb, p, st);
+}
+
 template <int EPI>
-int launch_gemm_bn(int BN, const CUtensorMap& ta, const CUtensorMap& tb, const cb::GemmParams& p, cudaStream_t st) {
+int launch_gemm_bn(int BN, int CL, const CUtensorMap& ta, const CUtensorMap& tb, const cb::GemmParams& p, cudaStream_t st) {
   switch (BN) {
-    case 32: return launch_gemm_t<32, EPI>(ta, tb, p, st);
-    case 64: return launch_gemm_t<64, EPI>(ta, tb, p, st);
-    case 128: return launch_gemm_t<128, EPI>(ta, tb, p, st);
-    case 256: return launch_gemm_t<256, EPI>(ta, tb, p, st);
+    case 32: return launch_gemm_cl<32, EPI>(CL, ta, tb, p, st);
+    case 64: return launch_gemm_cl<64, EPI>(CL, ta, tb, p, st);
+    case 128: return launch_gemm_cl<128, EPI>(CL, ta, tb, p, st);
+    case 256: return launch_gemm_cl<256, EPI>(CL, ta, tb, p, st);
   }
   return fail("gemm: unsupported BN %d", BN);
 }
@@ -207,8 +230,15 @@ int craft_shift_gemm(const craft_gemm_args* a, void* stream) {
     p.b_nbx = (a->b_W + bw - 1) / bw;
     if (a->Npad != p.b_nbx * ((a->b_H + 7) / 8) * a->BN) return fail("gemm: blocked B: Npad must be nblocks*BN");
     if (make_map_3d_keys(&tb, a->B, bg, a->ldb_, bw)) return -1;
-  } else {
-    if (make_map_2d(&tb, a->B, a->b_rows, a->ldb_, a->ldb_, a->BN)) return -1;
+  }
+  // cluster size: CL consecutive M tiles share (multicast) the weight tile
+  int CL = a->cluster > 0 ? a->cluster : 1;   // measured (profiles/gemm_sweep): multicast does not pay at M = 7280
+  if (a->b_blocked) CL = 1;
+  const int mtiles = (a->M + cb::kGemmBM - 1) / cb::kGemmBM;
+  while (CL > 1 && (mtiles < CL || a->BN % (8 * CL))) CL /= 2;
+  if (CL != 1 && CL != 2 && CL != 4) return fail("gemm: cluster must be 1, 2 or 4");
+  if (!a->b_blocked) {
+    if (make_map_2d(&tb, a->B, a->b_rows, a->ldb_, a->ldb_, a->BN / CL)) return -1;
   }
   p.M = a->M; p.Npad = a->Npad; p.K = a->K; p.T = a->T;
   p.a_koff = a->a_koff; p.b_koff = a->b_koff;
@@ -218,19 +248,24 @@ int craft_shift_gemm(const craft_gemm_args* a, void* stream) {
   p.out_b = static_cast<__nv_bfloat16*>(a->out_bf16); p.ldb = a->ldo_b; p.colb = a->colo_b;
   p.out_f = a->out_f32; p.ldf = a->ldo_f; p.colf = a->colo_f;
   p.aux_f0 = a->aux0; p.aux_f1 = a->aux1;
+  {
+    const int smax = a->BN >= 256 ? 4 : (a->BN >= 128 ? 6 : (a->BN >= 64 ? 8 : 10));
+    p.stages = (a->stages > 0 && a->stages < smax) ? a->stages : smax;
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (a->epilogue) {
-    case cb::EPI_STORE: return launch_gemm_bn<cb::EPI_STORE>(a->BN, ta, tb, p, st);
+    case cb::EPI_STORE: return launch_gemm_bn<cb::EPI_STORE>(a->BN, CL, ta, tb, p, st);
     case cb::EPI_GRU_ZR:
       if (a->Npad != 256 || !a->aux0 || !a->aux1 || !a->out_bf16) return fail("gemm: gru_zr needs Npad=256, Z, Hm, out");
       if (a->BN > 128) return fail("gemm: gru_zr needs BN <= 128");
-      return launch_gemm_bn<cb::EPI_GRU_ZR>(a->BN, ta, tb, p, st);
+      return launch_gemm_bn<cb::EPI_GRU_ZR>(a->BN, CL, ta, tb, p, st);
     case cb::EPI_GRU_Q:
       if (a->Npad != 128 || !a->aux0 || !a->aux1 || !a->out_bf16) return fail("gemm: gru_q needs Npad=128, Z, Hm, out");
-      return launch_gemm_bn<cb::EPI_GRU_Q>(a->BN, ta, tb, p, st);
+      if (a->BN > 64) return fail("gemm: gru_q needs BN <= 64 (state prefetch lives in registers)");
+      return launch_gemm_bn<cb::EPI_GRU_Q>(a->BN, CL, ta, tb, p, st);
     case cb::EPI_MOTION:
       if (a->Npad != 128 || !a->aux1 || !a->out_bf16) return fail("gemm: motion needs Npad=128, flow, out");
-      return launch_gemm_bn<cb::EPI_MOTION>(a->BN, ta, tb, p, st);
+      return launch_gemm_bn<cb::EPI_MOTION>(a->BN, CL, ta, tb, p, st);
   }
   return fail("gemm: unknown epilogue %d", a->epilogue);
 }

@@ -9,8 +9,17 @@
 // coordinate, rows that fall off either end are zero-filled by TMA, and the two halo cells at the
 // end of every grid row hold zeros, so no im2col buffer ever exists.  Projections are T = 1.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (thread == accumulator row == TMEM lane).
+// Thread-block clusters: CL consecutive M tiles form a cluster.  They all need the same weight
+// tile B(t, k), so each CTA fetches 1/CL of it and TMA-multicasts that slice into the shared
+// memory of every CTA of the cluster (L2 -> SM traffic for weights drops by CL and the L2 slices
+// holding the weights are no longer hit by every SM at once).  A stage is recycled when all CL
+// consumers have released it: the MMA warp's tcgen05.commit arrives on the `empty` barrier of
+// every CTA in the cluster.
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue (thread == accumulator row == TMEM lane; the two warps that share a lane
+// quadrant split the BN columns).  Epilogue operands that do not depend on the accumulator
+// (bias tile, GRU state) are fetched while the main loop runs.
 #pragma once
 #include "common.cuh"
 
@@ -18,7 +27,7 @@ namespace cb {
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;       // 64 bf16 = one 128-byte swizzle atom row
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;
 constexpr int kMaxTaps = 49;
 
 enum GemmEpilogue : int {
@@ -40,6 +49,7 @@ struct GemmParams {
   // then a [H][W][C] map).  Used to emit V^T with keys in the block order attn_pv consumes.
   int b_blocked, b_nbx;
   int tap_off[kMaxTaps];
+  int stages;   // pipeline depth actually used (<= GemmSmem<BN>::kStages); tuning knob
   // row validity: Wp > 0 => row m is a real token iff (m % Wp) < W and (m / Wp) < H;
   //               Wp == 0 => every m < M is valid.
   int Wp, W, H;
@@ -57,26 +67,38 @@ struct GemmParams {
 
 template <int BN>
 struct GemmSmem {
-  static constexpr int kStages = (BN >= 256) ? 4 : 6;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : (BN >= 64 ? 8 : 10));
   static constexpr int kABytes = kGemmBM * 128;
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTotal = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kTotal = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
 };
 
-template <int BN, int EPI>
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  return fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * x));
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  // 1 - 2/(1 + e^{2x}); saturates correctly for |x| large (ex2 -> inf or 0)
+  return 1.0f - 2.0f * fast_rcp(1.0f + fast_ex2(2.8853900817779268f * x));
+}
+
+template <int BN, int EPI, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ GemmParams p) {
   using S = GemmSmem<BN>;
+  static_assert(BN % (8 * CL) == 0, "weight slice per CTA must be whole 8-row swizzle groups");
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment is required by the 128B swizzle atoms.
+  // 1024-byte alignment is required by the 128B swizzle atoms.  The dynamic smem window starts at
+  // the same offset in every CTA of the cluster, so the aligned addresses agree too (multicast
+  // writes land at identical offsets).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
   uint64_t* empty_bar = full_bar + S::kStages;
   uint64_t* acc_bar = empty_bar + S::kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5;
   const int m0 = blockIdx.x * kGemmBM;
@@ -84,20 +106,24 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int kchunks = p.K / kGemmBK;
   const int nk = p.T * kchunks;
   constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  const int nstages = p.stages;
+  uint32_t cta_rank = 0;
+  if constexpr (CL > 1) cta_rank = cluster_ctarank();
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < S::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);
     }
     mbar_init(acc_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL > 1) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -109,7 +135,7 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int it = 0; it < nk; ++it) {
         const int t = it / kchunks;
         const int kc = it - t * kchunks;
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        mbar_wait(&empty_bar[stage], phase ^ 1u);     // all CL consumers released this stage
         uint8_t* sa = smem + stage * S::kStageBytes;
         uint8_t* sb = sa + S::kABytes;
         mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
@@ -117,10 +143,14 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (p.b_blocked) {
           const int by = static_cast<int>(blockIdx.y) / p.b_nbx, bx = static_cast<int>(blockIdx.y) - by * p.b_nbx;
           tma_load_3d(sb, &tmB, &full_bar[stage], p.b_koff + kc * kGemmBK, bx * (BN / 8), by * 8);
+        } else if constexpr (CL > 1) {
+          constexpr int kSlice = BN / CL;
+          tma_load_2d_mcast(sb + cta_rank * kSlice * 128, &tmB, &full_bar[stage], p.b_koff + kc * kGemmBK,
+                            t * p.Npad + n0 + static_cast<int>(cta_rank) * kSlice, kMask);
         } else {
           tma_load_2d(sb, &tmB, &full_bar[stage], p.b_koff + kc * kGemmBK, t * p.Npad + n0);
         }
-        if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
+        if (++stage == nstages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -140,17 +170,21 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
           umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, (it | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+        // frees the smem slot (in every CTA of the cluster) when these MMAs retire
+        if constexpr (CL > 1) umma_commit_mcast(&empty_bar[stage], kMask);
+        else umma_commit(&empty_bar[stage]);
         if (it == nk - 1) umma_commit(acc_bar);  // accumulator complete
       }
       __syncwarp();
-      if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
+      if (++stage == nstages) { stage = 0; phase ^= 1u; }
     }
   } else {
     // ------------------------------ epilogue ----------------------------------
-    mbar_wait(acc_bar, 0);
-    tc_fence_after();
-    const int lane_grp = warp & 3;                 // TMEM lanes this warp may read
+    constexpr int HALF = BN / 2;                       // columns per thread
+    constexpr int CW = HALF < 32 ? HALF : 32;          // columns per TMEM load
+    const int et = threadIdx.x - 64;                   // 0..255
+    const int lane_grp = warp & 3;                     // TMEM lanes this warp may read
+    const int half = (warp - 2) >> 2;                  // which half of the BN columns
     const int row = lane_grp * 32 + (threadIdx.x & 31);
     const int m = m0 + row;
     bool valid = m < p.M;
@@ -159,30 +193,120 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int x = m - y * p.Wp;
       valid = valid && (x < p.W) && (y < p.H);
     }
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16);
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t raw[32];
-      tmem_ld32(trow + c, raw);
-      tmem_ld_wait();
-      if (!valid) continue;
-      const int n = n0 + c;
-      float v[32];
+    // ---- work that does not depend on the accumulator overlaps the main loop
+    for (int i = et; i < BN; i += 256) s_bias[i] = p.bias ? p.bias[n0 + i] : 0.0f;
+    const int nbase = n0 + half * HALF;                // first global column of this thread
+    float pre_h[(EPI == EPI_GRU_ZR || EPI == EPI_GRU_Q) ? HALF : 1];
+    float pre_z[(EPI == EPI_GRU_Q) ? HALF : 1];
+    if constexpr (EPI == EPI_GRU_ZR) {
+      if (valid && nbase >= 128) {
+        const float4* hs = reinterpret_cast<const float4*>(p.aux_f1 + static_cast<size_t>(m) * 128 + (nbase - 128));
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float a = __uint_as_float(raw[j]) * p.alpha;
-        if (p.bias) a += __ldg(p.bias + n + j);
-        v[j] = a;
-      }
-      if constexpr (EPI == EPI_STORE) {
-        if (p.act == 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+        for (int q = 0; q < HALF / 4; ++q) {
+          const float4 h = hs[q];
+          pre_h[4 * q] = h.x; pre_h[4 * q + 1] = h.y; pre_h[4 * q + 2] = h.z; pre_h[4 * q + 3] = h.w;
         }
-        if (p.out_b) {
+      }
+    }
+    if constexpr (EPI == EPI_GRU_Q) {
+      if (valid) {
+        const float4* hs = reinterpret_cast<const float4*>(p.aux_f1 + static_cast<size_t>(m) * 128 + nbase);
+        const float4* zs = reinterpret_cast<const float4*>(p.aux_f0 + static_cast<size_t>(m) * 128 + nbase);
+#pragma unroll
+        for (int q = 0; q < HALF / 4; ++q) {
+          const float4 h = hs[q], z = zs[q];
+          pre_h[4 * q] = h.x; pre_h[4 * q + 1] = h.y; pre_h[4 * q + 2] = h.z; pre_h[4 * q + 3] = h.w;
+          pre_z[4 * q] = z.x; pre_z[4 * q + 1] = z.y; pre_z[4 * q + 2] = z.z; pre_z[4 * q + 3] = z.w;
+        }
+      }
+    }
+    asm volatile("bar.sync 1, 256;");                  // s_bias visible to all epilogue warps
+
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + half * HALF;
+#pragma unroll
+    for (int c = 0; c < HALF; c += CW) {
+      uint32_t raw[CW];
+      if constexpr (CW == 32) tmem_ld32(trow + c, raw); else tmem_ld16(trow + c, raw);
+      tmem_ld_wait();
+      if (valid) {
+        const int n = nbase + c;                       // global column of raw[0]
+        const int nl = half * HALF + c;                // column inside the CTA tile
+        float v[CW];
+#pragma unroll
+        for (int j = 0; j < CW; ++j) v[j] = fmaf(__uint_as_float(raw[j]), p.alpha, s_bias[nl + j]);
+        if constexpr (EPI == EPI_STORE) {
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) v[j] = fmaxf(v[j], 0.0f);
+          }
+          if (p.out_b) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out_b + static_cast<size_t>(m) * p.ldb + p.colb + n);
+#pragma unroll
+            for (int q = 0; q < CW / 8; ++q) {
+              uint4 u;
+              u.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+              u.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+              u.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+              u.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+              dst[q] = u;
+            }
+          }
+          if (p.out_f) {
+            float4* dst = reinterpret_cast<float4*>(p.out_f + static_cast<size_t>(m) * p.ldf + p.colf + n);
+#pragma unroll
+            for (int q = 0; q < CW / 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+        } else if constexpr (EPI == EPI_GRU_ZR) {
+          if (n < 128) {
+            float4* dst = reinterpret_cast<float4*>(p.aux_f0 + static_cast<size_t>(m) * 128 + n);
+#pragma unroll
+            for (int q = 0; q < CW / 4; ++q)
+              dst[q] = make_float4(sigmoid_fast(v[4 * q]), sigmoid_fast(v[4 * q + 1]),
+                                   sigmoid_fast(v[4 * q + 2]), sigmoid_fast(v[4 * q + 3]));
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(p.out_b + static_cast<size_t>(m) * p.ldb + p.colb + (n - 128));
+#pragma unroll
+            for (int q = 0; q < CW / 8; ++q) {
+              uint4 u;
+              u.x = pack_bf16x2(sigmoid_fast(v[8 * q + 0]) * pre_h[c + 8 * q + 0], sigmoid_fast(v[8 * q + 1]) * pre_h[c + 8 * q + 1]);
+              u.y = pack_bf16x2(sigmoid_fast(v[8 * q + 2]) * pre_h[c + 8 * q + 2], sigmoid_fast(v[8 * q + 3]) * pre_h[c + 8 * q + 3]);
+              u.z = pack_bf16x2(sigmoid_fast(v[8 * q + 4]) * pre_h[c + 8 * q + 4], sigmoid_fast(v[8 * q + 5]) * pre_h[c + 8 * q + 5]);
+              u.w = pack_bf16x2(sigmoid_fast(v[8 * q + 6]) * pre_h[c + 8 * q + 6], sigmoid_fast(v[8 * q + 7]) * pre_h[c + 8 * q + 7]);
+              dst[q] = u;
+            }
+          }
+        } else if constexpr (EPI == EPI_GRU_Q) {
+          float4* hptr = reinterpret_cast<float4*>(p.aux_f1 + static_cast<size_t>(m) * 128 + n);
+          uint4* dst = reinterpret_cast<uint4*>(p.out_b + static_cast<size_t>(m) * p.ldb + p.colb + n);
+          float hn[CW];
+#pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            const float z = pre_z[c + j];
+            hn[j] = (1.0f - z) * pre_h[c + j] + z * tanh_fast(v[j]);
+          }
+#pragma unroll
+          for (int q = 0; q < CW / 4; ++q) hptr[q] = make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
+#pragma unroll
+          for (int q = 0; q < CW / 8; ++q) {
+            uint4 u;
+            u.x = pack_bf16x2(hn[8 * q + 0], hn[8 * q + 1]);
+            u.y = pack_bf16x2(hn[8 * q + 2], hn[8 * q + 3]);
+            u.z = pack_bf16x2(hn[8 * q + 4], hn[8 * q + 5]);
+            u.w = pack_bf16x2(hn[8 * q + 6], hn[8 * q + 7]);
+            dst[q] = u;
+          }
+        } else if constexpr (EPI == EPI_MOTION) {
+#pragma unroll
+          for (int j = 0; j < CW; ++j) v[j] = fmaxf(v[j], 0.0f);
+          if (n + CW == 128) {   // last chunk: channels 126,127 carry the flow itself
+            v[CW - 2] = p.aux_f1[static_cast<size_t>(m) * 2 + 0];
+            v[CW - 1] = p.aux_f1[static_cast<size_t>(m) * 2 + 1];
+          }
           uint4* dst = reinterpret_cast<uint4*>(p.out_b + static_cast<size_t>(m) * p.ldb + p.colb + n);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < CW / 8; ++q) {
             uint4 u;
             u.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
             u.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
@@ -190,90 +314,20 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             u.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
             dst[q] = u;
           }
-        }
-        if (p.out_f) {
-          float4* dst = reinterpret_cast<float4*>(p.out_f + static_cast<size_t>(m) * p.ldf + p.colf + n);
+          if (p.out_f) {
+            float4* dstf = reinterpret_cast<float4*>(p.out_f + static_cast<size_t>(m) * p.ldf + p.colf + n);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        }
-      } else if constexpr (EPI == EPI_GRU_ZR) {
-        if (n < 128) {
-          float4* dst = reinterpret_cast<float4*>(p.aux_f0 + static_cast<size_t>(m) * 128 + n);
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            dst[q] = make_float4(sigmoidf_acc(v[4 * q]), sigmoidf_acc(v[4 * q + 1]),
-                                 sigmoidf_acc(v[4 * q + 2]), sigmoidf_acc(v[4 * q + 3]));
-        } else {
-          const int nh = n - 128;
-          const float4* hsrc = reinterpret_cast<const float4*>(p.aux_f1 + static_cast<size_t>(m) * 128 + nh);
-          uint4* dst = reinterpret_cast<uint4*>(p.out_b + static_cast<size_t>(m) * p.ldb + p.colb + nh);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 h0 = hsrc[2 * q], h1 = hsrc[2 * q + 1];
-            uint4 u;
-            u.x = pack_bf16x2(sigmoidf_acc(v[8 * q + 0]) * h0.x, sigmoidf_acc(v[8 * q + 1]) * h0.y);
-            u.y = pack_bf16x2(sigmoidf_acc(v[8 * q + 2]) * h0.z, sigmoidf_acc(v[8 * q + 3]) * h0.w);
-            u.z = pack_bf16x2(sigmoidf_acc(v[8 * q + 4]) * h1.x, sigmoidf_acc(v[8 * q + 5]) * h1.y);
-            u.w = pack_bf16x2(sigmoidf_acc(v[8 * q + 6]) * h1.z, sigmoidf_acc(v[8 * q + 7]) * h1.w);
-            dst[q] = u;
+            for (int q = 0; q < CW / 4; ++q) dstf[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
-        }
-      } else if constexpr (EPI == EPI_GRU_Q) {
-        float4* hptr = reinterpret_cast<float4*>(p.aux_f1 + static_cast<size_t>(m) * 128 + n);
-        const float4* zptr = reinterpret_cast<const float4*>(p.aux_f0 + static_cast<size_t>(m) * 128 + n);
-        uint4* dst = reinterpret_cast<uint4*>(p.out_b + static_cast<size_t>(m) * p.ldb + p.colb + n);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float hn[8];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float4 h = hptr[2 * q + e];
-            const float4 z = zptr[2 * q + e];
-            const float q0 = tanhf(v[8 * q + 4 * e + 0]), q1 = tanhf(v[8 * q + 4 * e + 1]);
-            const float q2 = tanhf(v[8 * q + 4 * e + 2]), q3 = tanhf(v[8 * q + 4 * e + 3]);
-            float4 o;
-            o.x = (1.0f - z.x) * h.x + z.x * q0;
-            o.y = (1.0f - z.y) * h.y + z.y * q1;
-            o.z = (1.0f - z.z) * h.z + z.z * q2;
-            o.w = (1.0f - z.w) * h.w + z.w * q3;
-            hptr[2 * q + e] = o;
-            hn[4 * e + 0] = o.x; hn[4 * e + 1] = o.y; hn[4 * e + 2] = o.z; hn[4 * e + 3] = o.w;
-          }
-          uint4 u;
-          u.x = pack_bf16x2(hn[0], hn[1]);
-          u.y = pack_bf16x2(hn[2], hn[3]);
-          u.z = pack_bf16x2(hn[4], hn[5]);
-          u.w = pack_bf16x2(hn[6], hn[7]);
-          dst[q] = u;
-        }
-      } else if constexpr (EPI == EPI_MOTION) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-        if (n + 32 == 128) {   // last chunk: channels 126,127 carry the flow itself
-          v[30] = p.aux_f1[static_cast<size_t>(m) * 2 + 0];
-          v[31] = p.aux_f1[static_cast<size_t>(m) * 2 + 1];
-        }
-        uint4* dst = reinterpret_cast<uint4*>(p.out_b + static_cast<size_t>(m) * p.ldb + p.colb + n);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u;
-          u.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
-          u.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
-          u.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
-          u.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
-          dst[q] = u;
-        }
-        if (p.out_f) {
-          float4* dstf = reinterpret_cast<float4*>(p.out_f + static_cast<size_t>(m) * p.ldf + p.colf + n);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) dstf[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
       }
+      __syncwarp();
     }
     tc_fence_before();
   }
 
-  __syncthreads();
+  // No CTA may leave while a peer can still multicast into its smem or arrive on its barriers.
+  if constexpr (CL > 1) cluster_sync(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);

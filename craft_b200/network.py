@@ -139,12 +139,28 @@ class CRAFT(nn.Module):
         image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
         image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
         amp = bool(getattr(self.args, "mixed_precision", False))
+        # fnet (two frames) and cnet (frame 1) are independent: run cnet on a side stream so their
+        # many small, latency-bound kernels overlap (fork/join is captured into the CUDA graph too).
+        main = torch.cuda.current_stream()
+        side = self._side_stream(image1.device)
+        side.wait_stream(main)
         with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark,
                                         deterministic=False, allow_tf32=self.encoder_tf32), \
                 torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+            with torch.cuda.stream(side):
+                cnet_feat = self.cnet(image1).float().contiguous()
             fmap1, fmap2 = self.fnet([image1, image2])
-            cnet_feat = self.cnet(image1)
-        return fmap1.float().contiguous(), fmap2.float().contiguous(), cnet_feat.float().contiguous()
+        main.wait_stream(side)
+        cnet_feat.record_stream(main)
+        return fmap1.float().contiguous(), fmap2.float().contiguous(), cnet_feat
+
+    def _side_stream(self, device):
+        key = str(device)
+        if not hasattr(self, "_streams"):
+            self._streams = {}
+        if key not in self._streams:
+            self._streams[key] = torch.cuda.Stream(device=device)
+        return self._streams[key]
 
     def _prepare_pair(self, ws, fmap1, fmap2, cnet_feat, flow_init):
         """Everything that happens once per pair (core/network.py:179-228) on one batch element."""

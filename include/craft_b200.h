@@ -53,6 +53,8 @@ typedef struct craft_gemm_args {
   int b_H, b_W;
   int M, Npad, K, T;
   int BN;             /* CTA tile width: 32, 64, 128 or 256 (Npad % BN == 0)                 */
+  int cluster;        /* M tiles per thread-block cluster sharing the weight tile: 0 auto,1,2,4 */
+  int stages;         /* TMA pipeline depth: 0 = maximum that fits                            */
   int tap_off[CRAFT_MAX_TAPS];
   int H, W;           /* >0: rows are a padded-flat grid, halo rows are not written; 0: plain */
   int epilogue;       /* 0 store, 1 gru_zr, 2 gru_q, 3 motion                                 */
