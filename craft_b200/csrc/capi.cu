@@ -11,6 +11,7 @@
 #include "../../include/craft_b200.h"
 #include "attn_pv.cuh"
 #include "common.cuh"
+#include "encoder.cuh"
 #include "gemm.cuh"
 #include "pointwise.cuh"
 #include "scores.cuh"
@@ -464,6 +465,31 @@ int craft_upsample_flow(const void* mask, int mask_is_bf16, int ldm, const float
   else
     cb::upsample_flow_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(mask), ldm, flow, g, out);
   return check_launch("upsample_flow");
+}
+
+
+int craft_nhwc_instnorm_stats(const float* x, int N, int HW, int C, float eps, float* sums, float* ab, void* stream) {
+  if (C % 4 || C > 1024 || C < 4) return fail("instnorm_stats: C=%d must be a multiple of 4 (<= 1024)", C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(sums, 0, sizeof(float) * 2 * N * C, st) != cudaSuccess) return fail("instnorm_stats: memset");
+  int chunks = (4 * sm_count() + N - 1) / N;          // ~4 blocks per SM in total
+  int rows = (HW + chunks - 1) / chunks;
+  if (rows < 64) rows = 64;
+  chunks = (HW + rows - 1) / rows;
+  cb::nhwc_stats_kernel<<<dim3(chunks, N), 256, 0, st>>>(x, HW, C, rows, sums);
+  if (check_launch("nhwc_stats")) return -1;
+  cb::instnorm_finalize_kernel<<<(N * C + 255) / 256, 256, 0, st>>>(sums, N * C, 1.0f / static_cast<float>(HW), eps, ab);
+  return check_launch("instnorm_finalize");
+}
+
+int craft_nhwc_affine(const float* v, const float* ab, int ab_nstride, const float* res, const float* rab,
+                      int rab_nstride, int relu_in, int relu_out, int N, int HW, int C, float* out, void* stream) {
+  if (C % 4) return fail("nhwc_affine: C must be a multiple of 4");
+  const long long per_image = static_cast<long long>(HW) * C;
+  const long long total4 = per_image * N / 4;
+  cb::nhwc_affine_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      v, ab, ab_nstride, res, rab, rab_nstride, relu_in, relu_out, per_image, C, total4, out);
+  return check_launch("nhwc_affine");
 }
 
 }  // extern "C"

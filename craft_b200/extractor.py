@@ -4,6 +4,7 @@ reference checkpoints load key for key (conv1, norm1, layer{1,2,3}.{0,1}.{conv1,
 norm3,downsample.{0,1}}, conv2)."""
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 
 def _norm(kind, ch):
@@ -38,6 +39,55 @@ class ResidualBlock(nn.Module):
             x = self.downsample(x)
         return self.relu(x + y)
 
+    def forward_fused(self, x, fz):
+        """Inference on channels-last activations: cuDNN convs + craft_b200 norm/relu/residual kernels."""
+        y = fz.conv(self.conv1, x)
+        y = fz.norm_act(self.norm1, y, self.conv1, relu=True)
+        y2 = fz.conv(self.conv2, y)
+        ab2 = fz.scale_shift(self.norm2, y2, self.conv2)
+        if self.downsample is not None:
+            xd = fz.conv(self.downsample[0], x)
+            return fz.affine(y2, ab2, res=xd, rab=fz.scale_shift(self.norm3, xd, self.downsample[0]),
+                             relu_in=True, relu_out=True)
+        return fz.affine(y2, ab2, res=x, relu_in=True, relu_out=True)
+
+
+class _Fused:
+    """Helpers of the fused inference path: convolutions stay cuDNN on
+    channels-last tensors (no NCHW<->NHWC conversion kernels); InstanceNorm / eval BatchNorm + ReLU +
+    residual add run as craft_b200 kernels (csrc/encoder.cuh)."""
+
+    def __init__(self, kind):
+        from . import hotpath, ops
+        self.kind, self.ops = kind, ops
+        self.cache = hotpath.PackedWeights()
+
+    def conv(self, m, x, bias=False):
+        """cuDNN convolution WITHOUT its bias: a conv bias in front of a normalisation is either a no-op
+        (instance norm subtracts the per-channel mean) or folds into the norm's shift (batch norm), which
+        saves one elementwise pass per convolution."""
+        w = self.cache.get(("w", id(m)), [m.weight], lambda: m.weight.detach().contiguous(memory_format=torch.channels_last))
+        return F.conv2d(x, w, m.bias if bias else None, m.stride, m.padding)
+
+    def scale_shift(self, norm, y, conv):
+        if self.kind == "instance":
+            return self.ops.instnorm_stats(y.permute(0, 2, 3, 1), eps=norm.eps)
+
+        def build():
+            a = norm.weight.detach().float() * torch.rsqrt(norm.running_var.detach().float() + norm.eps)
+            b = norm.bias.detach().float() + (conv.bias.detach().float() - norm.running_mean.detach().float()) * a
+            return torch.stack([a, b], dim=1)[None].contiguous()
+        return self.cache.get(("bn", id(norm)), [norm.weight, norm.bias, norm.running_mean, norm.running_var, conv.bias], build)
+
+    def affine(self, v, ab, res=None, rab=None, relu_in=False, relu_out=False):
+        out = torch.empty_like(v)     # keeps the channels-last strides
+        self.ops.nhwc_affine(v.permute(0, 2, 3, 1), ab, res.permute(0, 2, 3, 1) if res is not None else None, rab,
+                             relu_in, relu_out, out=out.permute(0, 2, 3, 1))
+        return out
+
+    def norm_act(self, norm, y, conv, relu=True):
+        return self.affine(y, self.scale_shift(norm, y, conv), relu_in=relu)
+
 
 class BasicEncoder(nn.Module):
     def __init__(self, output_dim=128, norm_fn="batch", dropout=0.0):
@@ -67,11 +117,29 @@ class BasicEncoder(nn.Module):
         self.in_planes = dim
         return nn.Sequential(*layers)
 
+    def _can_fuse(self, x):
+        return (x.is_cuda and not self.training and not torch.is_grad_enabled() and x.dtype == torch.float32
+                and self.norm_fn in ("instance", "batch") and not torch.is_autocast_enabled()
+                and getattr(self, "use_fused", True))
+
     def forward(self, x):
         is_list = isinstance(x, (tuple, list))
         if is_list:
             batch_dim = x[0].shape[0]
             x = torch.cat(x, dim=0)
+        if self._can_fuse(x):
+            if getattr(self, "_fz", None) is None or self._fz.kind != self.norm_fn:
+                self._fz = _Fused(self.norm_fn)
+            fz = self._fz
+            x = x.contiguous(memory_format=torch.channels_last)
+            x = fz.norm_act(self.norm1, fz.conv(self.conv1, x), self.conv1, relu=True)
+            for layer in (self.layer1, self.layer2, self.layer3):
+                for blk in layer:
+                    x = blk.forward_fused(x, fz)
+            x = fz.conv(self.conv2, x, bias=True).contiguous()      # back to NCHW for the token packer
+            if is_list:
+                x = torch.split(x, [batch_dim, batch_dim], dim=0)
+            return x
         x = self.relu1(self.norm1(self.conv1(x)))
         x = self.conv2(self.layer3(self.layer2(self.layer1(x))))
         if self.training and self.dropout is not None:

@@ -296,3 +296,29 @@ def upsample_flow(mask, flow, grid, out=None):
     is_b = 1 if mask.dtype == torch.bfloat16 else 0
     _lib.call("craft_upsample_flow", _ptr(mask), is_b, _ld(mask), _ptr(flow), grid.H, grid.W, _ptr(out), _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# encoder glue (channels-last f32 tensors)
+# ------------------------------------------------------------------------------------------------
+def instnorm_stats(x_nhwc, eps=1e-5):
+    """x: [N,H,W,C] contiguous f32 -> ab [N,C,2] = (rstd, -mean*rstd)."""
+    _chk(x_nhwc, torch.float32, "x")
+    N, H, W, Cc = x_nhwc.shape
+    sums = torch.empty((N, Cc, 2), dtype=torch.float32, device=x_nhwc.device)
+    ab = torch.empty((N, Cc, 2), dtype=torch.float32, device=x_nhwc.device)
+    _lib.call("craft_nhwc_instnorm_stats", _ptr(x_nhwc), N, H * W, Cc, float(eps), _ptr(sums), _ptr(ab), _stream())
+    return ab
+
+
+def nhwc_affine(v, ab=None, res=None, rab=None, relu_in=False, relu_out=False, out=None):
+    """out = relu_out([ra*res+rb] + relu_in(a*v+b)); v/res/out [N,H,W,C] f32; ab/rab [N or 1, C, 2]."""
+    _chk(v, torch.float32, "v")
+    _chk(res, torch.float32, "res")
+    N, H, W, Cc = v.shape
+    if out is None:
+        out = torch.empty_like(v)
+    st = lambda t: 0 if (t is None or t.shape[0] == 1) else 2 * Cc
+    _lib.call("craft_nhwc_affine", _ptr(v), _ptr(ab), st(ab), _ptr(res), _ptr(rab), st(rab), int(relu_in),
+              int(relu_out), N, H * W, Cc, _ptr(out), _stream())
+    return out

@@ -152,6 +152,17 @@ int craft_init_coords(float* coords1, const float* flow_init_nchw, int H, int W,
 int craft_upsample_flow(const void* mask, int mask_is_bf16, int ldm, const float* flow, int H, int W,
                         float* out_nchw, void* stream);
 
+/* ---- encoder glue (core/extractor.py; first row outside the named hot path) ------------------- */
+/* InstanceNorm2d statistics of a channels-last f32 tensor [N,HW,C] -> ab[N,C,2] = (rstd, -mean*rstd)
+ * (eps, biased variance, no affine: extractor.py:136-137).  sums: scratch [N,C,2].                 */
+int craft_nhwc_instnorm_stats(const float* x, int N, int HW, int C, float eps, float* sums, float* ab,
+                              void* stream);
+/* out = relu_out( [ra*res+rb] + relu_in(a*v+b) ): norm + ReLU + residual of ResidualBlock.forward
+ * (extractor.py:55-64).  ab / rab: [N or 1][C][2]; *_nstride = 2*C per image or 0 when shared.     */
+int craft_nhwc_affine(const float* v, const float* ab, int ab_nstride, const float* res, const float* rab,
+                      int rab_nstride, int relu_in, int relu_out, int N, int HW, int C, float* out,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

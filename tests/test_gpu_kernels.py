@@ -307,3 +307,43 @@ def test_attn_lse_pv_finalize(H, W, M, d, F_):
         ref = F.layer_norm(0.8 * x + agg, (F_,), eps=1e-12)
         gy = yf.reshape(grid.H, grid.Wp, F_)[:, :W].reshape(grid.U, F_)
         assert torch.allclose(gy, ref, atol=1e-3, rtol=1e-3), (gy - ref).abs().max()
+
+
+@pytest.mark.parametrize("Cc", [64, 96, 128, 256])
+def test_encoder_norm_kernels(Cc):
+    g = torch.Generator(device=DEV).manual_seed(Cc)
+    x = (torch.randn((2, Cc, 37, 50), device=DEV, generator=g) * 2 + 0.3).contiguous(memory_format=torch.channels_last)
+    r = torch.randn((2, Cc, 37, 50), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    ab = ops.instnorm_stats(x.permute(0, 2, 3, 1))
+    out = torch.empty_like(x)
+    ops.nhwc_affine(x.permute(0, 2, 3, 1), ab, r.permute(0, 2, 3, 1), None, True, True, out=out.permute(0, 2, 3, 1))
+    torch.cuda.synchronize()
+    ref = torch.relu(r + torch.relu(F.instance_norm(x, eps=1e-5)))
+    assert torch.allclose(out, ref, atol=2e-4, rtol=1e-4), (out - ref).abs().max()
+    # shared (batch-norm style) scale/shift on both branches
+    sab = torch.randn((1, Cc, 2), device=DEV, generator=g)
+    out2 = torch.empty_like(x)
+    ops.nhwc_affine(x.permute(0, 2, 3, 1), sab, r.permute(0, 2, 3, 1), sab, False, False, out=out2.permute(0, 2, 3, 1))
+    torch.cuda.synchronize()
+    a, b = sab[0, :, 0].view(1, Cc, 1, 1), sab[0, :, 1].view(1, Cc, 1, 1)
+    assert torch.allclose(out2, (a * x + b) + (a * r + b), atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("kind", ["instance", "batch"])
+def test_fused_encoder_matches_module_path(kind):
+    from craft_b200.extractor import BasicEncoder
+    torch.manual_seed(3)
+    enc = BasicEncoder(output_dim=256, norm_fn=kind).to(DEV).eval()
+    if kind == "batch":      # non-trivial running statistics
+        for m in enc.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.2); m.running_var.uniform_(0.5, 1.5); m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.2)
+    x = torch.rand((2, 3, 128, 192), device=DEV) * 2 - 1
+    torch.backends.cudnn.allow_tf32 = False
+    with torch.no_grad():
+        enc.use_fused = False
+        ref = enc(x)
+        enc.use_fused = True
+        got = enc(x)
+    torch.cuda.synchronize()
+    assert torch.allclose(got, ref, atol=2e-3, rtol=1e-3), (got - ref).abs().max()
