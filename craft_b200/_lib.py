@@ -84,6 +84,7 @@ SIGNATURES = {
     "craft_modes_finalize": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _i, _i, _i, _i,
                                   _vp, _i, _i, _vp, _i, _i, _vp]),
     "craft_corr_lookup": (_i, [C.POINTER(_vp), _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp]),
+    "craft_corr_lookup0": (_i, [_vp, _vp, _i, _i, _f, _f, _f, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     "craft_convf1": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _i, _vp]),
     "craft_flow_update": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "craft_init_coords": (_i, [_vp, _vp, _i, _i, _vp]),

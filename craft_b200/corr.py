@@ -1,8 +1,9 @@
 """CorrBlock / TransCorrBlock with the reference's signatures (core/corr.py), backed by the fused
 correlation-volume kernel (scores.cuh SC_CORR) and the pyramid lookup kernel (pointwise.cuh).
 
-The U x U level-0 volume is only written to HBM when `materialize_level0` is on (default in this
-round, see DESIGN.md section 6: the pooled levels 1..3 come out of the GEMM epilogue directly).
+The U x U level-0 volume is never written to HBM (unless SAVECORR asks for it): pyramid levels 1..3
+come out of the GEMM epilogue directly and the level-0 window of each lookup is recomputed on demand
+from the projected query/key rows (pointwise.cuh corr_lookup0).
 The global layer-norm of the volume (core/corr.py:200-204) is applied inside the lookup as a
 deferred affine, so no second pass over the volume exists.
 """
@@ -23,8 +24,13 @@ class _LookupMixin:
     def lookup_rows(self, ws, coords_rows, out_b=None, out_nchw=None):
         if self.radius != 4 or self.num_levels != 4:
             raise NotImplementedError("craft_b200 lookup kernel is built for radius 4, 4 levels (CRAFT default)")
+        first = 0
+        if ws.levels[0] is None:      # level 0 on demand: the U x U volume was never stored
+            ops.corr_lookup0(grid=ws.grid, coords=coords_rows, mean_rstd=ws.mean_rstd, out_b=out_b,
+                             out_nchw=out_nchw, **ws.corr_meta)
+            first = 1
         ops.corr_lookup(ws.levels, ws.grid, coords_rows, ws.mean_rstd, out_b=out_b, out_nchw=out_nchw,
-                        first_level=0)
+                        first_level=first)
 
     def __call__(self, coords):
         """coords [B,2,h,w] (x,y) -> [B,324,h,w] fp32."""
@@ -53,7 +59,7 @@ class CorrBlock(_LookupMixin):
         if Cc != 256:
             raise NotImplementedError("CorrBlock kernel instantiated for 256-channel fnet features")
         grid = TokenGrid(h, w)
-        ws = self._ws = get_workspace(grid, fmap1.device)
+        ws = self._ws = get_workspace(grid, fmap1.device, "SAVECORR" in os.environ)
         ops.pack_tokens(fmap1[0].float().contiguous(), grid, ops.PACK_COPY, out_b=ws.Qc)
         ops.pack_tokens(fmap2[0].float().contiguous(), grid, ops.PACK_COPY, out_b=ws.Kc)
         hp.build_correlation(ws, ws.Qc, ws.Kc, M=1, d=Cc, w_agg=0.0, table=None, w_pos=0.0,
@@ -92,7 +98,7 @@ class TransCorrBlock(_LookupMixin, nn.Module):
         if B != 1:
             raise NotImplementedError("standalone TransCorrBlock.update handles one pair per call")
         grid = TokenGrid(h, w)
-        ws = get_workspace(grid, fmap1.device)
+        ws = get_workspace(grid, fmap1.device, "SAVECORR" in os.environ)
         ops.pack_tokens(fmap1[0].float().contiguous(), grid, ops.PACK_LN, out_b=ws.T1)
         ops.pack_tokens(fmap2[0].float().contiguous(), grid, ops.PACK_LN, out_b=ws.T2f)
         self.build_rows(ws, ws.T1, ws.T2f)

@@ -223,15 +223,18 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc_fence_after();
         __syncwarp();
         uint8_t* pbuf = sP + sg * S::kPBytes;
+        // all of this thread's S columns are requested up front (one wait instead of one per chunk),
+        // then the S buffer is handed back to the MMA warp before any math happens
+        uint32_t raw_all[HALF];
+#pragma unroll
+        for (int c = 0; c < HALF; c += 32)
+          tmem_ld32(tlane + sg * BK + ch * HALF + c, *reinterpret_cast<uint32_t(*)[32]>(&raw_all[c]));
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_empty[sg]);
 #pragma unroll
         for (int c = 0; c < HALF; c += 32) {
-          uint32_t raw[32];
-          tmem_ld32(tlane + sg * BK + ch * HALF + c, raw);
-          tmem_ld_wait();
-          if (c + 32 >= HALF) {      // this thread's share of the S buffer is read
-            tc_fence_before();
-            mbar_arrive(&s_empty[sg]);
-          }
+          const uint32_t* raw = &raw_all[c];
           float x[32];
           if (!clamped) {
 #pragma unroll

@@ -436,6 +436,23 @@ int craft_corr_lookup(const float* const* lvl, int H, int W, const float* coords
   return check_launch("corr_lookup");
 }
 
+int craft_corr_lookup0(const void* Q, const void* K, int M, int d, float scale, float w_agg, float w_pos,
+                       const float* pos_table, int R, const float* clip, int H, int W, const float* coords,
+                       const float* mean_rstd, void* out_bf16, int ldb, float* out_nchw, void* stream) {
+  if (M * d != 256 || (d != 64 && d != 128 && d != 256)) return fail("corr_lookup0: needs M*d == 256, d in {64,128,256} (got %d x %d)", M, d);
+  if (!Q || !K || !clip || !coords || !mean_rstd) return fail("corr_lookup0: null operand");
+  if (pos_table && (2 * R + 1) * (2 * R + 1) > 225) return fail("corr_lookup0: pos radius too large");
+  cb::Grid2 g = make_grid(H, W);
+  cb::Lookup0Params p;
+  memset(&p, 0, sizeof(p));
+  p.Q = static_cast<const __nv_bfloat16*>(Q); p.K = static_cast<const __nv_bfloat16*>(K);
+  p.M = M; p.d = d; p.scale = scale; p.w_agg = w_agg; p.w_pos = w_pos; p.pos_table = pos_table; p.Rb = R;
+  p.clip = clip; p.coords = coords; p.stats = mean_rstd; p.out_b = static_cast<__nv_bfloat16*>(out_bf16);
+  p.ldb = ldb; p.out_nchw = out_nchw;
+  cb::corr_lookup0_kernel<<<(g.Mp + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g);
+  return check_launch("corr_lookup0");
+}
+
 int craft_convf1(const float* flow, const float* wt, const float* bias, int H, int W, void* out_bf16, int ldo,
                  int colo, void* stream) {
   cb::Grid2 g = make_grid(H, W);

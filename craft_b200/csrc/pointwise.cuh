@@ -160,6 +160,146 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(LookupParams p, Grid2 
 }
 
 // -------------------------------------------------------------------------------------------
+// corr_lookup0: level-0 window of the lookup computed ON DEMAND from the projected query / key
+// rows, so the U x U level-0 correlation volume never exists in HBM.  For each query the 10x10
+// cells around coords1 are recomputed exactly as the build kernel would have produced them:
+//   s_m = <q_m, k_m>/sqrt(d) -> clamp -> softmax-over-modes aggregation -> + w_pos*bias(dy,dx)
+// (core/setrans.py:514-550, 289-300), then the same deferred-LN bilinear taps as corr_lookup.
+// 100 cells x 256 channels = 25.6 kMAC per query (0.37 GFLOP per iteration at 448x1024) against a
+// key matrix (3.7 MB) that stays in L2.  One warp per query: every window cell is ONE coalesced 512-byte
+// row load (lane = 8 channels) followed by a shuffle reduction per mode.
+// -------------------------------------------------------------------------------------------
+struct Lookup0Params {
+  const __nv_bfloat16* Q;   // [Mp, 256] projected queries
+  const __nv_bfloat16* K;   // [Mp, 256] projected keys
+  int M, d;                 // modes, per-mode dim (M*d == 256)
+  float scale, w_agg, w_pos;
+  const float* pos_table;   // [(2R+1)^2] or nullptr
+  int Rb;                   // bias radius
+  const float* clip;        // device scalar
+  const float* coords;      // [Mp,2]
+  const float* stats;       // {mean, rstd}
+  __nv_bfloat16* out_b;     // [Mp, ldb], channels 0..80
+  int ldb;
+  float* out_nchw;          // [324,H,W] (channels 0..80) or nullptr
+};
+
+__global__ void __launch_bounds__(256) corr_lookup0_kernel(Lookup0Params p, Grid2 g) {
+  constexpr int R = 4, D = 2 * R + 1, WN = D + 1, C = 256, NC = WN * WN;
+  __shared__ float win[8][NC + 4];
+  __shared__ float smodes[8][NC][4];
+  __shared__ float tbl[232];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.pos_table) {
+    const int n = (2 * p.Rb + 1) * (2 * p.Rb + 1);
+    for (int i = threadIdx.x; i < n; i += 256) tbl[i] = p.pos_table[i] * p.w_pos;
+  }
+  __syncthreads();
+  const int q = blockIdx.x * 8 + wib;
+  const int qy = q / g.Wp, qx = q - qy * g.Wp;
+  if (q >= g.Mp || qx >= g.W) return;      // whole warp
+  // this lane's 8 query channels, fp32
+  float qf[8];
+  {
+    const uint4 raw = *reinterpret_cast<const uint4*>(p.Q + static_cast<size_t>(q) * C + lane * 8);
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      qf[2 * k] = __uint_as_float(w[k] << 16);
+      qf[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+    }
+  }
+  const float cx = p.coords[2 * q], cy = p.coords[2 * q + 1];
+  const float mean = p.stats[0], rstd = p.stats[1];
+  const float clipv = *p.clip;
+  const float fx0 = floorf(cx), fy0 = floorf(cy);
+  const float ax = cx - fx0, ay = cy - fy0;
+  const int x0 = static_cast<int>(fx0) - R, y0 = static_cast<int>(fy0) - R;
+  const int lanes_per_mode = p.d >> 3;    // 8 channels per lane; 8, 16 or 32 (d = 64, 128, 256)
+  const bool is_writer = (lane & (lanes_per_mode - 1)) == 0;
+  const int mode_of_lane = (lanes_per_mode == 8) ? (lane >> 3) : (lanes_per_mode == 16 ? (lane >> 4) : 0);
+  // phase 1: one coalesced 512-byte key row per window cell; per-mode dot products by shuffle.
+  // The 10 loads of a window row are issued back to back (memory-level parallelism: a dependent
+  // load -> shuffle chain per cell would serialise 100 L2 round trips).
+#pragma unroll 1
+  for (int r = 0; r < WN; ++r) {
+    const int ky = y0 + r;                  // warp-uniform
+    if (ky < 0 || ky >= g.H) continue;
+    const uint4* rowbase = reinterpret_cast<const uint4*>(p.K + (static_cast<size_t>(ky) * g.Wp) * C) + lane;
+    uint4 kk[WN];
+#pragma unroll
+    for (int c = 0; c < WN; ++c) {
+      const int kx = x0 + c;
+      kk[c] = (kx >= 0 && kx < g.W) ? __ldg(rowbase + static_cast<size_t>(kx) * (C / 8)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int c = 0; c < WN; ++c) {
+      float a = qf[0] * __uint_as_float(kk[c].x << 16) + qf[1] * __uint_as_float(kk[c].x & 0xffff0000u) +
+                qf[2] * __uint_as_float(kk[c].y << 16) + qf[3] * __uint_as_float(kk[c].y & 0xffff0000u) +
+                qf[4] * __uint_as_float(kk[c].z << 16) + qf[5] * __uint_as_float(kk[c].z & 0xffff0000u) +
+                qf[6] * __uint_as_float(kk[c].w << 16) + qf[7] * __uint_as_float(kk[c].w & 0xffff0000u);
+      a += __shfl_xor_sync(0xffffffffu, a, 1);           // d >= 64 always (M <= 4): 8 lanes per mode at least
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      if (lanes_per_mode > 8) a += __shfl_xor_sync(0xffffffffu, a, 8);
+      if (lanes_per_mode > 16) a += __shfl_xor_sync(0xffffffffu, a, 16);
+      if (is_writer) smodes[wib][r * WN + c][mode_of_lane] = a;
+    }
+  }
+  __syncwarp();
+  // phase 2: lane = cell: clamp, soft-aggregate the modes, positional bias, deferred-LN numerator
+  const float wl2 = p.w_agg * 1.4426950408889634f;
+  const int TD = 2 * p.Rb + 1;
+  float* wv = win[wib];
+  for (int e = lane; e < NC; e += 32) {
+    const int r = e / WN, c = e - r * WN;
+    const int ky = y0 + r, kx = x0 + c;
+    float val = 0.f;
+    if (ky >= 0 && ky < g.H && kx >= 0 && kx < g.W) {
+      if (p.M == 1) {
+        val = fminf(fmaxf(smodes[wib][e][0] * p.scale, -clipv), clipv);
+      } else {
+        float s[4], t[4];
+        float tm = -INFINITY;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          s[m] = (m < p.M) ? fminf(fmaxf(smodes[wib][e][m] * p.scale, -clipv), clipv) : -INFINITY;
+          t[m] = s[m] * wl2;
+          tm = fmaxf(tm, t[m]);
+        }
+        float num = 0.f, den = 0.f;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          if (m < p.M) {
+            const float em = fast_ex2(t[m] - tm);
+            num += em * s[m];
+            den += em;
+          }
+        }
+        val = __fdividef(num, den);
+      }
+      if (p.pos_table) {
+        const int dy = ky - qy, dx = kx - qx;
+        if (dy >= -p.Rb && dy <= p.Rb && dx >= -p.Rb && dx <= p.Rb) val += tbl[(dy + p.Rb) * TD + dx + p.Rb];
+      }
+      val -= mean;
+    }
+    wv[e] = val;
+  }
+  __syncwarp();
+  for (int e = lane; e < D * D; e += 32) {
+    const int i = e / D, j = e - i * D;
+    const float v00 = wv[j * WN + i], v01 = wv[j * WN + i + 1];
+    const float v10 = wv[(j + 1) * WN + i], v11 = wv[(j + 1) * WN + i + 1];
+    const float top = v00 + ax * (v01 - v00);
+    const float bot = v10 + ax * (v11 - v10);
+    const float val = (top + ay * (bot - top)) * rstd;
+    if (p.out_b) p.out_b[static_cast<size_t>(q) * p.ldb + e] = __float2bfloat16_rn(val);
+    if (p.out_nchw) p.out_nchw[(static_cast<size_t>(e) * g.H + qy) * g.W + qx] = val;
+  }
+}
+
+// -------------------------------------------------------------------------------------------
 // upsample_flow: convex 8x upsampling.
 //   reference: CRAFT.upsample_flow core/network.py:151-162.  mask channel = k*64 + sy*8 + sx,
 //   k = 3x3 neighbour (row-major, zero padded), softmax over k, output pixel (8y+sy, 8x+sx).

@@ -82,7 +82,11 @@ class Workspace:
         self.CORR = z(384); self.C1 = z(256); self.CF = z(256); self.F1 = z(128)
         self.HD = z(512)
         self.DELTA = z(32, f32)
-        self.MASK = z(576, f32)
+        # two mask buffers alternate by iteration so that upsample(it-1) on the side stream can overlap
+        # the mask head of iteration it
+        self.MASKS = [z(576, f32), z(576, f32)]
+        self.MASK = self.MASKS[0]
+        self.side = torch.cuda.Stream(device=device)    # second lane for independent branches (captured too)
         self.coords1 = z(2, f32); self.flow = z(2, f32)
 
     def opart(self, ks, M, F):
@@ -150,6 +154,8 @@ def value_aggregate(ws, Q, K, X, x_koff, W1p, *, M, d, F, table, w_pos, clip, ls
 def build_correlation(ws, Q, K, *, M, d, w_agg, table, w_pos, global_norm, attn_clip=100.0):
     """TransCorrBlock.update (core/corr.py:148-207) / CorrBlock.__init__ (:16-45): pyramid + LN stats."""
     g = ws.grid
+    # what the on-demand level-0 lookup needs to recompute volume cells (ops.corr_lookup0)
+    ws.corr_meta = dict(Q=Q, K=K, M=M, d=d, w_agg=w_agg, w_pos=w_pos, pos_table=table, R=7, clip=ws.clip_corr)
     ws.stat_sum.zero_()
     clip = ws.clip_corr
     clip.fill_(_INF)
@@ -210,11 +216,17 @@ def motion_encoder(ws, uw):
     """BasicMotionEncoder.forward core/update.py:79-87 -> X[:, 256:384] (126 features + the flow)."""
     g = ws.grid
     sg = ops.shift_gemm
+    # the correlation branch (convc1 -> convc2) and the flow branch (convf1 -> convf2) are independent
+    # until `conv` (update.py:80-86): run the flow branch on the side stream
+    main, side = torch.cuda.current_stream(), ws.side
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        ops.convf1(ws.flow, uw.f1_w, uw.f1_b, g, ws.F1)
+        sg(ws.F1, uw.f2_w, M=g.Mp, Npad=64, K=128, BN=64, taps=uw.taps3, grid=g, bias=uw.f2_b, act=1, out_b=ws.CF,
+           colb=192)
     sg(ws.CORR, uw.c1_w, M=g.Mp, Npad=256, K=384, BN=128, grid=g, bias=uw.c1_b, act=1, out_b=ws.C1)
     sg(ws.C1, uw.c2_w, M=g.Mp, Npad=192, K=256, BN=64, taps=uw.taps3, grid=g, bias=uw.c2_b, act=1, out_b=ws.CF)
-    ops.convf1(ws.flow, uw.f1_w, uw.f1_b, g, ws.F1)
-    sg(ws.F1, uw.f2_w, M=g.Mp, Npad=64, K=128, BN=64, taps=uw.taps3, grid=g, bias=uw.f2_b, act=1, out_b=ws.CF,
-       colb=192)
+    main.wait_stream(side)
     sg(ws.CF, uw.cv_w, M=g.Mp, Npad=128, K=256, BN=64, taps=uw.taps3, grid=g, bias=uw.cv_b,
        epilogue=ops.EPI_MOTION, out_b=ws.X, colb=256, aux1=ws.flow)
 
@@ -229,11 +241,16 @@ def sep_conv_gru(ws, uw):
                        epilogue=ops.EPI_GRU_Q, bias=bq, out_b=ws.X, colb=0, aux0=ws.Z, aux1=ws.Hm)
 
 
-def heads(ws, uw):
-    """FlowHead core/update.py:15-16 + mask head core/update.py:124-127,161 -> DELTA[:, :2], MASK."""
+def heads(ws, uw, it=0):
+    """FlowHead core/update.py:15-16 + mask head core/update.py:124-127,161 -> DELTA[:, :2], MASKS[it & 1].
+    The two second-layer convolutions are independent: the flow one runs on the side stream."""
     g = ws.grid
     sg = ops.shift_gemm
     sg(ws.X, uw.hd_w, M=g.Mp, Npad=512, K=128, BN=128, taps=uw.taps3, grid=g, bias=uw.hd_b, act=1, out_b=ws.HD)
-    sg(ws.HD, uw.fl_w, M=g.Mp, Npad=32, K=256, BN=32, taps=uw.taps3, grid=g, bias=uw.fl_b, out_f=ws.DELTA)
+    main, side = torch.cuda.current_stream(), ws.side
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        sg(ws.HD, uw.fl_w, M=g.Mp, Npad=32, K=256, BN=32, taps=uw.taps3, grid=g, bias=uw.fl_b, out_f=ws.DELTA)
     sg(ws.HD, uw.mk_w, M=g.Mp, Npad=576, K=256, BN=64, a_koff=256, grid=g, bias=uw.mk_b, alpha=0.25,
-       out_f=ws.MASK)
+       out_f=ws.MASKS[it & 1])
+    main.wait_stream(side)

@@ -101,7 +101,7 @@ class CRAFT(nn.Module):
 
         self.update_block = GMAUpdateBlock(self.args, hidden_dim=hdim)
         self.call_counter = 0
-        self.materialize_level0 = True
+        self.materialize_level0 = False    # True only for debugging / SAVECORR: writes the 205 MB level-0 volume
         # Inference calls are captured into one CUDA graph per (shape, iters, test_mode) and replayed:
         # the ~250 launches of a forward then cost no host time.  Set False (or CRAFT_B200_NO_GRAPH=1)
         # to launch eagerly.
@@ -266,13 +266,18 @@ class CRAFT(nn.Module):
         for b in range(B):
             fi = flow_init[b].float().contiguous() if flow_init is not None else None
             att = self._prepare_pair(ws, fmap1[b], fmap2[b], cnet_feat[b], fi)
+            main, side = torch.cuda.current_stream(), ws.side
             for itr in range(iters):
                 corr_fn.lookup_rows(ws, ws.coords1, out_b=ws.CORR)
-                self.update_block.step(ws, att)
+                self.update_block.step(ws, att, itr)
                 ops.flow_update(ws.coords1, ws.flow, ws.DELTA, g)
-                # the reference upsamples after every iteration (core/network.py:250-260)
+                # the reference upsamples after every iteration (core/network.py:250-260); nothing in the next
+                # iteration depends on it, so it runs on the side stream (mask buffers alternate, hotpath.heads)
                 dst = flow_ups[itr if test_mode != 1 else 0][b]
-                ops.upsample_flow(ws.MASK, ws.flow, g, out=dst)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    ops.upsample_flow(ws.MASKS[itr & 1], ws.flow, g, out=dst)
+            main.wait_stream(side)
             ops.unpack_tokens(ws.flow, 0, 2, g, out=flow_lo[b])
         self.call_counter += 1
         if test_mode == 1:

@@ -273,6 +273,17 @@ def corr_lookup(levels, grid, coords, mean_rstd, out_b=None, out_nchw=None, firs
               _ptr(out_nchw), first_level, _stream())
 
 
+def corr_lookup0(Q, K, grid, *, M, d, w_agg, w_pos, pos_table, R, clip, coords, mean_rstd, out_b=None, out_nchw=None):
+    """Level-0 lookup channels computed on demand from projected Q/K rows (no level-0 volume)."""
+    _chk(Q, torch.bfloat16, "Q")
+    _chk(K, torch.bfloat16, "K")
+    _chk(out_b, torch.bfloat16, "out_b")
+    _chk(out_nchw, torch.float32, "out_nchw")
+    _lib.call("craft_corr_lookup0", _ptr(Q), _ptr(K), M, d, 1.0 / math.sqrt(d), float(w_agg), float(w_pos),
+              _ptr(pos_table), R, _ptr(clip), grid.H, grid.W, _ptr(coords), _ptr(mean_rstd), _ptr(out_b), _ld(out_b),
+              _ptr(out_nchw), _stream())
+
+
 def convf1(flow, wt, bias, grid, out_b, colo=0):
     _chk(flow, torch.float32, "flow")
     _chk(wt, torch.float32, "wt")

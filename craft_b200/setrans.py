@@ -380,7 +380,7 @@ _WORKSPACES = {}
 def get_workspace(grid, device, materialize_level0=None):
     import os
     if materialize_level0 is None:
-        materialize_level0 = True
+        materialize_level0 = False
     key = (str(device), grid.H, grid.W, bool(materialize_level0))
     ws = _WORKSPACES.get(key)
     if ws is None:

@@ -139,6 +139,13 @@ int craft_corr_lookup(const float* const* lvl /*host array of 4 device ptrs*/, i
                       const float* coords /*[Mp,2]*/, const float* mean_rstd, void* out_bf16,
                       int ldb, float* out_nchw, int first_level, void* stream);
 
+/* Level 0 of the same lookup computed on demand from the projected query/key rows [Mp,256] (the
+ * U x U level-0 volume is then never stored): channels 0..80 of the output.  Pair it with
+ * craft_corr_lookup(first_level = 1).                                                             */
+int craft_corr_lookup0(const void* Q, const void* K, int M, int d, float scale, float w_agg, float w_pos,
+                       const float* pos_table, int R, const float* clip, int H, int W, const float* coords,
+                       const float* mean_rstd, void* out_bf16, int ldb, float* out_nchw, void* stream);
+
 /* ---- small HBM-bound pieces ---------------------------------------------------------------- */
 /* BasicMotionEncoder.convf1 (7x7, 2->128) + ReLU, core/update.py:75,82. wt [98][128], bias[128] */
 int craft_convf1(const float* flow, const float* wt, const float* bias, int H, int W, void* out_bf16,

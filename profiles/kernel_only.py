@@ -23,7 +23,7 @@ def main(which, reps):
         model(a, b, iters=1, test_mode=1)       # fills every workspace buffer with realistic data
         torch.cuda.synchronize()
         g = TokenGrid(H // 8, W // 8)
-        ws = get_workspace(g, dev, True)
+        ws = get_workspace(g, dev, model.materialize_level0)
         ub = model.update_block
         uw = ub.weights(g)
         att_tbl = model.att.vispos_encoder.table()
@@ -49,8 +49,10 @@ def main(which, reps):
                              stat_max=ws.stat_max[2:3], lse_part=ws.lse_part, lse2=ws.lse2_att, ksplit=ws.ks_sc)
             elif which in ("gru_zr", "gru_q"):
                 hp.sep_conv_gru(ws, uw)
+            elif which == "lookup0":
+                ops.corr_lookup0(grid=g, coords=ws.coords1, mean_rstd=ws.mean_rstd, out_b=ws.CORR, **ws.corr_meta)
             elif which == "lookup":
-                ops.corr_lookup(ws.levels, g, ws.coords1, ws.mean_rstd, out_b=ws.CORR)
+                ops.corr_lookup(ws.levels, g, ws.coords1, ws.mean_rstd, out_b=ws.CORR, first_level=1)
             elif which == "heads":
                 hp.heads(ws, uw)
             else:

@@ -108,7 +108,7 @@ def test_seams_match_reference(name):
         model(i1.cuda(), i2.cuda(), iters=1, test_mode=1)
     torch.cuda.synchronize()
     g = TokenGrid(rec["H"] // 8, rec["W"] // 8)
-    ws = get_workspace(g, torch.device("cuda", 0), True)
+    ws = get_workspace(g, torch.device("cuda", 0), model.materialize_level0)
 
     def rows(buf, c0, c1):
         return buf.float().view(g.H, g.Wp, -1)[:, :g.W, c0:c1].permute(2, 0, 1).cpu()
@@ -120,7 +120,7 @@ def test_seams_match_reference(name):
         "aggr_it0": rows(ws.X, 384, 512),
         "net_it0": rows(ws.Hm, 0, 128),
         "ub_it0.delta": rows(ws.DELTA, 0, 2),
-        "ub_it0.mask": rows(ws.MASK, 0, 576),
+        "ub_it0.mask": rows(ws.MASKS[0], 0, 576),
     }
     # f2_trans output: tokens after the transformer == LN'ed features the correlation encoder sees
     f2 = rec["f2_out"][0]

@@ -347,3 +347,27 @@ def test_fused_encoder_matches_module_path(kind):
         got = enc(x)
     torch.cuda.synchronize()
     assert torch.allclose(got, ref, atol=2e-3, rtol=1e-3), (got - ref).abs().max()
+
+
+@pytest.mark.parametrize("H,W,M,d,clipv", [(16, 24, 4, 64, float("inf")), (17, 22, 4, 64, 2.0), (16, 16, 1, 256, float("inf"))])
+def test_corr_lookup0_on_demand(H, W, M, d, clipv):
+    """Level-0 lookup recomputed from Q/K rows == lookup on the materialised (oracle) level-0 volume."""
+    grid = TokenGrid(H, W)
+    g = torch.Generator(device=DEV).manual_seed(31)
+    q, k = _rand_qk(grid, M * d, g, 0.6)
+    table = torch.randn((15, 15), device=DEV, generator=g) if M > 1 else None
+    w_agg, w_pos = 0.13, 0.5
+    s, _ = _scores_ref(q, k, M, table, w_pos, clipv)
+    raw = (s * torch.softmax(s * w_agg, dim=0)).sum(0) if M > 1 else s[0]
+    mean, rstd = raw.mean().item(), 1.0 / math.sqrt(raw.var(unbiased=False).item() + 1e-12)
+    vol = ((raw - mean) * rstd).reshape(1, grid.U, H, W)
+    coords = R.coords_grid(1, H, W, DEV) + torch.randn((1, 2, H, W), device=DEV, generator=g) * 5
+    ref = R.corr_lookup([vol.reshape(grid.U, 1, H, W)], coords)[0]          # level 0 only: [81,H,W]
+    Q, K = rows_from_nchw(q, grid), rows_from_nchw(k, grid)
+    cbuf = rows_from_nchw(coords[0], grid, dtype=torch.float32)
+    out_n = torch.zeros((324, H, W), device=DEV)
+    ops.corr_lookup0(Q, K, grid, M=M, d=d, w_agg=w_agg, w_pos=w_pos, pos_table=table, R=7,
+                     clip=torch.tensor([clipv], device=DEV), coords=cbuf,
+                     mean_rstd=torch.tensor([mean, rstd], device=DEV), out_nchw=out_n)
+    torch.cuda.synchronize()
+    assert torch.allclose(out_n[:81], ref, atol=3e-3, rtol=1e-3), (out_n[:81] - ref).abs().max()
