@@ -56,20 +56,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware instead of
+      : "memory");                                        // burning issue slots next to the math warps
   return ok != 0;
 }
 // Bounded wait: a protocol bug (wrong tx byte count, missing commit) must turn into a launch
-// failure that the host reports, never into a hung GPU.  try_wait sleeps in hardware, so the
-// bound (~2^26 probes) is seconds, far beyond any legitimate wait in these kernels.
+// failure that the host reports, never into a hung GPU.  Each probe may sleep in hardware for up to
+// the suspend-time hint, so 2^20 probes is far beyond any legitimate wait in these kernels.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 20)) __trap();
   }
 }
 
