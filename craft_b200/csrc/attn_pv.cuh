@@ -15,7 +15,7 @@
 //     MMA warp : S[j&1] = Q K_j^T                     (tcgen05, accumulator in TMEM)
 //     softmax  : P[j&1] = exp2(...) as bf16 -> smem    (4 groups of 4 warps: tile parity x column half)
 //     MMA warp : O += P[j&1] V_j                       (A = P from smem, B = V^T tile from TMA)
-// S(j+1) is issued before PV(j) so the tensor pipe never waits for the softmax groups.
+// S(j+2) is issued before PV(j): neither the tensor pipe nor the two softmax groups wait for each other.
 #pragma once
 #include "common.cuh"
 #include "pointwise.cuh"
@@ -36,6 +36,8 @@ struct PvParams {
   const float* lse2;       // [M][Mp] log2-domain log-sum-exp
   float* out;              // [ksplit][M][Mp][F] f32 partial sums
   int nkt, nbx;            // key tiles (blocks) in total / per block-row
+  long long* trace;        // CRAFT_PV_TRACE: clock64 timeline of CTA (0,0,0): [role 4][tile 64][slot 8]
+  int dbg;                 // timing experiments only (CRAFT_PV_DBG): bit0 no exp, bit1 no TMEM ld, bit2 no P store, bit3 no PV MMA, bit4 no S MMA
 };
 
 template <int D, int F, int BK, int KS, int VS>
@@ -69,8 +71,8 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t* v_full = k_empty + KS;
   uint64_t* v_empty = v_full + VS;
   uint64_t* s_full = v_empty + VS;     // [2]
-  uint64_t* s_empty = s_full + 2;      // [2] count 256
-  uint64_t* p_full = s_empty + 2;      // [2] count 256
+  uint64_t* s_empty = s_full + 2;      // [2] count 8
+  uint64_t* p_full = s_empty + 2;      // [2] count 8
   uint64_t* p_empty = p_full + 2;      // [2]
   uint64_t* o_full = p_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
@@ -96,8 +98,8 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     for (int s = 0; s < VS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_full[b], 1);
-      mbar_init(&s_empty[b], 256);
-      mbar_init(&p_full[b], 256);
+      mbar_init(&s_empty[b], 8);     // one arrival per softmax warp of the group
+      mbar_init(&p_full[b], 8);
       mbar_init(&p_empty[b], 1);
     }
     mbar_init(o_full, 1);
@@ -114,6 +116,9 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  const int WM = (p.dbg >> 8) & 3;
+  const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#define PV_TRACE(role, tile, slot) do { if (tr && (threadIdx.x & 31) == 0 && (tile) < 64) p.trace[((role) * 64 + (tile)) * 8 + (slot)] = clock64(); } while (0)
   if (ntiles > 0) {
     if (warp == 0) {
       // ------------------------------------ TMA producer ------------------------------------
@@ -121,21 +126,42 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         mbar_arrive_expect_tx(q_full, S::kQBytes);
         for (int a = 0; a < S::kQAtoms; ++a)
           tma_load_2d(sQ + a * 128 * 128, &tmQ, q_full, qk_col + a * 64, q0);
-        int ks = 0, vs = 0;
-        uint32_t kph = 0, vph = 0;
-        for (int i = 0; i < ntiles; ++i) {
-          const int kt = kt_begin + i;
-          const int by = kt / p.nbx, bx = kt - by * p.nbx;
-          mbar_wait(&k_empty[ks], kph ^ 1u);
-          mbar_arrive_expect_tx(&k_full[ks], S::kKBytes);
-          for (int a = 0; a < S::kQAtoms; ++a)
-            tma_load_3d(sK + ks * S::kKBytes + a * BK * 128, &tmK, &k_full[ks], qk_col + a * 64, bx * BW, by * 8);
-          if (++ks == KS) { ks = 0; kph ^= 1u; }
-          mbar_wait(&v_empty[vs], vph ^ 1u);
-          mbar_arrive_expect_tx(&v_full[vs], S::kVBytes);
-          for (int a = 0; a < BK / 64; ++a)
-            tma_load_2d(sV + vs * S::kVBytes + a * F * 128, &tmV, &v_full[vs], kt * BK + a * 64, mode * F);
-          if (++vs == VS) { vs = 0; vph ^= 1u; }
+        // K and V are two independent pipelines (K feeds S two tiles ahead of the P.V that frees a V
+        // stage), so one thread serves both with non-blocking probes instead of waiting on either.
+        int ks = 0, vs = 0, ki = 0, vi = 0;
+        uint32_t kph = 0, vph = 0, idle = 0;
+        while (ki < ntiles || vi < ntiles) {
+          bool moved = false;
+          if (ki < ntiles && mbar_test(&k_empty[ks], kph ^ 1u)) {
+            const int kt = kt_begin + ki;
+            const int by = kt / p.nbx, bx = kt - by * p.nbx;
+            if (p.dbg & 64) mbar_arrive(&k_full[ks]);
+            else {
+              mbar_arrive_expect_tx(&k_full[ks], S::kKBytes);
+              for (int a = 0; a < S::kQAtoms; ++a)
+                tma_load_3d(sK + ks * S::kKBytes + a * BK * 128, &tmK, &k_full[ks], qk_col + a * 64, bx * BW, by * 8);
+            }
+            PV_TRACE(3, ki, 0);
+            if (++ks == KS) { ks = 0; kph ^= 1u; }
+            ++ki; moved = true;
+          }
+          if (vi < ntiles && mbar_test(&v_empty[vs], vph ^ 1u)) {
+            const int kt = kt_begin + vi;
+            if (p.dbg & 32) mbar_arrive(&v_full[vs]);
+            else {
+              mbar_arrive_expect_tx(&v_full[vs], S::kVBytes);
+              for (int a = 0; a < BK / 64; ++a)
+                tma_load_2d(sV + vs * S::kVBytes + a * F * 128, &tmV, &v_full[vs], kt * BK + a * 64, mode * F);
+            }
+            PV_TRACE(3, vi, 1);
+            if (++vs == VS) { vs = 0; vph ^= 1u; }
+            ++vi; moved = true;
+          }
+          if (moved) idle = 0;
+          else {
+            __nanosleep(32);
+            if (++idle > (1u << 24)) __trap();     // protocol bug -> launch failure, never a hang
+          }
         }
       }
     } else if (warp == 1) {
@@ -144,12 +170,12 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       constexpr uint32_t idesc_o = umma_idesc_f16<128, F>();
       int ks = 0, vs = 0;
       uint32_t kph = 0, vph = 0;
-      mbar_wait(q_full, 0);
+      mbar_wait_mode(q_full, 0, WM);
       auto issue_s = [&](int j) {
         const int b = j & 1;
         const uint32_t use = static_cast<uint32_t>(j >> 1);
-        mbar_wait(&k_full[ks], kph);
-        mbar_wait(&s_empty[b], (use & 1u) ^ 1u);
+        mbar_wait_mode(&k_full[ks], kph, WM);
+        mbar_wait_mode(&s_empty[b], (use & 1u) ^ 1u, WM);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sq = smem_u32(sQ) + qk_inner;
@@ -159,7 +185,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const int ka = (k * 16) >> 6, kin = (k * 16) & 63;
             const uint64_t dq = umma_desc_sw128(sq + ka * 128 * 128 + kin * 2);
             const uint64_t dk = umma_desc_sw128(sk + ka * BK * 128 + kin * 2);
-            umma_f16(tmem_base + b * BK, dq, dk, idesc_s, k != 0 ? 1u : 0u);
+            if (!(p.dbg & 16)) umma_f16(tmem_base + b * BK, dq, dk, idesc_s, k != 0 ? 1u : 0u);
           }
           umma_commit(&k_empty[ks]);
           umma_commit(&s_full[b]);
@@ -167,13 +193,21 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         __syncwarp();
         if (++ks == KS) { ks = 0; kph ^= 1u; }
       };
+      // Tensor-pipe order: S(0) S(1) | S(2) PV(0) | S(3) PV(1) | ...  S(j+2) only needs the softmax group
+      // of tile j to have pulled S(j) into registers (s_empty), which happens right after S(j) lands, so
+      // it runs ahead of PV(j) and both softmax groups always find their next S tile ready.
       issue_s(0);
+      if (ntiles > 1) issue_s(1);
       for (int j = 0; j < ntiles; ++j) {
-        if (j + 1 < ntiles) issue_s(j + 1);
+        PV_TRACE(0, j, 0);
+        if (j + 2 < ntiles) issue_s(j + 2);
+        PV_TRACE(0, j, 1);
         const int b = j & 1;
         const uint32_t use = static_cast<uint32_t>(j >> 1);
-        mbar_wait(&p_full[b], use & 1u);
-        mbar_wait(&v_full[vs], vph);
+        mbar_wait_mode(&p_full[b], use & 1u, WM);
+        PV_TRACE(0, j, 2);
+        mbar_wait_mode(&v_full[vs], vph, WM);
+        PV_TRACE(0, j, 3);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sp = smem_u32(sP + b * S::kPBytes);
@@ -183,13 +217,14 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const int ka = (k * 16) >> 6, kin = (k * 16) & 63;
             const uint64_t dp = umma_desc_sw128(sp + ka * 128 * 128 + kin * 2);
             const uint64_t dv = umma_desc_sw128(sv + ka * F * 128 + kin * 2);
-            umma_f16(tmem_base + kTmemO, dp, dv, idesc_o, (j | k) != 0 ? 1u : 0u);
+            if (!(p.dbg & 8)) umma_f16(tmem_base + kTmemO, dp, dv, idesc_o, (j | k) != 0 ? 1u : 0u);
           }
           umma_commit(&p_empty[b]);
           umma_commit(&v_empty[vs]);
           if (j == ntiles - 1) umma_commit(o_full);
         }
         __syncwarp();
+        PV_TRACE(0, j, 4);
         if (++vs == VS) { vs = 0; vph ^= 1u; }
       }
     } else {
@@ -218,20 +253,30 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const int iy0 = by * 8 + ch * 4 - qy + R;       // table row of the first block row
         const int ix0 = bx * BW - qx + R;               // table column of the first block column
         const bool near = has_bias && (iy0 + 3 >= 0) && (iy0 <= 2 * R) && (ix0 + BW - 1 >= 0) && (ix0 <= 2 * R);
-        mbar_wait(&s_full[sg], use & 1u);
-        mbar_wait(&p_empty[sg], (use & 1u) ^ 1u);
+        const int trole = (warp == 2 || warp == 6) ? 1 + sg : 99;
+        if (trole < 4) PV_TRACE(trole, j, 0);
+        mbar_wait_mode(&s_full[sg], use & 1u, WM);
+        if (trole < 4) PV_TRACE(trole, j, 1);
+        mbar_wait_mode(&p_empty[sg], (use & 1u) ^ 1u, WM);
+        if (trole < 4) PV_TRACE(trole, j, 2);
         tc_fence_after();
         __syncwarp();
         uint8_t* pbuf = sP + sg * S::kPBytes;
         // all of this thread's S columns are requested up front (one wait instead of one per chunk),
         // then the S buffer is handed back to the MMA warp before any math happens
         uint32_t raw_all[HALF];
+        if (!(p.dbg & 2)) {
 #pragma unroll
-        for (int c = 0; c < HALF; c += 32)
-          tmem_ld32(tlane + sg * BK + ch * HALF + c, *reinterpret_cast<uint32_t(*)[32]>(&raw_all[c]));
-        tmem_ld_wait();
+          for (int c = 0; c < HALF; c += 32)
+            tmem_ld32(tlane + sg * BK + ch * HALF + c, *reinterpret_cast<uint32_t(*)[32]>(&raw_all[c]));
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int c = 0; c < HALF; ++c) raw_all[c] = static_cast<uint32_t>(j + c);
+        }
         tc_fence_before();
-        mbar_arrive(&s_empty[sg]);
+        mbar_arrive_warp(&s_empty[sg]);
+        if (trole < 4) PV_TRACE(trole, j, 3);
 #pragma unroll
         for (int c = 0; c < HALF; c += 32) {
           const uint32_t* raw = &raw_all[c];
@@ -257,6 +302,18 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           const int kcol = ch * HALF + c;                  // key column inside the tile
           const int atom = kcol >> 6;
           const int chunk0 = (kcol & 63) >> 3;
+          if (p.dbg & 1) {
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4) {
+              uint4 u;
+              u.x = pack_bf16x2(x[8 * v4 + 0], x[8 * v4 + 1]);
+              u.y = pack_bf16x2(x[8 * v4 + 2], x[8 * v4 + 3]);
+              u.z = pack_bf16x2(x[8 * v4 + 4], x[8 * v4 + 5]);
+              u.w = pack_bf16x2(x[8 * v4 + 6], x[8 * v4 + 7]);
+              *reinterpret_cast<uint4*>(pbuf + atom * 128 * 128 + swz128_offset(row, chunk0 + v4)) = u;
+            }
+            continue;
+          }
 #pragma unroll
           for (int v4 = 0; v4 < 4; ++v4) {
             uint4 u;
@@ -264,16 +321,19 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             u.y = pack_bf16x2(fast_ex2(x[8 * v4 + 2]), fast_ex2(x[8 * v4 + 3]));
             u.z = pack_bf16x2(fast_ex2(x[8 * v4 + 4]), fast_ex2(x[8 * v4 + 5]));
             u.w = pack_bf16x2(fast_ex2(x[8 * v4 + 6]), fast_ex2(x[8 * v4 + 7]));
-            *reinterpret_cast<uint4*>(pbuf + atom * 128 * 128 + swz128_offset(row, chunk0 + v4)) = u;
+            if (!(p.dbg & 4) || u.x == 0x12345678u)
+              *reinterpret_cast<uint4*>(pbuf + atom * 128 * 128 + swz128_offset(row, chunk0 + v4)) = u;
           }
         }
-        fence_proxy_async_smem();      // st.shared -> visible to the tensor core's async proxy
-        mbar_arrive(&p_full[sg]);
+        if (trole < 4) PV_TRACE(trole, j, 4);
+        if (!(p.dbg & 1024)) fence_proxy_async_smem();      // st.shared -> visible to the tensor core's async proxy
+        mbar_arrive_warp(&p_full[sg]);
+        if (trole < 4) PV_TRACE(trole, j, 5);
       }
 
       // ------------------------------------ O epilogue --------------------------------------
       // the four groups split the F columns in quarters
-      mbar_wait(o_full, 0);
+      mbar_wait_mode(o_full, 0, WM);
       tc_fence_after();
       __syncwarp();
       float* dst = p.out + ((static_cast<size_t>(blockIdx.z) * p.M + mode) * p.g.Mp + q) * F;
@@ -284,7 +344,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         uint32_t raw[32];
         tmem_ld32(tlane + kTmemO + c_begin + c, raw);
         tmem_ld_wait();
-        if (q < p.g.Mp) {
+        if (q < p.g.Mp && !(p.dbg & 128)) {
           float4* d4 = reinterpret_cast<float4*>(dst + c_begin + c);
 #pragma unroll
           for (int e = 0; e < 8; ++e)

@@ -250,7 +250,13 @@ int craft_shift_gemm(const craft_gemm_args* a, void* stream) {
   p.out_f = a->out_f32; p.ldf = a->ldo_f; p.colf = a->colo_f;
   p.aux_f0 = a->aux0; p.aux_f1 = a->aux1;
   {
-    const int smax = a->BN >= 256 ? 4 : (a->BN >= 128 ? 6 : (a->BN >= 64 ? 8 : 10));
+    // smem holds `slots` (A atom + B atom) pairs; a pipeline stage is kc of them (two when K allows it:
+    // the per-stage wait/commit round trip of the MMA warp is then paid once per 128 K columns)
+    const int slots = a->BN >= 256 ? 4 : (a->BN >= 128 ? 6 : (a->BN >= 64 ? 8 : 10));
+    const char* e = getenv("CRAFT_GEMM_KC");          // tuning/profiling override
+    p.kc = (a->K % 128 == 0) ? 2 : 1;
+    if (e && atoi(e) == 1) p.kc = 1;
+    const int smax = slots / p.kc;
     p.stages = (a->stages > 0 && a->stages < smax) ? a->stages : smax;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -373,11 +379,33 @@ static int launch_pv(const craft_pv_args* a, const cb::Grid2& g, cudaStream_t st
   p.g = g; p.M = a->M; p.ksplit = a->ksplit; p.scale = a->scale; p.w_pos = a->w_pos;
   p.pos_table = a->pos_table; p.R = a->R; p.clip = a->clip; p.lse2 = a->lse2; p.out = a->out;
   p.nkt = nkt; p.nbx = nbx;
+  { const char* e = getenv("CRAFT_PV_DBG"); p.dbg = e ? atoi(e) : 0; }
   auto kern = cb::attn_pv_kernel<D, F, BK, KS, VS>;
   static bool set = false;
   if (!set) { if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal) != cudaSuccess) return fail("pv: smem attr %d", S::kTotal); set = true; }
   dim3 grid((g.Mp + 127) / 128, a->M, a->ksplit);
+  static long long* d_trace = nullptr;
+  const char* trace_path = getenv("CRAFT_PV_TRACE");     // profiling aid: dumps CTA (0,0,0)'s clock64 timeline
+  if (trace_path) {
+    if (!d_trace) cudaMalloc(&d_trace, 4 * 64 * 8 * sizeof(long long));
+    cudaMemsetAsync(d_trace, 0, 4 * 64 * 8 * sizeof(long long), st);
+    p.trace = d_trace;
+  }
   kern<<<grid, cb::kPvThreads, S::kTotal, st>>>(tq, tk, tv, p);
+  if (trace_path) {
+    static long long h[4 * 64 * 8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int r = 0; r < 4; ++r)
+        for (int t = 0; t < 64; ++t) {
+          fprintf(f, "%d %d", r, t);
+          for (int k = 0; k < 8; ++k) fprintf(f, " %lld", h[(r * 64 + t) * 8 + k]);
+          fprintf(f, "\n");
+        }
+      fclose(f);
+    }
+  }
   return check_launch("attn_pv");
 }
 
@@ -390,7 +418,7 @@ int craft_attn_pv(const craft_pv_args* a, void* stream) {
   cb::Grid2 g = make_grid(a->H, a->W);
   if (a->ldv % 8) return fail("attn_pv: ldv=%d must be a multiple of 8", a->ldv);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (a->d == 32 && a->F == 128) return launch_pv<32, 128, 128, 2, 2>(a, g, st);
+  if (a->d == 32 && a->F == 128) return launch_pv<32, 128, 128, 3, 2>(a, g, st);
   if (a->d == 64 && a->F == 256) return launch_pv<64, 256, 64, 3, 3>(a, g, st);
   if (a->d == 128 && a->F == 128) return launch_pv<128, 128, 64, 3, 3>(a, g, st);
   if (a->d == 64 && a->F == 128) return launch_pv<64, 128, 128, 2, 2>(a, g, st);

@@ -63,6 +63,37 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");                                        // burning issue slots next to the math warps
   return ok != 0;
 }
+// Plain polling flavours (timing experiments / latency-critical handshakes)
+__device__ __forceinline__ bool mbar_try_wait_nohint(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Non-blocking probe (producer loops that serve several independent pipelines).
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// One arrival per warp: the warp's lanes first order their own accesses (__syncwarp), then a single
+// lane arrives.  256 per-thread arrivals on one barrier word serialise in the shared-memory atomic
+// unit and cost more than the work they guard.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31u) == 0) mbar_arrive(bar);
+}
 // Bounded wait: a protocol bug (wrong tx byte count, missing commit) must turn into a launch
 // failure that the host reports, never into a hung GPU.  Each probe may sleep in hardware for up to
 // the suspend-time hint, so 2^20 probes is far beyond any legitimate wait in these kernels.
@@ -71,6 +102,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 20)) __trap();
   }
+}
+__device__ __forceinline__ void mbar_wait_mode(uint64_t* bar, uint32_t parity, int mode) {
+  uint32_t spins = 0;
+  if (mode == 0) { mbar_wait(bar, parity); return; }
+  if (mode == 1) { while (!mbar_try_wait_nohint(bar, parity)) { if (++spins > (1u << 26)) __trap(); } return; }
+  while (!mbar_test(bar, parity)) { if (++spins > (1u << 26)) __trap(); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -173,6 +210,15 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Same with the accumulate predicate hard-wired to true (no setp in the issue loop).
+__device__ __forceinline__ void umma_f16_acc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.u32 p, 1, 1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc)
       : "memory");
 }
 // All previously issued MMAs of this thread arrive on `bar` when they retire (implies

@@ -49,7 +49,8 @@ struct GemmParams {
   // then a [H][W][C] map).  Used to emit V^T with keys in the block order attn_pv consumes.
   int b_blocked, b_nbx;
   int tap_off[kMaxTaps];
-  int stages;   // pipeline depth actually used (<= GemmSmem<BN>::kStages); tuning knob
+  int stages;   // pipeline depth actually used (stages * kc <= GemmSmem<BN>::kStages slots); tuning knob
+  int kc;       // 64-column K atoms per pipeline stage (1 or 2): 2 halves the per-stage handshake cost
   // row validity: Wp > 0 => row m is a real token iff (m % Wp) < W and (m / Wp) < H;
   //               Wp == 0 => every m < M is valid.
   int Wp, W, H;
@@ -129,55 +130,74 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
+    // A pipeline stage is `kc` consecutive smem slots (one slot = A atom + B atom of 64 K columns).
     if (elect_one()) {
+      const int KC = p.kc;
+      const int nst = nk / KC;
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < nk; ++it) {
-        const int t = it / kchunks;
-        const int kc = it - t * kchunks;
+      int t = 0, kc = 0;                                // tap and 64-column chunk of the next slot
+      for (int it = 0; it < nst; ++it) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);     // all CL consumers released this stage
-        uint8_t* sa = smem + stage * S::kStageBytes;
-        uint8_t* sb = sa + S::kABytes;
-        mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-        tma_load_2d(sa, &tmA, &full_bar[stage], p.a_koff + kc * kGemmBK, m0 + p.tap_off[t]);
-        if (p.b_blocked) {
-          const int by = static_cast<int>(blockIdx.y) / p.b_nbx, bx = static_cast<int>(blockIdx.y) - by * p.b_nbx;
-          tma_load_3d(sb, &tmB, &full_bar[stage], p.b_koff + kc * kGemmBK, bx * (BN / 8), by * 8);
-        } else if constexpr (CL > 1) {
-          constexpr int kSlice = BN / CL;
-          tma_load_2d_mcast(sb + cta_rank * kSlice * 128, &tmB, &full_bar[stage], p.b_koff + kc * kGemmBK,
-                            t * p.Npad + n0 + static_cast<int>(cta_rank) * kSlice, kMask);
-        } else {
-          tma_load_2d(sb, &tmB, &full_bar[stage], p.b_koff + kc * kGemmBK, t * p.Npad + n0);
+        mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(KC) * S::kStageBytes);
+        for (int a = 0; a < KC; ++a) {
+          uint8_t* sa = smem + (stage * KC + a) * S::kStageBytes;
+          uint8_t* sb = sa + S::kABytes;
+          tma_load_2d(sa, &tmA, &full_bar[stage], p.a_koff + kc * kGemmBK, m0 + p.tap_off[t]);
+          if (p.b_blocked) {
+            const int by = static_cast<int>(blockIdx.y) / p.b_nbx, bx = static_cast<int>(blockIdx.y) - by * p.b_nbx;
+            tma_load_3d(sb, &tmB, &full_bar[stage], p.b_koff + kc * kGemmBK, bx * (BN / 8), by * 8);
+          } else if constexpr (CL > 1) {
+            constexpr int kSlice = BN / CL;
+            tma_load_2d_mcast(sb + cta_rank * kSlice * 128, &tmB, &full_bar[stage], p.b_koff + kc * kGemmBK,
+                              t * p.Npad + n0 + static_cast<int>(cta_rank) * kSlice, kMask);
+          } else {
+            tma_load_2d(sb, &tmB, &full_bar[stage], p.b_koff + kc * kGemmBK, t * p.Npad + n0);
+          }
+          if (++kc == kchunks) { kc = 0; ++t; }
         }
         if (++stage == nstages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
+    // This warp's instruction latency is the pacing item of the whole kernel (a tcgen05.mma is one
+    // instruction, the 64 clk it keeps the tensor pipe busy are easily lost to descriptor arithmetic
+    // and barrier round trips), so the loop is kept minimal: descriptors advance by constant adds,
+    // the next stage's barrier is probed while the current MMAs execute, one commit per stage.
     constexpr uint32_t idesc = umma_idesc_f16<kGemmBM, (BN < 16 ? 16 : BN)>();
+    constexpr uint64_t kSlotStep = static_cast<uint64_t>(S::kStageBytes >> 4);
+    constexpr uint64_t kBOff = static_cast<uint64_t>(S::kABytes >> 4);
+    const int KC = p.kc;
+    const int nst = nk / KC;
+    const uint64_t desc_base = umma_desc_sw128(smem_u32(smem));
+    const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
-    for (int it = 0; it < nk; ++it) {
-      mbar_wait(&full_bar[stage], phase);
+    uint64_t da = desc_base;
+    bool ready = mbar_try_wait_nohint(&full_bar[0], 0);
+    for (int it = 0; it < nst; ++it) {
+      if (!ready) mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
-        const uint64_t da = umma_desc_sw128(sa);
-        const uint64_t db = umma_desc_sw128(sa + S::kABytes);
-#pragma unroll
-        for (int k = 0; k < kGemmBK / 16; ++k) {
+      if (leader) {
+        for (int a = 0; a < KC; ++a) {
+          const uint64_t d = da + static_cast<uint64_t>(a) * kSlotStep;
           // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-          umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, (it | k) != 0 ? 1u : 0u);
+          umma_f16(tmem_base, d, d + kBOff, idesc, (it | a) != 0 ? 1u : 0u);
+          umma_f16_acc(tmem_base, d + 2u, d + kBOff + 2u, idesc);
+          umma_f16_acc(tmem_base, d + 4u, d + kBOff + 4u, idesc);
+          umma_f16_acc(tmem_base, d + 6u, d + kBOff + 6u, idesc);
         }
-        // frees the smem slot (in every CTA of the cluster) when these MMAs retire
+        // frees the smem stage (in every CTA of the cluster) when these MMAs retire
         if constexpr (CL > 1) umma_commit_mcast(&empty_bar[stage], kMask);
         else umma_commit(&empty_bar[stage]);
-        if (it == nk - 1) umma_commit(acc_bar);  // accumulator complete
+        if (it == nst - 1) umma_commit(acc_bar);  // accumulator complete
       }
-      __syncwarp();
-      if (++stage == nstages) { stage = 0; phase ^= 1u; }
+      if (++stage == nstages) { stage = 0; phase ^= 1u; da = desc_base; }
+      else da += static_cast<uint64_t>(KC) * kSlotStep;
+      ready = (it + 1 < nst) && mbar_try_wait_nohint(&full_bar[stage], phase);
     }
+    __syncwarp();
   } else {
     // ------------------------------ epilogue ----------------------------------
     constexpr int HALF = BN / 2;                       // columns per thread

@@ -95,7 +95,7 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 128);
+      mbar_init(&acc_empty[b], 4);       // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -241,7 +241,7 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         }
         // TMEM buffer drained -> hand it back to the MMA warp before the slow part.
         tc_fence_before();
-        mbar_arrive(&acc_empty[eg]);
+        mbar_arrive_warp(&acc_empty[eg]);
 
         if (qvalid) {
           const int ky0 = by * 8, kx0 = bx * 8;
@@ -325,7 +325,7 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           }
           if (m == p.M - 1) {
             tc_fence_before();
-            mbar_arrive(&acc_empty[eg]);
+            mbar_arrive_warp(&acc_empty[eg]);
           }
           if (near) {
 #pragma unroll

@@ -206,6 +206,7 @@ class UpdateWeights:
         fh, mk = ub.flow_head, ub.mask
         self.hd_w = pc(torch.cat([fh.conv1.weight, mk[0].weight], 0))
         self.hd_b = torch.cat([fh.conv1.bias, mk[0].bias]).detach().float().contiguous()
+        self.hdf_w = pc(fh.conv1.weight); self.hdf_b = fh.conv1.bias.detach().float().contiguous()   # flow head alone
         self.fl_w = pc(fh.conv2.weight, Npad=32); self.fl_b = pb(fh.conv2.bias, 32)
         self.mk_w = pc(mk[2].weight); self.mk_b = (0.25 * mk[2].bias.detach().float()).contiguous()
         self.taps3 = ops.conv_taps(3, 3, grid)
@@ -241,11 +242,16 @@ def sep_conv_gru(ws, uw):
                        epilogue=ops.EPI_GRU_Q, bias=bq, out_b=ws.X, colb=0, aux0=ws.Z, aux1=ws.Hm)
 
 
-def heads(ws, uw, it=0):
+def heads(ws, uw, it=0, need_mask=True):
     """FlowHead core/update.py:15-16 + mask head core/update.py:124-127,161 -> DELTA[:, :2], MASKS[it & 1].
-    The two second-layer convolutions are independent: the flow one runs on the side stream."""
+    The two second-layer convolutions are independent: the flow one runs on the side stream.
+    need_mask=False computes the flow head only (the caller discards this iteration's mask)."""
     g = ws.grid
     sg = ops.shift_gemm
+    if not need_mask:
+        sg(ws.X, uw.hdf_w, M=g.Mp, Npad=256, K=128, BN=128, taps=uw.taps3, grid=g, bias=uw.hdf_b, act=1, out_b=ws.HD)
+        sg(ws.HD, uw.fl_w, M=g.Mp, Npad=32, K=256, BN=32, taps=uw.taps3, grid=g, bias=uw.fl_b, out_f=ws.DELTA)
+        return
     sg(ws.X, uw.hd_w, M=g.Mp, Npad=512, K=128, BN=128, taps=uw.taps3, grid=g, bias=uw.hd_b, act=1, out_b=ws.HD)
     main, side = torch.cuda.current_stream(), ws.side
     side.wait_stream(main)

@@ -109,6 +109,11 @@ class CRAFT(nn.Module):
         # fnet / cnet are outside the hot path; TF32 convolutions there cost ~6e-3 max abs error on
         # features of magnitude 20 and are 2.5x faster than strict fp32 (profiles/README.md).
         self.encoder_tf32 = True
+        # test_mode=1 returns only the LAST iteration's upsampled flow (core/network.py:262-263), yet the
+        # reference computes the mask head and the convex upsampling in every iteration and drops them.
+        # Eliding that dead work leaves every returned value bit-identical.
+        # Set False to execute the reference's schedule literally.
+        self.elide_dead_upsample = True
         self._graphs = {}
 
     def freeze_bn(self):
@@ -218,7 +223,7 @@ class CRAFT(nn.Module):
 
     def _forward_graphed(self, image1, image2, iters, flow_init, test_mode):
         key = (image1.device.index, tuple(image1.shape), int(iters), int(test_mode), flow_init is not None,
-               self.materialize_level0, self.encoder_tf32)
+               self.materialize_level0, self.encoder_tf32, self.elide_dead_upsample)
         sig = self._weights_signature()
         ent = self._graphs.get(key)
         if ent is None or ent["sig"] != sig:
@@ -268,9 +273,12 @@ class CRAFT(nn.Module):
             att = self._prepare_pair(ws, fmap1[b], fmap2[b], cnet_feat[b], fi)
             main, side = torch.cuda.current_stream(), ws.side
             for itr in range(iters):
+                need_up = not (test_mode == 1 and self.elide_dead_upsample) or itr == iters - 1
                 corr_fn.lookup_rows(ws, ws.coords1, out_b=ws.CORR)
-                self.update_block.step(ws, att, itr)
+                self.update_block.step(ws, att, itr, need_mask=need_up)
                 ops.flow_update(ws.coords1, ws.flow, ws.DELTA, g)
+                if not need_up:
+                    continue
                 # the reference upsamples after every iteration (core/network.py:250-260); nothing in the next
                 # iteration depends on it, so it runs on the side stream (mask buffers alternate, hotpath.heads)
                 dst = flow_ups[itr if test_mode != 1 else 0][b]

@@ -76,14 +76,14 @@ class GMAUpdateBlock(nn.Module):
         ps = [p for n, p in self.named_parameters() if not n.startswith("aggregator.")]
         return self._packed.get(("uw", grid.H, grid.W), ps, lambda: hp.UpdateWeights(self, grid))
 
-    def step(self, ws, attention, it=0):
+    def step(self, ws, attention, it=0, need_mask=True):
         """One refinement iteration on the workspace: CORR (looked-up correlation) and flow are in
-        place; writes the new hidden state (X[:, :128], Hm), DELTA and MASK."""
+        place; writes the new hidden state (X[:, :128], Hm), DELTA and (when need_mask) MASK."""
         uw = self.weights(ws.grid)
         hp.motion_encoder(ws, uw)
         self.aggregator.run(ws, attention, ws.X, 256, out_b=ws.X, colb=384)
         hp.sep_conv_gru(ws, uw)
-        hp.heads(ws, uw, it)
+        hp.heads(ws, uw, it, need_mask)
 
     def forward(self, net, inp, corr, flow, attention):
         """(net, inp, corr, flow, attention) -> (net, mask, delta_flow); NCHW fp32 at the boundary."""

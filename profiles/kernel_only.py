@@ -32,7 +32,7 @@ def main(which, reps):
 
         def run():
             if which == "pv":
-                ks = ws.pv_split(4)
+                ks = int(os.environ.get("PV_KS", ws.pv_split(4)))
                 ops.attn_pv(ws.Qa, ws.Ka, ws.Vt, g, M=4, d=32, F=128, w_pos=1.0, pos_table=att_tbl, R=7,
                             clip=ws.clip_att, lse2=ws.lse2_att, out=ws.opart(ks, 4, 128), ksplit=ks)
             elif which == "pv_f2":

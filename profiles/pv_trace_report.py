@@ -1,0 +1,15 @@
+"""Pretty-print the CRAFT_PV_TRACE timeline of attn_pv CTA (0,0,0): clock64 deltas per tile and role.
+usage: python profiles/pv_trace_report.py gpurun_out/pv_trace.txt"""
+import sys
+rows = [list(map(int, l.split())) for l in open(sys.argv[1])]
+t0 = min(v for r in rows for v in r[2:] if v > 0)
+names = {0: "MMA  [top, S(j+2) issued, p_full, v_full, PV issued]",
+         1: "SM g0 [top, s_full, p_empty, S loaded, P stored, p_full arrived]",
+         2: "SM g1 [top, s_full, p_empty, S loaded, P stored, p_full arrived]",
+         3: "TMA  [K issued, V issued]"}
+for role in range(4):
+    print(names[role])
+    for r in rows:
+        if r[0] != role or not any(r[2:]):
+            continue
+        print("  tile %2d: " % r[1] + " ".join("%7d" % (v - t0) if v else "      -" for v in r[2:8]))

@@ -141,3 +141,21 @@ def test_seams_match_reference(name):
     _report(name + ":seams", **errs)
     for k, e in errs.items():
         assert e["mean_abs"] <= tol[k] * max(1.0, 0.1 * e["ref_absmax"]), (k, e)
+
+
+def test_dead_upsample_elision_is_bit_identical():
+    """test_mode=1 returns only the last iteration's upsampled flow (core/network.py:262-263); skipping
+    the mask head + upsampling of the earlier iterations must not change a single bit, and test_mode=2
+    (which returns every iteration's flow) must agree with it on the last one."""
+    rec = torch.load(os.path.join(GOLD, "seeded_setrans_128.pt"), map_location="cpu")
+    model = _model(rec)
+    i1, i2 = (t.cuda() for t in _inputs(rec))
+    with torch.no_grad():
+        model.elide_dead_upsample = True
+        lo_a, up_a = model(i1, i2, iters=4, test_mode=1)
+        model.elide_dead_upsample = False
+        lo_b, up_b = model(i1, i2, iters=4, test_mode=1)
+        lo_c, ups = model(i1, i2, iters=4, test_mode=2)
+    torch.cuda.synchronize()
+    assert torch.equal(lo_a, lo_b) and torch.equal(up_a, up_b)
+    assert torch.equal(lo_a, lo_c) and torch.equal(up_a, ups[-1]) and len(ups) == 4
