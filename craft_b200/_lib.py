@@ -59,7 +59,7 @@ class PvArgs(C.Structure):
         ("scale", C.c_float), ("w_pos", C.c_float),
         ("pos_table", C.c_void_p), ("R", C.c_int),
         ("clip", C.c_void_p), ("lse2", C.c_void_p), ("out", C.c_void_p),
-        ("ksplit", C.c_int),
+        ("ksplit", C.c_int), ("zero_fill", C.c_int),
     ]
 
 
@@ -82,7 +82,7 @@ SIGNATURES = {
     "craft_clip_gate": (_i, [_vp, _f, _vp, _vp, _vp]),
     "craft_attn_pv": (_i, [C.POINTER(PvArgs), _vp]),
     "craft_modes_finalize": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _i, _i, _i, _i,
-                                  _vp, _i, _i, _vp, _i, _i, _vp]),
+                                  _vp, _i, _i, _vp, _i, _i, _i, _vp]),
     "craft_corr_lookup": (_i, [C.POINTER(_vp), _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp]),
     "craft_corr_lookup0": (_i, [_vp, _vp, _i, _i, _f, _f, _f, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     "craft_convf1": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _i, _vp]),

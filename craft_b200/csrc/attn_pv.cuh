@@ -7,37 +7,50 @@
 // out_m = P_m V_m); GMA: Attention.forward core/gma.py:78-100 + Aggregate.forward :131-134.
 //
 // The row log-sum-exp is known up front (scores.cuh SC_LSE), so no online rescaling is needed:
-// every key tile contributes an exact, final slice of P.  One CTA = (128 queries, one mode, one
-// key split).  Keys are visited in spatial blocks of 8 x (BK/8) tokens (3-D TMA box), so that the
+// every key tile contributes an exact, final slice of P.  The work is the list of (unit, key tile)
+// pairs, unit = (128-query tile, mode); it is cut into gridDim.x equal contiguous ranges, one per
+// PERSISTENT CTA (one CTA per SM), so every SM gets the same number of key tiles and the ~7 us a
+// CTA needs to start up / drain (TMEM allocation, pipeline fill, O write-back) is paid once per SM
+// instead of once per wave.  A CTA's range touches 2-3 units ("segments"); a unit cut by a range
+// boundary is finished by the next CTA and the partial O's land in different slots of `out`
+// (summed by modes_finalize_kernel).  Keys are visited in spatial blocks of 8 x (BK/8) tokens (3-D TMA box), so that the
 // positional-bias window (|dy|,|dx| <= R) touches only the few blocks around the query and every
 // other block takes the 3-instruction fast path.  V^T arrives in the same block order
-// (gemm.cuh b_blocked).  Pipeline per key tile j:
-//     MMA warp : S[j&1] = Q K_j^T                     (tcgen05, accumulator in TMEM)
-//     softmax  : P[j&1] = exp2(...) as bf16 -> smem    (4 groups of 4 warps: tile parity x column half)
-//     MMA warp : O += P[j&1] V_j                       (A = P from smem, B = V^T tile from TMA)
-// S(j+2) is issued before PV(j): neither the tensor pipe nor the two softmax groups wait for each other.
+// (gemm.cuh b_blocked).
+//
+// Data flow per key tile j (TMEM buffer b = j mod NSB):
+//     warp 1   : S[b] = Q K_j^T                     tcgen05.mma SS, fp32 accumulator in TMEM
+//     softmax  : P[b] = exp2(S[b]*c - lse) as bf16  written back into the SAME TMEM columns (tcgen05.st)
+//     warp 2   : O += P[b] V_j                       tcgen05.mma with the A operand read from TMEM
+// P never touches shared memory: no 32 KB/tile of st.shared, no proxy fence, and the P.V MMA reads
+// only V from smem.  With NSB = 3 S/P buffers and two softmax groups alternating tiles, S runs up to
+// three tiles ahead and neither the softmax groups nor the two MMA-issuing warps wait on each other
+// in steady state.  The two MMA streams are issued by different warps because the instruction
+// latency of an issuing warp (barrier probes, descriptor arithmetic, one UTCHMMA per 16 K columns)
+// -- not the tensor pipe -- is what paces a tile (profiles/README.md, "attn_pv timeline").
 #pragma once
 #include "common.cuh"
 #include "pointwise.cuh"
 
 namespace cb {
 
-constexpr int kPvThreads = 64 + 512;   // TMA warp, MMA warp, 16 softmax warps
+constexpr int kPvThreads = 128 + 512;   // TMA warp, S-MMA warp, PV-MMA warp, spare warp, 16 softmax warps
 
 struct PvParams {
   Grid2 g;
   int M;                   // modes
-  int ksplit;              // gridDim.z
+  int nslots;              // partial-sum slots in `out` (>= CTAs that can share one unit)
+  int zero_fill;           // != 0: slots a unit does not use are zero-filled (readers that sum all slots blindly)
+  int nqt;                 // query tiles
   float scale;             // 1/sqrt(d)
   float w_pos;
   const float* pos_table;  // [(2R+1)^2] or nullptr
   int R;
   const float* clip;       // device scalar (+inf or attn_clip)
   const float* lse2;       // [M][Mp] log2-domain log-sum-exp
-  float* out;              // [ksplit][M][Mp][F] f32 partial sums
+  float* out;              // [nslots][M][Mp][F] f32 partial sums
   int nkt, nbx;            // key tiles (blocks) in total / per block-row
   long long* trace;        // CRAFT_PV_TRACE: clock64 timeline of CTA (0,0,0): [role 4][tile 64][slot 8]
-  int dbg;                 // timing experiments only (CRAFT_PV_DBG): bit0 no exp, bit1 no TMEM ld, bit2 no P store, bit3 no PV MMA, bit4 no S MMA
 };
 
 template <int D, int F, int BK, int KS, int VS>
@@ -46,8 +59,8 @@ struct PvSmem {
   static constexpr int kQBytes = kQAtoms * 128 * 128;
   static constexpr int kKBytes = kQAtoms * BK * 128;
   static constexpr int kVBytes = (BK / 64) * F * 128;
-  static constexpr int kPBytes = (BK / 64) * 128 * 128;
-  static constexpr int kTotal = kQBytes + KS * kKBytes + VS * kVBytes + 2 * kPBytes + 1024 + 2048;
+  static constexpr int kTotal = 2 * kQBytes + KS * kKBytes + VS * kVBytes + 1024 + 512 + 4096;   // + align, barriers, bias table
+  static_assert(kTotal <= 227 * 1024, "attn_pv: shared memory budget");
 };
 
 template <int D, int F, int BK, int KS, int VS>
@@ -56,59 +69,85 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ PvParams p) {
   using S = PvSmem<D, F, BK, KS, VS>;
   constexpr int BW = BK / 8;             // block width in tokens (block height is 8)
-  constexpr int HALF = BK / 2;           // columns per softmax thread
+  constexpr int HALF = BK / 2;           // S columns per softmax thread
+  constexpr int PW = BK / 4;             // packed P columns (2 bf16 each) per softmax thread
+  constexpr int NSB = 3;                 // S/P buffers in TMEM
+  constexpr uint32_t kTmemO = NSB * BK;  // O accumulator starts after the S/P buffers
+  constexpr uint32_t kPOff = BK / 4;     // P sits at S + BK/4: every warp overwrites only columns it has read itself
+  static_assert(NSB * BK + F <= 512, "attn_pv: TMEM budget");
+  static_assert(HALF == 32 || HALF == 64, "attn_pv: BK must be 64 or 128");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + S::kQBytes;
+  uint8_t* sK = sQ + 2 * S::kQBytes;
   uint8_t* sV = sK + KS * S::kKBytes;
-  uint8_t* sP = sV + VS * S::kVBytes;
-  uint8_t* tail = sP + 2 * S::kPBytes;
-  uint64_t* q_full = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* k_full = q_full + 1;
+  uint8_t* tail = sV + VS * S::kVBytes;
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(tail);   // [2] Q of segment s lives in buffer s & 1
+  uint64_t* q_free = q_full + 2;                           // [2] all S MMAs of that segment retired
+  uint64_t* k_full = q_free + 2;
   uint64_t* k_empty = k_full + KS;
   uint64_t* v_full = k_empty + KS;
   uint64_t* v_empty = v_full + VS;
-  uint64_t* s_full = v_empty + VS;     // [2]
-  uint64_t* s_empty = s_full + 2;      // [2] count 8
-  uint64_t* p_full = s_empty + 2;      // [2] count 8
-  uint64_t* p_empty = p_full + 2;      // [2]
-  uint64_t* o_full = p_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
-  float* s_table = reinterpret_cast<float*>(tmem_slot + 4);
+  uint64_t* s_full = v_empty + VS;       // [NSB] S(j) complete in TMEM            (tcgen05.commit, count 1)
+  uint64_t* p_full = s_full + NSB;       // [NSB] P(j) stored to TMEM              (8 softmax warps)
+  uint64_t* sp_free = p_full + NSB;      // [NSB] P.V(j) retired: buffer reusable   (tcgen05.commit, count 1)
+  uint64_t* o_full = sp_free + NSB;      // O of the current segment complete           (tcgen05.commit)
+  uint64_t* o_free = o_full + 1;         // O read back by the 16 epilogue warps         (count 16)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
+  // positional-bias table, zero padded so that a thread's 4 x BW window can be read without range
+  // checks: row iy+3 (iy in [-3, 2R+3]), column ix+BW-1 (ix in [-(BW-1), 2R+BW-1]); log2 domain
+  float* s_table = reinterpret_cast<float*>(tail + 512);
+  const int TW = 2 * p.R + 1 + 2 * (BW - 1);
 
   const int warp = threadIdx.x >> 5;
-  const int q0 = blockIdx.x * 128;
-  const int mode = blockIdx.y;
-  const int kt_begin = static_cast<int>((static_cast<long long>(p.nkt) * blockIdx.z) / p.ksplit);
-  const int kt_end = static_cast<int>((static_cast<long long>(p.nkt) * (blockIdx.z + 1)) / p.ksplit);
-  const int ntiles = kt_end - kt_begin;
-  const int ch0 = mode * D;               // first channel of this mode in the Q/K rows
-  const int qk_col = (ch0 >> 6) << 6;     // TMA column of the 64-channel atom holding it
-  const uint32_t qk_inner = static_cast<uint32_t>(ch0 & 63) * 2u;
-  constexpr uint32_t kTmemO = 2 * BK;     // O accumulator starts after the two S buffers
+  // this CTA's contiguous range of the (unit, key tile) list
+  const long long NT = static_cast<long long>(p.nqt) * p.M * p.nkt;
+  const long long lin_begin = NT * blockIdx.x / gridDim.x;
+  const long long lin_end = NT * (blockIdx.x + 1) / gridDim.x;
+  // CTA that owns list position x (ranges are [NT*c/G, NT*(c+1)/G))
+  auto cta_of = [&](long long x) {
+    long long c = x * gridDim.x / NT;
+    while (c + 1 < static_cast<long long>(gridDim.x) && NT * (c + 1) / gridDim.x <= x) ++c;
+    while (c > 0 && NT * c / gridDim.x > x) --c;
+    return static_cast<int>(c);
+  };
+  struct Seg { int qt, mode, t0, nt; };
+  auto seg_at = [&](long long lin) {
+    Seg sgm;
+    const int unit = static_cast<int>(lin / p.nkt);
+    sgm.t0 = static_cast<int>(lin - static_cast<long long>(unit) * p.nkt);
+    const long long left = lin_end - lin;
+    sgm.nt = static_cast<int>(left < p.nkt - sgm.t0 ? left : p.nkt - sgm.t0);
+    sgm.qt = unit / p.M;
+    sgm.mode = unit - sgm.qt * p.M;
+    return sgm;
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&q_full[b], 1); mbar_init(&q_free[b], 1); }
     for (int s = 0; s < KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
     for (int s = 0; s < VS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < NSB; ++b) {
       mbar_init(&s_full[b], 1);
-      mbar_init(&s_empty[b], 8);     // one arrival per softmax warp of the group
-      mbar_init(&p_full[b], 8);
-      mbar_init(&p_empty[b], 1);
+      mbar_init(&p_full[b], 8);      // one arrival per softmax warp of the group
+      mbar_init(&sp_free[b], 1);
     }
     mbar_init(o_full, 1);
+    mbar_init(o_free, 16);
     fence_mbar_init();
   }
   if (p.pos_table) {
-    const int n = (2 * p.R + 1) * (2 * p.R + 1);
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-      s_table[i] = p.pos_table[i] * p.w_pos * 1.4426950408889634f;   // pre-scaled to the log2 domain
+    const int TDp = 2 * p.R + 1;
+    const int n = (TDp + 6) * TW;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int iy = i / TW - 3, ix = i % TW - (BW - 1);
+      const bool in = (iy >= 0) && (iy < TDp) && (ix >= 0) && (ix < TDp);
+      s_table[i] = in ? p.pos_table[iy * TDp + ix] * p.w_pos * 1.4426950408889634f : 0.f;
+    }
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -116,44 +155,49 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int WM = (p.dbg >> 8) & 3;
-  const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-#define PV_TRACE(role, tile, slot) do { if (tr && (threadIdx.x & 31) == 0 && (tile) < 64) p.trace[((role) * 64 + (tile)) * 8 + (slot)] = clock64(); } while (0)
-  if (ntiles > 0) {
-    if (warp == 0) {
-      // ------------------------------------ TMA producer ------------------------------------
-      if (elect_one()) {
-        mbar_arrive_expect_tx(q_full, S::kQBytes);
+  const bool tr = p.trace != nullptr && blockIdx.x == 0;
+#define PV_TRACE(role, tile, slot)                                                              \
+  do {                                                                                          \
+    if (tr && (threadIdx.x & 31) == 0 && (tile) < 64) p.trace[((role) * 64 + (tile)) * 8 + (slot)] = clock64(); \
+  } while (0)
+
+  if (warp == 0) {
+    // ------------------------------------ TMA producer ------------------------------------
+    if (elect_one()) {
+      int ks = 0, vs = 0;
+      uint32_t kph = 0, vph = 0;
+      int seg = 0, g0 = 0;
+      for (long long lin = lin_begin; lin < lin_end; ++seg) {
+        const Seg sgm = seg_at(lin);
+        const int ch0 = sgm.mode * D;               // first channel of this mode in the Q/K rows
+        const int qk_col = (ch0 >> 6) << 6;         // TMA column of the 64-channel atom holding it
+        const int qb = seg & 1;
+        mbar_wait(&q_free[qb], ((static_cast<uint32_t>(seg) >> 1) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&q_full[qb], S::kQBytes);
         for (int a = 0; a < S::kQAtoms; ++a)
-          tma_load_2d(sQ + a * 128 * 128, &tmQ, q_full, qk_col + a * 64, q0);
-        // K and V are two independent pipelines (K feeds S two tiles ahead of the P.V that frees a V
-        // stage), so one thread serves both with non-blocking probes instead of waiting on either.
-        int ks = 0, vs = 0, ki = 0, vi = 0;
-        uint32_t kph = 0, vph = 0, idle = 0;
-        while (ki < ntiles || vi < ntiles) {
+          tma_load_2d(sQ + qb * S::kQBytes + a * 128 * 128, &tmQ, &q_full[qb], qk_col + a * 64, sgm.qt * 128);
+        // K and V are two independent pipelines (K feeds S up to three tiles ahead of the P.V that
+        // frees a V stage), so one thread serves both with non-blocking probes.
+        int ki = 0, vi = 0;
+        uint32_t idle = 0;
+        while (ki < sgm.nt || vi < sgm.nt) {
           bool moved = false;
-          if (ki < ntiles && mbar_test(&k_empty[ks], kph ^ 1u)) {
-            const int kt = kt_begin + ki;
+          if (ki < sgm.nt && mbar_test(&k_empty[ks], kph ^ 1u)) {
+            const int kt = sgm.t0 + ki;
             const int by = kt / p.nbx, bx = kt - by * p.nbx;
-            if (p.dbg & 64) mbar_arrive(&k_full[ks]);
-            else {
-              mbar_arrive_expect_tx(&k_full[ks], S::kKBytes);
-              for (int a = 0; a < S::kQAtoms; ++a)
-                tma_load_3d(sK + ks * S::kKBytes + a * BK * 128, &tmK, &k_full[ks], qk_col + a * 64, bx * BW, by * 8);
-            }
-            PV_TRACE(3, ki, 0);
+            mbar_arrive_expect_tx(&k_full[ks], S::kKBytes);
+            for (int a = 0; a < S::kQAtoms; ++a)
+              tma_load_3d(sK + ks * S::kKBytes + a * BK * 128, &tmK, &k_full[ks], qk_col + a * 64, bx * BW, by * 8);
+            PV_TRACE(3, g0 + ki, 0);
             if (++ks == KS) { ks = 0; kph ^= 1u; }
             ++ki; moved = true;
           }
-          if (vi < ntiles && mbar_test(&v_empty[vs], vph ^ 1u)) {
-            const int kt = kt_begin + vi;
-            if (p.dbg & 32) mbar_arrive(&v_full[vs]);
-            else {
-              mbar_arrive_expect_tx(&v_full[vs], S::kVBytes);
-              for (int a = 0; a < BK / 64; ++a)
-                tma_load_2d(sV + vs * S::kVBytes + a * F * 128, &tmV, &v_full[vs], kt * BK + a * 64, mode * F);
-            }
-            PV_TRACE(3, vi, 1);
+          if (vi < sgm.nt && mbar_test(&v_empty[vs], vph ^ 1u)) {
+            const int kt = sgm.t0 + vi;
+            mbar_arrive_expect_tx(&v_full[vs], S::kVBytes);
+            for (int a = 0; a < BK / 64; ++a)
+              tma_load_2d(sV + vs * S::kVBytes + a * F * 128, &tmV, &v_full[vs], kt * BK + a * 64, sgm.mode * F);
+            PV_TRACE(3, g0 + vi, 1);
             if (++vs == VS) { vs = 0; vph ^= 1u; }
             ++vi; moved = true;
           }
@@ -163,120 +207,139 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             if (++idle > (1u << 24)) __trap();     // protocol bug -> launch failure, never a hang
           }
         }
+        lin += sgm.nt;
+        g0 += sgm.nt;
       }
-    } else if (warp == 1) {
-      // ------------------------------------ MMA issuer --------------------------------------
-      constexpr uint32_t idesc_s = umma_idesc_f16<128, BK>();
-      constexpr uint32_t idesc_o = umma_idesc_f16<128, F>();
-      int ks = 0, vs = 0;
-      uint32_t kph = 0, vph = 0;
-      mbar_wait_mode(q_full, 0, WM);
-      auto issue_s = [&](int j) {
-        const int b = j & 1;
-        const uint32_t use = static_cast<uint32_t>(j >> 1);
-        mbar_wait_mode(&k_full[ks], kph, WM);
-        mbar_wait_mode(&s_empty[b], (use & 1u) ^ 1u, WM);
+    }
+  } else if (warp == 1) {
+    // ------------------------------------ S = Q K^T issuer --------------------------------
+    constexpr uint32_t idesc_s = umma_idesc_f16<128, BK>();
+    constexpr uint64_t kKStep = static_cast<uint64_t>(S::kKBytes >> 4);
+    const bool leader = elect_one();
+    int ks = 0, b = 0, seg = 0, g = 0;
+    uint32_t kph = 0, bpar = 1;            // sp_free[b] parity for "previous use of b retired" (first use: free)
+    for (long long lin = lin_begin; lin < lin_end; ++seg) {
+      const Seg sgm = seg_at(lin);
+      const uint32_t qk_inner = static_cast<uint32_t>((sgm.mode * D) & 63) * 2u;
+      const int qb = seg & 1;
+      const uint64_t dq0 = umma_desc_sw128(smem_u32(sQ + qb * S::kQBytes) + qk_inner);
+      const uint64_t dk0 = umma_desc_sw128(smem_u32(sK) + qk_inner);
+      mbar_wait(&q_full[qb], (static_cast<uint32_t>(seg) >> 1) & 1u);
+      for (int i = 0; i < sgm.nt; ++i, ++g) {
+        const bool r1 = mbar_try_wait_nohint(&k_full[ks], kph);
+        const bool r2 = mbar_try_wait_nohint(&sp_free[b], bpar);
+        if (!r1) mbar_wait(&k_full[ks], kph);
+        if (!r2) mbar_wait(&sp_free[b], bpar);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sq = smem_u32(sQ) + qk_inner;
-          const uint32_t sk = smem_u32(sK + ks * S::kKBytes) + qk_inner;
+        if (leader) {
+          const uint32_t ts = tmem_base + static_cast<uint32_t>(b * BK);
+          const uint64_t dk = dk0 + static_cast<uint64_t>(ks) * kKStep;
 #pragma unroll
           for (int k = 0; k < D / 16; ++k) {
             const int ka = (k * 16) >> 6, kin = (k * 16) & 63;
-            const uint64_t dq = umma_desc_sw128(sq + ka * 128 * 128 + kin * 2);
-            const uint64_t dk = umma_desc_sw128(sk + ka * BK * 128 + kin * 2);
-            if (!(p.dbg & 16)) umma_f16(tmem_base + b * BK, dq, dk, idesc_s, k != 0 ? 1u : 0u);
+            const uint64_t oq = static_cast<uint64_t>((ka * 128 * 128 + kin * 2) >> 4);
+            const uint64_t ok = static_cast<uint64_t>((ka * BK * 128 + kin * 2) >> 4);
+            if (k == 0) umma_f16(ts, dq0 + oq, dk + ok, idesc_s, 0u);
+            else umma_f16_acc(ts, dq0 + oq, dk + ok, idesc_s);
           }
           umma_commit(&k_empty[ks]);
           umma_commit(&s_full[b]);
+          if (i == sgm.nt - 1) umma_commit(&q_free[qb]);    // this segment's Q may be overwritten
         }
-        __syncwarp();
+        PV_TRACE(0, g, 0);
         if (++ks == KS) { ks = 0; kph ^= 1u; }
-      };
-      // Tensor-pipe order: S(0) S(1) | S(2) PV(0) | S(3) PV(1) | ...  S(j+2) only needs the softmax group
-      // of tile j to have pulled S(j) into registers (s_empty), which happens right after S(j) lands, so
-      // it runs ahead of PV(j) and both softmax groups always find their next S tile ready.
-      issue_s(0);
-      if (ntiles > 1) issue_s(1);
-      for (int j = 0; j < ntiles; ++j) {
-        PV_TRACE(0, j, 0);
-        if (j + 2 < ntiles) issue_s(j + 2);
-        PV_TRACE(0, j, 1);
-        const int b = j & 1;
-        const uint32_t use = static_cast<uint32_t>(j >> 1);
-        mbar_wait_mode(&p_full[b], use & 1u, WM);
-        PV_TRACE(0, j, 2);
-        mbar_wait_mode(&v_full[vs], vph, WM);
-        PV_TRACE(0, j, 3);
+        if (++b == NSB) { b = 0; bpar ^= 1u; }
+      }
+      lin += sgm.nt;
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    // ------------------------------------ O += P V issuer (A = P from TMEM) ---------------
+    constexpr uint32_t idesc_o = umma_idesc_f16<128, F>();
+    constexpr uint64_t kVStep = static_cast<uint64_t>(S::kVBytes >> 4);
+    const uint64_t dv0 = umma_desc_sw128(smem_u32(sV));
+    const bool leader = elect_one();
+    int vs = 0, b = 0, seg = 0, g = 0;
+    uint32_t vph = 0, bpar = 0;
+    for (long long lin = lin_begin; lin < lin_end; ++seg) {
+      const Seg sgm = seg_at(lin);
+      // the previous segment's O must have been read back before its columns are overwritten
+      mbar_wait(o_free, (static_cast<uint32_t>(seg) & 1u) ^ 1u);
+      for (int i = 0; i < sgm.nt; ++i, ++g) {
+        const bool r1 = mbar_try_wait_nohint(&p_full[b], bpar);
+        const bool r2 = mbar_try_wait_nohint(&v_full[vs], vph);
+        if (!r1) mbar_wait(&p_full[b], bpar);
+        PV_TRACE(0, g, 2);
+        if (!r2) mbar_wait(&v_full[vs], vph);
+        PV_TRACE(0, g, 3);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sp = smem_u32(sP + b * S::kPBytes);
-          const uint32_t sv = smem_u32(sV + vs * S::kVBytes);
+        if (leader) {
+          const uint32_t tp = tmem_base + static_cast<uint32_t>(b * BK) + kPOff;
+          const uint64_t dv = dv0 + static_cast<uint64_t>(vs) * kVStep;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const int ka = (k * 16) >> 6, kin = (k * 16) & 63;
-            const uint64_t dp = umma_desc_sw128(sp + ka * 128 * 128 + kin * 2);
-            const uint64_t dv = umma_desc_sw128(sv + ka * F * 128 + kin * 2);
-            if (!(p.dbg & 8)) umma_f16(tmem_base + kTmemO, dp, dv, idesc_o, (j | k) != 0 ? 1u : 0u);
+            const uint64_t ov = static_cast<uint64_t>((ka * F * 128 + kin * 2) >> 4);
+            // 16 bf16 of P per row = 8 packed TMEM columns per K step
+            if (k == 0) umma_f16_ts(tmem_base + kTmemO, tp, dv + ov, idesc_o, i != 0 ? 1u : 0u);
+            else umma_f16_ts(tmem_base + kTmemO, tp + 8u * k, dv + ov, idesc_o, 1u);
           }
-          umma_commit(&p_empty[b]);
+          umma_commit(&sp_free[b]);
           umma_commit(&v_empty[vs]);
-          if (j == ntiles - 1) umma_commit(o_full);
+          if (i == sgm.nt - 1) umma_commit(o_full);
         }
-        __syncwarp();
-        PV_TRACE(0, j, 4);
+        PV_TRACE(0, g, 4);
         if (++vs == VS) { vs = 0; vph ^= 1u; }
+        if (++b == NSB) { b = 0; bpar ^= 1u; }
       }
-    } else {
-      // ------------------------------------ softmax groups ----------------------------------
-      // warp w (2..17): tile parity sg = ((w-2)>>2)&1, column half ch = (w-2)>>3, TMEM lane quadrant w&3
-      const int sg = ((warp - 2) >> 2) & 1;
-      const int ch = (warp - 2) >> 3;
-      const int lane_grp = warp & 3;
-      const int row = lane_grp * 32 + (threadIdx.x & 31);
-      const int q = q0 + row;
-      const int qy = q / p.g.Wp, qx = q - qy * p.g.Wp;
-      const float clipv = *p.clip;
-      const bool clamped = clipv < INFINITY;
-      const float lse = (q < p.g.Mp) ? p.lse2[static_cast<size_t>(mode) * p.g.Mp + q] : 0.f;
-      const float sc2 = p.scale * 1.4426950408889634f;
-      const float clip2 = clipv * 1.4426950408889634f;
-      const uint32_t tlane = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16);
-      const int R = p.R, TD = 2 * R + 1;
-      const bool has_bias = p.pos_table != nullptr;
+      lin += sgm.nt;
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------ softmax groups ----------------------------------
+    // warp w (4..19): tile parity sg = ((w-4)>>2)&1, column half ch = (w-4)>>3, TMEM lane quadrant w&3
+    const int sg = ((warp - 4) >> 2) & 1;
+    const int ch = (warp - 4) >> 3;
+    const int lane_grp = warp & 3;
+    const int row = lane_grp * 32 + (threadIdx.x & 31);
+    const float clipv = *p.clip;
+    const bool clamped = clipv < INFINITY;
+    const float sc2 = p.scale * 1.4426950408889634f;
+    const float clip2 = clipv * 1.4426950408889634f;
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16);
+    const int R = p.R;
+    const bool has_bias = p.pos_table != nullptr;
+    const int trole = (warp == 4 || warp == 8) ? 1 + sg : 99;
 
-      for (int j = sg; j < ntiles; j += 2) {
-        const uint32_t use = static_cast<uint32_t>(j >> 1);
-        const int kt = kt_begin + j;
+    int seg = 0, g0 = 0;                 // g = g0 + i: CTA-wide tile counter; tile g uses buffer g % NSB, group g & 1
+    for (long long lin = lin_begin; lin < lin_end; ++seg) {
+      const Seg sgm = seg_at(lin);
+      const int q = sgm.qt * 128 + row;
+      const int qy = q / p.g.Wp, qx = q - qy * p.g.Wp;
+      const float lse = (q < p.g.Mp) ? p.lse2[static_cast<size_t>(sgm.mode) * p.g.Mp + q] : 0.f;
+      for (int i = (g0 & 1) ^ sg; i < sgm.nt; i += 2) {
+        const int g = g0 + i;
+        const int b = g % NSB;
+        const uint32_t bpar = static_cast<uint32_t>(g / NSB) & 1u;
+        const int kt = sgm.t0 + i;
         const int by = kt / p.nbx, bx = kt - by * p.nbx;
         // this thread's half block: block rows [ch*4, ch*4+4), all BW columns
         const int iy0 = by * 8 + ch * 4 - qy + R;       // table row of the first block row
         const int ix0 = bx * BW - qx + R;               // table column of the first block column
         const bool near = has_bias && (iy0 + 3 >= 0) && (iy0 <= 2 * R) && (ix0 + BW - 1 >= 0) && (ix0 <= 2 * R);
-        const int trole = (warp == 2 || warp == 6) ? 1 + sg : 99;
-        if (trole < 4) PV_TRACE(trole, j, 0);
-        mbar_wait_mode(&s_full[sg], use & 1u, WM);
-        if (trole < 4) PV_TRACE(trole, j, 1);
-        mbar_wait_mode(&p_empty[sg], (use & 1u) ^ 1u, WM);
-        if (trole < 4) PV_TRACE(trole, j, 2);
+        if (trole < 4) PV_TRACE(trole, g, 0);
+        mbar_wait(&s_full[b], bpar);
+        if (trole < 4) PV_TRACE(trole, g, 1);
         tc_fence_after();
-        __syncwarp();
-        uint8_t* pbuf = sP + sg * S::kPBytes;
-        // all of this thread's S columns are requested up front (one wait instead of one per chunk),
-        // then the S buffer is handed back to the MMA warp before any math happens
+        const uint32_t tS = tlane + static_cast<uint32_t>(b * BK + ch * HALF);
+        const uint32_t tP = tlane + static_cast<uint32_t>(b * BK) + kPOff + static_cast<uint32_t>(ch * PW);
         uint32_t raw_all[HALF];
-        if (!(p.dbg & 2)) {
 #pragma unroll
-          for (int c = 0; c < HALF; c += 32)
-            tmem_ld32(tlane + sg * BK + ch * HALF + c, *reinterpret_cast<uint32_t(*)[32]>(&raw_all[c]));
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int c = 0; c < HALF; ++c) raw_all[c] = static_cast<uint32_t>(j + c);
-        }
-        tc_fence_before();
-        mbar_arrive_warp(&s_empty[sg]);
-        if (trole < 4) PV_TRACE(trole, j, 3);
+        for (int c = 0; c < HALF; c += 32)
+          tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&raw_all[c]));
+        tmem_ld_wait();
+        if (trole < 4) PV_TRACE(trole, g, 2);
+        uint32_t pk[PW];
 #pragma unroll
         for (int c = 0; c < HALF; c += 32) {
           const uint32_t* raw = &raw_all[c];
@@ -290,53 +353,37 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               x[e] = fminf(fmaxf(__uint_as_float(raw[e]) * sc2, -clip2), clip2) - lse;
           }
           if (near) {
+            const float* trow = s_table + (iy0 + 3) * TW + (ix0 + BW - 1);
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
               const int col = c + e;                       // column inside this half: row-major (4 x BW)
-              const int iy = iy0 + col / BW, ix = ix0 + col % BW;
-              if (static_cast<unsigned>(iy) <= static_cast<unsigned>(2 * R) &&
-                  static_cast<unsigned>(ix) <= static_cast<unsigned>(2 * R))
-                x[e] += s_table[iy * TD + ix];
+              x[e] += trow[(col / BW) * TW + (col % BW)];
             }
           }
-          const int kcol = ch * HALF + c;                  // key column inside the tile
-          const int atom = kcol >> 6;
-          const int chunk0 = (kcol & 63) >> 3;
-          if (p.dbg & 1) {
 #pragma unroll
-            for (int v4 = 0; v4 < 4; ++v4) {
-              uint4 u;
-              u.x = pack_bf16x2(x[8 * v4 + 0], x[8 * v4 + 1]);
-              u.y = pack_bf16x2(x[8 * v4 + 2], x[8 * v4 + 3]);
-              u.z = pack_bf16x2(x[8 * v4 + 4], x[8 * v4 + 5]);
-              u.w = pack_bf16x2(x[8 * v4 + 6], x[8 * v4 + 7]);
-              *reinterpret_cast<uint4*>(pbuf + atom * 128 * 128 + swz128_offset(row, chunk0 + v4)) = u;
-            }
-            continue;
-          }
-#pragma unroll
-          for (int v4 = 0; v4 < 4; ++v4) {
-            uint4 u;
-            u.x = pack_bf16x2(fast_ex2(x[8 * v4 + 0]), fast_ex2(x[8 * v4 + 1]));
-            u.y = pack_bf16x2(fast_ex2(x[8 * v4 + 2]), fast_ex2(x[8 * v4 + 3]));
-            u.z = pack_bf16x2(fast_ex2(x[8 * v4 + 4]), fast_ex2(x[8 * v4 + 5]));
-            u.w = pack_bf16x2(fast_ex2(x[8 * v4 + 6]), fast_ex2(x[8 * v4 + 7]));
-            if (!(p.dbg & 4) || u.x == 0x12345678u)
-              *reinterpret_cast<uint4*>(pbuf + atom * 128 * 128 + swz128_offset(row, chunk0 + v4)) = u;
-          }
+          for (int e = 0; e < 16; ++e) pk[c / 2 + e] = pack_bf16x2(fast_ex2(x[2 * e]), fast_ex2(x[2 * e + 1]));
         }
-        if (trole < 4) PV_TRACE(trole, j, 4);
-        if (!(p.dbg & 1024)) fence_proxy_async_smem();      // st.shared -> visible to the tensor core's async proxy
-        mbar_arrive_warp(&p_full[sg]);
-        if (trole < 4) PV_TRACE(trole, j, 5);
+        if (trole < 4) PV_TRACE(trole, g, 3);
+        // P -> TMEM (this warp's lanes, columns it has just read), then hand the buffer to the P.V issuer
+        if constexpr (PW == 32) tmem_st32(tP, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+        else tmem_st16(tP, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive_warp(&p_full[b]);
+        if (trole < 4) PV_TRACE(trole, g, 4);
       }
 
-      // ------------------------------------ O epilogue --------------------------------------
-      // the four groups split the F columns in quarters
-      mbar_wait_mode(o_full, 0, WM);
+      // -------------------------------- O write-back of this segment ------------------------
+      // the four (group, half) warp sets split the F columns in quarters.  Slot = position of this
+      // CTA among the CTAs that share the unit; the CTA finishing a unit zero-fills the unused slots.
+      const long long unit_lin0 = lin - sgm.t0;
+      const int slot = static_cast<int>(blockIdx.x) - cta_of(unit_lin0);
+      const bool last_part = (sgm.t0 + sgm.nt == p.nkt);
+      mbar_wait(o_full, static_cast<uint32_t>(seg) & 1u);
       tc_fence_after();
       __syncwarp();
-      float* dst = p.out + ((static_cast<size_t>(blockIdx.z) * p.M + mode) * p.g.Mp + q) * F;
+      const size_t slot_stride = static_cast<size_t>(p.M) * p.g.Mp * F;
+      float* dst = p.out + (static_cast<size_t>(slot) * p.M + sgm.mode) * p.g.Mp * F + static_cast<size_t>(q) * F;
       constexpr int kQuarter = F / 4;
       const int c_begin = (sg * 2 + ch) * kQuarter;
 #pragma unroll
@@ -344,7 +391,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         uint32_t raw[32];
         tmem_ld32(tlane + kTmemO + c_begin + c, raw);
         tmem_ld_wait();
-        if (q < p.g.Mp && !(p.dbg & 128)) {
+        if (q < p.g.Mp) {
           float4* d4 = reinterpret_cast<float4*>(dst + c_begin + c);
 #pragma unroll
           for (int e = 0; e < 8; ++e)
@@ -353,19 +400,19 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
       }
       tc_fence_before();
-    }
-  } else {
-    // empty key range: this split contributes zeros
-    if (warp >= 2) {
-      const int row = (warp & 3) * 32 + (threadIdx.x & 31);
-      const int part = (((warp - 2) >> 2) & 1) * 2 + ((warp - 2) >> 3);
-      const int q = q0 + row;
-      if (q < p.g.Mp) {
-        float* dst = p.out + ((static_cast<size_t>(blockIdx.z) * p.M + mode) * p.g.Mp + q) * F;
-        for (int c = part * (F / 4); c < (part + 1) * (F / 4); ++c) dst[c] = 0.f;
+      mbar_arrive_warp(o_free);
+      if (p.zero_fill && last_part && q < p.g.Mp) {
+        for (int sl = slot + 1; sl < p.nslots; ++sl) {
+          float4* z4 = reinterpret_cast<float4*>(dst + static_cast<size_t>(sl - slot) * slot_stride + c_begin);
+#pragma unroll
+          for (int e = 0; e < kQuarter / 4; ++e) z4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
+      lin += sgm.nt;
+      g0 += sgm.nt;
     }
   }
+#undef PV_TRACE
 
   __syncthreads();
   if (warp == 1) {

@@ -292,13 +292,38 @@ int craft_pv_block_keys(int d, int F) {
   if (d == 64 && F == 128) return 128;
   return 0;
 }
+// attn_pv runs persistent CTAs over equal contiguous ranges of the (unit, key tile) list
+// (attn_pv.cuh): grid size and the number of CTAs that can share one unit (= partial-sum slots).
+static int pv_grid(int nqt, int M, int nkt) {
+  const long long nunits = static_cast<long long>(nqt) * M;
+  long long G = sm_count();
+  if (G > nunits * nkt) G = nunits * nkt;
+  if (G > 3 * nunits) G = 3 * nunits;      // keeps a unit within <= 4 CTAs (modes_finalize sums <= 4 slots)
+  return static_cast<int>(G < 1 ? 1 : G);
+}
+static int pv_slots(int nqt, int M, int nkt) {
+  const long long NT = static_cast<long long>(nqt) * M * nkt;
+  const long long G = pv_grid(nqt, M, nkt);
+  auto cta_of = [&](long long x) {
+    long long c = x * G / NT;
+    while (c + 1 < G && NT * (c + 1) / G <= x) ++c;
+    while (c > 0 && NT * c / G > x) --c;
+    return c;
+  };
+  long long worst = 1;
+  for (long long u = 0; u < static_cast<long long>(nqt) * M; ++u) {
+    const long long parts = cta_of(u * nkt + nkt - 1) - cta_of(u * nkt) + 1;
+    if (parts > worst) worst = parts;
+  }
+  return static_cast<int>(worst);
+}
+/* number of partial-sum slots craft_attn_pv needs in `out` (covers both key-block widths) */
 int craft_pv_auto_ksplit(int H, int W, int M) {
   cb::Grid2 g = make_grid(H, W);
   const int nqt = (g.Mp + 127) / 128;
-  int s = pick_split(nqt * M, 4);
-  const int nkt = ((H + 7) / 8) * ((W + 15) / 16);
-  if (s > nkt) s = nkt;
-  return s < 1 ? 1 : s;
+  const int a = pv_slots(nqt, M, ((H + 7) / 8) * ((W + 15) / 16));
+  const int b = pv_slots(nqt, M, ((H + 7) / 8) * ((W + 7) / 8));
+  return a > b ? a : b;
 }
 
 }  // extern "C" (pause)
@@ -376,16 +401,19 @@ static int launch_pv(const craft_pv_args* a, const cb::Grid2& g, cudaStream_t st
   if (make_map_2d(&tv, a->Vt, static_cast<long long>(a->M) * F, static_cast<long long>(nkt) * BK, a->ldv, F)) return -1;
   cb::PvParams p;
   memset(&p, 0, sizeof(p));
-  p.g = g; p.M = a->M; p.ksplit = a->ksplit; p.scale = a->scale; p.w_pos = a->w_pos;
+  const int nqt = (g.Mp + 127) / 128;
+  const int need = pv_slots(nqt, a->M, nkt);
+  if (a->ksplit < need) return fail("attn_pv: out has %d partial slots, the persistent schedule needs %d", a->ksplit, need);
+  if (a->ksplit > 4) return fail("attn_pv: at most 4 partial slots");
+  p.g = g; p.M = a->M; p.nslots = a->ksplit; p.zero_fill = a->zero_fill; p.nqt = nqt; p.scale = a->scale; p.w_pos = a->w_pos;
   p.pos_table = a->pos_table; p.R = a->R; p.clip = a->clip; p.lse2 = a->lse2; p.out = a->out;
   p.nkt = nkt; p.nbx = nbx;
-  { const char* e = getenv("CRAFT_PV_DBG"); p.dbg = e ? atoi(e) : 0; }
   auto kern = cb::attn_pv_kernel<D, F, BK, KS, VS>;
   static bool set = false;
   if (!set) { if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal) != cudaSuccess) return fail("pv: smem attr %d", S::kTotal); set = true; }
-  dim3 grid((g.Mp + 127) / 128, a->M, a->ksplit);
+  dim3 grid(pv_grid(nqt, a->M, nkt));
   static long long* d_trace = nullptr;
-  const char* trace_path = getenv("CRAFT_PV_TRACE");     // profiling aid: dumps CTA (0,0,0)'s clock64 timeline
+  const char* trace_path = getenv("CRAFT_PV_TRACE");     // profiling aid: dumps CTA 0's clock64 timeline
   if (trace_path) {
     if (!d_trace) cudaMalloc(&d_trace, 4 * 64 * 8 * sizeof(long long));
     cudaMemsetAsync(d_trace, 0, 4 * 64 * 8 * sizeof(long long), st);
@@ -418,19 +446,25 @@ int craft_attn_pv(const craft_pv_args* a, void* stream) {
   cb::Grid2 g = make_grid(a->H, a->W);
   if (a->ldv % 8) return fail("attn_pv: ldv=%d must be a multiple of 8", a->ldv);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (a->d == 32 && a->F == 128) return launch_pv<32, 128, 128, 3, 2>(a, g, st);
-  if (a->d == 64 && a->F == 256) return launch_pv<64, 256, 64, 3, 3>(a, g, st);
-  if (a->d == 128 && a->F == 128) return launch_pv<128, 128, 64, 3, 3>(a, g, st);
-  if (a->d == 64 && a->F == 128) return launch_pv<64, 128, 128, 2, 2>(a, g, st);
+  if (a->d == 32 && a->F == 128) return launch_pv<32, 128, 128, 3, 4>(a, g, st);
+  if (a->d == 64 && a->F == 256) return launch_pv<64, 256, 64, 4, 4>(a, g, st);
+  if (a->d == 128 && a->F == 128) return launch_pv<128, 128, 64, 3, 4>(a, g, st);
+  if (a->d == 64 && a->F == 128) return launch_pv<64, 128, 128, 3, 4>(a, g, st);
   return fail("attn_pv: unsupported (d=%d, F=%d)", a->d, a->F);
 }
 
 int craft_modes_finalize(const float* O, int nsum, int M, int F, const float* w_score, const float* b_score,
                          const float* coeff, int gma, const void* x_bf16, int ldx, int colx,
                          const float* x_f32, int ldxf, int colxf, int H, int W, void* out_bf16, int ldb,
-                         int colb, float* out_f32, int ldf, int colf, void* stream) {
+                         int colb, float* out_f32, int ldf, int colf, int pv_bk, void* stream) {
   cb::Grid2 g = make_grid(H, W);
   if (M < 1 || M > 4) return fail("modes_finalize: M out of range");
+  int pv_G = 0, pv_nkt = 0;
+  if (pv_bk) {     // O comes from craft_attn_pv's persistent schedule with key blocks of pv_bk tokens
+    if (pv_bk != 64 && pv_bk != 128) return fail("modes_finalize: pv_bk must be 0, 64 or 128");
+    pv_nkt = ((H + 7) / 8) * ((W + pv_bk / 8 - 1) / (pv_bk / 8));
+    pv_G = pv_grid((g.Mp + 127) / 128, M, pv_nkt);
+  }
   if (nsum < 1 || nsum > 4) return fail("modes_finalize: nsum must be in [1,4]");
   if (!x_bf16 && !x_f32) return fail("modes_finalize: need the skip input");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -440,9 +474,9 @@ int craft_modes_finalize(const float* O, int nsum, int M, int F, const float* w_
   auto* xb = static_cast<const __nv_bfloat16*>(x_bf16);
   auto* ob = static_cast<__nv_bfloat16*>(out_bf16);
   if (F == 128)
-    cb::modes_finalize_kernel<128><<<grid, 256, 0, st>>>(O, nsum, part_stride, M, mode_stride, w_score, b_score, coeff, gma, xb, ldx, colx, x_f32, ldxf, colxf, g, ob, ldb, colb, out_f32, ldf, colf);
+    cb::modes_finalize_kernel<128><<<grid, 256, 0, st>>>(O, nsum, part_stride, M, mode_stride, w_score, b_score, coeff, gma, xb, ldx, colx, x_f32, ldxf, colxf, g, ob, ldb, colb, out_f32, ldf, colf, pv_G, pv_nkt);
   else if (F == 256)
-    cb::modes_finalize_kernel<256><<<grid, 256, 0, st>>>(O, nsum, part_stride, M, mode_stride, w_score, b_score, coeff, gma, xb, ldx, colx, x_f32, ldxf, colxf, g, ob, ldb, colb, out_f32, ldf, colf);
+    cb::modes_finalize_kernel<256><<<grid, 256, 0, st>>>(O, nsum, part_stride, M, mode_stride, w_score, b_score, coeff, gma, xb, ldx, colx, x_f32, ldxf, colxf, g, ob, ldb, colb, out_f32, ldf, colf, pv_G, pv_nkt);
   else return fail("modes_finalize: F must be 128 or 256");
   return check_launch("modes_finalize");
 }

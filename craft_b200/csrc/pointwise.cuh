@@ -447,7 +447,10 @@ __global__ void __launch_bounds__(256) modes_finalize_kernel(
     const float* __restrict__ b_score, const float* __restrict__ coeff, int gma,
     const __nv_bfloat16* __restrict__ xb, int ldx, int colx, const float* __restrict__ xf, int ldxf,
     int colxf, Grid2 g, __nv_bfloat16* __restrict__ out_b, int ldb, int colb,
-    float* __restrict__ out_f, int ldf, int colf) {
+    float* __restrict__ out_f, int ldf, int colf, int pv_G, int pv_nkt) {
+  // pv_G > 0: O was written by attn_pv's persistent schedule with pv_G CTAs and pv_nkt key tiles per
+  // unit; a (query tile, mode) unit then owns as many valid slots as CTAs shared it (1 or 2, rarely
+  // more) and the other slots hold garbage -- recompute that count instead of reading them.
   constexpr int PER = F / 32;
   const int lane = threadIdx.x & 31;
   const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -462,15 +465,27 @@ __global__ void __launch_bounds__(256) modes_finalize_kernel(
 #pragma unroll
     for (int e = 0; e < PER; ++e) o[m][e] = 0.f;
     if (m < M) {
+      int nvalid = nsum;
+      if (pv_G > 0) {
+        const long long NT = static_cast<long long>((g.Mp + 127) >> 7) * M * pv_nkt;
+        auto cta_of = [&](long long x) {
+          long long c = x * pv_G / NT;
+          while (c + 1 < pv_G && NT * (c + 1) / pv_G <= x) ++c;
+          while (c > 0 && NT * c / pv_G > x) --c;
+          return static_cast<int>(c);
+        };
+        const long long lin0 = (static_cast<long long>(p >> 7) * M + m) * pv_nkt;
+        nvalid = cta_of(lin0 + pv_nkt - 1) - cta_of(lin0) + 1;
+      }
       float s = 0.f;
 #pragma unroll
       for (int e = 0; e < PER; ++e) {
         const int f = lane + 32 * e;
-        // up to 4 key-split partials, loaded as independent requests (nsum <= 4, checked by the host)
+        // up to 4 partial slots, loaded as independent requests (nsum <= 4, checked by the host)
         const float* src = O + m * mode_stride + static_cast<long long>(p) * F + f;
         float part[4];
 #pragma unroll
-        for (int sp = 0; sp < 4; ++sp) part[sp] = (sp < nsum) ? __ldg(src + sp * part_stride) : 0.f;
+        for (int sp = 0; sp < 4; ++sp) part[sp] = (sp < nvalid) ? __ldg(src + sp * part_stride) : 0.f;
         const float acc = (part[0] + part[1]) + (part[2] + part[3]);
         o[m][e] = acc;
         if (!gma) s += acc * __ldg(w_score + f);

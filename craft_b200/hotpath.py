@@ -146,9 +146,9 @@ def value_aggregate(ws, Q, K, X, x_koff, W1p, *, M, d, F, table, w_pos, clip, ls
     ks = ws.pv_split(M)
     O = ws.opart(ks, M, F)
     ops.attn_pv(Q, K, ws.Vt, g, M=M, d=d, F=F, w_pos=w_pos, pos_table=table, R=7, clip=clip, lse2=lse2,
-                out=O, ksplit=ks)
+                out=O, ksplit=ks, zero_fill=False)
     ops.modes_finalize(O, ks, M, F, g, w_score=w_score, b_score=b_score, coeff=coeff, gma=gma, x_b=X, colx=x_koff,
-                       out_b=out_b, colb=colb, out_f=out_f, colf=colf)
+                       out_b=out_b, colb=colb, out_f=out_f, colf=colf, pv_bk=BK)
 
 
 def build_correlation(ws, Q, K, *, M, d, w_agg, table, w_pos, global_norm, attn_clip=100.0):

@@ -234,7 +234,9 @@ def clip_gate(stat_max, attn_clip, clip, flag):
     _lib.call("craft_clip_gate", _ptr(stat_max), float(attn_clip), _ptr(clip), _ptr(flag), _stream())
 
 
-def attn_pv(Q, K, Vt, grid, *, M, d, F, w_pos, pos_table, R, clip, lse2, out, ksplit):
+def attn_pv(Q, K, Vt, grid, *, M, d, F, w_pos, pos_table, R, clip, lse2, out, ksplit, zero_fill=True):
+    """`out` holds `ksplit` partial-sum slots [ksplit, M, Mp, F]; zero_fill=False leaves the slots a unit does
+    not use untouched (pair it with modes_finalize(pv_bk=...), which knows the schedule)."""
     _chk(Q, torch.bfloat16, "Q")
     _chk(K, torch.bfloat16, "K")
     _chk(Vt, torch.bfloat16, "Vt")
@@ -250,15 +252,16 @@ def attn_pv(Q, K, Vt, grid, *, M, d, F, w_pos, pos_table, R, clip, lse2, out, ks
     a.R = R
     a.clip, a.lse2, a.out = clip.data_ptr(), lse2.data_ptr(), out.data_ptr()
     a.ksplit = ksplit
+    a.zero_fill = 1 if zero_fill else 0
     _lib.call("craft_attn_pv", C.byref(a), _stream())
 
 
 def modes_finalize(O, nsum, M, F, grid, *, w_score, b_score, coeff, gma=0, x_b=None, colx=0, x_f=None, colxf=0,
-                   out_b=None, colb=0, out_f=None, colf=0):
+                   out_b=None, colb=0, out_f=None, colf=0, pv_bk=0):
     _chk(O, torch.float32, "O")
     _lib.call("craft_modes_finalize", _ptr(O), nsum, M, F, _ptr(w_score), _ptr(b_score), _ptr(coeff), gma,
               _ptr(x_b), _ld(x_b), colx, _ptr(x_f), _ld(x_f), colxf, grid.H, grid.W,
-              _ptr(out_b), _ld(out_b), colb, _ptr(out_f), _ld(out_f), colf, _stream())
+              _ptr(out_b), _ld(out_b), colb, _ptr(out_f), _ld(out_f), colf, int(pv_bk), _stream())
 
 
 # ------------------------------------------------------------------------------------------------

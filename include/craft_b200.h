@@ -120,8 +120,9 @@ typedef struct craft_pv_args {
   int R;
   const float* clip;
   const float* lse2;  /* [M][Mp]                                                               */
-  float* out;         /* f32 [ksplit][M][Mp][F]                                                */
-  int ksplit;
+  float* out;         /* f32 [ksplit][M][Mp][F]: partial sums, one slot per CTA sharing a unit   */
+  int ksplit;         /* slots available in out (>= craft_pv_auto_ksplit)                        */
+  int zero_fill;      /* != 0: slots a (query tile, mode) unit does not use are written as zeros */
 } craft_pv_args;
 /* ExpandedFeatTrans.forward core/setrans.py:373-383, gma.Aggregate.forward core/gma.py:131-134 */
 int craft_attn_pv(const craft_pv_args* a, void* stream);
@@ -132,6 +133,7 @@ int craft_modes_finalize(const float* O, int nsum, int M, int F, const float* w_
                          const float* b_score, const float* coeff, int gma, const void* x_bf16,
                          int ldx, int colx, const float* x_f32, int ldxf, int colxf, int H, int W,
                          void* out_bf16, int ldb, int colb, float* out_f32, int ldf, int colf,
+                         int pv_bk /* 0: all nsum slots valid; 64/128: O from craft_attn_pv with that key block */,
                          void* stream);
 
 /* ---- correlation lookup (CorrBlock.__call__ core/corr.py:47-71) --------------------------- */

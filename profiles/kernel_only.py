@@ -15,6 +15,7 @@ from craft_b200.setrans import get_workspace  # noqa: E402
 
 
 def main(which, reps):
+    trace = os.environ.pop("CRAFT_PV_TRACE", None)     # only the kernel under test is traced, not the warm-up forward
     dev = torch.device("cuda", 0)
     model, _ = _state_dict()
     model = model.to(dev).eval()
@@ -32,7 +33,7 @@ def main(which, reps):
 
         def run():
             if which == "pv":
-                ks = int(os.environ.get("PV_KS", ws.pv_split(4)))
+                ks = ws.pv_split(4)
                 ops.attn_pv(ws.Qa, ws.Ka, ws.Vt, g, M=4, d=32, F=128, w_pos=1.0, pos_table=att_tbl, R=7,
                             clip=ws.clip_att, lse2=ws.lse2_att, out=ws.opart(ks, 4, 128), ksplit=ks)
             elif which == "pv_f2":
@@ -58,6 +59,8 @@ def main(which, reps):
             else:
                 raise SystemExit("unknown kernel " + which)
 
+        if trace:
+            os.environ["CRAFT_PV_TRACE"] = trace
         run()
         torch.cuda.synchronize()
         e0.record()

@@ -3,7 +3,7 @@ usage: python profiles/pv_trace_report.py gpurun_out/pv_trace.txt"""
 import sys
 rows = [list(map(int, l.split())) for l in open(sys.argv[1])]
 t0 = min(v for r in rows for v in r[2:] if v > 0)
-names = {0: "MMA  [top, S(j+2) issued, p_full, v_full, PV issued]",
+names = {0: "MMA  [S(j) issued by S-warp, -, PV-warp: p_full, v_full, PV issued]",
          1: "SM g0 [top, s_full, p_empty, S loaded, P stored, p_full arrived]",
          2: "SM g1 [top, s_full, p_empty, S loaded, P stored, p_full arrived]",
          3: "TMA  [K issued, V issued]"}

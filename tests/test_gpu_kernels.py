@@ -284,7 +284,7 @@ def test_attn_lse_pv_finalize(H, W, M, d, F_):
     got = lse2.reshape(M, grid.H, grid.Wp)[:, :, :W].reshape(M, grid.U)
     assert torch.allclose(got, lse_ref, atol=2e-3, rtol=1e-4), (got - lse_ref).abs().max()
     assert abs(stat_max.item() - gmax.item()) < 1e-3
-    kp = 2
+    kp = ops.pv_auto_ksplit(grid, M)      # partial-sum slots the persistent schedule needs
     out = torch.full((kp, M, grid.Mp, F_), float("nan"), device=DEV)
     ops.attn_pv(Q, K, Vt, grid, M=M, d=d, F=F_, w_pos=w_pos, pos_table=table, R=7, clip=clip, lse2=lse2,
                 out=out, ksplit=kp)
@@ -307,6 +307,14 @@ def test_attn_lse_pv_finalize(H, W, M, d, F_):
         ref = F.layer_norm(0.8 * x + agg, (F_,), eps=1e-12)
         gy = yf.reshape(grid.H, grid.Wp, F_)[:, :W].reshape(grid.U, F_)
         assert torch.allclose(gy, ref, atol=1e-3, rtol=1e-3), (gy - ref).abs().max()
+        # production pairing: unused slots stay garbage (NaN here) and the finalize kernel skips them
+        out2 = torch.full((kp, M, grid.Mp, F_), float("nan"), device=DEV)
+        ops.attn_pv(Q, K, Vt, grid, M=M, d=d, F=F_, w_pos=w_pos, pos_table=table, R=7, clip=clip, lse2=lse2,
+                    out=out2, ksplit=kp, zero_fill=False)
+        yf2 = grid.zeros(F_, dtype=torch.float32)
+        ops.modes_finalize(out2, kp, M, F_, grid, w_score=w_sc, b_score=b_sc, coeff=coeff, x_b=xb, out_f=yf2, pv_bk=BK)
+        torch.cuda.synchronize()
+        assert torch.equal(yf2, yf)
 
 
 @pytest.mark.parametrize("Cc", [64, 96, 128, 256])
