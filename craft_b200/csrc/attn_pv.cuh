@@ -100,6 +100,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   float* s_table = reinterpret_cast<float*>(tail + 512);
   const int TW = 2 * p.R + 1 + 2 * (BW - 1);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   // this CTA's contiguous range of the (unit, key tile) list
   const long long NT = static_cast<long long>(p.nqt) * p.M * p.nkt;
@@ -140,6 +141,8 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     mbar_init(o_free, 16);
     fence_mbar_init();
   }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  pdl_wait();                                    // everything below reads tensors of earlier kernels
   if (p.pos_table) {
     const int TDp = 2 * p.R + 1;
     const int n = (TDp + 6) * TW;
@@ -149,7 +152,6 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       s_table[i] = in ? p.pos_table[iy * TDp + ix] * p.w_pos * 1.4426950408889634f : 0.f;
     }
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -312,11 +314,24 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int trole = (warp == 4 || warp == 8) ? 1 + sg : 99;
 
     int seg = 0, g0 = 0;                 // g = g0 + i: CTA-wide tile counter; tile g uses buffer g % NSB, group g & 1
+    float lse_next = 0.f;
+    if (lin_begin < lin_end) {
+      const Seg s0 = seg_at(lin_begin);
+      const int qn = s0.qt * 128 + row;
+      lse_next = (qn < p.g.Mp) ? p.lse2[static_cast<size_t>(s0.mode) * p.g.Mp + qn] : 0.f;
+    }
     for (long long lin = lin_begin; lin < lin_end; ++seg) {
       const Seg sgm = seg_at(lin);
       const int q = sgm.qt * 128 + row;
       const int qy = q / p.g.Wp, qx = q - qy * p.g.Wp;
-      const float lse = (q < p.g.Mp) ? p.lse2[static_cast<size_t>(sgm.mode) * p.g.Mp + q] : 0.f;
+      const float lse = lse_next;
+      // next segment's log-sum-exp is fetched now: at the segment end it would queue up behind the
+      // O write-back stores in the load/store unit
+      if (lin + sgm.nt < lin_end) {
+        const Seg nx = seg_at(lin + sgm.nt);
+        const int qn = nx.qt * 128 + row;
+        lse_next = (qn < p.g.Mp) ? p.lse2[static_cast<size_t>(nx.mode) * p.g.Mp + qn] : 0.f;
+      }
       for (int i = (g0 & 1) ^ sg; i < sgm.nt; i += 2) {
         const int g = g0 + i;
         const int b = g % NSB;
@@ -379,7 +394,10 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const long long unit_lin0 = lin - sgm.t0;
       const int slot = static_cast<int>(blockIdx.x) - cta_of(unit_lin0);
       const bool last_part = (sgm.t0 + sgm.nt == p.nkt);
+      const int g_last = g0 + sgm.nt - 1;
+      if (trole < 4) PV_TRACE(trole, g_last - (g_last & 1) + (trole - 1), 5);
       mbar_wait(o_full, static_cast<uint32_t>(seg) & 1u);
+      if (trole < 4) PV_TRACE(trole, g_last - (g_last & 1) + (trole - 1), 6);
       tc_fence_after();
       __syncwarp();
       const size_t slot_stride = static_cast<size_t>(p.M) * p.g.Mp * F;
@@ -401,6 +419,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       tc_fence_before();
       mbar_arrive_warp(o_free);
+      if (trole < 4) PV_TRACE(trole, g_last - (g_last & 1) + (trole - 1), 7);
       if (p.zero_fill && last_part && q < p.g.Mp) {
         for (int sl = slot + 1; sl < p.nslots; ++sl) {
           float4* z4 = reinterpret_cast<float4*>(dst + static_cast<size_t>(sl - slot) * slot_stride + c_begin);

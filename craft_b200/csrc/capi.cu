@@ -35,6 +35,29 @@ int check_launch(const char* what) {
   return 0;
 }
 
+// Every kernel of the library is launched with programmatic dependent launch (PDL): the next
+// kernel of the stream may be scheduled while this one drains, runs its prologue (barrier init,
+// TMEM allocation, table loads from constant parameters) and blocks in griddepcontrol.wait until
+// the predecessor has completed and flushed.  Inside a captured CUDA graph this becomes a
+// programmatic edge.  CRAFT_B200_NO_PDL=1 restores plain stream order.
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CRAFT_B200_NO_PDL"); v = (e && atoi(e) != 0) ? 0 : 1; }
+  return v == 1;
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 cb::Grid2 make_grid(int H, int W) {
   cb::Grid2 g;
   g.H = H;
@@ -134,13 +157,15 @@ int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const cb::GemmPa
   cfg.blockDim = dim3(cb::kGemmThreads, 1, 1);
   cfg.dynamicSmemBytes = S::kTotal;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
   if (e != cudaSuccess) return fail("shift_gemm launch: %s", cudaGetErrorString(e));
   return check_launch("shift_gemm");
@@ -189,8 +214,8 @@ int craft_pack_tokens(const float* src, int C, int H, int W, int mode, void* out
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(H * ((g.Wp + 31) / 32));
   auto* ob = static_cast<__nv_bfloat16*>(out_b);
-  if (C == 128) cb::pack_tokens_kernel<128><<<grid, 256, 0, st>>>(src, g, mode, ob, ldb, colb, out_f, ldf, colf);
-  else if (C == 256) cb::pack_tokens_kernel<256><<<grid, 256, 0, st>>>(src, g, mode, ob, ldb, colb, out_f, ldf, colf);
+  if (C == 128) launch_k(cb::pack_tokens_kernel<128>, dim3(grid), dim3(256), 0, st, src, g, mode, ob, ldb, colb, out_f, ldf, colf);
+  else if (C == 256) launch_k(cb::pack_tokens_kernel<256>, dim3(grid), dim3(256), 0, st, src, g, mode, ob, ldb, colb, out_f, ldf, colf);
   else return fail("pack_tokens: C must be 128 or 256 (got %d)", C);
   return check_launch("pack_tokens");
 }
@@ -201,9 +226,9 @@ int craft_unpack_tokens(const void* src, int is_bf16, int ld, int col, int C, in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(H * ((W + 31) / 32), (C + 31) / 32);
   if (is_bf16)
-    cb::unpack_tokens_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), ld, col, C, g, dst);
+    launch_k(cb::unpack_tokens_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(src), ld, col, C, g, dst);
   else
-    cb::unpack_tokens_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(src), ld, col, C, g, dst);
+    launch_k(cb::unpack_tokens_kernel<float>, dim3(grid), dim3(256), 0, st, static_cast<const float*>(src), ld, col, C, g, dst);
   return check_launch("unpack_tokens");
 }
 
@@ -359,17 +384,17 @@ static int scores_common(const craft_scores_args* a, int mode, void* stream) {
     auto kern = cb::scores_kernel<cb::SC_CORR>;
     static bool set = false;
     if (!set) { if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return fail("scores: smem attr"); set = true; }
-    kern<<<grid, cb::kScThreads, smem, st>>>(tq, tk, p);
+    launch_k(kern, dim3(grid), dim3(cb::kScThreads), smem, st, tq, tk, p);
     return check_launch("corr_build");
   } else {
     if (!a->lse_part || !a->lse2 || !a->stat_max) return fail("attn_lse: missing outputs");
     auto kern = cb::scores_kernel<cb::SC_LSE>;
     static bool set = false;
     if (!set) { if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return fail("scores: smem attr"); set = true; }
-    kern<<<grid, cb::kScThreads, smem, st>>>(tq, tk, p);
+    launch_k(kern, dim3(grid), dim3(cb::kScThreads), smem, st, tq, tk, p);
     if (check_launch("attn_lse")) return -1;
     const int n = a->M * g.Mp;
-    cb::lse_merge_kernel<<<(n + 255) / 256, 256, 0, st>>>(p.lse_part, p.ksplit, a->M, g.Mp, a->lse2);
+    launch_k(cb::lse_merge_kernel, dim3((n + 255) / 256), dim3(256), 0, st, p.lse_part, p.ksplit, a->M, g.Mp, a->lse2);
     return check_launch("lse_merge");
   }
 }
@@ -379,11 +404,11 @@ int craft_corr_build(const craft_scores_args* a, void* stream) { return scores_c
 int craft_attn_lse(const craft_scores_args* a, void* stream) { return scores_common(a, cb::SC_LSE, stream); }
 
 int craft_corr_stats_finalize(const double* stat_sum, double n, float* mean_rstd, void* stream) {
-  cb::corr_stats_finalize_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(stat_sum, n, mean_rstd);
+  launch_k(cb::corr_stats_finalize_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), stat_sum, n, mean_rstd);
   return check_launch("corr_stats_finalize");
 }
 int craft_clip_gate(const float* stat_max, float attn_clip, float* clip, int* flag, void* stream) {
-  cb::clip_gate_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(stat_max, attn_clip, clip, flag);
+  launch_k(cb::clip_gate_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), stat_max, attn_clip, clip, flag);
   return check_launch("clip_gate");
 }
 
@@ -419,7 +444,7 @@ static int launch_pv(const craft_pv_args* a, const cb::Grid2& g, cudaStream_t st
     cudaMemsetAsync(d_trace, 0, 4 * 64 * 8 * sizeof(long long), st);
     p.trace = d_trace;
   }
-  kern<<<grid, cb::kPvThreads, S::kTotal, st>>>(tq, tk, tv, p);
+  launch_k(kern, dim3(grid), dim3(cb::kPvThreads), S::kTotal, st, tq, tk, tv, p);
   if (trace_path) {
     static long long h[4 * 64 * 8];
     cudaStreamSynchronize(st);
@@ -474,9 +499,9 @@ int craft_modes_finalize(const float* O, int nsum, int M, int F, const float* w_
   auto* xb = static_cast<const __nv_bfloat16*>(x_bf16);
   auto* ob = static_cast<__nv_bfloat16*>(out_bf16);
   if (F == 128)
-    cb::modes_finalize_kernel<128><<<grid, 256, 0, st>>>(O, nsum, part_stride, M, mode_stride, w_score, b_score, coeff, gma, xb, ldx, colx, x_f32, ldxf, colxf, g, ob, ldb, colb, out_f32, ldf, colf, pv_G, pv_nkt);
+    launch_k(cb::modes_finalize_kernel<128>, dim3(grid), dim3(256), 0, st, O, nsum, part_stride, M, mode_stride, w_score, b_score, coeff, gma, xb, ldx, colx, x_f32, ldxf, colxf, g, ob, ldb, colb, out_f32, ldf, colf, pv_G, pv_nkt);
   else if (F == 256)
-    cb::modes_finalize_kernel<256><<<grid, 256, 0, st>>>(O, nsum, part_stride, M, mode_stride, w_score, b_score, coeff, gma, xb, ldx, colx, x_f32, ldxf, colxf, g, ob, ldb, colb, out_f32, ldf, colf, pv_G, pv_nkt);
+    launch_k(cb::modes_finalize_kernel<256>, dim3(grid), dim3(256), 0, st, O, nsum, part_stride, M, mode_stride, w_score, b_score, coeff, gma, xb, ldx, colx, x_f32, ldxf, colxf, g, ob, ldb, colb, out_f32, ldf, colf, pv_G, pv_nkt);
   else return fail("modes_finalize: F must be 128 or 256");
   return check_launch("modes_finalize");
 }
@@ -494,7 +519,7 @@ int craft_corr_lookup(const float* const* lvl, int H, int W, const float* coords
   }
   p.coords = coords; p.stats = mean_rstd; p.out_b = static_cast<__nv_bfloat16*>(out_bf16); p.ldb = ldb;
   p.out_nchw = out_nchw; p.first_level = first_level;
-  cb::corr_lookup_kernel<<<(g.Mp + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g);
+  launch_k(cb::corr_lookup_kernel, dim3((g.Mp + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), p, g);
   return check_launch("corr_lookup");
 }
 
@@ -511,7 +536,7 @@ int craft_corr_lookup0(const void* Q, const void* K, int M, int d, float scale, 
   p.M = M; p.d = d; p.scale = scale; p.w_agg = w_agg; p.w_pos = w_pos; p.pos_table = pos_table; p.Rb = R;
   p.clip = clip; p.coords = coords; p.stats = mean_rstd; p.out_b = static_cast<__nv_bfloat16*>(out_bf16);
   p.ldb = ldb; p.out_nchw = out_nchw;
-  cb::corr_lookup0_kernel<<<(g.Mp + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g);
+  launch_k(cb::corr_lookup0_kernel, dim3((g.Mp + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), p, g);
   return check_launch("corr_lookup0");
 }
 
@@ -519,18 +544,18 @@ int craft_convf1(const float* flow, const float* wt, const float* bias, int H, i
                  int colo, void* stream) {
   cb::Grid2 g = make_grid(H, W);
   dim3 grid(H * ((W + 15) / 16), 2);
-  cb::convf1_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(flow, wt, bias, g, static_cast<__nv_bfloat16*>(out_bf16), ldo, colo);
+  launch_k(cb::convf1_kernel, dim3(grid), dim3(128), 0, static_cast<cudaStream_t>(stream), flow, wt, bias, g, static_cast<__nv_bfloat16*>(out_bf16), ldo, colo);
   return check_launch("convf1");
 }
 
 int craft_flow_update(float* coords1, float* flow, const float* delta, int ldd, int H, int W, void* stream) {
   cb::Grid2 g = make_grid(H, W);
-  cb::flow_update_kernel<<<(g.Mp + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(coords1, flow, delta, ldd, g);
+  launch_k(cb::flow_update_kernel, dim3((g.Mp + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream), coords1, flow, delta, ldd, g);
   return check_launch("flow_update");
 }
 int craft_init_coords(float* coords1, const float* flow_init, int H, int W, void* stream) {
   cb::Grid2 g = make_grid(H, W);
-  cb::init_coords_kernel<<<(g.Mp + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(coords1, flow_init, g);
+  launch_k(cb::init_coords_kernel, dim3((g.Mp + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream), coords1, flow_init, g);
   return check_launch("init_coords");
 }
 
@@ -540,34 +565,45 @@ int craft_upsample_flow(const void* mask, int mask_is_bf16, int ldm, const float
   dim3 grid((H * W + 3) / 4);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (mask_is_bf16)
-    cb::upsample_flow_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(mask), ldm, flow, g, out);
+    launch_k(cb::upsample_flow_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(mask), ldm, flow, g, out);
   else
-    cb::upsample_flow_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(mask), ldm, flow, g, out);
+    launch_k(cb::upsample_flow_kernel<float>, dim3(grid), dim3(256), 0, st, static_cast<const float*>(mask), ldm, flow, g, out);
   return check_launch("upsample_flow");
 }
 
 
-int craft_nhwc_instnorm_stats(const float* x, int N, int HW, int C, float eps, float* sums, float* ab, void* stream) {
-  if (C % 4 || C > 1024 || C < 4) return fail("instnorm_stats: C=%d must be a multiple of 4 (<= 1024)", C);
+int craft_nhwc_instnorm_stats(const void* x, int is_half, int N, int HW, int C, float eps, float* part,
+                              long long part_capacity, float* ab, void* stream) {
+  const int V = is_half ? 8 : 4;
+  if (C % V || C > 256 * V || C < V) return fail("instnorm_stats: C=%d must be a multiple of %d (<= %d)", C, V, 256 * V);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (cudaMemsetAsync(sums, 0, sizeof(float) * 2 * N * C, st) != cudaSuccess) return fail("instnorm_stats: memset");
   int chunks = (4 * sm_count() + N - 1) / N;          // ~4 blocks per SM in total
   int rows = (HW + chunks - 1) / chunks;
   if (rows < 64) rows = 64;
   chunks = (HW + rows - 1) / rows;
-  cb::nhwc_stats_kernel<<<dim3(chunks, N), 256, 0, st>>>(x, HW, C, rows, sums);
+  if (static_cast<long long>(chunks) * N * C * 2 > part_capacity)
+    return fail("instnorm_stats: partial buffer holds %lld floats, needs %lld", part_capacity, static_cast<long long>(chunks) * N * C * 2);
+  if (is_half) launch_k(cb::nhwc_stats_kernel<__half>, dim3(chunks, N), dim3(256), 0, st, static_cast<const __half*>(x), HW, C, rows, part);
+  else launch_k(cb::nhwc_stats_kernel<float>, dim3(chunks, N), dim3(256), 0, st, static_cast<const float*>(x), HW, C, rows, part);
   if (check_launch("nhwc_stats")) return -1;
-  cb::instnorm_finalize_kernel<<<(N * C + 255) / 256, 256, 0, st>>>(sums, N * C, 1.0f / static_cast<float>(HW), eps, ab);
+  launch_k(cb::instnorm_finalize_kernel, dim3((N * C + 255) / 256), dim3(256), 0, st, part, chunks, N * C, 1.0f / static_cast<float>(HW), eps, ab);
   return check_launch("instnorm_finalize");
 }
 
-int craft_nhwc_affine(const float* v, const float* ab, int ab_nstride, const float* res, const float* rab,
-                      int rab_nstride, int relu_in, int relu_out, int N, int HW, int C, float* out, void* stream) {
-  if (C % 4) return fail("nhwc_affine: C must be a multiple of 4");
+int craft_nhwc_affine(const void* v, int is_half, const float* ab, int ab_nstride, const void* res, const float* rab,
+                      int rab_nstride, int relu_in, int relu_out, int N, int HW, int C, void* out, void* stream) {
+  const int V = is_half ? 8 : 4;
+  if (C % V) return fail("nhwc_affine: C must be a multiple of %d", V);
   const long long per_image = static_cast<long long>(HW) * C;
-  const long long total4 = per_image * N / 4;
-  cb::nhwc_affine_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      v, ab, ab_nstride, res, rab, rab_nstride, relu_in, relu_out, per_image, C, total4, out);
+  const long long totalv = per_image * N / V;
+  const dim3 grid(static_cast<unsigned>((totalv + 255) / 256));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_half)
+    launch_k(cb::nhwc_affine_kernel<__half>, grid, dim3(256), 0, st, static_cast<const __half*>(v), ab, ab_nstride,
+             static_cast<const __half*>(res), rab, rab_nstride, relu_in, relu_out, per_image, C, totalv, static_cast<__half*>(out));
+  else
+    launch_k(cb::nhwc_affine_kernel<float>, grid, dim3(256), 0, st, static_cast<const float*>(v), ab, ab_nstride,
+             static_cast<const float*>(res), rab, rab_nstride, relu_in, relu_out, per_image, C, totalv, static_cast<float*>(out));
   return check_launch("nhwc_affine");
 }
 

@@ -32,6 +32,20 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// programmatic dependent launch (every kernel of the library is launched with the PDL attribute)
+// ---------------------------------------------------------------------------------------------
+// Lets the next kernel of the stream be scheduled now; it must not touch global memory written
+// or read-then-overwritten by its predecessors before pdl_wait().
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+// Blocks until every prerequisite grid has completed and its memory operations are visible.
+// No-op when the kernel was launched without a programmatic dependency.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

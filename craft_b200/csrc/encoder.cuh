@@ -9,101 +9,150 @@
 //
 // with per-(image,channel) scale/shift (a, b): instance norm a = rstd, b = -mean*rstd (eps 1e-5,
 // biased variance, no affine: nn.InstanceNorm2d defaults); eval-mode batch norm a = gamma/sqrt(var+eps),
-// b = beta - mean*a.  Activations are channels-last fp32: lanes run over channels, so every access
-// is a coalesced float4.
+// b = beta - mean*a.  Activations are channels-last fp32 or fp16 (statistics and the affine arithmetic are
+// always fp32): lanes run over channels, so every access is a coalesced 16-byte vector.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace cb {
 
-// x: [N, HW, C] f32 (channels-last).  sums: [N, C, 2] f32, zeroed by the caller.
-// grid = (chunks, N); block = 256 threads = (C/4 channel-quads) x (256/(C/4) rows in flight).
-__global__ void __launch_bounds__(256) nhwc_stats_kernel(const float* __restrict__ x, int HW, int C,
-                                                         int rows_per_block, float* __restrict__ sums) {
-  __shared__ float4 red_s[256], red_q[256];
-  const int cq = C >> 2;                      // float4 columns
+// 16-byte vector of activations: 4 floats or 8 halves
+template <typename T> struct ActVec;
+template <> struct ActVec<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float (&v)[4]) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+  }
+  __device__ static void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct ActVec<__half> {
+  static constexpr int N = 8;
+  __device__ static void load(const __half* p, float (&v)[8]) {
+    const uint4 x = __ldg(reinterpret_cast<const uint4*>(p));
+    const __half2* h = reinterpret_cast<const __half2*>(&x);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(h[k]);
+      v[2 * k] = f.x; v[2 * k + 1] = f.y;
+    }
+  }
+  __device__ static void store(__half* p, const float (&v)[8]) {
+    uint4 x;
+    __half2* h = reinterpret_cast<__half2*>(&x);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+    *reinterpret_cast<uint4*>(p) = x;
+  }
+};
+
+// x: [N, HW, C] channels-last (f32 or f16).  part: [chunks][N][C][2] f32 partial (sum, sum of squares);
+// every block owns one slot, so the reduction order -- and therefore the result -- is fixed
+// (no atomics).  grid = (chunks, N); block = 256 threads = (C/VEC channel groups) x rows in flight.
+template <typename T>
+__global__ void __launch_bounds__(256) nhwc_stats_kernel(const T* __restrict__ x, int HW, int C,
+                                                         int rows_per_block, float* __restrict__ part) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int V = ActVec<T>::N;
+  __shared__ float red_s[256][V + 1], red_q[256][V + 1];
+  const int cq = C / V;                       // vector columns
   const int rpb = 256 / cq;                   // rows processed per pass
   const int tc = threadIdx.x % cq, tr = threadIdx.x / cq;
   const int n = blockIdx.y;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(HW, r0 + rows_per_block);
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+  float s[V], q[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { s[k] = 0.f; q[k] = 0.f; }
   if (tr < rpb) {
-    const float4* base = reinterpret_cast<const float4*>(x + (static_cast<size_t>(n) * HW) * C) + tc;
+    const T* base = x + (static_cast<size_t>(n) * HW) * C + tc * V;
     for (int r = r0 + tr; r < r1; r += rpb) {
-      const float4 v = __ldg(base + static_cast<size_t>(r) * cq);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-      q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
+      float v[V];
+      ActVec<T>::load(base + static_cast<size_t>(r) * C, v);
+#pragma unroll
+      for (int k = 0; k < V; ++k) { s[k] += v[k]; q[k] = fmaf(v[k], v[k], q[k]); }
     }
   }
-  red_s[threadIdx.x] = s;
-  red_q[threadIdx.x] = q;
+#pragma unroll
+  for (int k = 0; k < V; ++k) { red_s[threadIdx.x][k] = s[k]; red_q[threadIdx.x][k] = q[k]; }
   __syncthreads();
   if (tr == 0) {
-    for (int k = 1; k < rpb; ++k) {
-      const float4 a = red_s[k * cq + tc], b = red_q[k * cq + tc];
-      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
-      q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w;
+    for (int j = 1; j < rpb; ++j) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) { s[k] += red_s[j * cq + tc][k]; q[k] += red_q[j * cq + tc][k]; }
     }
-    float* dst = sums + (static_cast<size_t>(n) * C + 4 * tc) * 2;
-    atomicAdd(dst + 0, s.x); atomicAdd(dst + 1, q.x);
-    atomicAdd(dst + 2, s.y); atomicAdd(dst + 3, q.y);
-    atomicAdd(dst + 4, s.z); atomicAdd(dst + 5, q.z);
-    atomicAdd(dst + 6, s.w); atomicAdd(dst + 7, q.w);
+    float* dst = part + ((static_cast<size_t>(blockIdx.x) * gridDim.y + n) * C + V * tc) * 2;
+#pragma unroll
+    for (int k = 0; k < V; ++k) { dst[2 * k] = s[k]; dst[2 * k + 1] = q[k]; }
   }
 }
 
-// sums [N,C,2] -> ab [N,C,2] = (rstd, -mean*rstd)
-__global__ void instnorm_finalize_kernel(const float* __restrict__ sums, int NC, float inv_hw, float eps,
+// part [chunks][N*C][2] -> ab [N,C,2] = (rstd, -mean*rstd); chunks summed in index order
+__global__ void instnorm_finalize_kernel(const float* __restrict__ part, int chunks, int NC, float inv_hw, float eps,
                                          float* __restrict__ ab) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= NC) return;
-  const float mean = sums[2 * i] * inv_hw;
-  const float var = fmaxf(sums[2 * i + 1] * inv_hw - mean * mean, 0.f);
+  float s = 0.f, q = 0.f;
+  for (int c = 0; c < chunks; ++c) {
+    const float2 v = *reinterpret_cast<const float2*>(part + (static_cast<size_t>(c) * NC + i) * 2);
+    s += v.x; q += v.y;
+  }
+  const float mean = s * inv_hw;
+  const float var = fmaxf(q * inv_hw - mean * mean, 0.f);
   const float rstd = rsqrtf(var + eps);
   ab[2 * i] = rstd;
   ab[2 * i + 1] = -mean * rstd;
 }
 
 // out = relu_out( res_term + relu_in(a*v + b) ),  res_term = 0 | res | ra*res + rb
-// v, res, out: [N, HW, C] f32.  ab, rab: [N or 1][C][2] (per-image stride ab_nstride elements, 0 = shared).
-__global__ void __launch_bounds__(256) nhwc_affine_kernel(const float* __restrict__ v, const float* __restrict__ ab,
-                                                          int ab_nstride, const float* __restrict__ res,
+// v, res, out: [N, HW, C] (f32 or f16).  ab, rab: [N or 1][C][2] f32 (per-image stride ab_nstride elements, 0 = shared).
+template <typename T>
+__global__ void __launch_bounds__(256) nhwc_affine_kernel(const T* __restrict__ v, const float* __restrict__ ab,
+                                                          int ab_nstride, const T* __restrict__ res,
                                                           const float* __restrict__ rab, int rab_nstride,
                                                           int relu_in, int relu_out, long long per_image /*HW*C*/,
-                                                          int C, long long total4, float* __restrict__ out) {
-  const long long i4 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i4 >= total4) return;
-  const long long e = i4 * 4;
+                                                          int C, long long totalv, T* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int V = ActVec<T>::N;
+  const long long iv = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (iv >= totalv) return;
+  const long long e = iv * V;
   const int n = static_cast<int>(e / per_image);
   const int c = static_cast<int>(e % C);
-  const float4 x = __ldg(reinterpret_cast<const float4*>(v) + i4);
-  float r[4] = {x.x, x.y, x.z, x.w};
+  float r[V];
+  ActVec<T>::load(v + e, r);
   if (ab) {
     const float* p = ab + static_cast<size_t>(n) * ab_nstride + 2 * c;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) r[k] = fmaf(r[k], __ldg(p + 2 * k), __ldg(p + 2 * k + 1));
+    for (int k = 0; k < V; ++k) r[k] = fmaf(r[k], __ldg(p + 2 * k), __ldg(p + 2 * k + 1));
   }
   if (relu_in) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) r[k] = fmaxf(r[k], 0.f);
+    for (int k = 0; k < V; ++k) r[k] = fmaxf(r[k], 0.f);
   }
   if (res) {
-    const float4 y = __ldg(reinterpret_cast<const float4*>(res) + i4);
-    float s[4] = {y.x, y.y, y.z, y.w};
+    float sres[V];
+    ActVec<T>::load(res + e, sres);
     if (rab) {
       const float* p = rab + static_cast<size_t>(n) * rab_nstride + 2 * c;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) s[k] = fmaf(s[k], __ldg(p + 2 * k), __ldg(p + 2 * k + 1));
+      for (int k = 0; k < V; ++k) sres[k] = fmaf(sres[k], __ldg(p + 2 * k), __ldg(p + 2 * k + 1));
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) r[k] += s[k];
+    for (int k = 0; k < V; ++k) r[k] += sres[k];
   }
   if (relu_out) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) r[k] = fmaxf(r[k], 0.f);
+    for (int k = 0; k < V; ++k) r[k] = fmaxf(r[k], 0.f);
   }
-  reinterpret_cast<float4*>(out)[i4] = make_float4(r[0], r[1], r[2], r[3]);
+  ActVec<T>::store(out + e, r);
 }
 
 }  // namespace cb

@@ -89,6 +89,7 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const __grid_constant__ GemmParams p) {
   using S = GemmSmem<BN>;
   static_assert(BN % (8 * CL) == 0, "weight slice per CTA must be whole 8-row swizzle groups");
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms.  The dynamic smem window starts at
   // the same offset in every CTA of the cluster, so the aligned addresses agree too (multicast
@@ -123,6 +124,7 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  pdl_wait();                                    // A, bias and the GRU state come from earlier kernels
   tc_fence_before();
   if constexpr (CL > 1) cluster_sync(); else __syncthreads();
   tc_fence_after();

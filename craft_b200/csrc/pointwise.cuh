@@ -26,6 +26,9 @@ __global__ void __launch_bounds__(256) pack_tokens_kernel(const float* __restric
                                                           int mode, __nv_bfloat16* __restrict__ out_b,
                                                           int ldb, int colb, float* __restrict__ out_f,
                                                           int ldf, int colf) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   __shared__ float tile[C][33];
   const int tiles_per_row = (g.Wp + 31) / 32;
   const int y = blockIdx.x / tiles_per_row;
@@ -74,6 +77,9 @@ __global__ void __launch_bounds__(256) pack_tokens_kernel(const float* __restric
 template <typename T>
 __global__ void __launch_bounds__(256) unpack_tokens_kernel(const T* __restrict__ src, int ld, int col,
                                                             int C, Grid2 g, float* __restrict__ dst) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   __shared__ float tile[32][33];
   const int tiles_per_row = (g.W + 31) / 32;
   const int y = blockIdx.x / tiles_per_row;
@@ -118,6 +124,9 @@ struct LookupParams {
 };
 
 __global__ void __launch_bounds__(256) corr_lookup_kernel(LookupParams p, Grid2 g) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   constexpr int R = 4, D = 2 * R + 1, WN = D + 1;   // 9 taps, 10 cells
   __shared__ float win[8][WN * WN + 4];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -185,6 +194,9 @@ struct Lookup0Params {
 };
 
 __global__ void __launch_bounds__(256) corr_lookup0_kernel(Lookup0Params p, Grid2 g) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   constexpr int R = 4, D = 2 * R + 1, WN = D + 1, C = 256, NC = WN * WN;
   __shared__ float win[8][NC + 4];
   __shared__ float smodes[8][NC][4];
@@ -310,6 +322,9 @@ template <typename TM>
 __global__ void __launch_bounds__(256) upsample_flow_kernel(const TM* __restrict__ mask, int ldm,
                                                             const float* __restrict__ flow, Grid2 g,
                                                             float* __restrict__ out /*[2,8H,8W]*/) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   const int sub = threadIdx.x & 63;
   const int tok = blockIdx.x * 4 + (threadIdx.x >> 6);   // index over real tokens (y*W + x)
   if (tok >= g.H * g.W) return;
@@ -353,6 +368,9 @@ __global__ void __launch_bounds__(128) convf1_kernel(const float* __restrict__ f
                                                      const float* __restrict__ wt,
                                                      const float* __restrict__ bias, Grid2 g,
                                                      __nv_bfloat16* __restrict__ out, int ldo, int colo) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   constexpr int TX = 8;     // tokens per thread; block covers 16 tokens x 64 couts (gridDim.y = 2)
   __shared__ float in[2][7][16 + 6];
   __shared__ float ws[98 * 64];
@@ -398,6 +416,9 @@ __global__ void __launch_bounds__(128) convf1_kernel(const float* __restrict__ f
 // -------------------------------------------------------------------------------------------
 __global__ void flow_update_kernel(float* __restrict__ coords1, float* __restrict__ flow,
                                    const float* __restrict__ delta, int ldd, Grid2 g) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= g.Mp) return;
   const int y = p / g.Wp, x = p - y * g.Wp;
@@ -416,6 +437,9 @@ __global__ void flow_update_kernel(float* __restrict__ coords1, float* __restric
 // init_coords: coords1 = grid (+ flow_init NCHW [2,H,W]); reference core/network.py:142-149,221-222.
 __global__ void init_coords_kernel(float* __restrict__ coords1, const float* __restrict__ flow_init,
                                    Grid2 g) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= g.Mp) return;
   const int y = p / g.Wp, x = p - y * g.Wp;
@@ -448,6 +472,9 @@ __global__ void __launch_bounds__(256) modes_finalize_kernel(
     const __nv_bfloat16* __restrict__ xb, int ldx, int colx, const float* __restrict__ xf, int ldxf,
     int colxf, Grid2 g, __nv_bfloat16* __restrict__ out_b, int ldb, int colb,
     float* __restrict__ out_f, int ldf, int colf, int pv_G, int pv_nkt) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   // pv_G > 0: O was written by attn_pv's persistent schedule with pv_G CTAs and pv_nkt key tiles per
   // unit; a (query tile, mode) unit then owns as many valid slots as CTAs shared it (1 or 2, rarely
   // more) and the other slots hold garbage -- recompute that count instead of reading them.

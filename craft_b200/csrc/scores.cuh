@@ -59,7 +59,11 @@ template <int MODE>
 __global__ void __launch_bounds__(kScThreads, 1)
 scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ ScoreParams p) {
-  if (p.run_flag != nullptr && *p.run_flag == 0) return;   // clamp re-pass not needed (uniform)
+  pdl_launch_dependents();
+  if (p.run_flag != nullptr) {
+    pdl_wait();                                             // the flag is written by the preceding gate kernel
+    if (*p.run_flag == 0) return;                           // clamp re-pass not needed (uniform)
+  }
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -99,11 +103,12 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     }
     fence_mbar_init();
   }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  pdl_wait();                                    // everything below reads tensors of earlier kernels
   if (p.pos_table) {
     const int n = (2 * p.R + 1) * (2 * p.R + 1);
     for (int i = threadIdx.x; i < n; i += blockDim.x) s_table[i] = p.pos_table[i] * p.w_pos;
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -400,6 +405,9 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 //   lse2[m][q] = log2( sum_k exp(s_k) ) = (mx + ln(sum)) * log2(e)
 __global__ void lse_merge_kernel(const float2* __restrict__ part, int ksplit, int M, int Mp,
                                  float* __restrict__ lse2) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * Mp) return;
   float mx = -INFINITY;
@@ -416,6 +424,9 @@ __global__ void lse_merge_kernel(const float2* __restrict__ part, int ksplit, in
 // F.layer_norm semantics, core/corr.py:202) and the clamp gate: clip = (max > attn_clip) ? attn_clip : +inf.
 __global__ void corr_stats_finalize_kernel(const double* __restrict__ sums, double n,
                                            float* __restrict__ mean_rstd) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   const double mean = sums[0] / n;
   double var = sums[1] / n - mean * mean;
   if (var < 0) var = 0;
@@ -424,6 +435,9 @@ __global__ void corr_stats_finalize_kernel(const double* __restrict__ sums, doub
 }
 __global__ void clip_gate_kernel(const float* __restrict__ stat_max, float attn_clip,
                                  float* __restrict__ clip, int* __restrict__ flag) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   const bool hit = stat_max[0] > attn_clip;
   clip[0] = hit ? attn_clip : INFINITY;
   flag[0] = hit ? 1 : 0;

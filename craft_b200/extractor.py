@@ -57,17 +57,22 @@ class _Fused:
     channels-last tensors (no NCHW<->NHWC conversion kernels); InstanceNorm / eval BatchNorm + ReLU +
     residual add run as craft_b200 kernels (csrc/encoder.cuh)."""
 
-    def __init__(self, kind):
+    def __init__(self, kind, half=False):
         from . import hotpath, ops
-        self.kind, self.ops = kind, ops
+        self.kind, self.ops, self.half = kind, ops, half
+        self.dtype = torch.float16 if half else torch.float32     # activation / conv operand type (stats stay fp32)
         self.cache = hotpath.PackedWeights()
 
     def conv(self, m, x, bias=False):
         """cuDNN convolution WITHOUT its bias: a conv bias in front of a normalisation is either a no-op
         (instance norm subtracts the per-channel mean) or folds into the norm's shift (batch norm), which
         saves one elementwise pass per convolution."""
-        w = self.cache.get(("w", id(m)), [m.weight], lambda: m.weight.detach().contiguous(memory_format=torch.channels_last))
-        return F.conv2d(x, w, m.bias if bias else None, m.stride, m.padding)
+        w = self.cache.get(("w", id(m)), [m.weight],
+                           lambda: m.weight.detach().to(self.dtype).contiguous(memory_format=torch.channels_last))
+        b = None
+        if bias:
+            b = self.cache.get(("b", id(m)), [m.bias], lambda: m.bias.detach().to(self.dtype))
+        return F.conv2d(x, w, b, m.stride, m.padding)
 
     def scale_shift(self, norm, y, conv):
         if self.kind == "instance":
@@ -128,15 +133,16 @@ class BasicEncoder(nn.Module):
             batch_dim = x[0].shape[0]
             x = torch.cat(x, dim=0)
         if self._can_fuse(x):
-            if getattr(self, "_fz", None) is None or self._fz.kind != self.norm_fn:
-                self._fz = _Fused(self.norm_fn)
+            half = bool(getattr(self, "fused_half", False))
+            if getattr(self, "_fz", None) is None or self._fz.kind != self.norm_fn or self._fz.half != half:
+                self._fz = _Fused(self.norm_fn, half)
             fz = self._fz
-            x = x.contiguous(memory_format=torch.channels_last)
+            x = x.to(fz.dtype).contiguous(memory_format=torch.channels_last)
             x = fz.norm_act(self.norm1, fz.conv(self.conv1, x), self.conv1, relu=True)
             for layer in (self.layer1, self.layer2, self.layer3):
                 for blk in layer:
                     x = blk.forward_fused(x, fz)
-            x = fz.conv(self.conv2, x, bias=True).contiguous()      # back to NCHW for the token packer
+            x = fz.conv(self.conv2, x, bias=True).float().contiguous()      # back to NCHW fp32 for the token packer
             if is_list:
                 x = torch.split(x, [batch_dim, batch_dim], dim=0)
             return x

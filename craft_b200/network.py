@@ -109,6 +109,10 @@ class CRAFT(nn.Module):
         # fnet / cnet are outside the hot path; TF32 convolutions there cost ~6e-3 max abs error on
         # features of magnitude 20 and are 2.5x faster than strict fp32 (profiles/README.md).
         self.encoder_tf32 = True
+        # "fp16": encoder activations and conv operands in half precision (fp32 accumulation and fp32 norm
+        # statistics) -- an 11-bit mantissa, i.e. finer than TF32's 10 bits, at half the HBM traffic.
+        # The reference's own evaluation default is fp16 autocast (evaluate.py:1455-1456).
+        self.encoder_half = os.environ.get("CRAFT_B200_ENCODER", "fp16") == "fp16"
         # test_mode=1 returns only the LAST iteration's upsampled flow (core/network.py:262-263), yet the
         # reference computes the mask head and the convex upsampling in every iteration and drops them.
         # Eliding that dead work leaves every returned value bit-identical.
@@ -144,6 +148,7 @@ class CRAFT(nn.Module):
         image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
         image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
         amp = bool(getattr(self.args, "mixed_precision", False))
+        self.fnet.fused_half = self.cnet.fused_half = bool(self.encoder_half)
         # fnet (two frames) and cnet (frame 1) are independent: run cnet on a side stream so their
         # many small, latency-bound kernels overlap (fork/join is captured into the CUDA graph too).
         main = torch.cuda.current_stream()
@@ -223,7 +228,7 @@ class CRAFT(nn.Module):
 
     def _forward_graphed(self, image1, image2, iters, flow_init, test_mode):
         key = (image1.device.index, tuple(image1.shape), int(iters), int(test_mode), flow_init is not None,
-               self.materialize_level0, self.encoder_tf32, self.elide_dead_upsample)
+               self.materialize_level0, self.encoder_tf32, self.encoder_half, self.elide_dead_upsample)
         sig = self._weights_signature()
         ent = self._graphs.get(key)
         if ent is None or ent["sig"] != sig:

@@ -313,26 +313,35 @@ def upsample_flow(mask, flow, grid, out=None):
 
 
 # ------------------------------------------------------------------------------------------------
-# encoder glue (channels-last f32 tensors)
+# encoder glue (channels-last f32 or f16 tensors)
 # ------------------------------------------------------------------------------------------------
+def _act_dtype(t, name):
+    if t.dtype not in (torch.float32, torch.float16):
+        raise TypeError("%s: expected float32 or float16, got %s" % (name, t.dtype))
+    _chk(t, t.dtype, name)
+    return 1 if t.dtype == torch.float16 else 0
+
+
 def instnorm_stats(x_nhwc, eps=1e-5):
-    """x: [N,H,W,C] contiguous f32 -> ab [N,C,2] = (rstd, -mean*rstd)."""
-    _chk(x_nhwc, torch.float32, "x")
+    """x: [N,H,W,C] contiguous f32/f16 -> ab [N,C,2] f32 = (rstd, -mean*rstd).  Deterministic (no atomics)."""
+    half = _act_dtype(x_nhwc, "x")
     N, H, W, Cc = x_nhwc.shape
-    sums = torch.empty((N, Cc, 2), dtype=torch.float32, device=x_nhwc.device)
+    part = torch.empty((1024 * N * Cc * 2,), dtype=torch.float32, device=x_nhwc.device)   # per-block partial sums
     ab = torch.empty((N, Cc, 2), dtype=torch.float32, device=x_nhwc.device)
-    _lib.call("craft_nhwc_instnorm_stats", _ptr(x_nhwc), N, H * W, Cc, float(eps), _ptr(sums), _ptr(ab), _stream())
+    _lib.call("craft_nhwc_instnorm_stats", _ptr(x_nhwc), half, N, H * W, Cc, float(eps), _ptr(part), part.numel(),
+              _ptr(ab), _stream())
     return ab
 
 
 def nhwc_affine(v, ab=None, res=None, rab=None, relu_in=False, relu_out=False, out=None):
-    """out = relu_out([ra*res+rb] + relu_in(a*v+b)); v/res/out [N,H,W,C] f32; ab/rab [N or 1, C, 2]."""
-    _chk(v, torch.float32, "v")
-    _chk(res, torch.float32, "res")
+    """out = relu_out([ra*res+rb] + relu_in(a*v+b)); v/res/out [N,H,W,C] f32 or f16; ab/rab f32 [N or 1, C, 2]."""
+    half = _act_dtype(v, "v")
+    _chk(res, v.dtype, "res")
     N, H, W, Cc = v.shape
     if out is None:
         out = torch.empty_like(v)
+    _chk(out, v.dtype, "out")
     st = lambda t: 0 if (t is None or t.shape[0] == 1) else 2 * Cc
-    _lib.call("craft_nhwc_affine", _ptr(v), _ptr(ab), st(ab), _ptr(res), _ptr(rab), st(rab), int(relu_in),
+    _lib.call("craft_nhwc_affine", _ptr(v), half, _ptr(ab), st(ab), _ptr(res), _ptr(rab), st(rab), int(relu_in),
               int(relu_out), N, H * W, Cc, _ptr(out), _stream())
     return out

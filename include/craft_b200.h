@@ -162,15 +162,18 @@ int craft_upsample_flow(const void* mask, int mask_is_bf16, int ldm, const float
                         float* out_nchw, void* stream);
 
 /* ---- encoder glue (core/extractor.py; first row outside the named hot path) ------------------- */
-/* InstanceNorm2d statistics of a channels-last f32 tensor [N,HW,C] -> ab[N,C,2] = (rstd, -mean*rstd)
- * (eps, biased variance, no affine: extractor.py:136-137).  sums: scratch [N,C,2].                 */
-int craft_nhwc_instnorm_stats(const float* x, int N, int HW, int C, float eps, float* sums, float* ab,
-                              void* stream);
+/* InstanceNorm2d statistics of a channels-last tensor [N,HW,C] (f32, or f16 when is_half) ->
+ * ab[N,C,2] = (rstd, -mean*rstd) (eps, biased variance, no affine: extractor.py:136-137).
+ * part: f32 scratch for per-block partial sums (part_capacity floats, >= 1024*N*C*2 is always
+ * enough); the partials are reduced in a fixed order, so the result is run-to-run deterministic. */
+int craft_nhwc_instnorm_stats(const void* x, int is_half, int N, int HW, int C, float eps, float* part,
+                              long long part_capacity, float* ab, void* stream);
 /* out = relu_out( [ra*res+rb] + relu_in(a*v+b) ): norm + ReLU + residual of ResidualBlock.forward
- * (extractor.py:55-64).  ab / rab: [N or 1][C][2]; *_nstride = 2*C per image or 0 when shared.     */
-int craft_nhwc_affine(const float* v, const float* ab, int ab_nstride, const float* res, const float* rab,
-                      int rab_nstride, int relu_in, int relu_out, int N, int HW, int C, float* out,
-                      void* stream);
+ * (extractor.py:55-64).  v/res/out: f32 or f16 (is_half); ab / rab: f32 [N or 1][C][2];
+ * *_nstride = 2*C per image or 0 when shared.                                                       */
+int craft_nhwc_affine(const void* v, int is_half, const float* ab, int ab_nstride, const void* res,
+                      const float* rab, int rab_nstride, int relu_in, int relu_out, int N, int HW, int C,
+                      void* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -335,6 +335,16 @@ def test_encoder_norm_kernels(Cc):
     torch.cuda.synchronize()
     a, b = sab[0, :, 0].view(1, Cc, 1, 1), sab[0, :, 1].view(1, Cc, 1, 1)
     assert torch.allclose(out2, (a * x + b) + (a * r + b), atol=1e-5, rtol=1e-5)
+    # statistics are reduced in a fixed order: bit-identical run to run
+    assert torch.equal(ab, ops.instnorm_stats(x.permute(0, 2, 3, 1)))
+    # fp16 activations (fp32 statistics / arithmetic); Cc must be a multiple of 8
+    xh, rh = x.half(), r.half()
+    abh = ops.instnorm_stats(xh.permute(0, 2, 3, 1))
+    outh = torch.empty_like(xh)
+    ops.nhwc_affine(xh.permute(0, 2, 3, 1), abh, rh.permute(0, 2, 3, 1), None, True, True, out=outh.permute(0, 2, 3, 1))
+    torch.cuda.synchronize()
+    refh = torch.relu(rh.float() + torch.relu(F.instance_norm(xh.float(), eps=1e-5)))
+    assert outh.dtype == torch.float16 and torch.allclose(outh.float(), refh, atol=4e-3, rtol=2e-3), (outh.float() - refh).abs().max()
 
 
 @pytest.mark.parametrize("kind", ["instance", "batch"])
@@ -353,8 +363,15 @@ def test_fused_encoder_matches_module_path(kind):
         ref = enc(x)
         enc.use_fused = True
         got = enc(x)
+        enc.fused_half = True
+        got_h = enc(x)
+        enc.fused_half = False
     torch.cuda.synchronize()
     assert torch.allclose(got, ref, atol=2e-3, rtol=1e-3), (got - ref).abs().max()
+    # half-precision activations: features are O(1..20); bound the error relative to their scale
+    assert got_h.dtype == torch.float32
+    assert (got_h - ref).abs().max() <= 2e-2 * max(1.0, ref.abs().max().item()), (got_h - ref).abs().max()
+    assert (got_h - ref).abs().mean() <= 4e-3 * max(1.0, ref.abs().mean().item()), (got_h - ref).abs().mean()
 
 
 @pytest.mark.parametrize("H,W,M,d,clipv", [(16, 24, 4, 64, float("inf")), (17, 22, 4, 64, 2.0), (16, 16, 1, 256, float("inf"))])
