@@ -489,6 +489,7 @@ int craft_modes_finalize(const float* O, int nsum, int M, int F, const float* w_
     if (pv_bk != 64 && pv_bk != 128) return fail("modes_finalize: pv_bk must be 0, 64 or 128");
     pv_nkt = ((H + 7) / 8) * ((W + pv_bk / 8 - 1) / (pv_bk / 8));
     pv_G = pv_grid((g.Mp + 127) / 128, M, pv_nkt);
+    if (static_cast<long long>((g.Mp + 127) / 128) * M * pv_nkt * pv_G >= (1ll << 31)) return fail("modes_finalize: schedule too large");
   }
   if (nsum < 1 || nsum > 4) return fail("modes_finalize: nsum must be in [1,4]");
   if (!x_bf16 && !x_f32) return fail("modes_finalize: need the skip input");
@@ -586,7 +587,7 @@ int craft_nhwc_instnorm_stats(const void* x, int is_half, int N, int HW, int C, 
   if (is_half) launch_k(cb::nhwc_stats_kernel<__half>, dim3(chunks, N), dim3(256), 0, st, static_cast<const __half*>(x), HW, C, rows, part);
   else launch_k(cb::nhwc_stats_kernel<float>, dim3(chunks, N), dim3(256), 0, st, static_cast<const float*>(x), HW, C, rows, part);
   if (check_launch("nhwc_stats")) return -1;
-  launch_k(cb::instnorm_finalize_kernel, dim3((N * C + 255) / 256), dim3(256), 0, st, part, chunks, N * C, 1.0f / static_cast<float>(HW), eps, ab);
+  launch_k(cb::instnorm_finalize_kernel, dim3((N * C + 7) / 8), dim3(256), 0, st, part, chunks, N * C, 1.0f / static_cast<float>(HW), eps, ab);
   return check_launch("instnorm_finalize");
 }
 

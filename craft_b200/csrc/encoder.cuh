@@ -91,23 +91,30 @@ __global__ void __launch_bounds__(256) nhwc_stats_kernel(const T* __restrict__ x
   }
 }
 
-// part [chunks][N*C][2] -> ab [N,C,2] = (rstd, -mean*rstd); chunks summed in index order
-__global__ void instnorm_finalize_kernel(const float* __restrict__ part, int chunks, int NC, float inv_hw, float eps,
-                                         float* __restrict__ ab) {
+// part [chunks][N*C][2] -> ab [N,C,2] = (rstd, -mean*rstd).  One warp per (image, channel): lane l adds
+// chunks l, l+32, ... in index order and the lanes are combined by a fixed xor tree, so the result
+// does not depend on scheduling.
+__global__ void __launch_bounds__(256) instnorm_finalize_kernel(const float* __restrict__ part, int chunks, int NC,
+                                                                float inv_hw, float eps, float* __restrict__ ab) {
   pdl_launch_dependents();
   pdl_wait();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (i >= NC) return;
   float s = 0.f, q = 0.f;
-  for (int c = 0; c < chunks; ++c) {
-    const float2 v = *reinterpret_cast<const float2*>(part + (static_cast<size_t>(c) * NC + i) * 2);
+  for (int c = lane; c < chunks; c += 32) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(part + (static_cast<size_t>(c) * NC + i) * 2));
     s += v.x; q += v.y;
   }
-  const float mean = s * inv_hw;
-  const float var = fmaxf(q * inv_hw - mean * mean, 0.f);
-  const float rstd = rsqrtf(var + eps);
-  ab[2 * i] = rstd;
-  ab[2 * i + 1] = -mean * rstd;
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if (lane == 0) {
+    const float mean = s * inv_hw;
+    const float var = fmaxf(q * inv_hw - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    ab[2 * i] = rstd;
+    ab[2 * i + 1] = -mean * rstd;
+  }
 }
 
 // out = relu_out( res_term + relu_in(a*v + b) ),  res_term = 0 | res | ra*res + rb

@@ -494,14 +494,16 @@ __global__ void __launch_bounds__(256) modes_finalize_kernel(
     if (m < M) {
       int nvalid = nsum;
       if (pv_G > 0) {
-        const long long NT = static_cast<long long>((g.Mp + 127) >> 7) * M * pv_nkt;
-        auto cta_of = [&](long long x) {
-          long long c = x * pv_G / NT;
-          while (c + 1 < pv_G && NT * (c + 1) / pv_G <= x) ++c;
-          while (c > 0 && NT * c / pv_G > x) --c;
+        // the host guarantees NT * pv_G < 2^31 (craft_modes_finalize), so 32-bit arithmetic is exact
+        const unsigned NT = static_cast<unsigned>((g.Mp + 127) >> 7) * M * pv_nkt;
+        const unsigned G = static_cast<unsigned>(pv_G);
+        auto cta_of = [&](unsigned x) {
+          unsigned c = x * G / NT;
+          while (c + 1 < G && NT * (c + 1) / G <= x) ++c;
+          while (c > 0 && NT * c / G > x) --c;
           return static_cast<int>(c);
         };
-        const long long lin0 = (static_cast<long long>(p >> 7) * M + m) * pv_nkt;
+        const unsigned lin0 = (static_cast<unsigned>(p >> 7) * M + m) * pv_nkt;
         nvalid = cta_of(lin0 + pv_nkt - 1) - cta_of(lin0) + 1;
       }
       float s = 0.f;

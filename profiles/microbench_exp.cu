@@ -28,6 +28,32 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(bits);
 }
 
+// packed (f32x2) flavour of the same polynomial: two elements per FMA-pipe instruction
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  return (static_cast<uint64_t>(__float_as_uint(b)) << 32) | __float_as_uint(a);
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ void ex2_poly2(float x0, float x1, float& y0, float& y1) {
+  x0 = fmaxf(x0, -125.0f); x1 = fmaxf(x1, -125.0f);
+  const uint64_t magic = pk2(12582912.0f, 12582912.0f), nmagic = pk2(-12582912.0f, -12582912.0f);
+  const uint64_t x = pk2(x0, x1);
+  const uint64_t t = add2(x, magic);
+  const uint64_t n = add2(t, nmagic);
+  const uint64_t f = fma2(n, pk2(-1.0f, -1.0f), x);
+  uint64_t p = fma2(f, pk2(0.05550410866f, 0.05550410866f), pk2(0.2402265070f, 0.2402265070f));
+  p = fma2(p, f, pk2(0.6931471806f, 0.6931471806f));
+  p = fma2(p, f, pk2(1.0f, 1.0f));
+  const uint32_t plo = static_cast<uint32_t>(p), phi = static_cast<uint32_t>(p >> 32);
+  const uint32_t tlo = static_cast<uint32_t>(t), thi = static_cast<uint32_t>(t >> 32);
+  y0 = __uint_as_float(plo + (tlo << 23));
+  y1 = __uint_as_float(phi + (thi << 23));
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(512, 1) k(float* out, const float* in, int iters, float sc, float lse) {
   float acc[32];
@@ -64,6 +90,27 @@ __global__ void __launch_bounds__(512, 1) k(float* out, const float* in, int ite
     } else if (MODE == 5) {   // bf16x2 MUFU
 #pragma unroll
       for (int e = 0; e < 16; ++e) pk[e] ^= ex2b2(pack_b2(x[2 * e], x[2 * e + 1]));
+    } else if (MODE == 8) {   // packed polynomial only
+#pragma unroll
+      for (int e = 0; e < 16; ++e) { float a, b; ex2_poly2(x[2 * e], x[2 * e + 1], a, b); pk[e] ^= pack_b2(a, b); }
+    } else if (MODE == 9) {   // 3/4 MUFU, 1/4 packed polynomial
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        if ((e & 3) == 3) { float a, b; ex2_poly2(x[2 * e], x[2 * e + 1], a, b); pk[e] ^= pack_b2(a, b); }
+        else pk[e] ^= pack_b2(ex2f(x[2 * e]), ex2f(x[2 * e + 1]));
+      }
+    } else if (MODE == 10) {  // 5/8 MUFU, 3/8 packed polynomial
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        if ((e & 7) < 3) { float a, b; ex2_poly2(x[2 * e], x[2 * e + 1], a, b); pk[e] ^= pack_b2(a, b); }
+        else pk[e] ^= pack_b2(ex2f(x[2 * e]), ex2f(x[2 * e + 1]));
+      }
+    } else if (MODE == 11) {  // 1/2 MUFU, 1/2 packed polynomial
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        if (e & 1) { float a, b; ex2_poly2(x[2 * e], x[2 * e + 1], a, b); pk[e] ^= pack_b2(a, b); }
+        else pk[e] ^= pack_b2(ex2f(x[2 * e]), ex2f(x[2 * e + 1]));
+      }
     } else if (MODE == 7) {   // 5/8 MUFU f32, 3/8 polynomial
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
@@ -128,6 +175,10 @@ int main() {
   run<3>("3/4 MUFU + 1/4 poly", out, in);
   run<7>("5/8 MUFU + 3/8 poly", out, in);
   run<4>("1/2 MUFU + 1/2 poly", out, in);
+  run<8>("packed poly only", out, in);
+  run<9>("3/4 MUFU + 1/4 packed poly", out, in);
+  run<10>("5/8 MUFU + 3/8 packed poly", out, in);
+  run<11>("1/2 MUFU + 1/2 packed poly", out, in);
   acc_check<<<1, 256>>>(out);
   float h[512];
   cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
