@@ -48,7 +48,7 @@ struct PvParams {
   int R;
   const float* clip;       // device scalar (+inf or attn_clip)
   const float* lse2;       // [M][Mp] log2-domain log-sum-exp
-  float* out;              // [nslots][M][Mp][F] f32 partial sums
+  float* out;              // [nslots][M][F/8][Mp][8] f32 partial sums (8-column chunks, see the write-back)
   int nkt, nbx;            // key tiles (blocks) in total / per block-row
   long long* trace;        // CRAFT_PV_TRACE: clock64 timeline of CTA (0,0,0): [role 4][tile 64][slot 8]
 };
@@ -400,8 +400,11 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (trole < 4) PV_TRACE(trole, g_last - (g_last & 1) + (trole - 1), 6);
       tc_fence_after();
       __syncwarp();
+      // out[slot][mode][F/8][Mp][8]: a thread (= query row) stores 32-byte pieces, consecutive lanes
+      // hit consecutive pieces, so each store instruction covers 1 KB of whole sectors instead of
+      // 32 scattered half sectors (row-major [Mp][F] would put the lanes 4*F bytes apart)
       const size_t slot_stride = static_cast<size_t>(p.M) * p.g.Mp * F;
-      float* dst = p.out + (static_cast<size_t>(slot) * p.M + sgm.mode) * p.g.Mp * F + static_cast<size_t>(q) * F;
+      float* dst = p.out + (static_cast<size_t>(slot) * p.M + sgm.mode) * p.g.Mp * F + static_cast<size_t>(q) * 8;
       constexpr int kQuarter = F / 4;
       const int c_begin = (sg * 2 + ch) * kQuarter;
 #pragma unroll
@@ -410,11 +413,14 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tmem_ld32(tlane + kTmemO + c_begin + c, raw);
         tmem_ld_wait();
         if (q < p.g.Mp) {
-          float4* d4 = reinterpret_cast<float4*>(dst + c_begin + c);
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            d4[e] = make_float4(__uint_as_float(raw[4 * e]), __uint_as_float(raw[4 * e + 1]),
-                                __uint_as_float(raw[4 * e + 2]), __uint_as_float(raw[4 * e + 3]));
+          for (int e = 0; e < 4; ++e) {
+            float4* d4 = reinterpret_cast<float4*>(dst + static_cast<size_t>((c_begin + c) / 8 + e) * p.g.Mp * 8);
+            d4[0] = make_float4(__uint_as_float(raw[8 * e]), __uint_as_float(raw[8 * e + 1]),
+                                __uint_as_float(raw[8 * e + 2]), __uint_as_float(raw[8 * e + 3]));
+            d4[1] = make_float4(__uint_as_float(raw[8 * e + 4]), __uint_as_float(raw[8 * e + 5]),
+                                __uint_as_float(raw[8 * e + 6]), __uint_as_float(raw[8 * e + 7]));
+          }
         }
       }
       tc_fence_before();
@@ -422,9 +428,13 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (trole < 4) PV_TRACE(trole, g_last - (g_last & 1) + (trole - 1), 7);
       if (p.zero_fill && last_part && q < p.g.Mp) {
         for (int sl = slot + 1; sl < p.nslots; ++sl) {
-          float4* z4 = reinterpret_cast<float4*>(dst + static_cast<size_t>(sl - slot) * slot_stride + c_begin);
 #pragma unroll
-          for (int e = 0; e < kQuarter / 4; ++e) z4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int e = 0; e < kQuarter / 8; ++e) {
+            float4* z4 = reinterpret_cast<float4*>(dst + static_cast<size_t>(sl - slot) * slot_stride +
+                                                   static_cast<size_t>(c_begin / 8 + e) * p.g.Mp * 8);
+            z4[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            z4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
       }
       lin += sgm.nt;

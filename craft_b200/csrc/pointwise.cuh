@@ -462,7 +462,9 @@ __global__ void init_coords_kernel(float* __restrict__ coords1, const float* __r
 // LearnedSoftAggregate (num_feat = F) core/setrans.py:289-300:
 //     s_m = <w, O_m> + b ; p = softmax_m(s) ; agg = sum_m p_m O_m ; y = LN(coeff * x + agg)
 // GMA variant (core/gma.py:140): M = 1, y = x + gamma * O  (no LN) -- `gma` != 0.
-// O: [M][Mp][F] f32.  x: token-major bf16 (ldx, colx).  One warp per token.
+// O: [slot][M][F/8][Mp][8] f32 (8-column chunks, token-major inside a chunk: the layout attn_pv's
+// one-row-per-thread write-back can store with full 32-byte sectors).  x: token-major bf16 (ldx, colx).
+// One warp per token; lane l owns columns 8*(l/2 + 16j) + 4*(l%2) + {0..3}, j < F/128.
 // -------------------------------------------------------------------------------------------
 template <int F>
 __global__ void __launch_bounds__(256) modes_finalize_kernel(
@@ -508,16 +510,21 @@ __global__ void __launch_bounds__(256) modes_finalize_kernel(
       }
       float s = 0.f;
 #pragma unroll
-      for (int e = 0; e < PER; ++e) {
-        const int f = lane + 32 * e;
-        // up to 4 partial slots, loaded as independent requests (nsum <= 4, checked by the host)
-        const float* src = O + m * mode_stride + static_cast<long long>(p) * F + f;
-        float part[4];
+      for (int j = 0; j < PER / 4; ++j) {
+        // up to 4 partial slots, loaded as independent 16-byte requests (nsum <= 4, checked by the host)
+        const int chunk = (lane >> 1) + 16 * j;
+        const float* src = O + m * mode_stride + (static_cast<long long>(chunk) * g.Mp + p) * 8 + 4 * (lane & 1);
+        float4 part[4];
 #pragma unroll
-        for (int sp = 0; sp < 4; ++sp) part[sp] = (sp < nvalid) ? __ldg(src + sp * part_stride) : 0.f;
-        const float acc = (part[0] + part[1]) + (part[2] + part[3]);
-        o[m][e] = acc;
-        if (!gma) s += acc * __ldg(w_score + f);
+        for (int sp = 0; sp < 4; ++sp)
+          part[sp] = (sp < nvalid) ? __ldg(reinterpret_cast<const float4*>(src + sp * part_stride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float acc[4] = {(part[0].x + part[1].x) + (part[2].x + part[3].x), (part[0].y + part[1].y) + (part[2].y + part[3].y),
+                              (part[0].z + part[1].z) + (part[2].z + part[3].z), (part[0].w + part[1].w) + (part[2].w + part[3].w)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          o[m][4 * j + k] = acc[k];
+          if (!gma) s += acc[k] * __ldg(w_score + 8 * chunk + 4 * (lane & 1) + k);
+        }
       }
       sc[m] = gma ? 0.f : warp_sum(s) + b_score[0];
     }
@@ -534,7 +541,7 @@ __global__ void __launch_bounds__(256) modes_finalize_kernel(
   float s1 = 0.f;
 #pragma unroll
   for (int e = 0; e < PER; ++e) {
-    const int f = lane + 32 * e;
+    const int f = 8 * ((lane >> 1) + 16 * (e >> 2)) + 4 * (lane & 1) + (e & 3);
     float agg = 0.f;
 #pragma unroll
     for (int m = 0; m < 4; ++m) agg += sc[m] * o[m][e];
@@ -558,7 +565,7 @@ __global__ void __launch_bounds__(256) modes_finalize_kernel(
   }
 #pragma unroll
   for (int e = 0; e < PER; ++e) {
-    const int f = lane + 32 * e;
+    const int f = 8 * ((lane >> 1) + 16 * (e >> 2)) + 4 * (lane & 1) + (e & 3);
     if (out_b) out_b[static_cast<size_t>(p) * ldb + colb + f] = __float2bfloat16_rn(yv[e]);
     if (out_f) out_f[static_cast<size_t>(p) * ldf + colf + f] = yv[e];
   }

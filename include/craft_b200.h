@@ -120,7 +120,7 @@ typedef struct craft_pv_args {
   int R;
   const float* clip;
   const float* lse2;  /* [M][Mp]                                                               */
-  float* out;         /* f32 [ksplit][M][Mp][F]: partial sums, one slot per CTA sharing a unit   */
+  float* out;         /* f32 [ksplit][M][F/8][Mp][8]: partial sums, one slot per CTA sharing a unit */
   int ksplit;         /* slots available in out (>= craft_pv_auto_ksplit)                        */
   int zero_fill;      /* != 0: slots a (query tile, mode) unit does not use are written as zeros */
 } craft_pv_args;
@@ -128,7 +128,7 @@ typedef struct craft_pv_args {
 int craft_attn_pv(const craft_pv_args* a, void* stream);
 
 /* mode soft-pooling + input skip + LayerNorm (core/setrans.py:395-407, :289-300);
- * gma != 0: y = x + gamma*O (core/gma.py:140).  O: [nsum][M][Mp][F] partials are summed.      */
+ * gma != 0: y = x + gamma*O (core/gma.py:140).  O: [nsum][M][F/8][Mp][8] partials are summed.  */
 int craft_modes_finalize(const float* O, int nsum, int M, int F, const float* w_score,
                          const float* b_score, const float* coeff, int gma, const void* x_bf16,
                          int ldx, int colx, const float* x_f32, int ldxf, int colxf, int H, int W,

@@ -289,7 +289,9 @@ def test_attn_lse_pv_finalize(H, W, M, d, F_):
     ops.attn_pv(Q, K, Vt, grid, M=M, d=d, F=F_, w_pos=w_pos, pos_table=table, R=7, clip=clip, lse2=lse2,
                 out=out, ksplit=kp)
     torch.cuda.synchronize()
-    O = out.sum(0).reshape(M, grid.H, grid.Wp, F_)[:, :, :W].reshape(M, grid.U, F_)
+    # partial sums are stored as [slot][M][F/8][Mp][8]
+    O = out.reshape(kp, M, F_ // 8, grid.Mp, 8).permute(0, 1, 3, 2, 4).reshape(kp, M, grid.Mp, F_).sum(0)
+    O = O.reshape(M, grid.H, grid.Wp, F_)[:, :, :W].reshape(M, grid.U, F_)
     assert torch.allclose(O, O_ref, atol=2e-2, rtol=2e-2), (O - O_ref).abs().max()
     # finalize (setrans flavour) against the restatement fed with the kernel's own O
     if M > 1:
