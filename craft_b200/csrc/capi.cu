@@ -302,13 +302,32 @@ int craft_shift_gemm(const craft_gemm_args* a, void* stream) {
   return fail("gemm: unknown epilogue %d", a->epilogue);
 }
 
+// scores kernels run persistent CTAs over equal contiguous ranges of the (query tile, key tile) list
+// (scores.cuh); the number of CTAs that can share one query tile is the number of partial slots.
+static int sc_grid(int nqt, int nkt) {
+  long long G = sm_count();
+  if (G > static_cast<long long>(nqt) * nkt) G = static_cast<long long>(nqt) * nkt;
+  return static_cast<int>(G < 1 ? 1 : G);
+}
+static int sc_slots(int nqt, int nkt) {
+  const long long NT = static_cast<long long>(nqt) * nkt, G = sc_grid(nqt, nkt);
+  auto cta_of = [&](long long x) {
+    long long c = x * G / NT;
+    while (c + 1 < G && NT * (c + 1) / G <= x) ++c;
+    while (c > 0 && NT * c / G > x) --c;
+    return c;
+  };
+  long long worst = 1;
+  for (long long u = 0; u < nqt; ++u) {
+    const long long parts = cta_of(u * nkt + nkt - 1) - cta_of(u * nkt) + 1;
+    if (parts > worst) worst = parts;
+  }
+  return static_cast<int>(worst);
+}
+/* partial (max, sum) slots craft_attn_lse needs in lse_part */
 int craft_scores_auto_ksplit(int H, int W) {
   cb::Grid2 g = make_grid(H, W);
-  const int nqt = (g.Mp + 127) / 128;
-  const int nkt = ((H + 7) / 8) * ((W + 7) / 8);
-  int s = pick_split(nqt, 12);
-  if (s > nkt) s = nkt;
-  return s < 1 ? 1 : s;
+  return sc_slots((g.Mp + 127) / 128, ((H + 7) / 8) * ((W + 7) / 8));
 }
 int craft_pv_block_keys(int d, int F) {
   if (d == 32 && F == 128) return 128;
@@ -367,7 +386,10 @@ static int scores_common(const craft_scores_args* a, int mode, void* stream) {
   p.g = g; p.C = a->C; p.M = a->M; p.d = a->d; p.scale = a->scale; p.w_pos = a->w_pos;
   p.pos_table = a->pos_table; p.R = a->R; p.clip = a->clip; p.run_flag = a->run_flag;
   p.nkt_y = (a->H + 7) / 8; p.nkt_x = (a->W + 7) / 8;
-  p.ksplit = a->ksplit > 0 ? a->ksplit : craft_scores_auto_ksplit(a->H, a->W);
+  p.nqt = (g.Mp + 127) / 128;
+  const int need = sc_slots(p.nqt, p.nkt_y * p.nkt_x);
+  p.nslots = a->ksplit > 0 ? a->ksplit : need;
+  if (mode == cb::SC_LSE && p.nslots < need) return fail("attn_lse: lse_part has %d slots, the schedule needs %d", p.nslots, need);
   p.w_agg = a->w_agg; p.stat_sum = a->stat_sum; p.stat_max = a->stat_max;
   int h = a->H, w = a->W;
   for (int l = 0; l < 4; ++l) {
@@ -376,8 +398,8 @@ static int scores_common(const craft_scores_args* a, int mode, void* stream) {
   }
   p.lse_part = static_cast<float2*>(a->lse_part);
   const int atoms = a->C / 64;
-  const int smem = 1024 + atoms * 128 * 128 + cb::kScKStages * atoms * 64 * 128 + 2048;
-  dim3 grid((g.Mp + 127) / 128, p.ksplit);
+  const int smem = 1024 + atoms * 128 * 128 + cb::kScKStages * atoms * 64 * 128 + cb::kScTailBytes;
+  dim3 grid(sc_grid(p.nqt, p.nkt_y * p.nkt_x));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (mode == cb::SC_CORR) {
     if (!a->stat_sum || !a->stat_max || !a->lvl[1] || !a->lvl[2] || !a->lvl[3]) return fail("corr_build: missing outputs");
@@ -394,7 +416,7 @@ static int scores_common(const craft_scores_args* a, int mode, void* stream) {
     launch_k(kern, dim3(grid), dim3(cb::kScThreads), smem, st, tq, tk, p);
     if (check_launch("attn_lse")) return -1;
     const int n = a->M * g.Mp;
-    launch_k(cb::lse_merge_kernel, dim3((n + 255) / 256), dim3(256), 0, st, p.lse_part, p.ksplit, a->M, g.Mp, a->lse2);
+    launch_k(cb::lse_merge_kernel, dim3((n + 255) / 256), dim3(256), 0, st, p.lse_part, p.nslots, a->M, g.Mp, a->lse2);
     return check_launch("lse_merge");
   }
 }

@@ -483,6 +483,27 @@ __global__ void __launch_bounds__(256) modes_finalize_kernel(
   constexpr int PER = F / 32;
   const int lane = threadIdx.x & 31;
   const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
+  // valid slots per mode: the block's 8 tokens share one 128-query tile, so 4 threads work it out once
+  __shared__ int s_nvalid[4];
+  if (threadIdx.x < 4) {
+    const int m = threadIdx.x;
+    int nvalid = nsum;
+    if (pv_G > 0 && m < M) {
+      // the host guarantees NT * pv_G < 2^31 (craft_modes_finalize), so 32-bit arithmetic is exact
+      const unsigned NT = static_cast<unsigned>((g.Mp + 127) >> 7) * M * pv_nkt;
+      const unsigned G = static_cast<unsigned>(pv_G);
+      auto cta_of = [&](unsigned x) {
+        unsigned c = x * G / NT;
+        while (c + 1 < G && NT * (c + 1) / G <= x) ++c;
+        while (c > 0 && NT * c / G > x) --c;
+        return static_cast<int>(c);
+      };
+      const unsigned lin0 = (static_cast<unsigned>((blockIdx.x * 8) >> 7) * M + m) * pv_nkt;
+      nvalid = cta_of(lin0 + pv_nkt - 1) - cta_of(lin0) + 1;
+    }
+    s_nvalid[m] = nvalid;
+  }
+  __syncthreads();
   if (p >= g.Mp) return;
   const int y = p / g.Wp, x = p - y * g.Wp;
   if (x >= g.W) return;
@@ -494,20 +515,7 @@ __global__ void __launch_bounds__(256) modes_finalize_kernel(
 #pragma unroll
     for (int e = 0; e < PER; ++e) o[m][e] = 0.f;
     if (m < M) {
-      int nvalid = nsum;
-      if (pv_G > 0) {
-        // the host guarantees NT * pv_G < 2^31 (craft_modes_finalize), so 32-bit arithmetic is exact
-        const unsigned NT = static_cast<unsigned>((g.Mp + 127) >> 7) * M * pv_nkt;
-        const unsigned G = static_cast<unsigned>(pv_G);
-        auto cta_of = [&](unsigned x) {
-          unsigned c = x * G / NT;
-          while (c + 1 < G && NT * (c + 1) / G <= x) ++c;
-          while (c > 0 && NT * c / G > x) --c;
-          return static_cast<int>(c);
-        };
-        const unsigned lin0 = (static_cast<unsigned>(p >> 7) * M + m) * pv_nkt;
-        nvalid = cta_of(lin0 + pv_nkt - 1) - cta_of(lin0) + 1;
-      }
+      const int nvalid = s_nvalid[m];
       float s = 0.f;
 #pragma unroll
       for (int j = 0; j < PER / 4; ++j) {

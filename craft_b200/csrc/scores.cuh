@@ -4,25 +4,34 @@
 //            core/setrans.py:501-550 + LearnedSoftAggregate(1) core/setrans.py:289-300):
 //            clamp -> soft-aggregate the M modes -> + w_pos*bias -> accumulate the global
 //            layer-norm statistics (sum, sum^2) and the global raw max (clamp gate,
-//            core/setrans.py:520-529) -> 2x2/4x4/8x8 average pooling of each thread's private
-//            8x8 key block -> store pyramid levels 1..3 (level 0 optional).  The level-0 volume
+//            core/setrans.py:520-529) -> 2x2/4x4/8x8 average pooling of the 8x8 key block
+//            -> store pyramid levels 1..3 (level 0 optional).  The level-0 volume
 //            (U x U) therefore never has to reach HBM.
 //  SC_LSE   (CrossAttFeatTrans softmax, core/setrans.py:540-553): per (mode, query) running
 //            max / sum-exp over the key range -> partial log-sum-exp, merged by lse_merge_kernel.
 //            The P.V kernel (attn_pv.cuh) then recomputes P = exp(S - lse) tile by tile.
 //
 // Tile: 128 queries (TMEM lanes) x 64 keys (an 8x8 spatial block fetched by a 3-D TMA box) x M
-// modes (M*64 = 256 TMEM columns, double buffered).  grid = (query tiles, key splits).
-// Warps: 0 = TMA, 1 = MMA (+TMEM alloc), 2..5 = epilogue group 0, 6..9 = epilogue group 1
-// (groups alternate key tiles / TMEM buffers).
+// modes (M*64 = 256 TMEM columns, double buffered).
+//
+// Schedule: the (query tile, key tile) list is cut into gridDim.x equal contiguous ranges, one per
+// PERSISTENT CTA (one per SM): every SM gets the same number of tiles and pays the start-up once.
+// A range touches 1-2 query tiles ("segments"); in SC_LSE a query tile shared by several CTAs
+// leaves one partial (max, sum) per CTA in consecutive slots of lse_part, the CTA that finishes
+// the query tile fills the unused slots with the neutral element.
+//
+// Warps (576 threads): 0 = TMA, 1 = MMA issuer (+TMEM alloc), 2..17 = epilogue:
+// group eg = tile parity (TMEM buffer), half ch = key-block rows 0-3 / 4-7 (columns 0-31 / 32-63 of
+// every mode), TMEM lane quadrant = warp & 3.  Thread = one query x 32 keys x M modes per tile.
 #pragma once
 #include "common.cuh"
 #include "pointwise.cuh"
 
 namespace cb {
 
-constexpr int kScThreads = 320;
+constexpr int kScThreads = 64 + 512;   // 576 threads -> 112 registers each
 constexpr int kScKStages = 3;
+constexpr int kScTailBytes = 512 /*barriers*/ + 2560 /*bias table*/ + 2048 /*level-3 exchange*/ + 16384 /*lse merge*/;
 
 enum ScoreMode : int { SC_CORR = 0, SC_LSE = 1 };
 
@@ -38,7 +47,8 @@ struct ScoreParams {
   const float* clip;       // device scalar: +inf (no clamp) or attn_clip
   const int* run_flag;     // optional: whole kernel is a no-op when *run_flag == 0
   int nkt_y, nkt_x;        // key tiles (8x8 blocks) in y / x
-  int ksplit;              // gridDim.y
+  int nqt;                 // query tiles
+  int nslots;              // SC_LSE: partial slots in lse_part
   // SC_CORR
   float w_agg;             // LearnedSoftAggregate(1).feat2score.weight
   double* stat_sum;        // [2]: sum, sumsq   (atomics)
@@ -46,7 +56,7 @@ struct ScoreParams {
   float* lvl[4];           // pooled volumes [Mp][h_l*w_l]; lvl[0] optional
   int hl[4], wl[4];
   // SC_LSE
-  float2* lse_part;        // [ksplit][M][Mp] (max, sumexp) natural-exp domain
+  float2* lse_part;        // [nslots][M][Mp] (max, sumexp) natural-exp domain
 };
 
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
@@ -54,7 +64,7 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
-// smem: Q tile (C/64 atoms x 16 KB) + K stages (C/64 atoms x 8 KB each) + barriers + table
+// smem: Q tile (C/64 atoms x 16 KB) + K stages (C/64 atoms x 8 KB each) + tail
 template <int MODE>
 __global__ void __launch_bounds__(kScThreads, 1)
 scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -74,40 +84,66 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint8_t* sK = smem + q_bytes;
   uint8_t* tail = sK + kScKStages * k_bytes;
   uint64_t* q_full = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* k_full = q_full + 1;
+  uint64_t* q_free = q_full + 1;               // all MMAs of the segment retired: Q may be overwritten
+  uint64_t* k_full = q_free + 1;
   uint64_t* k_empty = k_full + kScKStages;
   uint64_t* acc_full = k_empty + kScKStages;   // [2]
-  uint64_t* acc_empty = acc_full + 2;          // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2] count 8 (warps of the group)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* s_table = reinterpret_cast<float*>(tmem_slot + 4);   // (2R+1)^2 floats
-  float* s_red = s_table + 232;                                // 8 warps x 4
+  // positional-bias table, zero padded so that a thread's 4 x 8 window needs no range checks:
+  // row iy+3 (iy in [-3, 2R+3]), column ix+7 (ix in [-7, 2R+7]); natural domain, times w_pos
+  float* s_table = reinterpret_cast<float*>(tail + 512);
+  float* s_l3 = reinterpret_cast<float*>(tail + 512 + 2560);             // [2 slots][2 eg][128 rows]
+  float2* s_merge = reinterpret_cast<float2*>(tail + 512 + 2560 + 2048);  // [4 sets][4 modes][128 rows]
+  const int TW = 2 * p.R + 1 + 14;
 
   const int warp = threadIdx.x >> 5;
-  const int q0 = blockIdx.x * 128;
   const int nkt = p.nkt_y * p.nkt_x;
-  const int kt_begin = static_cast<int>((static_cast<long long>(nkt) * blockIdx.y) / p.ksplit);
-  const int kt_end = static_cast<int>((static_cast<long long>(nkt) * (blockIdx.y + 1)) / p.ksplit);
-  const int ntiles = kt_end - kt_begin;
+  // this CTA's contiguous range of the (query tile, key tile) list
+  const long long NT = static_cast<long long>(p.nqt) * nkt;
+  const long long lin_begin = NT * blockIdx.x / gridDim.x;
+  const long long lin_end = NT * (blockIdx.x + 1) / gridDim.x;
+  auto cta_of = [&](long long x) {
+    long long c = x * gridDim.x / NT;
+    while (c + 1 < static_cast<long long>(gridDim.x) && NT * (c + 1) / gridDim.x <= x) ++c;
+    while (c > 0 && NT * c / gridDim.x > x) --c;
+    return static_cast<int>(c);
+  };
+  struct Seg { int qt, t0, nt; };
+  auto seg_at = [&](long long lin) {
+    Seg s;
+    s.qt = static_cast<int>(lin / nkt);
+    s.t0 = static_cast<int>(lin - static_cast<long long>(s.qt) * nkt);
+    const long long left = lin_end - lin;
+    s.nt = static_cast<int>(left < nkt - s.t0 ? left : nkt - s.t0);
+    return s;
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     mbar_init(q_full, 1);
+    mbar_init(q_free, 1);
     for (int s = 0; s < kScKStages; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 4);       // one arrival per epilogue warp
+      mbar_init(&acc_empty[b], 8);       // one arrival per epilogue warp of the group
     }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   pdl_wait();                                    // everything below reads tensors of earlier kernels
   if (p.pos_table) {
-    const int n = (2 * p.R + 1) * (2 * p.R + 1);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s_table[i] = p.pos_table[i] * p.w_pos;
+    const int TDp = 2 * p.R + 1;
+    const int n = (TDp + 6) * TW;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int iy = i / TW - 3, ix = i % TW - 7;
+      const bool in = (iy >= 0) && (iy < TDp) && (ix >= 0) && (ix < TDp);
+      s_table[i] = in ? p.pos_table[iy * TDp + ix] * p.w_pos : 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -117,270 +153,343 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
     if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, q_bytes);
-      for (int a = 0; a < atoms; ++a) tma_load_2d(sQ + a * 128 * 128, &tmQ, q_full, a * 64, q0);
-      int stage = 0;
+      int stage = 0, seg = 0;
       uint32_t phase = 0;
-      for (int i = 0; i < ntiles; ++i) {
-        const int kt = kt_begin + i;
-        const int by = kt / p.nkt_x, bx = kt - by * p.nkt_x;
-        mbar_wait(&k_empty[stage], phase ^ 1u);
-        mbar_arrive_expect_tx(&k_full[stage], k_bytes);
-        uint8_t* dst = sK + stage * k_bytes;
-        for (int a = 0; a < atoms; ++a)
-          tma_load_3d(dst + a * 64 * 128, &tmK, &k_full[stage], a * 64, bx * 8, by * 8);
-        if (++stage == kScKStages) { stage = 0; phase ^= 1u; }
+      for (long long lin = lin_begin; lin < lin_end; ++seg) {
+        const Seg sg = seg_at(lin);
+        mbar_wait(q_free, (static_cast<uint32_t>(seg) & 1u) ^ 1u);       // previous segment's MMAs retired
+        mbar_arrive_expect_tx(q_full, q_bytes);
+        for (int a = 0; a < atoms; ++a) tma_load_2d(sQ + a * 128 * 128, &tmQ, q_full, a * 64, sg.qt * 128);
+        for (int i = 0; i < sg.nt; ++i) {
+          const int kt = sg.t0 + i;
+          const int by = kt / p.nkt_x, bx = kt - by * p.nkt_x;
+          mbar_wait(&k_empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&k_full[stage], k_bytes);
+          uint8_t* dst = sK + stage * k_bytes;
+          for (int a = 0; a < atoms; ++a)
+            tma_load_3d(dst + a * 64 * 128, &tmK, &k_full[stage], a * 64, bx * 8, by * 8);
+          if (++stage == kScKStages) { stage = 0; phase ^= 1u; }
+        }
+        lin += sg.nt;
       }
     }
   } else if (warp == 1) {
     // ------------------------------------ MMA issuer --------------------------------------
+    // lean issue loop (see gemm.cuh): constant-add descriptors, both barriers probed up front
     constexpr uint32_t idesc = umma_idesc_f16<128, 64>();
-    mbar_wait(q_full, 0);
-    int stage = 0;
-    uint32_t phase = 0;
+    const bool leader = elect_one();
+    const uint64_t dq0 = umma_desc_sw128(smem_u32(sQ));
+    const uint64_t dk0 = umma_desc_sw128(smem_u32(sK));
+    const uint64_t k_step = static_cast<uint64_t>(k_bytes >> 4);
     const int ksteps = p.d / 16;
-    for (int i = 0; i < ntiles; ++i) {
-      const int b = i & 1;
-      const uint32_t use = static_cast<uint32_t>(i >> 1);
-      mbar_wait(&k_full[stage], phase);
-      mbar_wait(&acc_empty[b], (use & 1u) ^ 1u);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sq = smem_u32(sQ);
-        const uint32_t sk = smem_u32(sK + stage * k_bytes);
-        for (int m = 0; m < p.M; ++m) {
-          const int ch0 = m * p.d;                 // first channel of this mode
-          const int atom = ch0 >> 6;
-          const uint32_t inner = static_cast<uint32_t>(ch0 & 63) * 2u;   // byte offset inside the 128-B row
-          const uint64_t dq = umma_desc_sw128(sq + atom * 128 * 128 + inner);
-          const uint64_t dk = umma_desc_sw128(sk + atom * 64 * 128 + inner);
-          const uint32_t tcol = tmem_base + static_cast<uint32_t>(b * 256 + m * 64);
-          for (int k = 0; k < ksteps; ++k) {
-            // K steps past the first 64 channels of a mode (d = 128) move to the next atom.
-            const int ka = (k * 16) >> 6, kin = (k * 16) & 63;
-            const uint64_t oq = static_cast<uint64_t>((ka * 128 * 128 + kin * 2) >> 4);
-            const uint64_t ok = static_cast<uint64_t>((ka * 64 * 128 + kin * 2) >> 4);
-            umma_f16(tcol, dq + oq, dk + ok, idesc, k != 0 ? 1u : 0u);
+    int stage = 0, seg = 0, g = 0;
+    uint32_t phase = 0;
+    for (long long lin = lin_begin; lin < lin_end; ++seg) {
+      const Seg sg = seg_at(lin);
+      mbar_wait(q_full, static_cast<uint32_t>(seg) & 1u);
+      for (int i = 0; i < sg.nt; ++i, ++g) {
+        const int b = g & 1;
+        const uint32_t par = ((static_cast<uint32_t>(g) >> 1) & 1u) ^ 1u;
+        const bool r1 = mbar_try_wait_nohint(&k_full[stage], phase);
+        const bool r2 = mbar_try_wait_nohint(&acc_empty[b], par);
+        if (!r1) mbar_wait(&k_full[stage], phase);
+        if (!r2) mbar_wait(&acc_empty[b], par);
+        tc_fence_after();
+        if (leader) {
+          const uint64_t dk = dk0 + static_cast<uint64_t>(stage) * k_step;
+          for (int m = 0; m < p.M; ++m) {
+            const int ch0 = m * p.d;                 // first channel of this mode
+            const int atom = ch0 >> 6;
+            const uint32_t inner = static_cast<uint32_t>(ch0 & 63) * 2u;   // byte offset inside the 128-B row
+            const uint64_t dqm = dq0 + static_cast<uint64_t>((atom * 128 * 128 + inner) >> 4);
+            const uint64_t dkm = dk + static_cast<uint64_t>((atom * 64 * 128 + inner) >> 4);
+            const uint32_t tcol = tmem_base + static_cast<uint32_t>(b * 256 + m * 64);
+            for (int k = 0; k < ksteps; ++k) {
+              // K steps past the first 64 channels of a mode (d = 128) move to the next atom.
+              const int ka = (k * 16) >> 6, kin = (k * 16) & 63;
+              const uint64_t oq = static_cast<uint64_t>((ka * 128 * 128 + kin * 2) >> 4);
+              const uint64_t ok = static_cast<uint64_t>((ka * 64 * 128 + kin * 2) >> 4);
+              umma_f16(tcol, dqm + oq, dkm + ok, idesc, k != 0 ? 1u : 0u);
+            }
           }
+          umma_commit(&k_empty[stage]);
+          umma_commit(&acc_full[b]);
+          if (i == sg.nt - 1) umma_commit(q_free);
         }
-        umma_commit(&k_empty[stage]);
-        umma_commit(&acc_full[b]);
+        if (++stage == kScKStages) { stage = 0; phase ^= 1u; }
       }
-      __syncwarp();
-      if (++stage == kScKStages) { stage = 0; phase ^= 1u; }
+      lin += sg.nt;
     }
+    __syncwarp();
   } else {
     // ------------------------------------ epilogue ----------------------------------------
-    const int eg = (warp - 2) >> 2;                 // epilogue group 0/1 <-> TMEM buffer
+    const int eg = ((warp - 2) >> 2) & 1;           // epilogue group <-> TMEM buffer / tile parity
+    const int ch = (warp - 2) >> 3;                 // key-block rows ch*4 .. ch*4+3
     const int lane_grp = warp & 3;
     const int row = lane_grp * 32 + (threadIdx.x & 31);
-    const int q = q0 + row;
-    const int qy = q / p.g.Wp, qx = q - qy * p.g.Wp;
-    const bool qvalid = (q < p.g.Mp) && (qx < p.g.W);
     const float clipv = *p.clip;
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + eg * 256;
+    const bool clamped = clipv < INFINITY;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + eg * 256 + ch * 32;
     const int R = p.R;
-    const int TD = 2 * R + 1;
+    const bool has_bias = p.pos_table != nullptr;
+    constexpr float kLog2e = 1.4426950408889634f;
 
-    float st_sum = 0.f, st_sq = 0.f, st_max = -INFINITY;
-    float run_m[4], run_l[4];
+    float st_sum = 0.f, st_sq = 0.f, st_rawmax = -INFINITY;   // st_rawmax: max of the UNSCALED accumulators
+    const float wl2 = p.w_agg * kLog2e;
+    const float sc2 = p.scale * kLog2e;
+
+    int seg = 0, g0 = 0;
+    for (long long lin = lin_begin; lin < lin_end; ++seg) {
+      const Seg sgm = seg_at(lin);
+      const int q = sgm.qt * 128 + row;
+      const int qy = q / p.g.Wp, qx = q - qy * p.g.Wp;
+      const bool qvalid = (q < p.g.Mp) && (qx < p.g.W);
+      if constexpr (MODE == SC_LSE) {     // this thread's running (max, sum) per mode: its own smem cells
+        for (int m = 0; m < 4; ++m) s_merge[((eg * 2 + ch) * 4 + m) * 128 + row] = make_float2(-INFINITY, 0.f);
+      }
+      float seg_rawmax = -INFINITY;              // merged into st_rawmax only for real query rows
+
+      for (int i = (g0 & 1) ^ eg; i < sgm.nt; i += 2) {
+        const int g = g0 + i;
+        const uint32_t par = (static_cast<uint32_t>(g) >> 1) & 1u;
+        const int kt = sgm.t0 + i;
+        const int by = kt / p.nkt_x, bx = kt - by * p.nkt_x;
+        const int ky0 = by * 8 + ch * 4, kx0 = bx * 8;          // this thread's 4 x 8 key window
+        const int iy0 = ky0 - qy + R, ix0 = kx0 - qx + R;       // table coordinates of its first key
+        const bool near = has_bias && (iy0 + 3 >= 0) && (iy0 <= 2 * R) && (ix0 + 7 >= 0) && (ix0 <= 2 * R);
+        const bool full = (ky0 + 4 <= p.g.H) && (kx0 + 8 <= p.g.W);
+        const float* trow_tab = s_table + (iy0 + 3) * TW + (ix0 + 7);
+        mbar_wait(&acc_full[eg], par);
+        tc_fence_after();
+
+        if constexpr (MODE == SC_CORR) {
+          float agg[32];
 #pragma unroll
-    for (int m = 0; m < 4; ++m) { run_m[m] = -INFINITY; run_l[m] = 0.f; }
-    const float wl2 = p.w_agg * 1.4426950408889634f;
-
-    for (int i = eg; i < ntiles; i += 2) {
-      const uint32_t use = static_cast<uint32_t>(i >> 1);
-      const int kt = kt_begin + i;
-      const int by = kt / p.nkt_x, bx = kt - by * p.nkt_x;
-      mbar_wait(&acc_full[eg], use & 1u);
-      tc_fence_after();
-      __syncwarp();
-
-      const bool near = p.pos_table && (by * 8 + 7 >= qy - R) && (by * 8 <= qy + R) &&
-                        (bx * 8 + 7 >= qx - R) && (bx * 8 <= qx + R);
-
-      if constexpr (MODE == SC_CORR) {
-        float agg[64];
+          for (int c = 0; c < 32; c += 16) {
+            uint32_t r0[16], r1[16], r2[16], r3[16];
+            tmem_ld16(trow + c, r0);
+            if (p.M > 1) tmem_ld16(trow + 64 + c, r1);
+            if (p.M > 2) {
+              tmem_ld16(trow + 128 + c, r2);
+              tmem_ld16(trow + 192 + c, r3);
+            }
+            tmem_ld_wait();
+            if (c == 16) {
+              // TMEM buffer drained -> hand it back to the MMA warp before the math
+              tc_fence_before();
+              mbar_arrive_warp(&acc_empty[eg]);
+            }
 #pragma unroll
-        for (int c = 0; c < 64; c += 16) {
-          uint32_t r0[16], r1[16], r2[16], r3[16];
-          tmem_ld16(trow + c, r0);
-          if (p.M > 1) tmem_ld16(trow + 64 + c, r1);
-          if (p.M > 2) {
-            tmem_ld16(trow + 128 + c, r2);
-            tmem_ld16(trow + 192 + c, r3);
+            for (int j = 0; j < 16; ++j) {
+              const float a0 = __uint_as_float(r0[j]);
+              float v;
+              if (p.M == 1) {
+                seg_rawmax = fmaxf(seg_rawmax, a0);
+                const float s0 = a0 * p.scale;
+                v = clamped ? fminf(fmaxf(s0, -clipv), clipv) : s0;
+              } else {
+                const float a1 = __uint_as_float(r1[j]);
+                const float a2 = (p.M > 2) ? __uint_as_float(r2[j]) : -INFINITY;
+                const float a3 = (p.M > 2) ? __uint_as_float(r3[j]) : -INFINITY;
+                seg_rawmax = fmaxf(seg_rawmax, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));
+                float s0 = a0 * p.scale, s1 = a1 * p.scale, s2 = a2 * p.scale, s3 = a3 * p.scale;
+                if (clamped) {
+                  s0 = fminf(fmaxf(s0, -clipv), clipv);
+                  s1 = fminf(fmaxf(s1, -clipv), clipv);
+                  if (p.M > 2) {
+                    s2 = fminf(fmaxf(s2, -clipv), clipv);
+                    s3 = fminf(fmaxf(s3, -clipv), clipv);
+                  }
+                }
+                // softmax over modes of w*s (the Linear(1,1) bias cancels), in the exp2 domain.
+                const float t0 = s0 * wl2, t1 = s1 * wl2, t2 = s2 * wl2, t3 = s3 * wl2;
+                const float tm = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
+                const float e0 = fast_ex2(t0 - tm), e1 = fast_ex2(t1 - tm);
+                float num = e0 * s0 + e1 * s1, den = e0 + e1;
+                if (p.M > 2) {
+                  const float e2 = fast_ex2(t2 - tm), e3 = fast_ex2(t3 - tm);
+                  num += e2 * s2 + e3 * s3;
+                  den += e2 + e3;
+                }
+                v = __fdividef(num, den);
+              }
+              agg[c + j] = v;
+            }
           }
-          tmem_ld_wait();
+
+          if (qvalid) {
+            if (near) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float s0 = __uint_as_float(r0[j]) * p.scale;
-            float v;
-            if (p.M == 1) {
-              st_max = fmaxf(st_max, s0);
-              v = fminf(fmaxf(s0, -clipv), clipv);
+              for (int e = 0; e < 32; ++e) agg[e] += trow_tab[(e >> 3) * TW + (e & 7)];
+            }
+            if (full) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) { st_sum += agg[e]; st_sq = fmaf(agg[e], agg[e], st_sq); }
             } else {
-              float s1 = __uint_as_float(r1[j]) * p.scale;
-              float s2 = (p.M > 2) ? __uint_as_float(r2[j]) * p.scale : -INFINITY;
-              float s3 = (p.M > 2) ? __uint_as_float(r3[j]) * p.scale : -INFINITY;
-              st_max = fmaxf(st_max, fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)));
-              s0 = fminf(fmaxf(s0, -clipv), clipv);
-              s1 = fminf(fmaxf(s1, -clipv), clipv);
-              if (p.M > 2) {
-                s2 = fminf(fmaxf(s2, -clipv), clipv);
-                s3 = fminf(fmaxf(s3, -clipv), clipv);
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                if ((ky0 + (e >> 3) < p.g.H) && (kx0 + (e & 7) < p.g.W)) { st_sum += agg[e]; st_sq = fmaf(agg[e], agg[e], st_sq); }
               }
-              // softmax over modes of w*s (the Linear(1,1) bias cancels), in the exp2 domain.
-              const float t0 = s0 * wl2, t1 = s1 * wl2, t2 = s2 * wl2, t3 = s3 * wl2;
-              const float tm = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
-              const float e0 = fast_ex2(t0 - tm), e1 = fast_ex2(t1 - tm);
-              float num = e0 * s0 + e1 * s1, den = e0 + e1;
-              if (p.M > 2) {
-                const float e2 = fast_ex2(t2 - tm), e3 = fast_ex2(t3 - tm);
-                num += e2 * s2 + e3 * s3;
-                den += e2 + e3;
+            }
+            // level 0 (optional, debugging / SAVECORR)
+            if (p.lvl[0]) {
+              float* dst = p.lvl[0] + static_cast<size_t>(q) * (p.hl[0] * p.wl[0]);
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                const int yy = ky0 + (e >> 3), xx = kx0 + (e & 7);
+                if (yy < p.hl[0] && xx < p.wl[0]) dst[yy * p.wl[0] + xx] = agg[e];
               }
-              v = __fdividef(num, den);
-            }
-            agg[c + j] = v;
-          }
-        }
-        // TMEM buffer drained -> hand it back to the MMA warp before the slow part.
-        tc_fence_before();
-        mbar_arrive_warp(&acc_empty[eg]);
-
-        if (qvalid) {
-          const int ky0 = by * 8, kx0 = bx * 8;
-          if (near) {
-#pragma unroll
-            for (int e = 0; e < 64; ++e) {
-              const int dy = ky0 + (e >> 3) - qy, dx = kx0 + (e & 7) - qx;
-              if (dy >= -R && dy <= R && dx >= -R && dx <= R) agg[e] += s_table[(dy + R) * TD + dx + R];
             }
           }
-          const bool full = (ky0 + 8 <= p.g.H) && (kx0 + 8 <= p.g.W);
+          // level 1: 2 x 4 cells, level 2: 1 x 2 cells of this half (floor-mode avg_pool2d chain, corr.py:186-189)
+          float l1[8];
 #pragma unroll
-          for (int e = 0; e < 64; ++e) {
-            const bool kv = full || ((ky0 + (e >> 3) < p.g.H) && (kx0 + (e & 7) < p.g.W));
-            if (kv) {
-              st_sum += agg[e];
-              st_sq += agg[e] * agg[e];
-            }
-          }
-          // level 0 (optional, debugging / SAVECORR)
-          if (p.lvl[0]) {
-            float* dst = p.lvl[0] + static_cast<size_t>(q) * (p.hl[0] * p.wl[0]);
-#pragma unroll
-            for (int e = 0; e < 64; ++e) {
-              const int yy = ky0 + (e >> 3), xx = kx0 + (e & 7);
-              if (yy < p.hl[0] && xx < p.wl[0]) dst[yy * p.wl[0] + xx] = agg[e];
-            }
-          }
-          // level 1: 4x4 cells, level 2: 2x2, level 3: 1 (floor-mode avg_pool2d chain, corr.py:186-189)
-          float l1[16];
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
+          for (int r = 0; r < 2; ++r)
 #pragma unroll
             for (int c = 0; c < 4; ++c)
               l1[r * 4 + c] = 0.25f * (agg[(2 * r) * 8 + 2 * c] + agg[(2 * r) * 8 + 2 * c + 1] +
                                        agg[(2 * r + 1) * 8 + 2 * c] + agg[(2 * r + 1) * 8 + 2 * c + 1]);
-          {
-            float* dst = p.lvl[1] + static_cast<size_t>(q) * (p.hl[1] * p.wl[1]);
+          if (qvalid) {
+            const int w1 = p.wl[1];
+            float* dst = p.lvl[1] + static_cast<size_t>(q) * (p.hl[1] * w1);
+            const int yy0 = by * 4 + ch * 2, xx0 = bx * 4;
+            const bool vec = ((w1 & 3) == 0) && (((p.hl[1] * w1) & 3) == 0) && (xx0 + 4 <= w1);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const int yy = by * 4 + (e >> 2), xx = bx * 4 + (e & 3);
-              if (yy < p.hl[1] && xx < p.wl[1]) dst[yy * p.wl[1] + xx] = l1[e];
+            for (int r = 0; r < 2; ++r) {
+              const int yy = yy0 + r;
+              if (yy >= p.hl[1]) continue;
+              if (vec) {
+                *reinterpret_cast<float4*>(dst + yy * w1 + xx0) = make_float4(l1[r * 4], l1[r * 4 + 1], l1[r * 4 + 2], l1[r * 4 + 3]);
+              } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                  if (xx0 + c < w1) dst[yy * w1 + xx0 + c] = l1[r * 4 + c];
+              }
             }
           }
-          float l2[4];
+          float l2[2];
 #pragma unroll
-          for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int c = 0; c < 2; ++c)
-              l2[r * 2 + c] = 0.25f * (l1[(2 * r) * 4 + 2 * c] + l1[(2 * r) * 4 + 2 * c + 1] +
-                                       l1[(2 * r + 1) * 4 + 2 * c] + l1[(2 * r + 1) * 4 + 2 * c + 1]);
-          {
-            float* dst = p.lvl[2] + static_cast<size_t>(q) * (p.hl[2] * p.wl[2]);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int yy = by * 2 + (e >> 1), xx = bx * 2 + (e & 1);
-              if (yy < p.hl[2] && xx < p.wl[2]) dst[yy * p.wl[2] + xx] = l2[e];
+          for (int c = 0; c < 2; ++c) l2[c] = 0.25f * (l1[2 * c] + l1[2 * c + 1] + l1[4 + 2 * c] + l1[4 + 2 * c + 1]);
+          if (qvalid) {
+            const int w2 = p.wl[2];
+            float* dst = p.lvl[2] + static_cast<size_t>(q) * (p.hl[2] * w2);
+            const int yy = by * 2 + ch, xx0 = bx * 2;
+            if (yy < p.hl[2]) {
+              if (((w2 & 1) == 0) && (((p.hl[2] * w2) & 1) == 0) && (xx0 + 2 <= w2))
+                *reinterpret_cast<float2*>(dst + yy * w2 + xx0) = make_float2(l2[0], l2[1]);
+              else {
+                if (xx0 < w2) dst[yy * w2 + xx0] = l2[0];
+                if (xx0 + 1 < w2) dst[yy * w2 + xx0 + 1] = l2[1];
+              }
             }
           }
-          if (by < p.hl[3] && bx < p.wl[3])
-            p.lvl[3][static_cast<size_t>(q) * (p.hl[3] * p.wl[3]) + by * p.wl[3] + bx] =
-                0.25f * (l2[0] + l2[1] + l2[2] + l2[3]);
-        }
-      } else {
-        // ------------------------------ SC_LSE ------------------------------
-        const int ky0 = by * 8, kx0 = bx * 8;
-        const bool full = (ky0 + 8 <= p.g.H) && (kx0 + 8 <= p.g.W);
-        for (int m = 0; m < p.M; ++m) {
-          float sv[64];
+          // level 3 needs both halves of the block: the lower half hands its share over through smem
+          // (pair barrier: the two warps of one (group, lane quadrant); ids 2..9)
+          const float half3 = 0.25f * (l2[0] + l2[1]);
+          float* xs = s_l3 + ((g >> 1) & 1) * 256 + eg * 128 + row;
+          if (ch == 1) *xs = half3;
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + eg * 4 + lane_grp) : "memory");
+          if (ch == 0 && qvalid && by < p.hl[3] && bx < p.wl[3])
+            p.lvl[3][static_cast<size_t>(q) * (p.hl[3] * p.wl[3]) + by * p.wl[3] + bx] = half3 + *xs;
+        } else {
+          // ------------------------------ SC_LSE ------------------------------
+          // one mode at a time: 32 accumulator registers live (two modes in flight spill at 96 regs/thread)
+          // (the mode loop stays rolled: unrolled, the tile loop no longer fits the instruction cache;
+          //  the running (max, sum) of each mode therefore lives in shared memory, not in an indexed
+          //  register array)
+#pragma unroll 1
+          for (int m = 0; m < p.M; ++m) {
+            {
+              float2* rs = s_merge + ((eg * 2 + ch) * 4 + m) * 128 + row;
+              const float2 run = *rs;
+              float run_m_new = run.x, run_l_new = run.y;
+              uint32_t raw[32];
+              tmem_ld32(trow + m * 64, raw);
+              tmem_ld_wait();
+              if (m == p.M - 1) {
+                tc_fence_before();
+                mbar_arrive_warp(&acc_empty[eg]);
+              }
+              float rmax = __uint_as_float(raw[0]);
 #pragma unroll
-          for (int c = 0; c < 64; c += 16) {
-            uint32_t r0[16];
-            tmem_ld16(trow + m * 64 + c, r0);
-            tmem_ld_wait();
+              for (int e = 1; e < 32; ++e) rmax = fmaxf(rmax, __uint_as_float(raw[e]));
+              seg_rawmax = fmaxf(seg_rawmax, rmax);
+              if (!near && !clamped && full) {
+                // fast path: exp2(raw * scale*log2e - max*log2e), one FFMA + one MUFU per key
+                const float nm = fmaxf(run.x, rmax * p.scale);
+                const float nm2 = nm * kLog2e;
+                float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float s = __uint_as_float(r0[j]) * p.scale;
-              st_max = fmaxf(st_max, s);
-              sv[c + j] = fminf(fmaxf(s, -clipv), clipv);
+                for (int e = 0; e < 32; e += 2) {
+                  acc0 += fast_ex2(fmaf(__uint_as_float(raw[e]), sc2, -nm2));
+                  acc1 += fast_ex2(fmaf(__uint_as_float(raw[e + 1]), sc2, -nm2));
+                }
+                run_l_new = run.y * fast_ex2((run.x - nm) * kLog2e) + (acc0 + acc1);
+                run_m_new = nm;
+              } else {
+                // rare path (near the query, clamped, or a ragged edge block): the value of a key is
+                // recomputed in both passes instead of being kept in a second 32-register array
+                auto val = [&](int e) {
+                  float s = fminf(fmaxf(__uint_as_float(raw[e]) * p.scale, -clipv), clipv);
+                  if (near) s += trow_tab[(e >> 3) * TW + (e & 7)];
+                  if (!full && !((ky0 + (e >> 3) < p.g.H) && (kx0 + (e & 7) < p.g.W))) s = -INFINITY;
+                  return s;
+                };
+                float tmax = val(0);
+#pragma unroll
+                for (int e = 1; e < 32; ++e) tmax = fmaxf(tmax, val(e));
+                const float nm = fmaxf(run.x, tmax);
+                if (nm > -INFINITY) {
+                  float acc = 0.f;
+#pragma unroll
+                  for (int e = 0; e < 32; ++e) acc += fast_ex2((val(e) - nm) * kLog2e);
+                  run_l_new = run.y * fast_ex2((run.x - nm) * kLog2e) + acc;
+                  run_m_new = nm;
+                }
+              }
+              *rs = make_float2(run_m_new, run_l_new);
             }
           }
-          if (m == p.M - 1) {
-            tc_fence_before();
-            mbar_arrive_warp(&acc_empty[eg]);
-          }
-          if (near) {
-#pragma unroll
-            for (int e = 0; e < 64; ++e) {
-              const int dy = ky0 + (e >> 3) - qy, dx = kx0 + (e & 7) - qx;
-              if (dy >= -R && dy <= R && dx >= -R && dx <= R) sv[e] += s_table[(dy + R) * TD + dx + R];
-            }
-          }
-          if (!full) {
-#pragma unroll
-            for (int e = 0; e < 64; ++e)
-              if (!((ky0 + (e >> 3) < p.g.H) && (kx0 + (e & 7) < p.g.W))) sv[e] = -INFINITY;
-          }
-          float tmax = sv[0];
-#pragma unroll
-          for (int e = 1; e < 64; ++e) tmax = fmaxf(tmax, sv[e]);
-          const float nm = fmaxf(run_m[m], tmax);
-          float acc = 0.f;
-#pragma unroll
-          for (int e = 0; e < 64; ++e) acc += fast_ex2((sv[e] - nm) * 1.4426950408889634f);
-          run_l[m] = run_l[m] * fast_ex2((run_m[m] - nm) * 1.4426950408889634f) + acc;
-          run_m[m] = nm;
         }
       }
+
+      // ------------------------- end of segment: SC_LSE partial of this query tile ----------
+      if constexpr (MODE == SC_LSE) {
+        // the four (group, half) sets saw disjoint keys: merge through shared memory
+        const int set = eg * 2 + ch;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (set == 0 && q < p.g.Mp) {
+          const int slot = static_cast<int>(blockIdx.x) - cta_of(lin - sgm.t0);
+          const bool last_part = (sgm.t0 + sgm.nt == nkt);
+          for (int m = 0; m < p.M; ++m) {
+            float nm = -INFINITY;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) nm = fmaxf(nm, s_merge[(s * 4 + m) * 128 + row].x);
+            float l = 0.f;
+            if (nm > -INFINITY) {
+#pragma unroll
+              for (int s = 0; s < 4; ++s) {
+                const float2 o = s_merge[(s * 4 + m) * 128 + row];
+                if (o.x > -INFINITY) l += o.y * __expf(o.x - nm);
+              }
+            }
+            p.lse_part[(static_cast<size_t>(slot) * p.M + m) * p.g.Mp + q] = make_float2(nm, l);
+            if (last_part)
+              for (int sl = slot + 1; sl < p.nslots; ++sl)
+                p.lse_part[(static_cast<size_t>(sl) * p.M + m) * p.g.Mp + q] = make_float2(-INFINITY, 0.f);
+          }
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");   // s_merge is reused by the next segment
+      }
+      if (qvalid) st_rawmax = fmaxf(st_rawmax, seg_rawmax);
+      lin += sgm.nt;
+      g0 += sgm.nt;
     }
 
-    // ------------------------- per-CTA reductions / partial writes -------------------------
-    if constexpr (MODE == SC_LSE) {
-      // the two epilogue groups saw alternate key tiles: merge through shared memory.
-      float2* xch = reinterpret_cast<float2*>(sK);   // K stages are idle now (all MMAs retired)
-      // make sure every MMA that reads sK has retired: the last acc_full wait above implies it
-      // for this group's tiles; the other group's tiles are covered by the named barrier below.
-      asm volatile("bar.sync 1, 256;");
-      if (eg == 1) {
-        for (int m = 0; m < p.M; ++m) xch[m * 128 + row] = make_float2(run_m[m], run_l[m]);
-      }
-      asm volatile("bar.sync 1, 256;");
-      if (eg == 0 && q < p.g.Mp) {
-        for (int m = 0; m < p.M; ++m) {
-          const float2 o = xch[m * 128 + row];
-          const float nm = fmaxf(run_m[m], o.x);
-          float l = 0.f;
-          if (nm > -INFINITY) l = run_l[m] * __expf(run_m[m] - nm) + o.y * __expf(o.x - nm);
-          p.lse_part[(static_cast<size_t>(blockIdx.y) * p.M + m) * p.g.Mp + q] = make_float2(nm, l);
-        }
-      }
-    }
+    // ------------------------- per-CTA reductions -----------------------------------------
     // global max of raw scores (clamp gate) -- both modes
     {
-      const float wm = warp_max(qvalid ? st_max : -INFINITY);
+      const float wm = warp_max(st_rawmax) * p.scale;
       if ((threadIdx.x & 31) == 0 && wm > -INFINITY) atomic_max_float(p.stat_max, wm);
     }
     if constexpr (MODE == SC_CORR) {
@@ -398,16 +507,14 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
-  (void)s_red;
 }
 
-// lse_merge: combine ksplit partial (max, sumexp) pairs -> lse in the log2 domain.
+// lse_merge: combine the partial (max, sumexp) pairs of all slots -> lse in the log2 domain.
 //   lse2[m][q] = log2( sum_k exp(s_k) ) = (mx + ln(sum)) * log2(e)
 __global__ void lse_merge_kernel(const float2* __restrict__ part, int ksplit, int M, int Mp,
                                  float* __restrict__ lse2) {
   pdl_launch_dependents();
   pdl_wait();
-
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * Mp) return;
   float mx = -INFINITY;
@@ -426,7 +533,6 @@ __global__ void corr_stats_finalize_kernel(const double* __restrict__ sums, doub
                                            float* __restrict__ mean_rstd) {
   pdl_launch_dependents();
   pdl_wait();
-
   const double mean = sums[0] / n;
   double var = sums[1] / n - mean * mean;
   if (var < 0) var = 0;
@@ -437,7 +543,6 @@ __global__ void clip_gate_kernel(const float* __restrict__ stat_max, float attn_
                                  float* __restrict__ clip, int* __restrict__ flag) {
   pdl_launch_dependents();
   pdl_wait();
-
   const bool hit = stat_max[0] > attn_clip;
   clip[0] = hit ? attn_clip : INFINITY;
   flag[0] = hit ? 1 : 0;
