@@ -426,8 +426,26 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 }
                 run_l_new = run.y * fast_ex2((run.x - nm) * kLog2e) + (acc0 + acc1);
                 run_m_new = nm;
+              } else if (!clamped && full) {
+                // near the query: the positional bias enters the max; values are built in place
+                float x[32];
+#pragma unroll
+                for (int e = 0; e < 32; ++e) x[e] = fmaf(__uint_as_float(raw[e]), p.scale, trow_tab[(e >> 3) * TW + (e & 7)]);
+                float tmax = x[0];
+#pragma unroll
+                for (int e = 1; e < 32; ++e) tmax = fmaxf(tmax, x[e]);
+                const float nm = fmaxf(run.x, tmax);
+                const float nm2 = nm * kLog2e;
+                float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                  acc0 += fast_ex2(fmaf(x[e], kLog2e, -nm2));
+                  acc1 += fast_ex2(fmaf(x[e + 1], kLog2e, -nm2));
+                }
+                run_l_new = run.y * fast_ex2((run.x - nm) * kLog2e) + (acc0 + acc1);
+                run_m_new = nm;
               } else {
-                // rare path (near the query, clamped, or a ragged edge block): the value of a key is
+                // rare path (clamped re-pass or a ragged edge block): the value of a key is
                 // recomputed in both passes instead of being kept in a second 32-register array
                 auto val = [&](int e) {
                   float s = fminf(fmaxf(__uint_as_float(raw[e]) * p.scale, -clipv), clipv);

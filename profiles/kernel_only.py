@@ -29,6 +29,8 @@ def main(which, reps):
         uw = ub.weights(g)
         att_tbl = model.att.vispos_encoder.table()
         f2_tbl = model.f2_trans.vispos_encoder.table()
+        if os.environ.get("KO_NOBIAS") == "1":      # experiment: no positional bias -> no "near" slow path
+            att_tbl = f2_tbl = None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
         def run():
@@ -45,6 +47,9 @@ def main(which, reps):
                 ops.corr_build(ws.Qc, ws.Kc, g, M=4, d=64, w_agg=0.1285, w_pos=0.5, pos_table=f2_tbl, R=7,
                                clip=ws.inf_clip, stat_sum=ws.stat_sum[0], stat_max=ws.stat_max[0:1], levels=ws.levels,
                                ksplit=ws.ks_sc)
+            elif which == "lse_f2":
+                ops.attn_lse(ws.Q2, ws.K2, g, M=4, d=64, w_pos=0.5, pos_table=f2_tbl, R=7, clip=ws.inf_clip,
+                             stat_max=ws.stat_max[1:2], lse_part=ws.lse_part, lse2=ws.lse2_f2, ksplit=ws.ks_sc)
             elif which == "lse":
                 ops.attn_lse(ws.Qa, ws.Ka, g, M=4, d=32, w_pos=1.0, pos_table=att_tbl, R=7, clip=ws.inf_clip,
                              stat_max=ws.stat_max[2:3], lse_part=ws.lse_part, lse2=ws.lse2_att, ksplit=ws.ks_sc)
