@@ -21,14 +21,22 @@ from .setrans import CrossAttFeatTrans, SETransInputFeatEncoder, get_workspace, 
 class _LookupMixin:
     """CorrBlock.__call__ core/corr.py:47-71."""
 
-    def lookup_rows(self, ws, coords_rows, out_b=None, out_nchw=None):
+    def lookup_rows(self, ws, coords_rows, out_b=None, out_nchw=None, part="all"):
+        """part: "all", or -- when level 0 is computed on demand -- "level0" (channels 0..80) / "pooled"
+        (channels 81..323): the two halves are independent kernels writing disjoint channels, so the
+        caller may run them on different streams."""
         if self.radius != 4 or self.num_levels != 4:
             raise NotImplementedError("craft_b200 lookup kernel is built for radius 4, 4 levels (CRAFT default)")
         first = 0
         if ws.levels[0] is None:      # level 0 on demand: the U x U volume was never stored
-            ops.corr_lookup0(grid=ws.grid, coords=coords_rows, mean_rstd=ws.mean_rstd, out_b=out_b,
-                             out_nchw=out_nchw, **ws.corr_meta)
+            if part in ("all", "level0"):
+                ops.corr_lookup0(grid=ws.grid, coords=coords_rows, mean_rstd=ws.mean_rstd, out_b=out_b,
+                                 out_nchw=out_nchw, **ws.corr_meta)
             first = 1
+            if part == "level0":
+                return
+        elif part == "level0":
+            return                    # materialised level 0: the single pass below covers everything
         ops.corr_lookup(ws.levels, ws.grid, coords_rows, ws.mean_rstd, out_b=out_b, out_nchw=out_nchw,
                         first_level=first)
 

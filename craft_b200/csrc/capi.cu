@@ -185,6 +185,9 @@ int launch_gemm_bn(int BN, int CL, const CUtensorMap& ta, const CUtensorMap& tb,
   switch (BN) {
     case 32: return launch_gemm_cl<32, EPI>(CL, ta, tb, p, st);
     case 64: return launch_gemm_cl<64, EPI>(CL, ta, tb, p, st);
+    case 96:
+      if constexpr (EPI == cb::EPI_STORE) return launch_gemm_t<96, EPI, 1>(ta, tb, p, st);   // plain epilogue only, no multicast
+      break;
     case 128: return launch_gemm_cl<128, EPI>(CL, ta, tb, p, st);
     case 256: return launch_gemm_cl<256, EPI>(CL, ta, tb, p, st);
   }

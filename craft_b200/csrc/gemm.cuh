@@ -107,7 +107,7 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int n0 = blockIdx.y * BN;
   const int kchunks = p.K / kGemmBK;
   const int nk = p.T * kchunks;
-  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  constexpr uint32_t kTmemCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));   // power of two >= BN
   const int nstages = p.stages;
   uint32_t cta_rank = 0;
   if constexpr (CL > 1) cta_rank = cluster_ctarank();
@@ -203,7 +203,7 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     // ------------------------------ epilogue ----------------------------------
     constexpr int HALF = BN / 2;                       // columns per thread
-    constexpr int CW = HALF < 32 ? HALF : 32;          // columns per TMEM load
+    constexpr int CW = (HALF % 32 == 0) ? 32 : 16;     // columns per TMEM load (BN = 96 / 32: 16)
     const int et = threadIdx.x - 64;                   // 0..255
     const int lane_grp = warp & 3;                     // TMEM lanes this warp may read
     const int half = (warp - 2) >> 2;                  // which half of the BN columns

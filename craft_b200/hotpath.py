@@ -87,6 +87,7 @@ class Workspace:
         self.MASKS = [z(576, f32), z(576, f32)]
         self.MASK = self.MASKS[0]
         self.side = torch.cuda.Stream(device=device)    # second lane for independent branches (captured too)
+        self.ev_lookup = torch.cuda.Event()
         self.coords1 = z(2, f32); self.flow = z(2, f32)
 
     def opart(self, ks, M, F):
@@ -213,20 +214,30 @@ class UpdateWeights:
         self.device = dev
 
 
-def motion_encoder(ws, uw):
-    """BasicMotionEncoder.forward core/update.py:79-87 -> X[:, 256:384] (126 features + the flow)."""
+def motion_encoder(ws, uw, lookup=None):
+    """BasicMotionEncoder.forward core/update.py:79-87 -> X[:, 256:384] (126 features + the flow).
+
+    `lookup(part)` (optional) is the correlation lookup of this iteration (core/corr.py:47-71).  Its
+    level-0 part runs on the main stream; the pooled levels and the flow branch (convf1 -> convf2), all
+    of which depend only on the current coordinates, run on the side stream next to it; the
+    correlation branch (convc1 -> convc2) starts as soon as both lookup halves are in."""
     g = ws.grid
     sg = ops.shift_gemm
-    # the correlation branch (convc1 -> convc2) and the flow branch (convf1 -> convf2) are independent
-    # until `conv` (update.py:80-86): run the flow branch on the side stream
     main, side = torch.cuda.current_stream(), ws.side
     side.wait_stream(main)
     with torch.cuda.stream(side):
+        if lookup is not None:
+            lookup("pooled")
+            ws.ev_lookup.record(side)
         ops.convf1(ws.flow, uw.f1_w, uw.f1_b, g, ws.F1)
         sg(ws.F1, uw.f2_w, M=g.Mp, Npad=64, K=128, BN=64, taps=uw.taps3, grid=g, bias=uw.f2_b, act=1, out_b=ws.CF,
            colb=192)
+    if lookup is not None:
+        lookup("level0")
+        main.wait_event(ws.ev_lookup)
     sg(ws.CORR, uw.c1_w, M=g.Mp, Npad=256, K=384, BN=128, grid=g, bias=uw.c1_b, act=1, out_b=ws.C1)
-    sg(ws.C1, uw.c2_w, M=g.Mp, Npad=192, K=256, BN=64, taps=uw.taps3, grid=g, bias=uw.c2_b, act=1, out_b=ws.CF)
+    # N = 192 as two 96-wide tiles: 114 CTAs = one wave (three 64-wide tiles would need 171 CTAs = two waves)
+    sg(ws.C1, uw.c2_w, M=g.Mp, Npad=192, K=256, BN=96, taps=uw.taps3, grid=g, bias=uw.c2_b, act=1, out_b=ws.CF)
     main.wait_stream(side)
     sg(ws.CF, uw.cv_w, M=g.Mp, Npad=128, K=256, BN=64, taps=uw.taps3, grid=g, bias=uw.cv_b,
        epilogue=ops.EPI_MOTION, out_b=ws.X, colb=256, aux1=ws.flow)

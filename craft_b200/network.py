@@ -279,8 +279,8 @@ class CRAFT(nn.Module):
             main, side = torch.cuda.current_stream(), ws.side
             for itr in range(iters):
                 need_up = not (test_mode == 1 and self.elide_dead_upsample) or itr == iters - 1
-                corr_fn.lookup_rows(ws, ws.coords1, out_b=ws.CORR)
-                self.update_block.step(ws, att, itr, need_mask=need_up)
+                lookup = lambda part: corr_fn.lookup_rows(ws, ws.coords1, out_b=ws.CORR, part=part)
+                self.update_block.step(ws, att, itr, need_mask=need_up, lookup=lookup)
                 ops.flow_update(ws.coords1, ws.flow, ws.DELTA, g)
                 if not need_up:
                     continue

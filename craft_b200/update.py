@@ -76,11 +76,12 @@ class GMAUpdateBlock(nn.Module):
         ps = [p for n, p in self.named_parameters() if not n.startswith("aggregator.")]
         return self._packed.get(("uw", grid.H, grid.W), ps, lambda: hp.UpdateWeights(self, grid))
 
-    def step(self, ws, attention, it=0, need_mask=True):
+    def step(self, ws, attention, it=0, need_mask=True, lookup=None):
         """One refinement iteration on the workspace: CORR (looked-up correlation) and flow are in
-        place; writes the new hidden state (X[:, :128], Hm), DELTA and (when need_mask) MASK."""
+        place (or produced by `lookup(part)`, see hotpath.motion_encoder); writes the new hidden state
+        (X[:, :128], Hm), DELTA and (when need_mask) MASK."""
         uw = self.weights(ws.grid)
-        hp.motion_encoder(ws, uw)
+        hp.motion_encoder(ws, uw, lookup)
         self.aggregator.run(ws, attention, ws.X, 256, out_b=ws.X, colb=384)
         hp.sep_conv_gru(ws, uw)
         hp.heads(ws, uw, it, need_mask)

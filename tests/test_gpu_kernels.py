@@ -49,7 +49,7 @@ def test_gemm_plain(BN, Npad, K, M):
 
 
 @pytest.mark.parametrize("kh,kw,Cin,Cout,BN", [(3, 3, 64, 128, 128), (1, 5, 128, 64, 64), (5, 1, 192, 256, 128),
-                                               (1, 1, 384, 256, 256), (3, 3, 256, 32, 32)])
+                                               (1, 1, 384, 256, 256), (3, 3, 256, 32, 32), (3, 3, 256, 192, 96)])
 def test_gemm_conv(kh, kw, Cin, Cout, BN):
     grid = TokenGrid(13, 21)
     g = torch.Generator(device=DEV).manual_seed(kh * 10 + kw)
