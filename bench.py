@@ -263,9 +263,9 @@ def run_ours(args):
         ks = ws.pv_split(4)
         O = ws.opart(ks, 4, 128)
         tbl = model.att.vispos_encoder.table()
-        def pv():
+        def pv():   # exactly the call hotpath.value_aggregate makes 12x per pair
             ops.attn_pv(ws.Qa, ws.Ka, ws.Vt, g, M=4, d=32, F=128, w_pos=1.0, pos_table=tbl, R=7,
-                        clip=ws.clip_att, lse2=ws.lse2_att, out=O, ksplit=ks)
+                        clip=ws.clip_att, lse2=ws.lse2_att, out=O, ksplit=ks, zero_fill=False)
         for _ in range(3):
             pv()
         torch.cuda.synchronize()
@@ -281,9 +281,20 @@ def run_ours(args):
         flops = 2.0 * U * U * 128 + 2.0 * 4 * U * U * 128          # QK^T (C=128) + P.V (M=4, F=128), algorithmic
         pk = _peaks()
         ach = flops / (us * 1e-6) / 1e12
+        # DRAM bytes of one launch from the committed `ncu --set full` capture (profiles/r01_pv_ncu_full.txt)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_pv_traffic.json")
+        if os.path.isfile(tpath):
+            t = json.load(open(tpath))
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+        # second ceiling of this kernel: one MUFU ex2 per (query, key, mode) at 16 per clock per SM
+        mufu_us = 4.0 * U * U / (16.0 * 148 * 1.965e9) * 1e6
         roof = dict(bound="tensor", kernel="attn_pv_kernel<32,128,128> (motion aggregator P.V, x12 per pair)",
-                    achieved=ach, peak=pk["tf_burst"], unit="TFLOP/s", frac=ach / pk["tf_burst"], traffic=None,
-                    us_per_launch=us, flops_per_launch=flops, peak_source=pk["src"] + " bf16 burst")
+                    achieved=ach, peak=pk["tf_burst"], unit="TFLOP/s", frac=ach / pk["tf_burst"], traffic=traffic,
+                    us_per_launch=us, flops_per_launch=flops, peak_source=pk["src"] + " bf16 burst",
+                    note="exp-bound before tensor-bound: 4*U^2 ex2 at the measured 15.2/clk/SM MUFU rate = %.1f us "
+                         "per launch (profiles/r01_mb_exp.txt), i.e. the kernel runs at %.2f of its MUFU ceiling" % (
+                             mufu_us * 16.0 / 15.2, mufu_us * 16.0 / 15.2 / us))
 
     if rank == 0:
         cpu = None
@@ -300,8 +311,13 @@ def run_ours(args):
                     config=dict(workload=WORKLOAD, parallelism="pairs sharded over %d ranks, no collective" % world,
                                 l2="per-step working set (corr pyramid + P.V partials, >300 MB) exceeds the 126 MB L2; "
                                    "4 distinct input pairs rotate",
-                                encoders="fnet/cnet stock PyTorch/cuDNN, TF32 convolutions (outside the hot path)",
-                                launch="whole forward replayed as one CUDA graph"),
+                                encoders="fnet/cnet (outside the hot path): cuDNN fp16 convolutions with fp32 accumulation "
+                                         "+ craft_b200 norm/relu/residual kernels",
+                                launch="whole forward replayed as one CUDA graph; craft_b200 kernels use programmatic "
+                                       "dependent launch",
+                                dead_work="test_mode=1 returns only the last upsampled flow: the mask head + convex "
+                                          "upsampling of iterations 1..11 (discarded by the reference) are elided, "
+                                          "outputs bit-identical (tests/test_gpu_e2e.py)"),
                     e2e=dict(value=total / (ms_e2e * 1e-3), unit="pairs/s", h2d_bytes_per_step=2 * 3 * H * W,
                              d2h_bytes_per_step=2 * H * W * 4),
                     gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu)

@@ -1,6 +1,6 @@
 """Launch one hot-path kernel a few times on realistic buffers (448x1024 grid) so that
 `ncu --set full -k regex:<name>` can capture it without profiling a whole forward.
-usage: python profiles/kernel_only.py {pv|pv_f2|corr|lse|gru_zr|gru_q|lookup|heads} [reps]"""
+usage: python profiles/kernel_only.py {pv|pv_f2|corr|lse|lse_f2|gru_zr|lookup0|lookup|heads}[,more] [reps]"""
 import os
 import sys
 
@@ -33,7 +33,7 @@ def main(which, reps):
             att_tbl = f2_tbl = None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-        def run():
+        def run(which=which):
             if which == "pv":
                 ks = ws.pv_split(4)
                 ops.attn_pv(ws.Qa, ws.Ka, ws.Vt, g, M=4, d=32, F=128, w_pos=1.0, pos_table=att_tbl, R=7,
@@ -66,14 +66,15 @@ def main(which, reps):
 
         if trace:
             os.environ["CRAFT_PV_TRACE"] = trace
-        run()
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(reps):
-            run()
-        e1.record()
-        torch.cuda.synchronize()
-        print("%s: %.2f us per call (avg of %d)" % (which, 1000 * e0.elapsed_time(e1) / reps, reps))
+        for w in which.split(","):          # several kernels in one process: "pv,corr,lse"
+            run(w)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                run(w)
+            e1.record()
+            torch.cuda.synchronize()
+            print("%s: %.2f us per call (avg of %d)" % (w, 1000 * e0.elapsed_time(e1) / reps, reps), flush=True)
 
 
 if __name__ == "__main__":

@@ -36,7 +36,7 @@ KEYS = [
 ]
 
 
-def main(path):
+def main(path, json_out=None):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
@@ -46,7 +46,16 @@ def main(path):
         for k, label in KEYS:
             if k in idx:
                 print("  %-28s %14s %s" % (label, r[idx[k]], units[idx[k]]))
+        if json_out:      # DRAM bytes of this launch, for bench.py's roofline.traffic
+            import json
+
+            def to_bytes(key):
+                v, u = float(r[idx[key]].replace(",", "")), units[idx[key]].lower()
+                return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+            json.dump(dict(kernel=r[idx["Kernel Name"]][:80], dram_bytes_read=to_bytes("dram__bytes_read.sum"),
+                           dram_bytes_write=to_bytes("dram__bytes_write.sum"), source=path), open(json_out, "w"))
+            json_out = None
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)
