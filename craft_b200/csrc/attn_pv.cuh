@@ -50,7 +50,7 @@ struct PvParams {
   const float* lse2;       // [M][Mp] log2-domain log-sum-exp
   float* out;              // [nslots][M][F/8][Mp][8] f32 partial sums (8-column chunks, see the write-back)
   int nkt, nbx;            // key tiles (blocks) in total / per block-row
-  long long* trace;        // CRAFT_PV_TRACE: clock64 timeline of CTA (0,0,0): [role 4][tile 64][slot 8]
+  long long* trace;        // CRAFT_PV_TRACE: clock64 timeline of CTA 0: [role 4][tile 64][slot 8], then globaltimer (start, end) of every CTA
 };
 
 template <int D, int F, int BK, int KS, int VS>
@@ -158,6 +158,8 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   const bool tr = p.trace != nullptr && blockIdx.x == 0;
+  auto gtime = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return static_cast<long long>(t); };
+  if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 256) p.trace[2048 + 2 * blockIdx.x] = gtime();
 #define PV_TRACE(role, tile, slot)                                                              \
   do {                                                                                          \
     if (tr && (threadIdx.x & 31) == 0 && (tile) < 64) p.trace[((role) * 64 + (tile)) * 8 + (slot)] = clock64(); \
@@ -325,13 +327,6 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int q = sgm.qt * 128 + row;
       const int qy = q / p.g.Wp, qx = q - qy * p.g.Wp;
       const float lse = lse_next;
-      // next segment's log-sum-exp is fetched now: at the segment end it would queue up behind the
-      // O write-back stores in the load/store unit
-      if (lin + sgm.nt < lin_end) {
-        const Seg nx = seg_at(lin + sgm.nt);
-        const int qn = nx.qt * 128 + row;
-        lse_next = (qn < p.g.Mp) ? p.lse2[static_cast<size_t>(nx.mode) * p.g.Mp + qn] : 0.f;
-      }
       for (int i = (g0 & 1) ^ sg; i < sgm.nt; i += 2) {
         const int g = g0 + i;
         const int b = g % NSB;
@@ -395,14 +390,24 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int slot = static_cast<int>(blockIdx.x) - cta_of(unit_lin0);
       const bool last_part = (sgm.t0 + sgm.nt == p.nkt);
       const int g_last = g0 + sgm.nt - 1;
+      // The next segment's log-sum-exp is fetched HERE: the 64 KB of write-back stores below take
+      // ~2000 clk to drain from the load/store unit and any global load issued behind them (e.g. at the
+      // top of the next segment) would stall the warp for that long; this one completes while the
+      // warp waits for the last P.V anyway.
+      if (lin + sgm.nt < lin_end) {
+        const Seg nx = seg_at(lin + sgm.nt);
+        const int qn = nx.qt * 128 + row;
+        lse_next = (qn < p.g.Mp) ? p.lse2[static_cast<size_t>(nx.mode) * p.g.Mp + qn] : 0.f;
+      }
       if (trole < 4) PV_TRACE(trole, g_last - (g_last & 1) + (trole - 1), 5);
       mbar_wait(o_full, static_cast<uint32_t>(seg) & 1u);
       if (trole < 4) PV_TRACE(trole, g_last - (g_last & 1) + (trole - 1), 6);
       tc_fence_after();
       __syncwarp();
-      // out[slot][mode][F/8][Mp][8]: a thread (= query row) stores 32-byte pieces, consecutive lanes
-      // hit consecutive pieces, so each store instruction covers 1 KB of whole sectors instead of
-      // 32 scattered half sectors (row-major [Mp][F] would put the lanes 4*F bytes apart)
+      // out[slot][mode][F/8][Mp][8]: a thread (= query row) stores one 32-byte sector per chunk with a
+      // single 256-bit store and consecutive lanes hit consecutive sectors, so a store instruction
+      // covers 1 KB contiguous (row-major [Mp][F] would scatter 32 half sectors 4*F bytes apart and
+      // the load/store unit then needs ~8000 clk per 64 KB tile -- measured, profiles/README.md)
       const size_t slot_stride = static_cast<size_t>(p.M) * p.g.Mp * F;
       float* dst = p.out + (static_cast<size_t>(slot) * p.M + sgm.mode) * p.g.Mp * F + static_cast<size_t>(q) * 8;
       constexpr int kQuarter = F / 4;
@@ -414,13 +419,9 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tmem_ld_wait();
         if (q < p.g.Mp) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float4* d4 = reinterpret_cast<float4*>(dst + static_cast<size_t>((c_begin + c) / 8 + e) * p.g.Mp * 8);
-            d4[0] = make_float4(__uint_as_float(raw[8 * e]), __uint_as_float(raw[8 * e + 1]),
-                                __uint_as_float(raw[8 * e + 2]), __uint_as_float(raw[8 * e + 3]));
-            d4[1] = make_float4(__uint_as_float(raw[8 * e + 4]), __uint_as_float(raw[8 * e + 5]),
-                                __uint_as_float(raw[8 * e + 6]), __uint_as_float(raw[8 * e + 7]));
-          }
+          for (int e = 0; e < 4; ++e)      // one 256-bit store per chunk: consecutive lanes -> 1 KB contiguous
+            st_global_v8(dst + static_cast<size_t>((c_begin + c) / 8 + e) * p.g.Mp * 8,
+                         *reinterpret_cast<const uint32_t(*)[8]>(&raw[8 * e]));
         }
       }
       tc_fence_before();
@@ -444,6 +445,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #undef PV_TRACE
 
   __syncthreads();
+  if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 256) p.trace[2048 + 2 * blockIdx.x + 1] = gtime();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);

@@ -465,13 +465,13 @@ static int launch_pv(const craft_pv_args* a, const cb::Grid2& g, cudaStream_t st
   static long long* d_trace = nullptr;
   const char* trace_path = getenv("CRAFT_PV_TRACE");     // profiling aid: dumps CTA 0's clock64 timeline
   if (trace_path) {
-    if (!d_trace) cudaMalloc(&d_trace, 4 * 64 * 8 * sizeof(long long));
-    cudaMemsetAsync(d_trace, 0, 4 * 64 * 8 * sizeof(long long), st);
+    if (!d_trace) cudaMalloc(&d_trace, (4 * 64 * 8 + 512) * sizeof(long long));
+    cudaMemsetAsync(d_trace, 0, (4 * 64 * 8 + 512) * sizeof(long long), st);
     p.trace = d_trace;
   }
   launch_k(kern, dim3(grid), dim3(cb::kPvThreads), S::kTotal, st, tq, tk, tv, p);
   if (trace_path) {
-    static long long h[4 * 64 * 8];
+    static long long h[4 * 64 * 8 + 512];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
     if (FILE* f = fopen(trace_path, "w")) {
@@ -481,6 +481,8 @@ static int launch_pv(const craft_pv_args* a, const cb::Grid2& g, cudaStream_t st
           for (int k = 0; k < 8; ++k) fprintf(f, " %lld", h[(r * 64 + t) * 8 + k]);
           fprintf(f, "\n");
         }
+      for (int c = 0; c < 256; ++c)      // role 9: per-CTA (start, end) in ns
+        if (h[2048 + 2 * c]) fprintf(f, "9 %d %lld %lld\n", c, h[2048 + 2 * c], h[2048 + 2 * c + 1]);
       fclose(f);
     }
   }
