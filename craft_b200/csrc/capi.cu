@@ -126,20 +126,6 @@ int sm_count() {
   return n;
 }
 
-// number of key splits so that tiles*split fills whole waves as evenly as possible
-int pick_split(int base_ctas, int max_split) {
-  const int sms = sm_count();
-  int best = 1;
-  double best_eff = 0;
-  for (int s = 1; s <= max_split; ++s) {
-    const int ctas = base_ctas * s;
-    const int waves = (ctas + sms - 1) / sms;
-    const double eff = static_cast<double>(ctas) / (static_cast<double>(waves) * sms);
-    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
-  }
-  return best;
-}
-
 template <int BN, int EPI, int CL>
 int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const cb::GemmParams& p, cudaStream_t st) {
   using S = cb::GemmSmem<BN>;

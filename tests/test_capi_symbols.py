@@ -43,3 +43,46 @@ def test_missing_device_fails_loudly():
     grid = ops.TokenGrid(4, 4)
     with pytest.raises((_lib.CraftB200Error, AssertionError)):
         ops.pack_tokens(torch.zeros((128, 4, 4)), grid, out_f=torch.zeros((grid.Mp, 128)))
+
+
+def _ranges(NT, G):
+    return [(NT * c // G, NT * (c + 1) // G) for c in range(G)]
+
+
+@pytest.mark.parametrize("H,W,M", [(56, 128, 4), (48, 156, 4), (55, 128, 4), (16, 16, 4), (16, 16, 1), (50, 90, 1)])
+def test_persistent_schedule_slot_counts(H, W, M):
+    """Host-side arithmetic of the persistent-CTA schedules (no kernel launch): the slot counts the
+    library reports must equal the largest number of CTA ranges that intersect one unit when the
+    (unit, key tile) list is cut into equal contiguous ranges -- the same formula the kernels and
+    modes_finalize evaluate on the device (attn_pv.cuh, scores.cuh, pointwise.cuh)."""
+    from craft_b200 import _lib
+    lib = _lib.load()
+    info = (3 * __import__("ctypes").c_int)()
+    sms = 148                                  # the library falls back to 148 SMs without a device
+    if lib.craft_b200_device_info(info) == 0 and info[0] > 0:
+        sms = info[0]
+    Mp = H * (W + 2)
+    nqt = (Mp + 127) // 128
+
+    def worst(nunits, nkt, G):
+        NT = nunits * nkt
+        rng = _ranges(NT, G)
+        assert rng[0][0] == 0 and rng[-1][1] == NT and all(a < b for a, b in rng)      # cover, non-empty
+        out = 0
+        for u in range(nunits):
+            lo, hi = u * nkt, (u + 1) * nkt
+            out = max(out, sum(1 for a, b in rng if a < hi and b > lo))
+        return out
+
+    # scores kernels: unit = query tile, 8x8 key blocks
+    nkt = ((H + 7) // 8) * ((W + 7) // 8)
+    G = max(1, min(sms, nqt * nkt))
+    assert lib.craft_scores_auto_ksplit(H, W) == worst(nqt, nkt, G)
+    # P.V kernel: unit = (query tile, mode); 8x16 or 8x8 key blocks; grid capped at 3 CTAs per unit
+    want = 0
+    for bw in (16, 8):
+        nkt = ((H + 7) // 8) * ((W + bw - 1) // bw)
+        G = max(1, min(sms, nqt * M * nkt, 3 * nqt * M))
+        want = max(want, worst(nqt * M, nkt, G))
+    got = lib.craft_pv_auto_ksplit(H, W, M)
+    assert got == want and got <= 4
