@@ -32,6 +32,7 @@ class GemmArgs(C.Structure):
         ("out_bf16", C.c_void_p), ("ldo_b", C.c_int), ("colo_b", C.c_int),
         ("out_f32", C.c_void_p), ("ldo_f", C.c_int), ("colo_f", C.c_int),
         ("aux0", C.c_void_p), ("aux1", C.c_void_p),
+        ("a_share", C.c_int),
     ]
 
 

@@ -233,9 +233,21 @@ int craft_shift_gemm(const craft_gemm_args* a, void* stream) {
   if (a->out_bf16 && ((a->ldo_b % 8) || (a->colo_b % 8))) return fail("gemm: bf16 output ld/col must be multiples of 8");
   if (a->out_f32 && ((a->ldo_f % 4) || (a->colo_f % 4))) return fail("gemm: f32 output ld/col must be multiples of 4");
   CUtensorMap ta, tb;
-  if (make_map_2d(&ta, a->A, a->a_rows, a->lda, a->lda, cb::kGemmBM)) return -1;
   cb::GemmParams p;
   memset(&p, 0, sizeof(p));
+  // shared-A mode (gemm.cuh): taps in groups of consecutive row offsets, e.g. the kw taps of a conv row
+  {
+    static int env_mode = -1;
+    if (env_mode < 0) { const char* e = getenv("CRAFT_GEMM_ASHARE"); env_mode = (e && atoi(e) != 0) ? 1 : 0; }
+    const int mode = (a->a_share != 0 || env_mode != 0) ? 1 : 0;
+    int gs = 1;
+    while (gs < a->T && a->tap_off[gs] == a->tap_off[gs - 1] + 1) ++gs;
+    bool ok = mode != 0 && gs > 1 && gs <= 5 && a->T % gs == 0 && !a->b_blocked && a->cluster <= 1;
+    for (int t = 1; ok && t < a->T; ++t)
+      if (t % gs != 0 && a->tap_off[t] != a->tap_off[t - 1] + 1) ok = false;
+    if (ok) { p.ashare = mode; p.gsize = gs; }
+  }
+  if (make_map_2d(&ta, a->A, a->a_rows, a->lda, a->lda, p.ashare ? 136 : cb::kGemmBM)) return -1;
   if (a->b_blocked) {
     if (a->T != 1 || (a->BN != 64 && a->BN != 128)) return fail("gemm: blocked B needs T=1 and BN in {64,128}");
     cb::Grid2 bg = make_grid(a->b_H, a->b_W);

@@ -51,6 +51,12 @@ struct GemmParams {
   int tap_off[kMaxTaps];
   int stages;   // pipeline depth actually used (stages * kc <= GemmSmem<BN>::kStages slots); tuning knob
   int kc;       // 64-column K atoms per pipeline stage (1 or 2): 2 halves the per-stage handshake cost
+  // ashare != 0: the taps come in groups of `gsize` consecutive row offsets (the kw taps of one kernel
+  // row); the A rows of a group are loaded ONCE (128 + 8 rows) and every tap reads them through a
+  // descriptor whose start address is shifted by whole rows, so only the weights are fetched per tap.
+  // (Measured: the 128-byte swizzle is a function of the absolute smem address, so the shifted start
+  // needs NO base-offset correction in the descriptor -- setting bits 49-51 gives wrong results.)
+  int ashare, gsize;
   // row validity: Wp > 0 => row m is a real token iff (m % Wp) < W and (m / Wp) < H;
   //               Wp == 0 => every m < M is valid.
   int Wp, W, H;
@@ -96,11 +102,24 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // writes land at identical offsets).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
-  uint64_t* empty_bar = full_bar + S::kStages;
-  uint64_t* acc_bar = empty_bar + S::kStages;
+  // barrier block (256 B): [acc_bar][tmem_slot][ring barriers ...]
+  uint64_t* acc_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  uint64_t* full_bar = acc_bar + 2;
+  uint64_t* empty_bar = full_bar + S::kStages;
   float* s_bias = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes + 256);
+  // shared-A mode: an A ring of kAsSlots x (136 rows x 128 B) followed by a B ring of kBsSlots weight tiles
+  constexpr int kAsBytes = 136 * 128;
+  constexpr int kAsSlots = 3;
+  constexpr int kBsFit = (S::kStages * S::kStageBytes - kAsSlots * kAsBytes) / S::kBBytes;
+  constexpr int kBsSlots = kBsFit < 12 ? kBsFit : 12;
+  static_assert(2 * (kAsSlots + kBsSlots) * 8 + 16 <= 256, "barrier block");
+  uint64_t* a_full = acc_bar + 2;
+  uint64_t* a_empty = a_full + kAsSlots;
+  uint64_t* b_full = a_empty + kAsSlots;
+  uint64_t* b_empty = b_full + kBsSlots;
+  uint8_t* sAs = smem;
+  uint8_t* sBs = smem + kAsSlots * kAsBytes;
 
   const int warp = threadIdx.x >> 5;
   const int m0 = blockIdx.x * kGemmBM;
@@ -116,9 +135,13 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < S::kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CL);
+    if (p.ashare) {
+      for (int s = 0; s < 2 * (kAsSlots + kBsSlots); ++s) mbar_init(&a_full[s], 1);
+    } else {
+      for (int s = 0; s < S::kStages; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], CL);
+      }
     }
     mbar_init(acc_bar, 1);
     fence_mbar_init();
@@ -133,7 +156,27 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     // A pipeline stage is `kc` consecutive smem slots (one slot = A atom + B atom of 64 K columns).
-    if (elect_one()) {
+    if (p.ashare) {
+      if (elect_one()) {
+        const int GS = p.gsize, ngr = p.T / GS;
+        int as = 0, bs = 0;
+        uint32_t aph = 0, bph = 0;
+        for (int gi = 0; gi < ngr; ++gi)
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(&a_empty[as], aph ^ 1u);
+            mbar_arrive_expect_tx(&a_full[as], kAsBytes);
+            // rows m0 + off(first tap of the group) .. +136: every tap of the group is a row shift of it
+            tma_load_2d(sAs + as * kAsBytes, &tmA, &a_full[as], p.a_koff + kc * kGemmBK, m0 + p.tap_off[gi * GS]);
+            if (++as == kAsSlots) { as = 0; aph ^= 1u; }
+            for (int j = 0; j < GS; ++j) {
+              mbar_wait(&b_empty[bs], bph ^ 1u);
+              mbar_arrive_expect_tx(&b_full[bs], S::kBBytes);
+              tma_load_2d(sBs + bs * S::kBBytes, &tmB, &b_full[bs], p.b_koff + kc * kGemmBK, (gi * GS + j) * p.Npad + n0);
+              if (++bs == kBsSlots) { bs = 0; bph ^= 1u; }
+            }
+          }
+      }
+    } else if (elect_one()) {
       const int KC = p.kc;
       const int nst = nk / KC;
       int stage = 0;
@@ -174,6 +217,39 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int nst = nk / KC;
     const uint64_t desc_base = umma_desc_sw128(smem_u32(smem));
     const bool leader = elect_one();
+    if (p.ashare) {
+      const int GS = p.gsize, ngr = p.T / GS;
+      const uint64_t da_base = umma_desc_sw128(smem_u32(sAs));
+      const uint64_t db_base = umma_desc_sw128(smem_u32(sBs));
+      constexpr uint64_t kAStep = static_cast<uint64_t>(kAsBytes >> 4);
+      constexpr uint64_t kBStep = static_cast<uint64_t>(S::kBBytes >> 4);
+      int as = 0, bs = 0, first = 1;
+      uint32_t aph = 0, bph = 0;
+      for (int gi = 0; gi < ngr; ++gi)
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&a_full[as], aph);
+          for (int j = 0; j < GS; ++j) {
+            mbar_wait(&b_full[bs], bph);
+            tc_fence_after();
+            if (leader) {
+              // tap j of the group reads the A rows j*128 bytes further down the same smem tile
+              const uint64_t da = da_base + static_cast<uint64_t>(as) * kAStep + static_cast<uint64_t>(j) * 8u;
+              const uint64_t db = db_base + static_cast<uint64_t>(bs) * kBStep;
+              umma_f16(tmem_base, da, db, idesc, first ? 0u : 1u);
+              umma_f16_acc(tmem_base, da + 2u, db + 2u, idesc);
+              umma_f16_acc(tmem_base, da + 4u, db + 4u, idesc);
+              umma_f16_acc(tmem_base, da + 6u, db + 6u, idesc);
+              umma_commit(&b_empty[bs]);
+              if (j == GS - 1) umma_commit(&a_empty[as]);
+              if (gi == ngr - 1 && kc == kchunks - 1 && j == GS - 1) umma_commit(acc_bar);
+            }
+            first = 0;
+            if (++bs == kBsSlots) { bs = 0; bph ^= 1u; }
+          }
+          if (++as == kAsSlots) { as = 0; aph ^= 1u; }
+        }
+      __syncwarp();
+    } else {
     int stage = 0;
     uint32_t phase = 0;
     uint64_t da = desc_base;
@@ -200,6 +276,7 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ready = (it + 1 < nst) && mbar_try_wait_nohint(&full_bar[stage], phase);
     }
     __syncwarp();
+    }
   } else {
     // ------------------------------ epilogue ----------------------------------
     constexpr int HALF = BN / 2;                       // columns per thread

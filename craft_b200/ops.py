@@ -91,8 +91,9 @@ def unpack_tokens(buf, col, Cc, grid, out=None):
 # ------------------------------------------------------------------------------------------------
 def shift_gemm(A, Bw, *, M, Npad, K, BN, taps=(0,), a_koff=0, b_koff=0, grid=None, epilogue=EPI_STORE,
                alpha=1.0, act=0, bias=None, out_b=None, colb=0, out_f=None, colf=0, aux0=None, aux1=None,
-               b_block_grid=None, cluster=0, stages=0):
-    """b_block_grid: B rows are the tokens of that grid and n-tile j is its j-th 8 x BN/8 spatial block."""
+               b_block_grid=None, cluster=0, stages=0, a_share=0):
+    """b_block_grid: B rows are the tokens of that grid and n-tile j is its j-th 8 x BN/8 spatial block.
+    a_share=1 (experimental): load the A rows of a kernel row once for all of its taps."""
     _chk(A, torch.bfloat16, "A")
     _chk(Bw, torch.bfloat16, "B")
     _chk(bias, torch.float32, "bias")
@@ -106,6 +107,7 @@ def shift_gemm(A, Bw, *, M, Npad, K, BN, taps=(0,), a_koff=0, b_koff=0, grid=Non
     a.M, a.Npad, a.K, a.T, a.BN = M, Npad, K, len(taps), BN
     a.cluster = cluster
     a.stages = stages
+    a.a_share = a_share
     if b_block_grid is not None:
         a.b_blocked, a.b_H, a.b_W = 1, b_block_grid.H, b_block_grid.W
     for i, t in enumerate(taps):

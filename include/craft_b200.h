@@ -67,6 +67,9 @@ typedef struct craft_gemm_args {
   int ldo_f, colo_f;
   float* aux0;        /* gru: Z [M,128]                                                       */
   float* aux1;        /* gru: Hm [M,128]; motion: flow [M,2]                                  */
+  int a_share;        /* experimental, default 0.  1: the taps come in groups of consecutive row offsets (the kw
+                         taps of one kernel row); the A rows of a group are loaded once and every tap reads
+                         them through a row-shifted descriptor.  Correct, but currently slower */
 } craft_gemm_args;
 int craft_shift_gemm(const craft_gemm_args* a, void* stream);
 

@@ -50,7 +50,8 @@ def test_gemm_plain(BN, Npad, K, M):
 
 @pytest.mark.parametrize("kh,kw,Cin,Cout,BN", [(3, 3, 64, 128, 128), (1, 5, 128, 64, 64), (5, 1, 192, 256, 128),
                                                (1, 1, 384, 256, 256), (3, 3, 256, 32, 32), (3, 3, 256, 192, 96)])
-def test_gemm_conv(kh, kw, Cin, Cout, BN):
+@pytest.mark.parametrize("a_share", [0, 1])
+def test_gemm_conv(kh, kw, Cin, Cout, BN, a_share):
     grid = TokenGrid(13, 21)
     g = torch.Generator(device=DEV).manual_seed(kh * 10 + kw)
     x = bf16r(torch.randn((Cin, grid.H, grid.W), device=DEV, generator=g))
@@ -60,7 +61,7 @@ def test_gemm_conv(kh, kw, Cin, Cout, BN):
     Wp = ops.pack_conv_weight(w)
     out = grid.zeros(Cout, dtype=torch.float32)
     ops.shift_gemm(X, Wp, M=grid.Mp, Npad=Cout, K=Wp.shape[1], BN=BN, taps=ops.conv_taps(kh, kw, grid), grid=grid,
-                   bias=b, act=0, out_f=out)
+                   bias=b, act=0, out_f=out, a_share=a_share)
     torch.cuda.synchronize()
     ref = F.conv2d(x[None], w, b, padding=(kh // 2, kw // 2))[0]
     got = nchw_from_rows(out, grid, Cout)
