@@ -159,3 +159,37 @@ def test_dead_upsample_elision_is_bit_identical():
     torch.cuda.synchronize()
     assert torch.equal(lo_a, lo_b) and torch.equal(up_a, up_b)
     assert torch.equal(lo_a, lo_c) and torch.equal(up_a, ups[-1]) and len(ups) == 4
+
+
+def test_batch_of_two_equals_two_single_pairs():
+    """CRAFT.forward iterates over the batch itself (one workspace, pair after pair): a batch of two
+    different pairs must reproduce the two single-pair results.  Not bit for bit: cuDNN picks other
+    algorithms for the encoders at batch 2, which moves the features in the last bits."""
+    rec = torch.load(os.path.join(GOLD, "seeded_setrans_128.pt"), map_location="cpu")
+    model = _model(rec)
+    a1, a2 = synthetic_pair(128, 128)
+    b1, b2 = smooth_pair(128, 128)
+    with torch.no_grad():
+        lo_a, up_a = model(a1.cuda(), a2.cuda(), iters=3, test_mode=1)
+        lo_b, up_b = model(b1.cuda(), b2.cuda(), iters=3, test_mode=1)
+        lo, up = model(torch.cat([a1, b1]).cuda(), torch.cat([a2, b2]).cuda(), iters=3, test_mode=1)
+    torch.cuda.synchronize()
+    assert lo.shape == (2, 2, 16, 16) and up.shape == (2, 2, 128, 128)
+    assert _epe(up[0].cpu(), up_a[0].cpu()) <= 2e-3 and _epe(up[1].cpu(), up_b[0].cpu()) <= 2e-3
+    assert _epe(8 * lo[0].cpu(), 8 * lo_a[0].cpu()) <= 4e-3 and _epe(8 * lo[1].cpu(), 8 * lo_b[0].cpu()) <= 4e-3
+    assert _epe(up[0].cpu(), up[1].cpu()) > 0.05          # the two pairs really are different problems
+
+
+def test_stored_level0_volume_agrees_with_on_demand_lookup():
+    """materialize_level0=True (the SAVECORR / debugging path) writes the U x U level-0 volume from the
+    build kernel's tensor-core tiles; the default path recomputes each 10x10 window from the Q/K rows.
+    Same bf16 products, different fp32 summation order: the flows must agree far inside the parity bound."""
+    rec = torch.load(os.path.join(GOLD, "seeded_setrans_128.pt"), map_location="cpu")
+    model = _model(rec)
+    i1, i2 = (t.cuda() for t in _inputs(rec))
+    with torch.no_grad():
+        _, up_a = model(i1, i2, iters=4, test_mode=1)
+        model.materialize_level0 = True
+        _, up_b = model(i1, i2, iters=4, test_mode=1)
+    torch.cuda.synchronize()
+    assert _epe(up_a[0].cpu(), up_b[0].cpu()) <= 2e-3
