@@ -2,8 +2,8 @@
 
 Functional fp32 restatement (plain torch ops, device-agnostic) of the reference algorithm on the
 CRAFT hot path.  Each function cites the reference lines it follows.  It is pinned against the
-*executed* reference by tests/test_oracle_vs_reference.py (runs only where /root/reference is
-mounted) and against the frozen outputs in tests/golden/ (runs everywhere).  The reference has no
+*executed* reference by tests/test_oracle_golden.py: live against /root/reference where it is
+mounted, and against the frozen outputs in tests/golden/ everywhere.  The reference has no
 tests, golden vectors or fixtures of its own, so the executed reference
 is the only pin there is.
 
