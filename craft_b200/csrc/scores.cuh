@@ -91,7 +91,8 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint64_t* acc_empty = acc_full + 2;          // [2] count 8 (warps of the group)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   // positional-bias table, zero padded so that a thread's 4 x 8 window needs no range checks:
-  // row iy+3 (iy in [-3, 2R+3]), column ix+7 (ix in [-7, 2R+7]); natural domain, times w_pos
+  // row iy+4 (iy in [-4, 2R+3]; rows 0..3 are all zero and double as the window of lanes that are
+  // outside the bias range), column ix+7 (ix in [-7, 2R+7]); natural domain, times w_pos
   float* s_table = reinterpret_cast<float*>(tail + 512);
   float* s_l3 = reinterpret_cast<float*>(tail + 512 + 2560);             // [2 slots][2 eg][128 rows]
   float2* s_merge = reinterpret_cast<float2*>(tail + 512 + 2560 + 2048);  // [4 sets][4 modes][128 rows]
@@ -138,9 +139,9 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   pdl_wait();                                    // everything below reads tensors of earlier kernels
   if (p.pos_table) {
     const int TDp = 2 * p.R + 1;
-    const int n = (TDp + 6) * TW;
+    const int n = (TDp + 7) * TW;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const int iy = i / TW - 3, ix = i % TW - 7;
+      const int iy = i / TW - 4, ix = i % TW - 7;
       const bool in = (iy >= 0) && (iy < TDp) && (ix >= 0) && (ix < TDp);
       s_table[i] = in ? p.pos_table[iy * TDp + ix] * p.w_pos : 0.f;
     }
@@ -258,7 +259,10 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const int iy0 = ky0 - qy + R, ix0 = kx0 - qx + R;       // table coordinates of its first key
         const bool near = has_bias && (iy0 + 3 >= 0) && (iy0 <= 2 * R) && (ix0 + 7 >= 0) && (ix0 <= 2 * R);
         const bool full = (ky0 + 4 <= p.g.H) && (kx0 + 8 <= p.g.W);
-        const float* trow_tab = s_table + (iy0 + 3) * TW + (ix0 + 7);
+        // lanes outside the bias range read the all-zero rows, so the window path can be taken by the
+        // whole warp at once (no divergence between the plain and the window path)
+        const float* trow_tab = near ? s_table + (iy0 + 4) * TW + (ix0 + 7) : s_table;
+        const bool near_w = __any_sync(0xffffffffu, near);
         mbar_wait(&acc_full[eg], par);
         tc_fence_after();
 
@@ -318,7 +322,7 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           }
 
           if (qvalid) {
-            if (near) {
+            if (near_w) {      // warp-uniform: lanes outside the range add the zero rows
 #pragma unroll
               for (int e = 0; e < 32; ++e) agg[e] += trow_tab[(e >> 3) * TW + (e & 7)];
             }
@@ -414,7 +418,7 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
               for (int e = 1; e < 32; ++e) rmax = fmaxf(rmax, __uint_as_float(raw[e]));
               seg_rawmax = fmaxf(seg_rawmax, rmax);
-              if (!near && !clamped && full) {
+              if (!near_w && !clamped && full) {
                 // fast path: exp2(raw * scale*log2e - max*log2e), one FFMA + one MUFU per key
                 const float nm = fmaxf(run.x, rmax * p.scale);
                 const float nm2 = nm * kLog2e;
