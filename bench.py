@@ -309,8 +309,9 @@ def run_ours(args):
                     vs_baseline=None, dtype="bf16",
                     data="synthetic integer-noise pairs (distinct per step), weights: " + wsrc,
                     config=dict(workload=WORKLOAD, parallelism="pairs sharded over %d ranks, no collective" % world,
-                                l2="per-step working set (corr pyramid + P.V partials, >300 MB) exceeds the 126 MB L2; "
-                                   "4 distinct input pairs rotate",
+                                l2="inputs larger than L2: the per-step working set (68 MB pooled correlation pyramid, 30 MB "
+                                   "P.V partial sums, >100 MB of encoder activations) exceeds the 126 MB L2 and every "
+                                   "buffer is rewritten each step; 4 distinct input pairs rotate",
                                 encoders="fnet/cnet (outside the hot path): cuDNN fp16 convolutions with fp32 accumulation "
                                          "+ craft_b200 norm/relu/residual kernels",
                                 launch="whole forward replayed as one CUDA graph; craft_b200 kernels use programmatic "
