@@ -86,3 +86,34 @@ def test_persistent_schedule_slot_counts(H, W, M):
         want = max(want, worst(nqt * M, nkt, G))
     got = lib.craft_pv_auto_ksplit(H, W, M)
     assert got == want and got <= 4
+
+
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """The three argument structs are mirrored by hand in craft_b200/_lib.py: compile the header with gcc
+    and compare size and the offset of every field, so a field added on one side only cannot go unnoticed."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from craft_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    pairs = [("craft_gemm_args", _lib.GemmArgs), ("craft_scores_args", _lib.ScoresArgs), ("craft_pv_args", _lib.PvArgs)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "craft_b200.h"', 'int main(void) {']
+    for cname, st in pairs:
+        lines.append('printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in st._fields_:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    got = {}
+    for ln in out.splitlines():
+        s, f, v = ln.split()
+        got[(s, f)] = int(v)
+    for cname, st in pairs:
+        assert got[(cname, "sizeof")] == C.sizeof(st), cname
+        for fname, _ in st._fields_:
+            assert got[(cname, fname)] == getattr(st, fname).offset, (cname, fname)
