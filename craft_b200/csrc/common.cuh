@@ -117,12 +117,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 20)) __trap();
   }
 }
-__device__ __forceinline__ void mbar_wait_mode(uint64_t* bar, uint32_t parity, int mode) {
-  uint32_t spins = 0;
-  if (mode == 0) { mbar_wait(bar, parity); return; }
-  if (mode == 1) { while (!mbar_try_wait_nohint(bar, parity)) { if (++spins > (1u << 26)) __trap(); } return; }
-  while (!mbar_test(bar, parity)) { if (++spins > (1u << 26)) __trap(); }
-}
 
 // ---------------------------------------------------------------------------------------------
 // TMA (tensor maps are passed as __grid_constant__ kernel parameters)
