@@ -117,3 +117,40 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
         assert got[(cname, "sizeof")] == C.sizeof(st), cname
         for fname, _ in st._fields_:
             assert got[(cname, fname)] == getattr(st, fname).offset, (cname, fname)
+
+
+def test_hot_kernels_are_tcgen05_and_tma_in_sass():
+    """The built library must carry Blackwell tensor-core / TMA / TMEM instructions in its hot kernels
+    (SASS mnemonics from the profiling guide: UTCHMMA = tcgen05.mma, UTMALDG = TMA load, LDTM/STTM =
+    tcgen05.ld/st, UTCBAR = tcgen05.commit) and be compiled for sm_100a only -- a guard against a silent
+    fallback to mma.sync / plain loads creeping in."""
+    import shutil
+    import subprocess
+    from craft_b200 import _lib
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    if not os.path.isfile(_lib.LIB_PATH):
+        import __graft_entry__ as ge
+        ge.build()
+    archs = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in archs and "sm_90" not in archs and "sm_80" not in archs, archs
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    per_kernel, name = {}, None
+    for ln in sass.splitlines():
+        if "Function :" in ln:
+            name = ln.split("Function :")[1].strip()
+            per_kernel[name] = set()
+        elif name:
+            for m in ("UTCHMMA", "UTMALDG", "LDTM", "STTM", "UTCBAR", "HMMA"):
+                if re.search(r"\b" + m + r"\b", ln):          # whole mnemonic: HMMA must not match UTCHMMA
+                    per_kernel[name].add(m)
+
+    def ops_of(fragment):
+        hits = [v for k, v in per_kernel.items() if fragment in k]
+        assert hits, "no kernel matching %s in the library" % fragment
+        return set.union(*hits)
+    for frag in ("shift_gemm_kernel", "scores_kernel", "attn_pv_kernel"):
+        ops = ops_of(frag)
+        assert {"UTCHMMA", "UTMALDG", "LDTM", "UTCBAR"} <= ops, (frag, ops)
+        assert "HMMA" not in ops, frag                       # no legacy mma.sync in the tensor kernels
+    assert "STTM" in ops_of("attn_pv_kernel")                # P is written back to TMEM (tcgen05.st)
