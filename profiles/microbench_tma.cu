@@ -1,5 +1,6 @@
-// Micro-benchmark (not yet run -- written at the end of round 1 for the first GPU minutes of the next
-// one): TMA load latency and per-SM throughput as a function of the bytes kept in flight.
+// Micro-benchmark: TMA load latency and per-SM throughput as a function of the bytes kept in flight
+// (first results: profiles/r01_mb_tma.txt; the boxes-per-barrier rows were added afterwards and have
+// not been run yet).
 //
 // Question it answers: the shift-GEMM main loop costs ~215 ns per
 // 64 K columns (32 KB of A+B per CTA) with no unit above 25 %.  If that is Little's law --
@@ -24,13 +25,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-template <int NS, int ROWS>
+template <int NS, int ROWS, int BPB>
 __global__ void __launch_bounds__(64, 1) k(const __grid_constant__ CUtensorMap tm, int iters, int rows_total,
                                            long long* out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  constexpr int kBox = ROWS * 128;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * kBox);
+  constexpr int kBox = ROWS * 128;                 // one TMA box
+  constexpr int kSlot = BPB * kBox;                // BPB boxes share one barrier (like the GEMM's A+B atoms)
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * kSlot);
   uint64_t* empty = full + NS;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm);
@@ -45,10 +47,12 @@ __global__ void __launch_bounds__(64, 1) k(const __grid_constant__ CUtensorMap t
       int s = 0; uint32_t ph = 0;
       for (int it = 0; it < iters; ++it) {
         mbar_wait(&empty[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&full[s], kBox);
+        mbar_arrive_expect_tx(&full[s], kSlot);
         // different rows / column chunks per step and per CTA, all inside an L2-resident matrix
         const int row = (blockIdx.x * 128 + it * 7) % (rows_total - ROWS);
-        tma_load_2d(smem + s * kBox, &tm, &full[s], (it % 8) * 64, row);
+#pragma unroll
+        for (int b = 0; b < BPB; ++b)
+          tma_load_2d(smem + s * kSlot + b * kBox, &tm, &full[s], ((it + b) % 8) * 64, row);
         if (++s == NS) { s = 0; ph ^= 1u; }
       }
     }
@@ -67,12 +71,13 @@ __global__ void __launch_bounds__(64, 1) k(const __grid_constant__ CUtensorMap t
   }
 }
 
-template <int NS, int ROWS>
+template <int NS, int ROWS, int BPB = 1>
 void run(const CUtensorMap& tm, int grid, int rows_total, long long* d_out) {
   constexpr int kBox = ROWS * 128;
-  const int smem = NS * kBox + 1024 + 256;
+  constexpr int kSlot = BPB * kBox;
+  const int smem = NS * kSlot + 1024 + 256;
   if (smem > 227 * 1024) return;
-  auto kern = k<NS, ROWS>;
+  auto kern = k<NS, ROWS, BPB>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int iters = 4000;
   kern<<<grid, 64, smem>>>(tm, 200, rows_total, d_out);
@@ -81,9 +86,9 @@ void run(const CUtensorMap& tm, int grid, int rows_total, long long* d_out) {
   cudaMemcpy(h, d_out, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
   long long mx = 0;
   for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
-  const double clk_per_box = static_cast<double>(mx) / iters;
-  printf("grid=%3d  box=%2d KB  in flight=%2d (%3d KB)  %7.0f clk/box  %6.1f B/clk/SM   (%s)\n", grid, kBox / 1024, NS,
-         NS * kBox / 1024, clk_per_box, kBox / clk_per_box, cudaGetErrorString(cudaGetLastError()));
+  const double clk_per_slot = static_cast<double>(mx) / iters;
+  printf("grid=%3d  box=%2d KB x%d per barrier  slots in flight=%2d (%3d KB)  %7.0f clk/barrier  %6.1f B/clk/SM   (%s)\n", grid,
+         kBox / 1024, BPB, NS, NS * kSlot / 1024, clk_per_slot, kSlot / clk_per_slot, cudaGetErrorString(cudaGetLastError()));
 }
 
 int main() {
@@ -122,6 +127,11 @@ int main() {
     run<4, 64>(m64, grid, rows, d_out);
     run<8, 64>(m64, grid, rows, d_out);
     run<16, 64>(m64, grid, rows, d_out);
+    // several boxes per barrier: separates the cost of a TMA instruction from the cost of a barrier round
+    run<3, 128, 2>(m128, grid, rows, d_out);
+    run<3, 128, 4>(m128, grid, rows, d_out);
+    run<6, 128, 2>(m128, grid, rows, d_out);
+    run<6, 64, 4>(m64, grid, rows, d_out);
   }
   return 0;
 }
