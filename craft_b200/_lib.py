@@ -70,6 +70,7 @@ SIGNATURES = {
     "craft_b200_abi_version": (_i, []),
     "craft_b200_last_error": (C.c_char_p, []),
     "craft_b200_launch_count": (C.c_longlong, []),
+    "craft_b200_bigbox_gemm_count": (C.c_longlong, []),
     "craft_b200_device_info": (_i, [C.POINTER(_i)]),
     "craft_pack_tokens": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp]),
     "craft_unpack_tokens": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),

@@ -100,6 +100,23 @@ int make_map_2d(CUtensorMap* m, const void* base, long long rows, long long cols
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(2d) failed: %d", static_cast<int>(r));
   return 0;
 }
+// 3-D bf16 map over a row-major [rows, ld] matrix viewed as [64 cols][rows][ld/64 chunks]: one box
+// [64][box_rows][2] lands as two consecutive 128-byte-swizzled K atoms (experimental big-box GEMM mode).
+// Returns 1 (not an error) when the driver rejects the encoding, so the caller can fall back.
+int make_map_3d_k2(CUtensorMap* m, const void* base, long long rows, long long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc || (reinterpret_cast<uintptr_t>(base) & 15) || ld % 64) return 1;
+  cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(ld / 64)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, 128};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 1;
+}
+std::atomic<long long> g_bigbox_launches{0};   // GEMM launches that really took the big-box path
+
 // 3-D bf16 map over token rows viewed as [H][W][C] with row pitch Wp: box = [8][bw][64].
 int make_map_3d_keys(CUtensorMap* m, const void* base, const cb::Grid2& g, int C, int bw = 8) {
   EncodeTiledFn enc = get_encode();
@@ -187,6 +204,7 @@ extern "C" {
 int craft_b200_abi_version(void) { return CRAFT_B200_ABI_VERSION; }
 const char* craft_b200_last_error(void) { return g_err; }
 long long craft_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+long long craft_b200_bigbox_gemm_count(void) { return g_bigbox_launches.load(std::memory_order_relaxed); }
 
 int craft_b200_device_info(int* out3) {
   int dev = 0;
@@ -267,6 +285,20 @@ int craft_shift_gemm(const craft_gemm_args* a, void* stream) {
   if (!a->b_blocked) {
     if (make_map_2d(&tb, a->B, a->b_rows, a->ldb_, a->ldb_, a->BN / CL)) return -1;
   }
+  // experimental big-box mode (CRAFT_GEMM_BIGBOX=1|2, gemm.cuh): replaces both maps by 3-D ones
+  {
+    static int env_big = -1;
+    if (env_big < 0) { const char* e = getenv("CRAFT_GEMM_BIGBOX"); env_big = e ? atoi(e) : 0; }
+    if ((env_big == 1 || env_big == 2) && !p.ashare && !a->b_blocked && CL == 1 && a->K % 128 == 0 && a->BN <= 256) {
+      CUtensorMap ta3, tb3;
+      if (make_map_3d_k2(&ta3, a->A, a->a_rows, a->lda, cb::kGemmBM) == 0 &&
+          make_map_3d_k2(&tb3, a->B, a->b_rows, a->ldb_, a->BN) == 0) {
+        ta = ta3; tb = tb3;
+        p.bigbox = env_big;
+        g_bigbox_launches.fetch_add(1, std::memory_order_relaxed);
+      }
+    }
+  }
   p.M = a->M; p.Npad = a->Npad; p.K = a->K; p.T = a->T;
   p.a_koff = a->a_koff; p.b_koff = a->b_koff;
   for (int t = 0; t < a->T; ++t) p.tap_off[t] = a->tap_off[t];
@@ -281,7 +313,8 @@ int craft_shift_gemm(const craft_gemm_args* a, void* stream) {
     const int slots = a->BN >= 256 ? 4 : (a->BN >= 128 ? 6 : (a->BN >= 64 ? 8 : 10));
     const char* e = getenv("CRAFT_GEMM_KC");          // tuning/profiling override
     p.kc = (a->K % 128 == 0) ? 2 : 1;
-    if (e && atoi(e) == 1) p.kc = 1;
+    if (e && atoi(e) == 1 && !p.bigbox) p.kc = 1;
+    if (p.bigbox) p.kc = 2;
     const int smax = slots / p.kc;
     p.stages = (a->stages > 0 && a->stages < smax) ? a->stages : smax;
   }

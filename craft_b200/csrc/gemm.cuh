@@ -57,6 +57,11 @@ struct GemmParams {
   // (Measured: the 128-byte swizzle is a function of the absolute smem address, so the shifted start
   // needs NO base-offset correction in the descriptor -- setting bits 49-51 gives wrong results.)
   int ashare, gsize;
+  // bigbox != 0 (experimental, untested on hardware at the end of round 1 -- profiles/r01_mb_tma.txt shows
+  // a TMA box costs ~257 clk whatever its size): tmA / tmB are 3-D maps over [64][rows][K/64] and ONE box
+  // per operand brings both K atoms of a stage; stage layout [A0][A1][B0][B1].  bigbox == 2: A and B are
+  // issued by two lanes of the producer warp.  Needs kc == 2, no cluster, no blocked B.
+  int bigbox;
   // row validity: Wp > 0 => row m is a real token iff (m % Wp) < W and (m / Wp) < H;
   //               Wp == 0 => every m < M is valid.
   int Wp, W, H;
@@ -139,7 +144,7 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int s = 0; s < 2 * (kAsSlots + kBsSlots); ++s) mbar_init(&a_full[s], 1);
     } else {
       for (int s = 0; s < S::kStages; ++s) {
-        mbar_init(&full_bar[s], 1);
+        mbar_init(&full_bar[s], p.bigbox == 2 ? 2 : 1);     // one arrive.expect_tx per producer lane
         mbar_init(&empty_bar[s], CL);
       }
     }
@@ -175,6 +180,26 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (++bs == kBsSlots) { bs = 0; bph ^= 1u; }
             }
           }
+      }
+    } else if (p.bigbox) {
+      const uint32_t lane = lane_id();
+      const bool two = p.bigbox == 2;
+      if (lane < (two ? 2u : 1u)) {
+        const bool do_a = !two || lane == 0, do_b = !two || lane == 1;
+        const uint32_t bytes = (do_a ? 2u * S::kABytes : 0u) + (do_b ? 2u * S::kBBytes : 0u);
+        const int nst = nk / 2;
+        int stage = 0, t = 0, kc = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < nst; ++it) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], bytes);
+          uint8_t* sa = smem + stage * 2 * S::kStageBytes;       // [A atom 0][A atom 1][B atom 0][B atom 1]
+          if (do_a) tma_load_3d(sa, &tmA, &full_bar[stage], 0, m0 + p.tap_off[t], (p.a_koff >> 6) + kc);
+          if (do_b) tma_load_3d(sa + 2 * S::kABytes, &tmB, &full_bar[stage], 0, t * p.Npad + n0, (p.b_koff >> 6) + kc);
+          kc += 2;
+          if (kc == kchunks) { kc = 0; ++t; }
+          if (++stage == nstages) { stage = 0; phase ^= 1u; }
+        }
       }
     } else if (elect_one()) {
       const int KC = p.kc;
@@ -259,12 +284,15 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_after();
       if (leader) {
         for (int a = 0; a < KC; ++a) {
-          const uint64_t d = da + static_cast<uint64_t>(a) * kSlotStep;
+          // legacy stage: [A0 B0][A1 B1]; big-box stage: [A0 A1][B0 B1]
+          const uint64_t d = da + static_cast<uint64_t>(a) * (p.bigbox ? kBOff : kSlotStep);
+          const uint64_t e = p.bigbox ? da + 2u * kBOff + static_cast<uint64_t>(a) * static_cast<uint64_t>(S::kBBytes >> 4)
+                                      : d + kBOff;
           // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-          umma_f16(tmem_base, d, d + kBOff, idesc, (it | a) != 0 ? 1u : 0u);
-          umma_f16_acc(tmem_base, d + 2u, d + kBOff + 2u, idesc);
-          umma_f16_acc(tmem_base, d + 4u, d + kBOff + 4u, idesc);
-          umma_f16_acc(tmem_base, d + 6u, d + kBOff + 6u, idesc);
+          umma_f16(tmem_base, d, e, idesc, (it | a) != 0 ? 1u : 0u);
+          umma_f16_acc(tmem_base, d + 2u, e + 2u, idesc);
+          umma_f16_acc(tmem_base, d + 4u, e + 4u, idesc);
+          umma_f16_acc(tmem_base, d + 6u, e + 6u, idesc);
         }
         // frees the smem stage (in every CTA of the cluster) when these MMAs retire
         if constexpr (CL > 1) umma_commit_mcast(&empty_bar[stage], kMask);

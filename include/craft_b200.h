@@ -26,6 +26,8 @@ int craft_b200_abi_version(void);
 const char* craft_b200_last_error(void);
 /* number of kernels this library has launched so far in this process (host-side counter) */
 long long craft_b200_launch_count(void);
+/* GEMM launches that took the experimental big-box TMA path (CRAFT_GEMM_BIGBOX=1|2); 0 otherwise.   */
+long long craft_b200_bigbox_gemm_count(void);
 /* device properties the host uses for grid sizing: [0]=sm count, [1]=cc major, [2]=cc minor */
 int craft_b200_device_info(int* out3);
 

@@ -1,6 +1,7 @@
 """Kernel-level parity on the GPU: every C-ABI entry point against the oracle restatement
 (oracle/restate.py, plain torch fp32) on identical, bf16-representable inputs."""
 import math
+import os
 
 import pytest
 import torch
@@ -13,6 +14,7 @@ from craft_b200.ops import TokenGrid            # noqa: E402
 from oracle import restate as R                 # noqa: E402
 
 DEV = "cuda"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def bf16r(t):
@@ -399,3 +401,21 @@ def test_corr_lookup0_on_demand(H, W, M, d, clipv):
                      mean_rstd=torch.tensor([mean, rstd], device=DEV), out_nchw=out_n)
     torch.cuda.synchronize()
     assert torch.allclose(out_n[:81], ref, atol=3e-3, rtol=1e-3), (out_n[:81] - ref).abs().max()
+
+
+@pytest.mark.skipif(os.environ.get("CRAFT_B200_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental big-box TMA mode of the shift-GEMM: written at the end of round 1 without "
+                           "GPU time left to validate it; run with CRAFT_B200_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_gemm_bigbox_mode_in_subprocess(mode):
+    """CRAFT_GEMM_BIGBOX is read once per process, so the GEMM tests are re-run in a child process with it
+    set; the child also checks that the big-box path was really taken (no silent fallback)."""
+    import subprocess
+    import sys
+    env = dict(os.environ, CRAFT_GEMM_BIGBOX=mode, CRAFT_B200_TEST_EXPERIMENTAL="0")
+    code = ("import sys, pytest; rc = pytest.main(['-q', '-x', '-m', 'gpu', '-k', 'test_gemm_plain or test_gemm_conv or "
+            "test_gemm_gru_epilogues', %r]); "
+            "from craft_b200 import _lib; n = _lib.load().craft_b200_bigbox_gemm_count(); print('bigbox launches', n); "
+            "sys.exit(int(rc) or (0 if n > 0 else 3))" % os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
