@@ -282,7 +282,7 @@ def run_ours(args):
     roof = None
     if rank == 0:
         g = TokenGrid(H // 8, W // 8)
-        ws = get_workspace(g, dev, model.materialize_level0)
+        ws = model._workspaces.get(g, dev, model.materialize_level0)
         ks = ws.pv_split(4)
         O = ws.opart(ks, 4, 128)
         tbl = model.att.vispos_encoder.table()

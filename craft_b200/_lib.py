@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcraft_b200.so")
 MAX_TAPS = 49
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class CraftB200Error(RuntimeError):
@@ -49,6 +49,7 @@ class ScoresArgs(C.Structure):
         ("stat_sum", C.c_void_p), ("stat_max", C.c_void_p),
         ("lvl", C.c_void_p * 4),
         ("lse_part", C.c_void_p), ("lse2", C.c_void_p),
+        ("mask_radius", C.c_int),
     ]
 
 
@@ -60,7 +61,19 @@ class PvArgs(C.Structure):
         ("scale", C.c_float), ("w_pos", C.c_float),
         ("pos_table", C.c_void_p), ("R", C.c_int),
         ("clip", C.c_void_p), ("lse2", C.c_void_p), ("out", C.c_void_p),
-        ("ksplit", C.c_int), ("zero_fill", C.c_int),
+        ("ksplit", C.c_int), ("zero_fill", C.c_int), ("mask_radius", C.c_int),
+    ]
+
+
+class DenseAttnArgs(C.Structure):
+    _fields_ = [
+        ("Q", C.c_void_p), ("K", C.c_void_p),
+        ("C", C.c_int), ("M", C.c_int), ("d", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("scale", C.c_float), ("w_pos", C.c_float),
+        ("pos_table", C.c_void_p), ("R", C.c_int),
+        ("clip", C.c_void_p), ("lse2", C.c_void_p),
+        ("mask_radius", C.c_int),
+        ("out", C.c_void_p),
     ]
 
 
@@ -80,11 +93,13 @@ SIGNATURES = {
     "craft_scores_auto_ksplit": (_i, [_i, _i]),
     "craft_pv_auto_ksplit": (_i, [_i, _i, _i]),
     "craft_pv_block_keys": (_i, [_i, _i]),
-    "craft_corr_stats_finalize": (_i, [_vp, _d, _vp, _vp]),
-    "craft_clip_gate": (_i, [_vp, _f, _vp, _vp, _vp]),
+    "craft_corr_stats_finalize": (_i, [_vp, _vp, _d, _vp, _vp]),
+    "craft_clip_gate": (_i, [_vp, _f, _vp, _vp, _vp, _vp]),
     "craft_attn_pv": (_i, [C.POINTER(PvArgs), _vp]),
     "craft_modes_finalize": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _i, _i, _i, _i,
                                   _vp, _i, _i, _vp, _i, _i, _i, _vp]),
+    "craft_soft_aggregate": (_i, [_vp, _vp, _i, C.c_longlong, _i, _vp, _vp, _vp, _vp]),
+    "craft_attn_dense": (_i, [C.POINTER(DenseAttnArgs), _vp]),
     "craft_corr_lookup": (_i, [C.POINTER(_vp), _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp]),
     "craft_corr_lookup0": (_i, [_vp, _vp, _i, _i, _f, _f, _f, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     "craft_convf1": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _i, _vp]),

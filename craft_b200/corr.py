@@ -41,17 +41,20 @@ class _LookupMixin:
                         first_level=first)
 
     def __call__(self, coords):
-        """coords [B,2,h,w] (x,y) -> [B,324,h,w] fp32."""
+        """coords [B,2,h,w] (x,y) -> [B,324,h,w] fp32 (core/corr.py:47-71)."""
         B, _, h, w = coords.shape
         if B != 1:
-            raise NotImplementedError("standalone CorrBlock lookup handles one pair per call; CRAFT.forward "
-                                      "iterates over the batch itself")
+            raise NotImplementedError("standalone CorrBlock lookup handles one pair per call (one pyramid is held); "
+                                      "CRAFT.forward iterates over the batch itself")
         ws = self._ws
+        if ws is None:
+            raise RuntimeError("call update() / construct the CorrBlock before looking up")
         g = ws.grid
-        crow = torch.zeros((g.Mp, 2), dtype=torch.float32, device=coords.device)
-        crow.view(g.H, g.Wp, 2)[:, :g.W] = coords[0].permute(1, 2, 0)
-        out = torch.empty((1, 324, h, w), dtype=torch.float32, device=coords.device)
-        self.lookup_rows(ws, crow, out_nchw=out[0])
+        with torch.cuda.device(coords.device):
+            crow = torch.zeros((g.Mp, 2), dtype=torch.float32, device=coords.device)
+            crow.view(g.H, g.Wp, 2)[:, :g.W] = coords[0].float().permute(1, 2, 0)
+            out = torch.empty((1, 324, h, w), dtype=torch.float32, device=coords.device)
+            self.lookup_rows(ws, crow, out_nchw=out[0])
         return out
 
 
@@ -67,11 +70,12 @@ class CorrBlock(_LookupMixin):
         if Cc != 256:
             raise NotImplementedError("CorrBlock kernel instantiated for 256-channel fnet features")
         grid = TokenGrid(h, w)
-        ws = self._ws = get_workspace(grid, fmap1.device, "SAVECORR" in os.environ)
-        ops.pack_tokens(fmap1[0].float().contiguous(), grid, ops.PACK_COPY, out_b=ws.Qc)
-        ops.pack_tokens(fmap2[0].float().contiguous(), grid, ops.PACK_COPY, out_b=ws.Kc)
-        hp.build_correlation(ws, ws.Qc, ws.Kc, M=1, d=Cc, w_agg=0.0, table=None, w_pos=0.0,
-                             global_norm=do_corr_global_norm)
+        with torch.cuda.device(fmap1.device):
+            ws = self._ws = get_workspace(grid, fmap1.device, "SAVECORR" in os.environ)
+            ops.pack_tokens(fmap1[0].float().contiguous(), grid, ops.PACK_COPY, out_b=ws.Qc)
+            ops.pack_tokens(fmap2[0].float().contiguous(), grid, ops.PACK_COPY, out_b=ws.Kc)
+            hp.build_correlation(ws, ws.Qc, ws.Kc, M=1, d=Cc, w_agg=0.0, table=None, w_pos=0.0,
+                                 global_norm=do_corr_global_norm)
 
 
 class TransCorrBlock(_LookupMixin, nn.Module):
@@ -95,9 +99,10 @@ class TransCorrBlock(_LookupMixin, nn.Module):
         hp.build_correlation(ws, ws.Qc, ws.Kc, M=st.num_modes, d=st.attention_mode_dim,
                              w_agg=pk.get("w_agg", 0.0), table=self.vispos_encoder.table(),
                              w_pos=st.pos_code_weight, global_norm=self.do_corr_global_norm,
-                             attn_clip=st.attn_clip)
+                             attn_clip=st.attn_clip, diag=st.diag(ws.Qc.device))
         self._ws = ws
 
+    @ops.on_device
     def update(self, fmap1, fmap2, fmap1o, fmap2o, coords1, coords2=None):
         if fmap1o is not None and fmap2o is not None:
             raise NotImplementedError("two-way correlation (--f1 shared/private) is an ablation outside the hot path")

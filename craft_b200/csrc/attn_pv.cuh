@@ -50,6 +50,7 @@ struct PvParams {
   const float* lse2;       // [M][Mp] log2-domain log-sum-exp
   float* out;              // [nslots][M][F/8][Mp][8] f32 partial sums (8-column chunks, see the write-back)
   int nkt, nbx;            // key tiles (blocks) in total / per block-row
+  int mask_radius;         // > 0: keys farther than this (Chebyshev) from the query get probability 0 (--f2radius)
   long long* trace;        // CRAFT_PV_TRACE: clock64 timeline of CTA 0: [role 4][tile 64][slot 8], then globaltimer (start, end) of every CTA
 };
 
@@ -63,7 +64,7 @@ struct PvSmem {
   static_assert(kTotal <= 227 * 1024, "attn_pv: shared memory budget");
 };
 
-template <int D, int F, int BK, int KS, int VS>
+template <int D, int F, int BK, int KS, int VS, int POLY = 0, bool MASKED = false>
 __global__ void __launch_bounds__(kPvThreads, 1)
 attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ PvParams p) {
@@ -370,8 +371,17 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               x[e] += trow[(col / BW) * TW + (col % BW)];
             }
           }
+          if constexpr (MASKED) {     // --f2radius (default off): exp2(-inf) = 0, as exp(s - 1e9 - max) is in the reference
 #pragma unroll
-          for (int e = 0; e < 16; ++e) pk[c / 2 + e] = pack_bf16x2(fast_ex2(x[2 * e]), fast_ex2(x[2 * e + 1]));
+            for (int e = 0; e < 32; ++e) {
+              const int col = c + e;
+              const int dy = by * 8 + ch * 4 + col / BW - qy, dx = bx * BW + col % BW - qx;
+              if (abs(dy) > p.mask_radius || abs(dx) > p.mask_radius) x[e] = -INFINITY;
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            pk[c / 2 + e] = pack_bf16x2(ex2_mix<POLY>(x[2 * e], 2 * e), ex2_mix<POLY>(x[2 * e + 1], 2 * e + 1));
         }
         if (trole < 4) PV_TRACE(trole, g, 3);
         // P -> TMEM (this warp's lanes, columns it has just read), then hand the buffer to the P.V issuer

@@ -15,6 +15,7 @@
 #include "gemm.cuh"
 #include "pointwise.cuh"
 #include "scores.cuh"
+#include "standalone.cuh"
 
 namespace {
 
@@ -132,27 +133,43 @@ int make_map_3d_keys(CUtensorMap* m, const void* base, const cb::Grid2& g, int C
   return 0;
 }
 
+// Per-device caches: a process may drive several GPUs (nn.DataParallel replicates the module, one
+// thread per device), and both the SM count and cudaFuncSetAttribute are per device.
+constexpr int kMaxDevices = 64;
+int cur_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
 int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static std::atomic<int> n[kMaxDevices];
+  const int dev = cur_device();
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (!v) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+    n[dev].store(v, std::memory_order_relaxed);
   }
-  return n;
+  return v;
+}
+// Opt a kernel in to `bytes` of dynamic shared memory once per device; `done` is the call site's
+// own bitmap (one bit per device).
+template <typename K>
+int ensure_smem(K kern, int bytes, std::atomic<unsigned long long>& done, const char* what) {
+  const int dev = cur_device();
+  if ((done.load(std::memory_order_acquire) >> dev) & 1ull) return 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess)
+    return fail("%s: cannot opt in to %d bytes of dynamic shared memory", what, bytes);
+  done.fetch_or(1ull << dev, std::memory_order_release);
+  return 0;
 }
 
 template <int BN, int EPI, int CL>
 int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const cb::GemmParams& p, cudaStream_t st) {
   using S = cb::GemmSmem<BN>;
-  static bool attr_set = false;
+  static std::atomic<unsigned long long> attr_set{0};
   auto kern = cb::shift_gemm_kernel<BN, EPI, CL>;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal) != cudaSuccess)
-      return fail("gemm: cannot set dynamic smem %d", S::kTotal);
-    attr_set = true;
-  }
+  if (ensure_smem(kern, S::kTotal, attr_set, "shift_gemm")) return -1;
   const int mtiles = (p.M + cb::kGemmBM - 1) / cb::kGemmBM;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -423,6 +440,7 @@ static int scores_common(const craft_scores_args* a, int mode, void* stream) {
   p.nqt = (g.Mp + 127) / 128;
   const int need = sc_slots(p.nqt, p.nkt_y * p.nkt_x);
   p.nslots = a->ksplit > 0 ? a->ksplit : need;
+  p.mask_radius = (mode == cb::SC_LSE) ? a->mask_radius : 0;
   if (mode == cb::SC_LSE && p.nslots < need) return fail("attn_lse: lse_part has %d slots, the schedule needs %d", p.nslots, need);
   p.w_agg = a->w_agg; p.stat_sum = a->stat_sum; p.stat_max = a->stat_max;
   int h = a->H, w = a->W;
@@ -438,16 +456,23 @@ static int scores_common(const craft_scores_args* a, int mode, void* stream) {
   if (mode == cb::SC_CORR) {
     if (!a->stat_sum || !a->stat_max || !a->lvl[1] || !a->lvl[2] || !a->lvl[3]) return fail("corr_build: missing outputs");
     auto kern = cb::scores_kernel<cb::SC_CORR>;
-    static bool set = false;
-    if (!set) { if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return fail("scores: smem attr"); set = true; }
+    static std::atomic<unsigned long long> set{0};
+    if (ensure_smem(kern, 200 * 1024, set, "scores")) return -1;
     launch_k(kern, dim3(grid), dim3(cb::kScThreads), smem, st, tq, tk, p);
     return check_launch("corr_build");
   } else {
     if (!a->lse_part || !a->lse2 || !a->stat_max) return fail("attn_lse: missing outputs");
-    auto kern = cb::scores_kernel<cb::SC_LSE>;
-    static bool set = false;
-    if (!set) { if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return fail("scores: smem attr"); set = true; }
-    launch_k(kern, dim3(grid), dim3(cb::kScThreads), smem, st, tq, tk, p);
+    if (p.mask_radius > 0) {
+      auto kern = cb::scores_kernel<cb::SC_LSE_MASKED>;
+      static std::atomic<unsigned long long> set{0};
+      if (ensure_smem(kern, 200 * 1024, set, "scores")) return -1;
+      launch_k(kern, dim3(grid), dim3(cb::kScThreads), smem, st, tq, tk, p);
+    } else {
+      auto kern = cb::scores_kernel<cb::SC_LSE>;
+      static std::atomic<unsigned long long> set{0};
+      if (ensure_smem(kern, 200 * 1024, set, "scores")) return -1;
+      launch_k(kern, dim3(grid), dim3(cb::kScThreads), smem, st, tq, tk, p);
+    }
     if (check_launch("attn_lse")) return -1;
     const int n = a->M * g.Mp;
     launch_k(cb::lse_merge_kernel, dim3((n + 255) / 256), dim3(256), 0, st, p.lse_part, p.nslots, a->M, g.Mp, a->lse2);
@@ -459,17 +484,17 @@ extern "C" {
 int craft_corr_build(const craft_scores_args* a, void* stream) { return scores_common(a, cb::SC_CORR, stream); }
 int craft_attn_lse(const craft_scores_args* a, void* stream) { return scores_common(a, cb::SC_LSE, stream); }
 
-int craft_corr_stats_finalize(const double* stat_sum, double n, float* mean_rstd, void* stream) {
-  launch_k(cb::corr_stats_finalize_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), stat_sum, n, mean_rstd);
+int craft_corr_stats_finalize(const double* stat_sum, const int* flag, double n, float* mean_rstd, void* stream) {
+  launch_k(cb::corr_stats_finalize_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), stat_sum, flag, n, mean_rstd);
   return check_launch("corr_stats_finalize");
 }
-int craft_clip_gate(const float* stat_max, float attn_clip, float* clip, int* flag, void* stream) {
-  launch_k(cb::clip_gate_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), stat_max, attn_clip, clip, flag);
+int craft_clip_gate(const float* stat_max, float attn_clip, float* clip, int* flag, float* diag, void* stream) {
+  launch_k(cb::clip_gate_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), stat_max, attn_clip, clip, flag, diag);
   return check_launch("clip_gate");
 }
 
 }  // extern "C" (pause)
-template <int D, int F, int BK, int KS, int VS>
+template <int D, int F, int BK, int KS, int VS, int POLY = 0, bool MASKED = false>
 static int launch_pv(const craft_pv_args* a, const cb::Grid2& g, cudaStream_t st) {
   using S = cb::PvSmem<D, F, BK, KS, VS>;
   CUtensorMap tq, tk, tv;
@@ -488,10 +513,10 @@ static int launch_pv(const craft_pv_args* a, const cb::Grid2& g, cudaStream_t st
   if (a->ksplit > 4) return fail("attn_pv: at most 4 partial slots");
   p.g = g; p.M = a->M; p.nslots = a->ksplit; p.zero_fill = a->zero_fill; p.nqt = nqt; p.scale = a->scale; p.w_pos = a->w_pos;
   p.pos_table = a->pos_table; p.R = a->R; p.clip = a->clip; p.lse2 = a->lse2; p.out = a->out;
-  p.nkt = nkt; p.nbx = nbx;
-  auto kern = cb::attn_pv_kernel<D, F, BK, KS, VS>;
-  static bool set = false;
-  if (!set) { if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal) != cudaSuccess) return fail("pv: smem attr %d", S::kTotal); set = true; }
+  p.nkt = nkt; p.nbx = nbx; p.mask_radius = a->mask_radius;
+  auto kern = cb::attn_pv_kernel<D, F, BK, KS, VS, POLY, MASKED>;
+  static std::atomic<unsigned long long> set{0};
+  if (ensure_smem(kern, S::kTotal, set, "attn_pv")) return -1;
   dim3 grid(pv_grid(nqt, a->M, nkt));
   static long long* d_trace = nullptr;
   const char* trace_path = getenv("CRAFT_PV_TRACE");     // profiling aid: dumps CTA 0's clock64 timeline
@@ -529,7 +554,23 @@ int craft_attn_pv(const craft_pv_args* a, void* stream) {
   cb::Grid2 g = make_grid(a->H, a->W);
   if (a->ldv % 8) return fail("attn_pv: ldv=%d must be a multiple of 8", a->ldv);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (a->d == 32 && a->F == 128) return launch_pv<32, 128, 128, 3, 4>(a, g, st);
+  if (a->d == 32 && a->F == 128) {
+    // fraction (POLY / 8) of the exponentials evaluated on the FMA pipe instead of the MUFU unit
+    static int poly = -1;
+    if (poly < 0) { const char* e = getenv("CRAFT_PV_POLY"); poly = e ? atoi(e) : 0; }
+    switch (poly) {
+      case 1: return launch_pv<32, 128, 128, 3, 4, 1>(a, g, st);
+      case 2: return launch_pv<32, 128, 128, 3, 4, 2>(a, g, st);
+      case 3: return launch_pv<32, 128, 128, 3, 4, 3>(a, g, st);
+      case 4: return launch_pv<32, 128, 128, 3, 4, 4>(a, g, st);
+      case 8: return launch_pv<32, 128, 128, 3, 4, 8>(a, g, st);
+      default: return launch_pv<32, 128, 128, 3, 4>(a, g, st);
+    }
+  }
+  if (a->mask_radius > 0) {
+    if (a->d == 64 && a->F == 256) return launch_pv<64, 256, 64, 4, 4, 0, true>(a, g, st);
+    return fail("attn_pv: the --f2radius key mask is built for the F2 transformer shape (d=64, F=256) only");
+  }
   if (a->d == 64 && a->F == 256) return launch_pv<64, 256, 64, 4, 4>(a, g, st);
   if (a->d == 128 && a->F == 128) return launch_pv<128, 128, 64, 3, 4>(a, g, st);
   if (a->d == 64 && a->F == 128) return launch_pv<64, 128, 128, 3, 4>(a, g, st);
@@ -563,6 +604,37 @@ int craft_modes_finalize(const float* O, int nsum, int M, int F, const float* w_
     launch_k(cb::modes_finalize_kernel<256>, dim3(grid), dim3(256), 0, st, O, nsum, part_stride, M, mode_stride, w_score, b_score, coeff, gma, xb, ldx, colx, x_f32, ldxf, colxf, g, ob, ldb, colb, out_f32, ldf, colf, pv_G, pv_nkt);
   else return fail("modes_finalize: F must be 128 or 256");
   return check_launch("modes_finalize");
+}
+
+int craft_soft_aggregate(const float* x, const float* basis, int M, long long n, int F, const float* w,
+                         const float* b, float* out, void* stream) {
+  if (!x || !w || !b || !out) return fail("soft_aggregate: null operand");
+  if (M < 1 || M > 8 || n < 1 || F < 1) return fail("soft_aggregate: bad shape M=%d n=%lld F=%d", M, n, F);
+  if (!basis) basis = x;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (F == 1) {
+    long long blocks = (n + 255) / 256;
+    if (blocks > 8ll * sm_count()) blocks = 8ll * sm_count();
+    launch_k(cb::soft_aggregate_scalar_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, x, basis, M, n, w, b, out);
+  } else {
+    launch_k(cb::soft_aggregate_feat_kernel, dim3(static_cast<unsigned>((n + 7) / 8)), dim3(256), 0, st, x, basis, M, n, F, w, b, out);
+  }
+  return check_launch("soft_aggregate");
+}
+
+int craft_attn_dense(const craft_dense_attn_args* a, void* stream) {
+  if (!a || !a->Q || !a->K || !a->clip || !a->out) return fail("attn_dense: null operand");
+  if (a->C != a->M * a->d || a->d % 2) return fail("attn_dense: bad C/M/d");
+  if (a->pos_table && (2 * a->R + 1) * (2 * a->R + 1) > 225) return fail("attn_dense: pos radius too large");
+  cb::Grid2 g = make_grid(a->H, a->W);
+  cb::DenseAttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.Q = static_cast<const __nv_bfloat16*>(a->Q); p.K = static_cast<const __nv_bfloat16*>(a->K);
+  p.C = a->C; p.M = a->M; p.d = a->d; p.scale = a->scale; p.w_pos = a->w_pos; p.pos_table = a->pos_table; p.R = a->R;
+  p.clip = a->clip; p.lse2 = a->lse2; p.mask_radius = a->mask_radius; p.out = a->out;
+  const long long units = static_cast<long long>(a->M) * a->H * a->W;
+  launch_k(cb::attn_dense_kernel, dim3(static_cast<unsigned>((units + 7) / 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), p, g);
+  return check_launch("attn_dense");
 }
 
 int craft_corr_lookup(const float* const* lvl, int H, int W, const float* coords, const float* mean_rstd,

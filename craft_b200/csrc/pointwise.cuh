@@ -275,9 +275,9 @@ __global__ void __launch_bounds__(256) corr_lookup0_kernel(Lookup0Params p, Grid
         float tm = -INFINITY;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-          s[m] = (m < p.M) ? fminf(fmaxf(smodes[wib][e][m] * p.scale, -clipv), clipv) : -INFINITY;
-          t[m] = s[m] * wl2;
-          tm = fmaxf(tm, t[m]);
+          s[m] = (m < p.M) ? fminf(fmaxf(smodes[wib][e][m] * p.scale, -clipv), clipv) : 0.f;
+          t[m] = s[m] * wl2;                      // w_agg is signed: unused modes must not enter the max
+          if (m < p.M) tm = fmaxf(tm, t[m]);
         }
         float num = 0.f, den = 0.f;
 #pragma unroll

@@ -33,7 +33,7 @@ constexpr int kScThreads = 64 + 512;   // 576 threads -> 112 registers each
 constexpr int kScKStages = 3;
 constexpr int kScTailBytes = 512 /*barriers*/ + 2560 /*bias table*/ + 2048 /*level-3 exchange*/ + 16384 /*lse merge*/;
 
-enum ScoreMode : int { SC_CORR = 0, SC_LSE = 1 };
+enum ScoreMode : int { SC_CORR = 0, SC_LSE = 1, SC_LSE_MASKED = 2 };   // MASKED: SC_LSE with the --f2radius key mask
 
 struct ScoreParams {
   Grid2 g;                 // token grid (queries and keys share it)
@@ -49,6 +49,7 @@ struct ScoreParams {
   int nkt_y, nkt_x;        // key tiles (8x8 blocks) in y / x
   int nqt;                 // query tiles
   int nslots;              // SC_LSE: partial slots in lse_part
+  int mask_radius;         // SC_LSE: > 0 masks keys farther than this (Chebyshev) from the query (--f2radius)
   // SC_CORR
   float w_agg;             // LearnedSoftAggregate(1).feat2score.weight
   double* stat_sum;        // [2]: sum, sumsq   (atomics)
@@ -65,10 +66,12 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
 }
 
 // smem: Q tile (C/64 atoms x 16 KB) + K stages (C/64 atoms x 8 KB each) + tail
-template <int MODE>
+template <int MODE_>
 __global__ void __launch_bounds__(kScThreads, 1)
 scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ ScoreParams p) {
+  constexpr int MODE = (MODE_ == SC_LSE_MASKED) ? SC_LSE : MODE_;
+  constexpr bool masking = (MODE_ == SC_LSE_MASKED);
   pdl_launch_dependents();
   if (p.run_flag != nullptr) {
     pdl_wait();                                             // the flag is written by the preceding gate kernel
@@ -293,17 +296,17 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 v = clamped ? fminf(fmaxf(s0, -clipv), clipv) : s0;
               } else {
                 const float a1 = __uint_as_float(r1[j]);
-                const float a2 = (p.M > 2) ? __uint_as_float(r2[j]) : -INFINITY;
-                const float a3 = (p.M > 2) ? __uint_as_float(r3[j]) : -INFINITY;
+                // M == 2: the unused modes duplicate mode 0/1, so that neither the max nor the (signed!)
+                // soft-aggregation weight ever sees an infinity
+                const float a2 = (p.M > 2) ? __uint_as_float(r2[j]) : a0;
+                const float a3 = (p.M > 2) ? __uint_as_float(r3[j]) : a1;
                 seg_rawmax = fmaxf(seg_rawmax, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));
                 float s0 = a0 * p.scale, s1 = a1 * p.scale, s2 = a2 * p.scale, s3 = a3 * p.scale;
                 if (clamped) {
                   s0 = fminf(fmaxf(s0, -clipv), clipv);
                   s1 = fminf(fmaxf(s1, -clipv), clipv);
-                  if (p.M > 2) {
-                    s2 = fminf(fmaxf(s2, -clipv), clipv);
-                    s3 = fminf(fmaxf(s3, -clipv), clipv);
-                  }
+                  s2 = fminf(fmaxf(s2, -clipv), clipv);
+                  s3 = fminf(fmaxf(s3, -clipv), clipv);
                 }
                 // softmax over modes of w*s (the Linear(1,1) bias cancels), in the exp2 domain.
                 const float t0 = s0 * wl2, t1 = s1 * wl2, t2 = s2 * wl2, t3 = s3 * wl2;
@@ -418,7 +421,7 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
               for (int e = 1; e < 32; ++e) rmax = fmaxf(rmax, __uint_as_float(raw[e]));
               seg_rawmax = fmaxf(seg_rawmax, rmax);
-              if (!near_w && !clamped && full) {
+              if (!near_w && !clamped && full && !masking) {
                 // fast path: exp2(raw * scale*log2e - max*log2e), one FFMA + one MUFU per key
                 const float nm = fmaxf(run.x, rmax * p.scale);
                 const float nm2 = nm * kLog2e;
@@ -430,7 +433,7 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 }
                 run_l_new = run.y * fast_ex2((run.x - nm) * kLog2e) + (acc0 + acc1);
                 run_m_new = nm;
-              } else if (!clamped && full) {
+              } else if (!clamped && full && !masking) {
                 // near the query: the positional bias enters the max; values are built in place
                 float x[32];
 #pragma unroll
@@ -455,6 +458,8 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                   float s = fminf(fmaxf(__uint_as_float(raw[e]) * p.scale, -clipv), clipv);
                   if (near) s += trow_tab[(e >> 3) * TW + (e & 7)];
                   if (!full && !((ky0 + (e >> 3) < p.g.H) && (kx0 + (e & 7) < p.g.W))) s = -INFINITY;
+                  // --f2radius: the reference adds -1e9 (core/setrans.py:583), whose exp is exactly 0 in fp32
+                  if (masking && (abs(ky0 + (e >> 3) - qy) > p.mask_radius || abs(kx0 + (e & 7) - qx) > p.mask_radius)) s = -INFINITY;
                   return s;
                 };
                 float tmax = val(0);
@@ -551,23 +556,32 @@ __global__ void lse_merge_kernel(const float2* __restrict__ part, int ksplit, in
 
 // corr_stats_finalize: {sum, sumsq} over n elements -> {mean, rstd} (biased variance, eps 1e-12,
 // F.layer_norm semantics, core/corr.py:202) and the clamp gate: clip = (max > attn_clip) ? attn_clip : +inf.
-__global__ void corr_stats_finalize_kernel(const double* __restrict__ sums, double n,
+// sums: [2][2] -- slot 0 from the unclamped pass, slot 1 from the clamped re-pass, selected by *flag.
+__global__ void corr_stats_finalize_kernel(const double* __restrict__ sums, const int* __restrict__ flag, double n,
                                            float* __restrict__ mean_rstd) {
   pdl_launch_dependents();
   pdl_wait();
+  if (flag != nullptr && *flag != 0) sums += 2;
   const double mean = sums[0] / n;
   double var = sums[1] / n - mean * mean;
   if (var < 0) var = 0;
   mean_rstd[0] = static_cast<float>(mean);
   mean_rstd[1] = static_cast<float>(1.0 / sqrt(var + 1e-12));
 }
+// diag (optional, [2] f32): the module's running diagnostics {max_attn, clamp_count} that the reference
+// keeps on the host with two .item() syncs per call (core/setrans.py:520-529); here they stay on the device
+// and are read lazily.
 __global__ void clip_gate_kernel(const float* __restrict__ stat_max, float attn_clip,
-                                 float* __restrict__ clip, int* __restrict__ flag) {
+                                 float* __restrict__ clip, int* __restrict__ flag, float* __restrict__ diag) {
   pdl_launch_dependents();
   pdl_wait();
   const bool hit = stat_max[0] > attn_clip;
   clip[0] = hit ? attn_clip : INFINITY;
   flag[0] = hit ? 1 : 0;
+  if (diag) {
+    diag[0] = fmaxf(diag[0], stat_max[0]);
+    if (hit) diag[1] += 1.0f;
+  }
 }
 
 }  // namespace cb

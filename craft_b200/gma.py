@@ -61,15 +61,23 @@ class Attention(nn.Module):
                      lse_part=ws.lse_part, lse2=lse2, ksplit=ws.ks_sc)
         return AttentionHandle(g, Q, K, lse2, clip, None, 0.0, 1, 128)
 
+    @ops.on_device
     def forward(self, fmap):
+        """[B,128,h,w] -> AttentionHandle (list for B > 1) standing for softmax(q.k) (core/gma.py:74-102).
+        Handles of a standalone call own their buffers."""
         _require_inference(self.to_qk.weight)
         B, Cc, h, w = fmap.shape
-        if B != 1:
-            raise NotImplementedError("standalone gma.Attention handles one pair per call")
         grid = TokenGrid(h, w)
-        ws = get_workspace(grid, fmap.device)
-        ops.pack_tokens(fmap[0].float().contiguous(), grid, ops.PACK_COPY, out_b=ws.Ta)
-        return self.attend(ws, ws.Ta, ws.Qa, ws.Ka, ws.lse2_att, ws.clip_att)
+        dev = fmap.device
+        ws = get_workspace(grid, dev)
+        outs = []
+        for b in range(B):
+            T, Q, K = (grid.zeros(Cc, device=dev) for _ in range(3))
+            lse2 = torch.zeros((1, grid.Mp), dtype=torch.float32, device=dev)
+            clip = torch.full((1,), float("inf"), dtype=torch.float32, device=dev)
+            ops.pack_tokens(fmap[b].float().contiguous(), grid, ops.PACK_COPY, out_b=T)
+            outs.append(self.attend(ws, T, Q, K, lse2, clip))
+        return outs[0] if B == 1 else outs
 
 
 class Aggregate(nn.Module):
@@ -99,15 +107,24 @@ class Aggregate(nn.Module):
                            clip=att.clip, lse2=att.lse2, w_score=pk["gamma"], b_score=pk["gamma"],
                            coeff=pk["gamma"], gma=1, out_b=out_b, colb=colb, out_f=out_f, colf=colf)
 
+    @ops.on_device
     def forward(self, attn, fmap):
-        if not isinstance(attn, AttentionHandle):
+        """(AttentionHandle(s), fmap [B,128,h,w]) -> fmap + gamma * (attn @ to_v(fmap)) (core/gma.py:128-142)."""
+        atts = attn if isinstance(attn, (list, tuple)) else [attn]
+        if not all(isinstance(a, AttentionHandle) for a in atts):
             raise TypeError("craft_b200.gma.Aggregate takes the AttentionHandle returned by gma.Attention")
         _require_inference(self.to_v.weight)
         B, Cc, h, w = fmap.shape
-        grid = attn.grid
-        ws = get_workspace(grid, fmap.device)
-        xb = torch.zeros((grid.Mp, Cc), dtype=torch.bfloat16, device=fmap.device)
-        yf = torch.zeros((grid.Mp, Cc), dtype=torch.float32, device=fmap.device)
-        ops.pack_tokens(fmap[0].float().contiguous(), grid, ops.PACK_COPY, out_b=xb)
-        self.run(ws, attn, xb, 0, out_f=yf)
-        return ops.unpack_tokens(yf, 0, Cc, grid)[None]
+        if len(atts) != B:
+            raise ValueError("need one attention handle per batch element")
+        grid = atts[0].grid
+        dev = fmap.device
+        ws = get_workspace(grid, dev)
+        xb = grid.zeros(Cc, device=dev)
+        yf = grid.zeros(Cc, dtype=torch.float32, device=dev)
+        out = torch.empty((B, Cc, h, w), dtype=torch.float32, device=dev)
+        for b in range(B):
+            ops.pack_tokens(fmap[b].float().contiguous(), grid, ops.PACK_COPY, out_b=xb)
+            self.run(ws, atts[b], xb, 0, out_f=yf)
+            ops.unpack_tokens(yf, 0, Cc, grid, out=out[b])
+        return out

@@ -54,11 +54,15 @@ class Workspace:
         self.Ta = z(128); self.Qa = z(128); self.Ka = z(128)   # intra-frame attention
         self.Vt = torch.zeros((1024, self.ldv), dtype=torch.bfloat16, device=device)
         self.ks_sc = ops.scores_auto_ksplit(g)
-        self.ks_pv = {}
         self.lse_part = torch.zeros((self.ks_sc, 4, g.Mp, 2), dtype=f32, device=device)
         self.lse2_f2 = torch.zeros((4, g.Mp), dtype=f32, device=device)
         self.lse2_att = torch.zeros((4, g.Mp), dtype=f32, device=device)
-        self.Opart = None
+        # P.V partial sums: sized ONCE for the largest consumer this grid can see (a captured CUDA graph bakes
+        # the address in, so the buffer must never be reallocated): F2 transformer M=4 x F=256, the motion
+        # aggregator M=4 x F=128, GMA M=1 x F=128.
+        self.ks_pv = {M: ops.pv_auto_ksplit(g, M) for M in (1, 2, 4)}
+        n = max(self.ks_pv[4] * 4 * 256, self.ks_pv[2] * 2 * 256, self.ks_pv[1] * 256) * g.Mp
+        self.Opart = torch.zeros((n,), dtype=f32, device=device)
         # --- scalars
         self.clip_corr = torch.full((1,), _INF, dtype=f32, device=device)
         self.clip_f2 = torch.full((1,), _INF, dtype=f32, device=device)
@@ -91,14 +95,11 @@ class Workspace:
         self.coords1 = z(2, f32); self.flow = z(2, f32)
 
     def opart(self, ks, M, F):
-        n = ks * M * self.grid.Mp * F
-        if self.Opart is None or self.Opart.numel() < n:
-            self.Opart = torch.zeros((n,), dtype=torch.float32, device=self.device)
+        if ks * M * self.grid.Mp * F > self.Opart.numel():
+            raise ValueError("P.V partial-sum buffer is sized for M*F <= 1024 (got ks=%d, M=%d, F=%d)" % (ks, M, F))
         return self.Opart
 
     def pv_split(self, M):
-        if M not in self.ks_pv:
-            self.ks_pv[M] = ops.pv_auto_ksplit(self.grid, M)
         return self.ks_pv[M]
 
 
@@ -119,24 +120,25 @@ def project(grid, A, Wp, bias, out_b, *, K, a_koff=0, Npad=None):
                    out_b=out_b)
 
 
-def attention_stats(ws, Q, K, *, M, d, table, w_pos, clip, lse2, slot, attn_clip=100.0):
+def attention_stats(ws, Q, K, *, M, d, table, w_pos, clip, lse2, slot, attn_clip=100.0, diag=None, mask_radius=-1):
     """Softmax statistics with the reference's data-dependent clamp (core/setrans.py:520-529):
     pass 1 runs unclamped and records the global max; the gate kernel arms `clip`; pass 2 is a
-    device-side no-op unless the gate fired.  No host synchronisation."""
+    device-side no-op unless the gate fired.  No host synchronisation.  `diag`: the owning module's
+    device-side {max_attn, clamp_count}."""
     g = ws.grid
     clip.fill_(_INF)
     smax = ws.stat_max[slot:slot + 1]
     smax.fill_(-_INF)
     flag = ws.flag[slot:slot + 1]
     ops.attn_lse(Q, K, g, M=M, d=d, w_pos=w_pos, pos_table=table, R=7, clip=clip, stat_max=smax,
-                 lse_part=ws.lse_part, lse2=lse2, ksplit=ws.ks_sc)
-    ops.clip_gate(smax, attn_clip, clip, flag)
+                 lse_part=ws.lse_part, lse2=lse2, ksplit=ws.ks_sc, mask_radius=mask_radius)
+    ops.clip_gate(smax, attn_clip, clip, flag, diag)
     ops.attn_lse(Q, K, g, M=M, d=d, w_pos=w_pos, pos_table=table, R=7, clip=clip, stat_max=ws.stat_max[3:4],
-                 lse_part=ws.lse_part, lse2=lse2, ksplit=ws.ks_sc, run_flag=flag)
+                 lse_part=ws.lse_part, lse2=lse2, ksplit=ws.ks_sc, run_flag=flag, mask_radius=mask_radius)
 
 
 def value_aggregate(ws, Q, K, X, x_koff, W1p, *, M, d, F, table, w_pos, clip, lse2, w_score, b_score, coeff,
-                    out_b=None, colb=0, out_f=None, colf=0, gma=0):
+                    out_b=None, colb=0, out_f=None, colf=0, gma=0, mask_radius=-1):
     """ExpandedFeatTrans.forward core/setrans.py:364-410 without ever forming P:
     V^T = W1 X^T (tcgen05 GEMM) -> flash P.V per mode -> mode soft-pool + skip + LayerNorm."""
     g = ws.grid
@@ -147,12 +149,12 @@ def value_aggregate(ws, Q, K, X, x_koff, W1p, *, M, d, F, table, w_pos, clip, ls
     ks = ws.pv_split(M)
     O = ws.opart(ks, M, F)
     ops.attn_pv(Q, K, ws.Vt, g, M=M, d=d, F=F, w_pos=w_pos, pos_table=table, R=7, clip=clip, lse2=lse2,
-                out=O, ksplit=ks, zero_fill=False)
+                out=O, ksplit=ks, zero_fill=False, mask_radius=mask_radius)
     ops.modes_finalize(O, ks, M, F, g, w_score=w_score, b_score=b_score, coeff=coeff, gma=gma, x_b=X, colx=x_koff,
                        out_b=out_b, colb=colb, out_f=out_f, colf=colf, pv_bk=BK)
 
 
-def build_correlation(ws, Q, K, *, M, d, w_agg, table, w_pos, global_norm, attn_clip=100.0):
+def build_correlation(ws, Q, K, *, M, d, w_agg, table, w_pos, global_norm, attn_clip=100.0, diag=None):
     """TransCorrBlock.update (core/corr.py:148-207) / CorrBlock.__init__ (:16-45): pyramid + LN stats."""
     g = ws.grid
     # what the on-demand level-0 lookup needs to recompute volume cells (ops.corr_lookup0)
@@ -167,13 +169,13 @@ def build_correlation(ws, Q, K, *, M, d, w_agg, table, w_pos, global_norm, attn_
               ksplit=ws.ks_sc)
     ops.corr_build(Q, K, g, stat_sum=ws.stat_sum[0], stat_max=smax, **kw)
     if M > 1:   # the clamp exists only on the transformer path
-        ops.clip_gate(smax, attn_clip, clip, flag)
+        ops.clip_gate(smax, attn_clip, clip, flag, diag)
         ops.corr_build(Q, K, g, stat_sum=ws.stat_sum[1], stat_max=ws.stat_max[3:4], run_flag=flag, **kw)
-        sums = torch.where(flag.bool(), ws.stat_sum[1], ws.stat_sum[0])
+        gate = flag
     else:
-        sums = ws.stat_sum[0]
+        gate = None
     if global_norm:
-        ops.corr_stats_finalize(sums, float(g.U) * float(g.U), ws.mean_rstd)
+        ops.corr_stats_finalize(ws.stat_sum, float(g.U) * float(g.U), ws.mean_rstd, flag=gate)
     else:
         ws.mean_rstd.copy_(ws.identity_stats)
 
@@ -181,12 +183,26 @@ def build_correlation(ws, Q, K, *, M, d, w_agg, table, w_pos, global_norm, attn_
 # ------------------------------------------------------------------------------------------------
 # update block (one refinement iteration)
 # ------------------------------------------------------------------------------------------------
-class UpdateWeights:
-    """Packed parameters of GMAUpdateBlock (core/update.py:116-162)."""
+def pack_gru(gru, grid):
+    """[(w_zr, b_zr, w_q, b_q, taps)] for the 1x5 and the 5x1 pass of SepConvGRU (core/update.py:49-64)."""
+    pc = ops.pack_conv_weight
+    perm = list(range(128, 512)) + list(range(0, 128))      # q conv reads X[:, 128:640] = [x | r*h]
+    out = []
+    for tag in ("1", "2"):
+        cz, cr, cq = (getattr(gru, "conv%s%s" % (n, tag)) for n in "zrq")
+        wzr = pc(torch.cat([cz.weight, cr.weight], 0))
+        bzr = torch.cat([cz.bias, cr.bias]).detach().float().contiguous()
+        wq = pc(cq.weight, cin_perm=perm)
+        bq = cq.bias.detach().float().contiguous()
+        kh, kw = cz.weight.shape[2:]
+        out.append((wzr, bzr, wq, bq, ops.conv_taps(kh, kw, grid)))
+    return out
 
-    def __init__(self, ub, grid):
-        enc, gru = ub.encoder, ub.gru
-        dev = enc.convc1.weight.device
+
+class EncoderWeights:
+    """Packed parameters of BasicMotionEncoder (core/update.py:67-87)."""
+
+    def __init__(self, enc, grid):
         pc, pb = ops.pack_conv_weight, ops.pad_bias
         self.c1_w = pc(enc.convc1.weight, Kpad=384); self.c1_b = pb(enc.convc1.bias, 256)
         self.c2_w = pc(enc.convc2.weight); self.c2_b = pb(enc.convc2.bias, 192)
@@ -194,23 +210,36 @@ class UpdateWeights:
         self.f1_b = enc.convf1.bias.detach().float().contiguous()
         self.f2_w = pc(enc.convf2.weight); self.f2_b = pb(enc.convf2.bias, 64)
         self.cv_w = pc(enc.conv.weight, Npad=128); self.cv_b = pb(enc.conv.bias, 128)
-        perm = list(range(128, 512)) + list(range(0, 128))      # q conv reads X[:, 128:640] = [x | r*h]
-        self.gru = []
-        for tag in ("1", "2"):
-            cz, cr, cq = (getattr(gru, "conv%s%s" % (n, tag)) for n in "zrq")
-            wzr = pc(torch.cat([cz.weight, cr.weight], 0))
-            bzr = torch.cat([cz.bias, cr.bias]).detach().float().contiguous()
-            wq = pc(cq.weight, cin_perm=perm)
-            bq = cq.bias.detach().float().contiguous()
-            kh, kw = cz.weight.shape[2:]
-            self.gru.append((wzr, bzr, wq, bq, ops.conv_taps(kh, kw, grid)))
+        self.taps3 = ops.conv_taps(3, 3, grid)
+
+
+class EncoderBuffers:
+    """The slice of a Workspace that motion_encoder touches (standalone BasicMotionEncoder.forward)."""
+
+    def __init__(self, grid, device):
+        self.grid = grid
+        z = lambda cols, dt=torch.bfloat16: torch.zeros((grid.Mp, cols), dtype=dt, device=device)
+        self.X = z(640)
+        self.CORR = z(384); self.C1 = z(256); self.CF = z(256); self.F1 = z(128)
+        self.flow = z(2, torch.float32)
+        self.side = torch.cuda.Stream(device=device)
+        self.ev_lookup = torch.cuda.Event()
+
+
+class UpdateWeights(EncoderWeights):
+    """Packed parameters of GMAUpdateBlock (core/update.py:116-162)."""
+
+    def __init__(self, ub, grid):
+        super().__init__(ub.encoder, grid)
+        dev = ub.encoder.convc1.weight.device
+        pc, pb = ops.pack_conv_weight, ops.pad_bias
+        self.gru = pack_gru(ub.gru, grid)
         fh, mk = ub.flow_head, ub.mask
         self.hd_w = pc(torch.cat([fh.conv1.weight, mk[0].weight], 0))
         self.hd_b = torch.cat([fh.conv1.bias, mk[0].bias]).detach().float().contiguous()
         self.hdf_w = pc(fh.conv1.weight); self.hdf_b = fh.conv1.bias.detach().float().contiguous()   # flow head alone
         self.fl_w = pc(fh.conv2.weight, Npad=32); self.fl_b = pb(fh.conv2.bias, 32)
         self.mk_w = pc(mk[2].weight); self.mk_b = (0.25 * mk[2].bias.detach().float()).contiguous()
-        self.taps3 = ops.conv_taps(3, 3, grid)
         self.device = dev
 
 
@@ -243,14 +272,17 @@ def motion_encoder(ws, uw, lookup=None):
        epilogue=ops.EPI_MOTION, out_b=ws.X, colb=256, aux1=ws.flow)
 
 
+def sep_conv_gru_rows(g, X, Hm, Z, passes):
+    """SepConvGRU.forward core/update.py:49-64 on X = [h | x | r*h] (in place; fp32 master state in Hm)."""
+    for (wzr, bzr, wq, bq, taps) in passes:
+        ops.shift_gemm(X, wzr, M=g.Mp, Npad=256, K=512, BN=128, taps=taps, grid=g, epilogue=ops.EPI_GRU_ZR,
+                       bias=bzr, out_b=X, colb=512, aux0=Z, aux1=Hm)
+        ops.shift_gemm(X, wq, M=g.Mp, Npad=128, K=512, BN=64, taps=taps, a_koff=128, grid=g,
+                       epilogue=ops.EPI_GRU_Q, bias=bq, out_b=X, colb=0, aux0=Z, aux1=Hm)
+
+
 def sep_conv_gru(ws, uw):
-    """SepConvGRU.forward core/update.py:49-64 on X (in place; fp32 master state in Hm)."""
-    g = ws.grid
-    for (wzr, bzr, wq, bq, taps) in uw.gru:
-        ops.shift_gemm(ws.X, wzr, M=g.Mp, Npad=256, K=512, BN=128, taps=taps, grid=g, epilogue=ops.EPI_GRU_ZR,
-                       bias=bzr, out_b=ws.X, colb=512, aux0=ws.Z, aux1=ws.Hm)
-        ops.shift_gemm(ws.X, wq, M=g.Mp, Npad=128, K=512, BN=64, taps=taps, a_koff=128, grid=g,
-                       epilogue=ops.EPI_GRU_Q, bias=bq, out_b=ws.X, colb=0, aux0=ws.Z, aux1=ws.Hm)
+    sep_conv_gru_rows(ws.grid, ws.X, ws.Hm, ws.Z, uw.gru)
 
 
 def heads(ws, uw, it=0, need_mask=True):

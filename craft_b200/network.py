@@ -19,7 +19,9 @@ from .corr import CorrBlock, TransCorrBlock
 from .extractor import BasicEncoder
 from .gma import Attention
 from .ops import TokenGrid
-from .setrans import SETransConfig, SelfAttVisPosTrans, get_workspace, _require_inference
+import collections
+
+from .setrans import SETransConfig, SelfAttVisPosTrans, WorkspaceCache, _require_inference
 from .update import GMAUpdateBlock
 from .utils.utils import coords_grid, print0, upflow8
 
@@ -118,7 +120,9 @@ class CRAFT(nn.Module):
         # Eliding that dead work leaves every returned value bit-identical.
         # Set False to execute the reference's schedule literally.
         self.elide_dead_upsample = True
-        self._graphs = {}
+        self._graphs = collections.OrderedDict()   # LRU, bounded by max_cached_graphs
+        self.max_cached_graphs = 8
+        self._workspaces = WorkspaceCache(capacity=4)   # this model's own device buffers
 
     def freeze_bn(self):
         for m in self.modules():
@@ -134,13 +138,14 @@ class CRAFT(nn.Module):
         """[N,2,h,w], [N,576,h,w] -> [N,2,8h,8w] (core/network.py:151-162), via the upsample kernel."""
         N, _, h, w = flow.shape
         g = TokenGrid(h, w)
-        out = torch.empty((N, 2, 8 * h, 8 * w), dtype=torch.float32, device=flow.device)
-        fr = torch.zeros((g.Mp, 2), dtype=torch.float32, device=flow.device)
-        mr = torch.zeros((g.Mp, 576), dtype=torch.float32, device=flow.device)
-        for b in range(N):
-            fr.view(g.H, g.Wp, 2)[:, :g.W] = flow[b].permute(1, 2, 0)
-            mr.view(g.H, g.Wp, 576)[:, :g.W] = mask[b].permute(1, 2, 0)
-            ops.upsample_flow(mr, fr, g, out=out[b])
+        with torch.cuda.device(flow.device):
+            out = torch.empty((N, 2, 8 * h, 8 * w), dtype=torch.float32, device=flow.device)
+            fr = torch.zeros((g.Mp, 2), dtype=torch.float32, device=flow.device)
+            mr = torch.zeros((g.Mp, 576), dtype=torch.float32, device=flow.device)
+            for b in range(N):
+                fr.view(g.H, g.Wp, 2)[:, :g.W] = flow[b].float().permute(1, 2, 0)
+                mr.view(g.H, g.Wp, 576)[:, :g.W] = mask[b].float().permute(1, 2, 0)
+                ops.upsample_flow(mr, fr, g, out=out[b])
         return out
 
     # ------------------------------------------------------------------------------------------
@@ -217,10 +222,14 @@ class CRAFT(nn.Module):
         B, _, H, W = image1.shape
         if H % 8 or W % 8:
             raise ValueError("image sides must be multiples of 8 (use InputPadder, as the reference drivers do)")
-        if self.use_cuda_graph and not self.training and not torch.cuda.is_current_stream_capturing() \
-                and "SAVECORR" not in os.environ:
-            return self._forward_graphed(image1, image2, iters, flow_init, test_mode)
-        return self._forward_impl(image1, image2, iters, flow_init, test_mode)
+        # everything below (streams, workspaces, the library's per-device state) refers to the input's device:
+        # nn.DataParallel calls each replica from its own thread with another device current
+        with torch.cuda.device(image1.device):
+            savecorr = "SAVECORR" in os.environ      # core/corr.py:180-184 debugging hook: needs the stored volume
+            if self.use_cuda_graph and not self.training and not torch.cuda.is_current_stream_capturing() \
+                    and not savecorr:
+                return self._forward_graphed(image1, image2, iters, flow_init, test_mode)
+            return self._forward_impl(image1, image2, iters, flow_init, test_mode, savecorr=savecorr)
 
     def _weights_signature(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters()) + \
@@ -231,6 +240,8 @@ class CRAFT(nn.Module):
                self.materialize_level0, self.encoder_tf32, self.encoder_half, self.elide_dead_upsample)
         sig = self._weights_signature()
         ent = self._graphs.get(key)
+        if ent is not None:
+            self._graphs.move_to_end(key)
         if ent is None or ent["sig"] != sig:
             ent = dict(sig=sig)
             ent["i1"] = image1.float().clone()
@@ -250,7 +261,12 @@ class CRAFT(nn.Module):
                 ent["out"] = self._forward_impl(ent["i1"], ent["i2"], iters, ent["fi"], test_mode)
             ent["graph"] = g
             ent["launches"] = _lib.load().craft_b200_launch_count() - n0   # craft_b200 kernels per replay
+            # the graph bakes in the workspace's addresses: keep the buffers alive as long as the graph is
+            g8 = TokenGrid(image1.shape[2] // 8, image1.shape[3] // 8)
+            ent["ws"] = self._workspaces.get(g8, image1.device, self.materialize_level0)
             self._graphs[key] = ent
+            while len(self._graphs) > self.max_cached_graphs:
+                self._graphs.popitem(last=False)
         ent["i1"].copy_(image1)
         ent["i2"].copy_(image2)
         if flow_init is not None:
@@ -263,11 +279,11 @@ class CRAFT(nn.Module):
             return tuple([t.clone() for t in o] if isinstance(o, list) else o.clone() for o in out)
         return [t.clone() for t in out]
 
-    def _forward_impl(self, image1, image2, iters, flow_init, test_mode):
+    def _forward_impl(self, image1, image2, iters, flow_init, test_mode, savecorr=False):
         B, _, H, W = image1.shape
         fmap1, fmap2, cnet_feat = self._encoders(image1.float(), image2.float())
         g = TokenGrid(H // 8, W // 8)
-        ws = get_workspace(g, image1.device, self.materialize_level0)
+        ws = self._workspaces.get(g, image1.device, self.materialize_level0 or savecorr)
         dev = image1.device
         flow_lo = torch.empty((B, 2, g.H, g.W), dtype=torch.float32, device=dev)
         n_up = iters if test_mode != 1 else 1
@@ -276,6 +292,8 @@ class CRAFT(nn.Module):
         for b in range(B):
             fi = flow_init[b].float().contiguous() if flow_init is not None else None
             att = self._prepare_pair(ws, fmap1[b], fmap2[b], cnet_feat[b], fi)
+            if savecorr and self.args.craft:
+                self.corr_fn._save_volume(ws, os.environ["SAVECORR"])
             main, side = torch.cuda.current_stream(), ws.side
             for itr in range(iters):
                 need_up = not (test_mode == 1 and self.elide_dead_upsample) or itr == iters - 1

@@ -10,7 +10,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import GemmArgs, PvArgs, ScoresArgs
+from ._lib import DenseAttnArgs, GemmArgs, PvArgs, ScoresArgs
 
 EPI_STORE, EPI_GRU_ZR, EPI_GRU_Q, EPI_MOTION = 0, 1, 2, 3
 PACK_COPY, PACK_LN, PACK_TANH, PACK_RELU, PACK_RELU_LN = 0, 1, 2, 3, 4
@@ -37,7 +37,33 @@ class TokenGrid:
 
 
 def _stream():
+    # current stream of the CURRENT device: every public entry point (CRAFT.forward, the standalone module
+    # forwards) runs under `torch.cuda.device(input.device)`, see on_device() below
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def on_device(fn):
+    """Decorator for module forward()s: make the device of the first tensor argument current for the call,
+    so that streams, workspaces and the library's per-device state all refer to it (a model moved to cuda:1
+    must not launch on cuda:0's stream; nn.DataParallel calls replicas from one thread per device)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kw):
+        dev = None
+        for a in list(args) + list(kw.values()):
+            if isinstance(a, torch.Tensor):
+                dev = a.device
+                break
+            if isinstance(a, (list, tuple)) and a and isinstance(a[0], torch.Tensor):
+                dev = a[0].device
+                break
+        if dev is None or dev.type != "cuda":
+            raise _lib.CraftB200Error("%s.%s needs CUDA tensors: craft_b200 has no CPU path"
+                                      % (type(self).__name__, fn.__name__))
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kw)
+    return wrapped
 
 
 def _ptr(t):
@@ -218,8 +244,10 @@ def corr_build(Q, K, grid, *, M, d, w_agg, w_pos, pos_table, R, clip, stat_sum, 
     _lib.call("craft_corr_build", C.byref(a), _stream())
 
 
-def attn_lse(Q, K, grid, *, M, d, w_pos, pos_table, R, clip, stat_max, lse_part, lse2, run_flag=None, ksplit=0):
+def attn_lse(Q, K, grid, *, M, d, w_pos, pos_table, R, clip, stat_max, lse_part, lse2, run_flag=None, ksplit=0,
+             mask_radius=-1):
     a = _scores_args(Q, K, grid, M, d, w_pos, pos_table, R, clip, run_flag, ksplit)
+    a.mask_radius = int(mask_radius)
     _chk(stat_max, torch.float32, "stat_max")
     _chk(lse_part, torch.float32, "lse_part")
     _chk(lse2, torch.float32, "lse2")
@@ -228,15 +256,18 @@ def attn_lse(Q, K, grid, *, M, d, w_pos, pos_table, R, clip, stat_max, lse_part,
     _lib.call("craft_attn_lse", C.byref(a), _stream())
 
 
-def corr_stats_finalize(stat_sum, n, mean_rstd):
-    _lib.call("craft_corr_stats_finalize", _ptr(stat_sum), float(n), _ptr(mean_rstd), _stream())
+def corr_stats_finalize(stat_sum, n, mean_rstd, flag=None):
+    """stat_sum [2,2] f64: row 0 = unclamped pass, row 1 = clamped re-pass (used when *flag != 0)."""
+    _chk(stat_sum, torch.float64, "stat_sum")
+    _lib.call("craft_corr_stats_finalize", _ptr(stat_sum), _ptr(flag), float(n), _ptr(mean_rstd), _stream())
 
 
-def clip_gate(stat_max, attn_clip, clip, flag):
-    _lib.call("craft_clip_gate", _ptr(stat_max), float(attn_clip), _ptr(clip), _ptr(flag), _stream())
+def clip_gate(stat_max, attn_clip, clip, flag, diag=None):
+    _chk(diag, torch.float32, "diag")
+    _lib.call("craft_clip_gate", _ptr(stat_max), float(attn_clip), _ptr(clip), _ptr(flag), _ptr(diag), _stream())
 
 
-def attn_pv(Q, K, Vt, grid, *, M, d, F, w_pos, pos_table, R, clip, lse2, out, ksplit, zero_fill=True):
+def attn_pv(Q, K, Vt, grid, *, M, d, F, w_pos, pos_table, R, clip, lse2, out, ksplit, zero_fill=True, mask_radius=-1):
     """`out` holds `ksplit` partial-sum slots [ksplit, M, Mp, F]; zero_fill=False leaves the slots a unit does
     not use untouched (pair it with modes_finalize(pv_bk=...), which knows the schedule)."""
     _chk(Q, torch.bfloat16, "Q")
@@ -255,6 +286,7 @@ def attn_pv(Q, K, Vt, grid, *, M, d, F, w_pos, pos_table, R, clip, lse2, out, ks
     a.clip, a.lse2, a.out = clip.data_ptr(), lse2.data_ptr(), out.data_ptr()
     a.ksplit = ksplit
     a.zero_fill = 1 if zero_fill else 0
+    a.mask_radius = int(mask_radius)
     _lib.call("craft_attn_pv", C.byref(a), _stream())
 
 
@@ -264,6 +296,48 @@ def modes_finalize(O, nsum, M, F, grid, *, w_score, b_score, coeff, gma=0, x_b=N
     _lib.call("craft_modes_finalize", _ptr(O), nsum, M, F, _ptr(w_score), _ptr(b_score), _ptr(coeff), gma,
               _ptr(x_b), _ld(x_b), colx, _ptr(x_f), _ld(x_f), colxf, grid.H, grid.W,
               _ptr(out_b), _ld(out_b), colb, _ptr(out_f), _ld(out_f), colf, int(pv_bk), _stream())
+
+
+def soft_aggregate(x, w, b, basis=None, num_feat=1):
+    """LearnedSoftAggregate on a dense f32 tensor with the group axis leading: x [M, n] (num_feat 1) or
+    [M, n, F]; returns [n] / [n, F]."""
+    _chk(x, torch.float32, "x")
+    _chk(basis, torch.float32, "basis")
+    _chk(w, torch.float32, "w")
+    _chk(b, torch.float32, "b")
+    M = x.shape[0]
+    if num_feat == 1:
+        n, F_ = x[0].numel(), 1
+        out = torch.empty(x.shape[1:], dtype=torch.float32, device=x.device)
+    else:
+        F_ = x.shape[-1]
+        n = x[0].numel() // F_
+        out = torch.empty(x.shape[1:], dtype=torch.float32, device=x.device)
+        assert w.numel() == F_
+    _lib.call("craft_soft_aggregate", _ptr(x), _ptr(basis), M, n, F_, _ptr(w), _ptr(b), _ptr(out), _stream())
+    return out
+
+
+def attn_dense(Q, K, grid, *, M, d, w_pos, pos_table, R, clip, lse2=None, mask_radius=-1):
+    """Dense [M, U, U] scores (lse2 None) or softmax probabilities over the REAL tokens -- small grids only."""
+    _chk(Q, torch.bfloat16, "Q")
+    _chk(K, torch.bfloat16, "K")
+    _chk(lse2, torch.float32, "lse2")
+    if grid.U > 4096:
+        raise ValueError("attn_dense materialises [M,U,U] and is meant for small grids (U <= 4096), got U=%d" % grid.U)
+    out = torch.empty((M, grid.U, grid.U), dtype=torch.float32, device=Q.device)
+    a = DenseAttnArgs()
+    a.Q, a.K = Q.data_ptr(), K.data_ptr()
+    a.C, a.M, a.d, a.H, a.W = M * d, M, d, grid.H, grid.W
+    a.scale, a.w_pos = 1.0 / math.sqrt(d), float(w_pos)
+    a.pos_table = pos_table.data_ptr() if pos_table is not None else None
+    a.R = R
+    a.clip = clip.data_ptr()
+    a.lse2 = lse2.data_ptr() if lse2 is not None else None
+    a.mask_radius = int(mask_radius)
+    a.out = out.data_ptr()
+    _lib.call("craft_attn_dense", C.byref(a), _stream())
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -7,9 +7,11 @@ What differs from the reference, by design:
     opaque handle (`PosBiasHandle`, `AttentionHandle`) that the consuming module understands.
   * only the configuration space the CRAFT drivers can reach is implemented: pos_code_type 'bias',
     has_FFN False, pool_modes_feat 'softmax', no multi-head ablation.  Anything else raises.
-  * inference only in this round: dropout / drop-path are identity (eval semantics) and the ops
-    carry no autograd; calling them with grad enabled on parameters that require grad raises.
+  * the fused kernels are forward-only: dropout / drop-path are identity (eval semantics); calling
+    them with grad enabled on parameters that require grad raises (training: CRAFT.forward switches
+    to craft_b200/train_path.py).
 """
+import collections
 import copy
 import math
 
@@ -110,20 +112,44 @@ class AttentionHandle:
     """Stands for the [B,M,U,U] attention-probability tensor: projected Q/K rows plus the softmax
     log-sum-exp; the aggregator recomputes P tile by tile (attn_pv.cuh)."""
 
-    def __init__(self, grid, Q, K, lse2, clip, table, w_pos, M, d):
+    def __init__(self, grid, Q, K, lse2, clip, table, w_pos, M, d, mask_radius=-1):
         self.grid, self.Q, self.K, self.lse2, self.clip = grid, Q, K, lse2, clip
         self.table, self.w_pos, self.M, self.d = table, w_pos, M, d
-        self.shape = (len(Q), M, grid.U, grid.U)
+        self.mask_radius = mask_radius
+        self.shape = (1, M, grid.U, grid.U)
+
+    def dense(self):
+        """Materialise the [1,M,U,U] probabilities (small grids only; debugging and tests)."""
+        with torch.cuda.device(self.Q.device):
+            return ops.attn_dense(self.Q, self.K, self.grid, M=self.M, d=self.d, w_pos=self.w_pos, pos_table=self.table,
+                                  R=7, clip=self.clip, lse2=self.lse2, mask_radius=self.mask_radius)[None]
 
 
 # ------------------------------------------------------------------------------------------------
 class LearnedSoftAggregate(nn.Module):
-    """core/setrans.py:279-300 -- parameters only; the arithmetic is fused into kernel epilogues."""
+    """core/setrans.py:279-300.  Inside CRAFT.forward the arithmetic is fused into kernel epilogues
+    (scores.cuh for num_feat == 1, modes_finalize for num_feat == F); forward() is the standalone form."""
 
     def __init__(self, num_feat, group_dim, keepdim=False):
         super().__init__()
         self.group_dim, self.num_feat, self.keepdim = group_dim, num_feat, keepdim
         self.feat2score = nn.Linear(num_feat, 1)
+
+    @ops.on_device
+    def forward(self, x, score_basis=None):
+        """x [..., M at group_dim, ...(, F)] -> softmax-over-modes weighted sum (core/setrans.py:289-300)."""
+        _require_inference(self.feat2score.weight)
+        gd = self.group_dim % x.dim()
+        if self.num_feat > 1 and gd == x.dim() - 1:
+            raise ValueError("group_dim cannot be the feature axis")
+        xm = x.float().movedim(gd, 0).contiguous()
+        bm = score_basis.float().movedim(gd, 0).contiguous() if score_basis is not None else None
+        if xm.shape[0] > 8:
+            raise NotImplementedError("craft_b200 LearnedSoftAggregate: at most 8 modes")
+        w = self.feat2score.weight.detach().float().reshape(-1).contiguous()
+        b = self.feat2score.bias.detach().float().contiguous()
+        out = ops.soft_aggregate(xm, w, b, basis=bm, num_feat=self.num_feat)
+        return out.unsqueeze(gd) if self.keepdim else out
 
 
 class SlidingPosBiases2D(nn.Module):
@@ -155,6 +181,7 @@ class SETransInputFeatEncoder(nn.Module):
     def table(self):
         return self.pos_coder.biases.detach().float().contiguous()
 
+    @ops.on_device
     def forward(self, vis_feat, voxels_pos=None, return_pos_biases=True):
         """[B,C,h,w] -> [B,h*w,C] LayerNorm'ed tokens (+ PosBiasHandle)."""
         _require_inference()
@@ -213,8 +240,9 @@ class ExpandedFeatTrans(nn.Module):
         hp.value_aggregate(ws, att.Q, att.K, X, x_koff, pk["w1"], M=att.M, d=att.d, F=self.feat_dim,
                            table=att.table, w_pos=att.w_pos, clip=att.clip, lse2=att.lse2,
                            w_score=pk["ws"], b_score=pk["bs"], coeff=pk["coeff"],
-                           out_b=out_b, colb=colb, out_f=out_f, colf=colf)
+                           out_b=out_b, colb=colb, out_f=out_f, colf=colf, mask_radius=att.mask_radius)
 
+    @ops.on_device
     def forward(self, input_feat, attention_probs):
         """input_feat [B,U,C]; attention_probs: AttentionHandle from CrossAttFeatTrans/SelfAttVisPosTrans."""
         if not isinstance(attention_probs, (AttentionHandle, list)):
@@ -262,9 +290,47 @@ class CrossAttFeatTrans(nn.Module):
         self.pos_code_weight = config.pos_code_weight if config.pos_code_type == "bias" else 1
         self.attn_clip = config.attn_clip
         self.attn_diag_cycles = getattr(config, "attn_diag_cycles", 1000)
-        self.max_attn, self.clamp_count, self.call_count = 0, 0, 0
+        self.call_count = 0
+        self._diag = {}          # device -> f32[2] {max_attn, clamp_count}, updated by the gate kernel
+        self._diag_host = [0.0, 0]
         self._init_weights()
         self._packed = hp.PackedWeights()
+
+    # The reference reads the global score maximum back with two .item() calls per forward
+    # (core/setrans.py:520-529) to keep these counters; here they are accumulated on the device by the
+    # clamp-gate kernel and only read when somebody asks.
+    def diag(self, device):
+        key = str(device)
+        if key not in self._diag:
+            self._diag[key] = torch.zeros(2, dtype=torch.float32, device=device)
+        return self._diag[key]
+
+    def _diag_read(self):
+        mx, cnt = self._diag_host
+        for t in self._diag.values():
+            v = t.tolist()
+            mx, cnt = max(mx, v[0]), cnt + int(v[1])
+        return mx, cnt
+
+    @property
+    def max_attn(self):
+        return self._diag_read()[0]
+
+    @max_attn.setter
+    def max_attn(self, v):          # the reference resets both counters to 0 every attn_diag_cycles calls
+        for t in self._diag.values():
+            t[0] = 0.0
+        self._diag_host[0] = float(v)
+
+    @property
+    def clamp_count(self):
+        return self._diag_read()[1]
+
+    @clamp_count.setter
+    def clamp_count(self, v):
+        for t in self._diag.values():
+            t[1] = 0.0
+        self._diag_host[1] = int(v)
 
     def _init_weights(self):
         std = self.base_initializer_range
@@ -316,11 +382,78 @@ class CrossAttFeatTrans(nn.Module):
         hp.project(g, Tk, pk["wk"], pk["bk"], K, K=self.in_feat_dim)
         self.call_count += 1
 
+    @ops.on_device
     def forward(self, query_feat, key_feat=None, pos_biases=None, attention_mask=None):
-        raise NotImplementedError(
-            "craft_b200.CrossAttFeatTrans is driven through its owners (TransCorrBlock.update, "
-            "SelfAttVisPosTrans.forward): a standalone call would have to return a [B,M,U,U] tensor, which "
-            "this implementation never materialises")
+        """core/setrans.py:501-566 on token tensors [B,U,C] (already encoded by SETransInputFeatEncoder).
+
+        `pos_biases` is the PosBiasHandle the encoder returned (it also carries the (h, w) of the token
+        grid, which a [B,U,C] tensor alone does not); `attention_mask` is None or an int radius (the
+        --f2radius Chebyshev mask of SelfAttVisPosTrans, core/setrans.py:580-584) -- dense mask tensors do
+        not exist here.  Returns, per output mode:
+          out_attn_scores_only -> dense [B,1,U,U] mode-aggregated scores (the level-0 volume before the
+                                  global LayerNorm; fine for the grids a standalone call is used on),
+          out_attn_probs_only  -> AttentionHandle (list for B > 1); `.dense()` materialises small ones,
+          otherwise            -> [B,U,F] transformed features (out_trans)."""
+        _require_inference(self.query.weight)
+        if not isinstance(pos_biases, PosBiasHandle):
+            raise TypeError("craft_b200.CrossAttFeatTrans.forward needs the PosBiasHandle returned by "
+                            "SETransInputFeatEncoder.forward (it carries the token grid's (h, w))")
+        if attention_mask is not None and not isinstance(attention_mask, int):
+            raise TypeError("attention_mask must be None or the integer mask radius (dense masks are never built)")
+        h, w = pos_biases.shape
+        B, U, Cc = query_feat.shape
+        if U != h * w or Cc != self.in_feat_dim:
+            raise ValueError("query_feat %s does not match grid %dx%d / in_feat_dim %d" % (list(query_feat.shape), h, w, self.in_feat_dim))
+        grid = TokenGrid(h, w)
+        dev = query_feat.device
+        ws = get_workspace(grid, dev, materialize_level0=self.out_attn_scores_only)
+        table = pos_biases.table.detach().float().contiguous()
+        mr = attention_mask if attention_mask is not None else -1
+        M, d = self.num_modes, self.attention_mode_dim
+        pk = self.packed()
+        outs = []
+        for b in range(B):
+            Tq = tokens_to_rows(query_feat[b], grid)
+            Tk = Tq if key_feat is None else tokens_to_rows(key_feat[b], grid)
+            Q, K = grid.zeros(Cc, device=dev), grid.zeros(Cc, device=dev)
+            self.project(ws, Tq, Tk, Q, K)
+            if self.out_attn_scores_only:
+                if mr > 0:
+                    raise NotImplementedError("scores-only attention with a radius mask is not a CRAFT configuration")
+                hp.build_correlation(ws, Q, K, M=M, d=d, w_agg=pk.get("w_agg", 0.0), table=table,
+                                     w_pos=self.pos_code_weight, global_norm=False, attn_clip=self.attn_clip,
+                                     diag=self.diag(dev))
+                vol = ws.levels[0].view(grid.H, grid.Wp, U)[:, :grid.W].reshape(1, 1, U, U)
+                outs.append(vol.clone())
+                continue
+            lse2 = torch.zeros((M, grid.Mp), dtype=torch.float32, device=dev)
+            clip = torch.full((1,), float("inf"), dtype=torch.float32, device=dev)
+            hp.attention_stats(ws, Q, K, M=M, d=d, table=table, w_pos=self.pos_code_weight, clip=clip, lse2=lse2,
+                               slot=1, attn_clip=self.attn_clip, diag=self.diag(dev), mask_radius=mr)
+            att = AttentionHandle(grid, Q, K, lse2, clip, table, self.pos_code_weight, M, d, mask_radius=mr)
+            if self.out_attn_probs_only:
+                outs.append(att)
+                continue
+            yf = torch.zeros((grid.Mp, self.feat_dim), dtype=torch.float32, device=dev)
+            self.out_trans.run(ws, att, Tk, 0, out_f=yf)
+            outs.append(rows_to_tokens(yf, grid)[None])
+        if self.out_attn_probs_only:
+            return outs[0] if B == 1 else outs
+        return torch.cat(outs, 0)
+
+
+def tokens_to_rows(tok, grid, dtype=torch.bfloat16):
+    """[U, C] token tensor -> padded-flat rows [Mp, C] (halo cells zero)."""
+    Cc = tok.shape[-1]
+    rows = torch.zeros((grid.H, grid.Wp, Cc), dtype=dtype, device=tok.device)
+    rows[:, :grid.W] = tok.reshape(grid.H, grid.W, Cc).to(dtype)
+    return rows.reshape(grid.Mp, Cc)
+
+
+def rows_to_tokens(rows, grid):
+    """padded-flat rows [Mp, C] -> [U, C] fp32."""
+    Cc = rows.shape[-1]
+    return rows.float().view(grid.H, grid.Wp, Cc)[:, :grid.W].reshape(grid.U, Cc)
 
 
 class SelfAttVisPosTrans(nn.Module):
@@ -332,8 +465,9 @@ class SelfAttVisPosTrans(nn.Module):
         self.name = name
         self.out_attn_only = config.out_attn_scores_only or config.out_attn_probs_only
         self.attn_mask_radius = config.attn_mask_radius
-        if self.attn_mask_radius > 0:
-            raise NotImplementedError("craft_b200: --f2radius masking (default off) is not implemented")
+        if self.attn_mask_radius > 0 and (config.in_feat_dim != 256 or config.num_modes != 4 or self.out_attn_only):
+            raise NotImplementedError("craft_b200: the --f2radius mask is built for the F2 transformer (256 channels, "
+                                      "4 modes, feature output), the only place the drivers can enable it")
         self.setrans = CrossAttFeatTrans(self.config, name)
         self.vispos_encoder = SETransInputFeatEncoder(self.config)
 
@@ -344,29 +478,33 @@ class SelfAttVisPosTrans(nn.Module):
         ops.pack_tokens(feat_chw, g, pack_mode, out_b=T)
         st.project(ws, T, T, Q, K)
         table = self.vispos_encoder.table()
+        mr = self.attn_mask_radius if self.attn_mask_radius > 0 else -1
         hp.attention_stats(ws, Q, K, M=st.num_modes, d=st.attention_mode_dim, table=table,
-                           w_pos=st.pos_code_weight, clip=clip, lse2=lse2, slot=slot, attn_clip=st.attn_clip)
-        return AttentionHandle(g, Q, K, lse2, clip, table, st.pos_code_weight, st.num_modes, st.attention_mode_dim)
+                           w_pos=st.pos_code_weight, clip=clip, lse2=lse2, slot=slot, attn_clip=st.attn_clip,
+                           diag=st.diag(Q.device), mask_radius=mr)
+        return AttentionHandle(g, Q, K, lse2, clip, table, st.pos_code_weight, st.num_modes, st.attention_mode_dim,
+                               mask_radius=mr)
 
+    @ops.on_device
     def forward(self, x):
         _require_inference(self.setrans.query.weight)
         B, Cc, h, w = x.shape
         grid = TokenGrid(h, w)
         ws = get_workspace(grid, x.device)
         xf = x.float().contiguous()
+        dev = x.device
         if self.out_attn_only:
-            if B != 1:
-                # each handle owns its Q/K/lse buffers
-                outs = []
-                for b in range(B):
-                    Q, K, T = (torch.zeros((grid.Mp, Cc), dtype=torch.bfloat16, device=x.device) for _ in range(3))
-                    lse2 = torch.zeros((self.setrans.num_modes, grid.Mp), dtype=torch.float32, device=x.device)
-                    clip = torch.full((1,), float("inf"), dtype=torch.float32, device=x.device)
-                    outs.append(self.attend(ws, xf[b], T, Q, K, lse2, clip, slot=2))
-                return outs
-            return self.attend(ws, xf[0], ws.Ta, ws.Qa, ws.Ka, ws.lse2_att, ws.clip_att, slot=2)
+            # a standalone call hands out handles that OWN their Q/K/lse buffers (the shared workspace is
+            # overwritten by the next call); CRAFT.forward uses attend() on workspace buffers instead
+            outs = []
+            for b in range(B):
+                Q, K, T = (grid.zeros(Cc, device=dev) for _ in range(3))
+                lse2 = torch.zeros((self.setrans.num_modes, grid.Mp), dtype=torch.float32, device=dev)
+                clip = torch.full((1,), float("inf"), dtype=torch.float32, device=dev)
+                outs.append(self.attend(ws, xf[b], T, Q, K, lse2, clip, slot=2))
+            return outs[0] if B == 1 else outs
         out = torch.empty_like(xf)
-        yf = torch.zeros((grid.Mp, Cc), dtype=torch.float32, device=x.device)
+        yf = torch.zeros((grid.Mp, Cc), dtype=torch.float32, device=dev)
         for b in range(B):
             att = self.attend(ws, xf[b], ws.T2, ws.Q2, ws.K2, ws.lse2_f2, ws.clip_f2, slot=1)
             self.setrans.out_trans.run(ws, att, ws.T2, 0, out_f=yf)
@@ -374,16 +512,35 @@ class SelfAttVisPosTrans(nn.Module):
         return out
 
 
-_WORKSPACES = {}
+class WorkspaceCache:
+    """LRU of hotpath.Workspace objects keyed by (device, H, W, materialize_level0).  Each CRAFT instance
+    owns one (so that two models never share buffers a captured CUDA graph has baked in); standalone
+    module calls share the module-level one.  Bounded: KITTI-style variable input sizes would otherwise
+    accumulate ~150 MB per shape."""
+
+    def __init__(self, capacity=4):
+        self.capacity = capacity
+        self._lru = collections.OrderedDict()
+
+    def get(self, grid, device, materialize_level0=False):
+        key = (str(device), grid.H, grid.W, bool(materialize_level0))
+        ws = self._lru.get(key)
+        if ws is None:
+            with torch.cuda.device(device):
+                ws = hp.Workspace(grid, device, materialize_level0)
+            self._lru[key] = ws
+            while len(self._lru) > self.capacity:
+                self._lru.popitem(last=False)      # a graph that still needs the buffers holds its own reference
+        else:
+            self._lru.move_to_end(key)
+        return ws
+
+    def clear(self):
+        self._lru.clear()
 
 
-def get_workspace(grid, device, materialize_level0=None):
-    import os
-    if materialize_level0 is None:
-        materialize_level0 = False
-    key = (str(device), grid.H, grid.W, bool(materialize_level0))
-    ws = _WORKSPACES.get(key)
-    if ws is None:
-        ws = hp.Workspace(grid, device, materialize_level0)
-        _WORKSPACES[key] = ws
-    return ws
+_SHARED_WORKSPACES = WorkspaceCache()
+
+
+def get_workspace(grid, device, materialize_level0=None, cache=None):
+    return (cache or _SHARED_WORKSPACES).get(grid, device, bool(materialize_level0))

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define CRAFT_B200_ABI_VERSION 1
+#define CRAFT_B200_ABI_VERSION 2
 #define CRAFT_MAX_TAPS 49
 
 int craft_b200_abi_version(void);
@@ -96,6 +96,8 @@ typedef struct craft_scores_args {
   /* lse */
   void* lse_part;     /* float2 [ksplit][M][Mp] scratch                                       */
   float* lse2;        /* [M][Mp] out                                                          */
+  int mask_radius;    /* attn_lse only; > 0: keys with max(|dy|,|dx|) > mask_radius are masked out
+                         (--f2radius, SelfAttVisPosTrans.forward core/setrans.py:580-584); <= 0: off */
 } craft_scores_args;
 /* TransCorrBlock.update core/corr.py:148-207 (+ CorrBlock.__init__ :16-45 with M=1).         */
 int craft_corr_build(const craft_scores_args* a, void* stream);
@@ -107,10 +109,12 @@ int craft_pv_auto_ksplit(int H, int W, int M);
 /* keys per tile (8 x BK/8 spatial block) the P.V kernel uses for (d, F); V^T must be laid out in
  * that block order: column = block*BK + (y%8)*(BK/8) + x%(BK/8) (craft_shift_gemm b_blocked). */
 int craft_pv_block_keys(int d, int F);
-/* {sum,sumsq} -> {mean,rstd} (F.layer_norm, core/corr.py:200-204); n = number of elements.   */
-int craft_corr_stats_finalize(const double* stat_sum, double n, float* mean_rstd, void* stream);
-/* clip = (max > attn_clip) ? attn_clip : +inf ; flag = hit (core/setrans.py:527-529).        */
-int craft_clip_gate(const float* stat_max, float attn_clip, float* clip, int* flag, void* stream);
+/* {sum,sumsq} -> {mean,rstd} (F.layer_norm, core/corr.py:200-204); n = number of elements.
+ * flag (optional device int): when set, stat_sum + 2 (the clamped re-pass) is used instead.   */
+int craft_corr_stats_finalize(const double* stat_sum, const int* flag, double n, float* mean_rstd, void* stream);
+/* clip = (max > attn_clip) ? attn_clip : +inf ; flag = hit (core/setrans.py:527-529).  diag
+ * (optional, f32[2]) accumulates the module diagnostics {max_attn, clamp_count} (:524-529).   */
+int craft_clip_gate(const float* stat_max, float attn_clip, float* clip, int* flag, float* diag, void* stream);
 
 /* ---- flash P.V ---------------------------------------------------------------------------- */
 typedef struct craft_pv_args {
@@ -128,6 +132,7 @@ typedef struct craft_pv_args {
   float* out;         /* f32 [ksplit][M][F/8][Mp][8]: partial sums, one slot per CTA sharing a unit */
   int ksplit;         /* slots available in out (>= craft_pv_auto_ksplit)                        */
   int zero_fill;      /* != 0: slots a (query tile, mode) unit does not use are written as zeros */
+  int mask_radius;    /* as in craft_scores_args                                                  */
 } craft_pv_args;
 /* ExpandedFeatTrans.forward core/setrans.py:373-383, gma.Aggregate.forward core/gma.py:131-134 */
 int craft_attn_pv(const craft_pv_args* a, void* stream);
@@ -140,6 +145,30 @@ int craft_modes_finalize(const float* O, int nsum, int M, int F, const float* w_
                          void* out_bf16, int ldb, int colb, float* out_f32, int ldf, int colf,
                          int pv_bk /* 0: all nsum slots valid; 64/128: O from craft_attn_pv with that key block */,
                          void* stream);
+
+/* ---- standalone forms of operations that CRAFT.forward runs fused -------------------------- */
+/* LearnedSoftAggregate.forward core/setrans.py:289-300 on a dense f32 tensor whose group (mode) axis
+ * leads: F == 1: x,basis [M][n] -> out [n] (p_m = softmax_m(w*basis_m + b));  F > 1: x,basis
+ * [M][n][F] -> out [n][F] (p_m = softmax_m(<w, basis_m[r,:]> + b)).  M <= 8; basis may alias x.  */
+int craft_soft_aggregate(const float* x, const float* basis, int M, long long n, int F, const float* w,
+                         const float* b, float* out, void* stream);
+/* Dense [M][U][U] attention matrix over the real tokens from projected rows -- the tensor the
+ * production path never forms; for standalone CrossAttFeatTrans.forward on small grids and tests.
+ * lse2 == NULL: scores after clamp + bias + mask (core/setrans.py:514-542); else softmax
+ * probabilities exp(S - lse) (core/setrans.py:553).                                              */
+typedef struct craft_dense_attn_args {
+  const void* Q;
+  const void* K;      /* bf16 [Mp, C]                                                           */
+  int C, M, d, H, W;
+  float scale, w_pos;
+  const float* pos_table;
+  int R;
+  const float* clip;
+  const float* lse2;  /* [M][Mp] or NULL                                                        */
+  int mask_radius;
+  float* out;         /* f32 [M][U][U]                                                          */
+} craft_dense_attn_args;
+int craft_attn_dense(const craft_dense_attn_args* a, void* stream);
 
 /* ---- correlation lookup (CorrBlock.__call__ core/corr.py:47-71) --------------------------- */
 int craft_corr_lookup(const float* const* lvl /*host array of 4 device ptrs*/, int H, int W,

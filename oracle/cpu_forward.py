@@ -45,16 +45,23 @@ def _sub(sd, prefix):
 
 
 def craft_forward(sd, image1, image2, iters=12, flow_init=None, craft=True, use_setrans=True, f2trans=True,
-                  M=4, w_inter=0.5, w_f2=0.5, w_intra=1.0, return_all=False):
-    """-> (flow_lo [B,2,h,w], flow_up [B,2,H,W]) like test_mode=1 (or the list of all flow_up)."""
+                  M=4, w_inter=0.5, w_f2=0.5, w_intra=1.0, return_all=False, attn_clip=100.0, f2_mask_radius=-1,
+                  M_inter=None, M_intra=None, diag=None):
+    """-> (flow_lo [B,2,h,w], flow_up [B,2,H,W]) like test_mode=1 (or the list of all flow_up).
+    M_inter / M_intra: --inter_num_modes / --intra_num_modes when they differ from M (the F2 transformer keeps M);
+    diag (optional dict) receives the global score maxima the reference keeps as max_attn (core/setrans.py:520-529)."""
+    M_inter = M_inter or M
+    M_intra = M_intra or M
+    diag = diag if diag is not None else {}
     image1 = 2 * (image1 / 255.0) - 1.0
     image2 = 2 * (image2 / 255.0) - 1.0
     B = image1.shape[0]
     fm = basic_encoder(torch.cat([image1, image2], 0), sd, "fnet", "instance")
     fmap1, fmap2 = fm[:B], fm[B:]
     if f2trans:      # SelfAttVisPosTrans "F2 transformer" core/network.py:185-187, setrans.py:578-619
-        probs, tok, _ = R.self_attention_probs(fmap2, sd["f2_trans.setrans.query.weight"], sd["f2_trans.setrans.key.weight"],
-                                               M, sd["f2_trans.vispos_encoder.pos_coder.biases"], w_f2)
+        probs, tok, diag["f2_trans"] = R.self_attention_probs(
+            fmap2, sd["f2_trans.setrans.query.weight"], sd["f2_trans.setrans.key.weight"], M,
+            sd["f2_trans.vispos_encoder.pos_coder.biases"], w_f2, attn_clip, f2_mask_radius)
         y = R.expanded_feat_trans(tok, probs, sd["f2_trans.setrans.out_trans.first_linear.weight"],
                                   sd["f2_trans.setrans.out_trans.feat_softaggr.feat2score.weight"],
                                   sd["f2_trans.setrans.out_trans.feat_softaggr.feat2score.bias"],
@@ -62,10 +69,11 @@ def craft_forward(sd, image1, image2, iters=12, flow_init=None, craft=True, use_
         fmap2 = y.permute(0, 2, 1).reshape(fmap2.shape)
         del probs
     if craft:        # TransCorrBlock.update core/corr.py:148-207
-        vol, _, _ = R.trans_corr_volume(fmap1, fmap2, sd["corr_fn.setrans.query.weight"], sd["corr_fn.setrans.query.bias"],
-                                        sd["corr_fn.setrans.attn_softaggr.feat2score.weight"].reshape(()),
-                                        sd["corr_fn.setrans.attn_softaggr.feat2score.bias"].reshape(()),
-                                        sd["corr_fn.vispos_encoder.pos_coder.biases"], M, w_inter)
+        vol, _, diag["corr_fn"] = R.trans_corr_volume(
+            fmap1, fmap2, sd["corr_fn.setrans.query.weight"], sd["corr_fn.setrans.query.bias"],
+            sd["corr_fn.setrans.attn_softaggr.feat2score.weight"].reshape(()),
+            sd["corr_fn.setrans.attn_softaggr.feat2score.bias"].reshape(()),
+            sd["corr_fn.vispos_encoder.pos_coder.biases"], M_inter, w_inter, attn_clip)
     else:            # CorrBlock core/corr.py:16-45
         vol = R.plain_corr_volume(fmap1, fmap2)
     pyramid = R.corr_pyramid(vol)
@@ -73,8 +81,8 @@ def craft_forward(sd, image1, image2, iters=12, flow_init=None, craft=True, use_
     cnet = basic_encoder(image1, sd, "cnet", "batch")
     net, inp = torch.tanh(cnet[:, :128]), torch.relu(cnet[:, 128:])
     if use_setrans:  # intra-frame attention core/network.py:214
-        attn, _, _ = R.self_attention_probs(inp, sd["att.setrans.query.weight"], sd["att.setrans.key.weight"], M,
-                                            sd["att.vispos_encoder.pos_coder.biases"], w_intra)
+        attn, _, diag["att"] = R.self_attention_probs(inp, sd["att.setrans.query.weight"], sd["att.setrans.key.weight"],
+                                                      M_intra, sd["att.vispos_encoder.pos_coder.biases"], w_intra, attn_clip)
     else:
         attn = R.gma_attention(inp, sd["att.to_qk.weight"])
     _, _, h, w = net.shape
@@ -94,7 +102,7 @@ def craft_forward(sd, image1, image2, iters=12, flow_init=None, craft=True, use_
             glob = R.expanded_feat_trans(m3, attn, P["aggregator.first_linear.weight"],
                                          P["aggregator.feat_softaggr.feat2score.weight"],
                                          P["aggregator.feat_softaggr.feat2score.bias"],
-                                         P["aggregator.input_skip_coeff"], M)
+                                         P["aggregator.input_skip_coeff"], M_intra)
             glob = glob.reshape(B, h, w, 128).permute(0, 3, 1, 2)
         else:
             glob = R.gma_aggregate(attn, motion, P["aggregator.to_v.weight"], P["aggregator.gamma"])

@@ -138,17 +138,22 @@ def corr_lookup(pyramid, coords, radius=4):
 # --------------------------------------------------------------------------------------------
 # attention + value aggregation -- CrossAttFeatTrans / ExpandedFeatTrans core/setrans.py:364-410,553-566
 # --------------------------------------------------------------------------------------------
-def attention_probs(x, wq, wk, M, table, pos_weight, attn_clip=100.0):
-    """Self-attention probabilities of SelfAttVisPosTrans (core/setrans.py:578-600) on encoded tokens x [B,U,C]
-    given the grid (h,w) implied by table/bias -> [B,M,U,U]."""
-    raise NotImplementedError  # see self_attention_probs (needs h, w)
+def radius_mask(h, w, radius, device="cpu"):
+    """SelfAttVisPosTrans.forward core/setrans.py:579-584 (--f2radius): -1e9 where the Chebyshev distance between
+    query and key exceeds `radius` -> [1,1,U,U]."""
+    ys, xs = torch.meshgrid(torch.arange(h, device=device), torch.arange(w, device=device), indexing="ij")
+    c = torch.stack([ys, xs], -1).reshape(-1, 2)
+    far = (c[None] - c[:, None]).abs().max(dim=2)[0] > radius
+    return (far.float() * -1e9)[None, None]
 
 
-def self_attention_probs(feat, wq, wk, M, table, pos_weight, attn_clip=100.0):
+def self_attention_probs(feat, wq, wk, M, table, pos_weight, attn_clip=100.0, mask_radius=-1):
+    """SelfAttVisPosTrans.forward core/setrans.py:578-600 up to the softmax (:553) -> ([B,M,U,U], tokens, gmax)."""
     B, C, h, w = feat.shape
     tok = encode_tokens(feat)
     bias = sliding_pos_bias(table, h, w)[None, None]
-    s, gmax = mode_scores(tok, tok, wq, None, wk, None, M, bias, pos_weight, attn_clip)
+    mask = radius_mask(h, w, mask_radius, feat.device) if mask_radius > 0 else None
+    s, gmax = mode_scores(tok, tok, wq, None, wk, None, M, bias, pos_weight, attn_clip, mask)
     return torch.softmax(s, dim=-1), tok, gmax
 
 

@@ -24,7 +24,7 @@ def main(which, reps):
         model(a, b, iters=1, test_mode=1)       # fills every workspace buffer with realistic data
         torch.cuda.synchronize()
         g = TokenGrid(H // 8, W // 8)
-        ws = get_workspace(g, dev, model.materialize_level0)
+        ws = model._workspaces.get(g, dev, model.materialize_level0)
         ub = model.update_block
         uw = ub.weights(g)
         att_tbl = model.att.vispos_encoder.table()

@@ -23,11 +23,16 @@ OUT = os.path.join(ROOT, "tests", "golden")
 LOCAL = os.path.join(OUT, "_local")
 
 
-def seeded_state(args_kw):
+def seeded_state(args_kw, tweak=None):
+    """tweak: {state-dict key: scalar} -- parameters overwritten with a constant after the seeded init (e.g. GMA's
+    gamma, which initialises to 0 and would make the aggregation invisible)."""
     from craft_b200.network import CRAFT
     torch.manual_seed(1234)
     m = CRAFT(craft_args(**args_kw))
-    return {k: v.clone() for k, v in m.state_dict().items()}
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    for k, v in (tweak or {}).items():
+        sd[k].fill_(v)
+    return sd
 
 
 def capture(model, image1, image2, iters, flow_init=None, seams=False):
@@ -59,7 +64,9 @@ def capture(model, image1, image2, iters, flow_init=None, seams=False):
     for h in hooks:
         h.remove()
     out = dict(flow_lo=flow_lo[0].clone(), flow_up=ups[-1][0].clone(),
-               flow_up_first=ups[0][0].clone())
+               flow_up_first=ups[0][0].clone(),
+               # every iteration's upsampled flow on a stride-8 lattice: the error TRAJECTORY over the refinement loop
+               flow_up_iters_s8=torch.stack([u[0][:, ::8, ::8] for u in ups]).clone())
     for k, v in rec.items():
         if isinstance(v, dict):
             for kk, vv in v.items():
@@ -84,7 +91,15 @@ def main():
     cases = [
         # name, weights, args overrides, H, W, iters, input kind, seams
         ("seeded_setrans_128", "seeded", {}, 128, 128, 4, "noise", True),
-        ("seeded_gma_128", "seeded", dict(use_setrans=False), 128, 128, 4, "noise", False),
+        ("seeded_gma_128", "seeded", dict(use_setrans=False), 128, 128, 4, "noise", True),
+        ("seeded_gma_448x1024", "seeded", dict(use_setrans=False), 448, 1024, 12, "noise", False),
+        # attn_clip below the seeded score maxima (f2 0.51, corr 1.62, att 0.22): the data-dependent clamp of
+        # core/setrans.py:527-529 fires in all three attentions
+        ("seeded_clip02_128", "seeded", dict(attn_clip=0.2), 128, 128, 4, "noise", True),
+        # clamp fires in f2_trans and corr_fn but NOT in the intra-frame attention
+        ("seeded_clip03_128", "seeded", dict(attn_clip=0.3), 128, 128, 4, "noise", False),
+        ("seeded_f2radius_128", "seeded", dict(f2_attn_mask_radius=5), 128, 128, 4, "noise", True),
+        ("seeded_modes2_128", "seeded", dict(inter_num_modes=2, intra_num_modes=2), 128, 128, 4, "noise", True),
         ("seeded_plain_128", "seeded", dict(craft=False, use_setrans=False, f2trans="none", corr_multiplier=1),
          128, 128, 4, "noise", False),
         ("sintel_128", "sintel", {}, 128, 128, 4, "noise", True),
@@ -92,8 +107,14 @@ def main():
         ("sintel_flowinit_192x256", "sintel", {}, 192, 256, 6, "smooth_init", False),
         ("sintel_448x1024", "sintel", {}, 448, 1024, 12, "noise", False),
         ("sintel_kitti_384x1248", "sintel", {}, 384, 1248, 24, "smooth", False),
-        ("sintel_frames_440x1024", "sintel", {}, 440, 1024, 12, "frames", False),
+        ("sintel_frames_440x1024", "sintel", {}, 440, 1024, 12, "frames", True),
     ]
+    tweaks = {
+        "seeded_gma_128": {"update_block.aggregator.gamma": 0.5},
+        "seeded_gma_448x1024": {"update_block.aggregator.gamma": 0.5},
+        # negative soft-aggregation weight: with M == 2 a -inf sentinel for the unused modes would turn into NaN
+        "seeded_modes2_128": {"corr_fn.setrans.attn_softaggr.feat2score.weight": -0.8},
+    }
     only = sys.argv[1:]
     for name, wsrc, kw, H, W, iters, kind, seams in cases:
         if only and name not in only:
@@ -101,7 +122,7 @@ def main():
         args = craft_args(**kw)
         model, _ = build_reference_model(args, checkpoint=("craft-sintel.pth" if wsrc == "sintel" else None))
         if wsrc == "seeded":
-            model.load_state_dict(seeded_state(kw), strict=True)
+            model.load_state_dict(seeded_state(kw, tweaks.get(name)), strict=True)
         flow_init = None
         if kind == "noise":
             i1, i2 = synthetic_pair(H, W)
@@ -119,7 +140,7 @@ def main():
             i1, i2 = InputPadder(a.shape).pad(a, b)
         out = capture(model, i1, i2, iters, flow_init, seams)
         big = H * W > 256 * 320
-        rec = dict(name=name, weights=wsrc, args=kw, H=H, W=W, iters=iters, kind=kind,
+        rec = dict(name=name, weights=wsrc, args=kw, tweak=tweaks.get(name), H=H, W=W, iters=iters, kind=kind,
                    flow_lo=out["flow_lo"], flow_up_mean=out["flow_up"].mean((1, 2)),
                    flow_up_absmax=out["flow_up"].abs().max())
         if big:
@@ -139,7 +160,22 @@ def main():
             rec["ref_bf16_autocast_epe_median"] = float(e.median())
         for k, v in out.items():
             if k not in ("flow_lo", "flow_up", "flow_up_first"):
+                if big and k != "flow_up_iters_s8":
+                    if k in ("fnet_out", "cnet_out"):
+                        continue                      # 20 MB at this size; the seam report runs our own encoders
+                    v = v[..., ::4, ::4].contiguous() if v.dim() >= 3 and k != "aggr_it0" else v
+                    if k == "aggr_it0":               # [1,U,128] tokens -> stride-4 lattice like the NCHW seams
+                        v = v.reshape(1, H // 8, W // 8, -1)[:, ::4, ::4].contiguous()
+                    k = k + "_s4"
                 rec[k] = v
+        # the reference's attention diagnostics (core/setrans.py:524-529) after this single forward
+        diag = {}
+        for mod_name in ("corr_fn", "f2_trans", "att"):
+            mod = getattr(model, mod_name, None)
+            st = getattr(mod, "setrans", None)
+            if st is not None:
+                diag[mod_name] = dict(max_attn=float(st.max_attn), clamp_count=int(st.clamp_count))
+        rec["diag"] = diag
         torch.save(rec, os.path.join(OUT, name + ".pt"))
         print(name, "flow_up mean", rec["flow_up_mean"].tolist(), "absmax", float(rec["flow_up_absmax"]),
               "keys", len(rec), flush=True)

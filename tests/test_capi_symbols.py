@@ -97,7 +97,8 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
     from craft_b200 import _lib
     if shutil.which("gcc") is None:
         pytest.skip("gcc not available")
-    pairs = [("craft_gemm_args", _lib.GemmArgs), ("craft_scores_args", _lib.ScoresArgs), ("craft_pv_args", _lib.PvArgs)]
+    pairs = [("craft_gemm_args", _lib.GemmArgs), ("craft_scores_args", _lib.ScoresArgs), ("craft_pv_args", _lib.PvArgs),
+             ("craft_dense_attn_args", _lib.DenseAttnArgs)]
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "craft_b200.h"', 'int main(void) {']
     for cname, st in pairs:
         lines.append('printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))

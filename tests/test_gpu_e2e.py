@@ -31,6 +31,10 @@ def _model(rec):
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(1234)
     m = CRAFT(craft_args(**rec["args"]))
+    if rec.get("tweak"):
+        sd = m.state_dict()
+        for k, v in rec["tweak"].items():
+            sd[k].fill_(v)
     if rec["weights"] == "sintel":
         path = os.path.join(LOCAL, "craft-sintel-model.pth")
         if not os.path.isfile(path):
@@ -61,7 +65,10 @@ def _epe(a, b):
 
 
 CASES = ["seeded_setrans_128", "seeded_gma_128", "seeded_plain_128", "sintel_128", "sintel_smooth_256x320",
-         "sintel_flowinit_192x256", "sintel_448x1024", "sintel_kitti_384x1248", "sintel_frames_440x1024"]
+         "sintel_flowinit_192x256", "sintel_448x1024", "sintel_kitti_384x1248", "sintel_frames_440x1024",
+         # gamma = 0.5 (GMA aggregation visible), clamp gate firing in 3 / 2 of the attentions, --f2radius mask,
+         # two modes with a negative soft-aggregation weight, GMA at BASELINE configs[2] size
+         "seeded_clip02_128", "seeded_clip03_128", "seeded_f2radius_128", "seeded_modes2_128", "seeded_gma_448x1024"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -84,6 +91,11 @@ def test_flow_matches_reference(name):
     epe_up, epe_med = err.mean().item(), err.median().item()
     _report(name, epe_up=epe_up, epe_median=epe_med, epe_lo_x8=8 * epe_lo, mean_flow=flow_up.mean((1, 2)).tolist(),
             ref_mean_flow=rec["flow_up_mean"].tolist(), ref_bf16_autocast_epe=rec.get("ref_bf16_autocast_epe_mean"))
+    # the reference's attention diagnostics (core/setrans.py:520-529): global score maximum and clamp count
+    for mod, d in rec.get("diag", {}).items():
+        st = getattr(model, mod).setrans
+        assert abs(st.max_attn - d["max_attn"]) <= 2e-2 * max(1.0, abs(d["max_attn"])), (mod, st.max_attn, d)
+        assert st.clamp_count == d["clamp_count"], (mod, st.clamp_count, d)
     if "ref_bf16_autocast_epe_mean" in rec:
         # ill-conditioned real pair: the mean is dominated by a few chaotic (occluded) regions where
         # even the reference's own bf16-autocast run is 0.58 px away from its fp32 run.  Bound the
@@ -93,7 +105,8 @@ def test_flow_matches_reference(name):
     assert epe_up <= EPE_TOL, "EPE %.5f px vs reference (1/8-res EPE x8 = %.5f)" % (epe_up, 8 * epe_lo)
 
 
-@pytest.mark.parametrize("name", ["seeded_setrans_128", "sintel_128"])
+@pytest.mark.parametrize("name", ["seeded_setrans_128", "sintel_128", "seeded_clip02_128", "seeded_f2radius_128",
+                                  "seeded_modes2_128", "seeded_gma_128"])
 def test_seams_match_reference(name):
     """Feed the reference's encoder outputs and compare every hot-path seam after one iteration."""
     from craft_b200 import ops
@@ -108,11 +121,15 @@ def test_seams_match_reference(name):
         model(i1.cuda(), i2.cuda(), iters=1, test_mode=1)
     torch.cuda.synchronize()
     g = TokenGrid(rec["H"] // 8, rec["W"] // 8)
-    ws = get_workspace(g, torch.device("cuda", 0), model.materialize_level0)
+    ws = model._workspaces.get(g, torch.device("cuda", 0), model.materialize_level0)
 
     def rows(buf, c0, c1):
         return buf.float().view(g.H, g.Wp, -1)[:, :g.W, c0:c1].permute(2, 0, 1).cpu()
 
+    if name.startswith("seeded_clip"):
+        # every gate fired: flag == 1, the clamped re-pass ran, the LN statistics are the clamped pass's
+        assert ws.flag.tolist() == [1, 1, 1] and ws.clip_corr.item() == ws.clip_f2.item() == ws.clip_att.item() == 0.2
+        assert ws.stat_sum[1].abs().sum().item() > 0
     got = {
         "f2_out": None,
         "ub_it0.corr": rows(ws.CORR, 0, 324),
@@ -128,7 +145,8 @@ def test_seams_match_reference(name):
     got["f2_out"] = rows(ws.T2f, 0, 256)
     refs = dict(rec)
     refs["f2_out"] = f2_tok
-    refs["aggr_it0"] = rec["aggr_it0"][0].t().reshape(128, g.H, g.W)
+    # setrans aggregator output is [B,U,128] tokens, GMA's Aggregate returns NCHW
+    refs["aggr_it0"] = rec["aggr_it0"][0].t().reshape(128, g.H, g.W) if rec["aggr_it0"].dim() == 3 else rec["aggr_it0"][0]
     refs["motion_it0"] = rec["motion_it0"][0]
     refs["net_it0"] = rec["net_it0"][0]
     tol = {"f2_out": 0.06, "ub_it0.corr": 0.08, "motion_it0": 0.06, "aggr_it0": 0.08, "net_it0": 0.03,
@@ -197,3 +215,60 @@ def test_stored_level0_volume_agrees_with_on_demand_lookup():
         _, up_b = model(i1, i2, iters=4, test_mode=1)
     torch.cuda.synchronize()
     assert _epe(up_a[0].cpu(), up_b[0].cpu()) <= 2e-3
+
+
+def test_real_frame_pair_error_trajectory_and_seams():
+    """The shipped Sintel-like pair (436x1024, 200-px motions, occlusions) is the one case whose MEAN end-point
+    error exceeds the bf16 tolerance.  This test writes the evidence for why (gpurun_out/frames_report.json,
+    committed under profiles/): the per-iteration error trajectory against the reference's own iterations, its
+    percentiles, and the per-seam errors after the first iteration."""
+    from craft_b200.ops import TokenGrid
+    rec = torch.load(os.path.join(GOLD, "sintel_frames_440x1024.pt"), map_location="cpu")
+    model = _model(rec)
+    i1, i2 = _inputs(rec)
+    i1, i2 = i1.cuda(), i2.cuda()
+    with torch.no_grad():
+        _, ups = model(i1, i2, iters=rec["iters"], test_mode=2)
+    torch.cuda.synchronize()
+    ref = rec["flow_up_iters_s8"]
+    traj = []
+    for k, u in enumerate(ups):
+        e = (u[0][:, ::8, ::8].cpu() - ref[k]).pow(2).sum(0).sqrt().flatten()
+        q = torch.quantile(e, torch.tensor([0.5, 0.9, 0.99]))
+        traj.append(dict(iter=k + 1, mean=e.mean().item(), median=q[0].item(), p90=q[1].item(), p99=q[2].item(),
+                         frac_gt_0p1=(e > 0.1).float().mean().item(), frac_gt_1=(e > 1.0).float().mean().item(),
+                         ref_flow_absmax=ref[k].abs().max().item()))
+    # seams after ONE iteration, our own encoders included, on the golden's stride-4 token lattice
+    with torch.no_grad():
+        model(i1, i2, iters=1, test_mode=1)
+    torch.cuda.synchronize()
+    g = TokenGrid(rec["H"] // 8, rec["W"] // 8)
+    ws = model._workspaces.get(g, torch.device("cuda", 0), model.materialize_level0)
+
+    def rows(buf, c0, c1):
+        return buf.float().view(g.H, g.Wp, -1)[:, :g.W, c0:c1].permute(2, 0, 1)[:, ::4, ::4].cpu()
+    f2 = rec["f2_out_s4"][0]
+    got = {"f2_out": rows(ws.T2f, 0, 256), "ub_it0.corr": rows(ws.CORR, 0, 324), "motion_it0": rows(ws.X, 256, 384),
+           "aggr_it0": rows(ws.X, 384, 512), "net_it0": rows(ws.Hm, 0, 128), "ub_it0.delta": rows(ws.DELTA, 0, 2),
+           "ub_it0.mask": rows(ws.MASKS[0], 0, 576)}
+    refs = {"f2_out": torch.nn.functional.layer_norm(f2.permute(1, 2, 0), (256,), eps=1e-12).permute(2, 0, 1),
+            "ub_it0.corr": rec["ub_it0.corr_s4"], "motion_it0": rec["motion_it0_s4"][0],
+            "aggr_it0": rec["aggr_it0_s4"][0].permute(2, 0, 1), "net_it0": rec["net_it0_s4"][0],
+            "ub_it0.delta": rec["ub_it0.delta_s4"], "ub_it0.mask": rec["ub_it0.mask_s4"]}
+    seams = {}
+    for k, v in got.items():
+        r = refs[k]
+        d = (v - r).abs()
+        seams[k] = dict(mean_abs=d.mean().item(), p99_abs=torch.quantile(d.flatten()[:2_000_000], 0.99).item(),
+                        max_abs=d.max().item(), ref_rms=r.pow(2).mean().sqrt().item(), ref_absmax=r.abs().max().item())
+    report = dict(case="sintel_frames_440x1024", trajectory=traj, seams_after_iter1=seams,
+                  ref_bf16_autocast_epe_mean=rec["ref_bf16_autocast_epe_mean"],
+                  ref_bf16_autocast_epe_median=rec["ref_bf16_autocast_epe_median"])
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "frames_report.json"), "w") as f:
+        json.dump(report, f, indent=1)
+    # what must hold whatever the amplification: every seam of the first iteration is inside the bf16 budget and
+    # the typical (median) pixel stays inside the bf16 tolerance through all 12 iterations
+    for k, e in seams.items():
+        assert e["mean_abs"] <= 0.03 * max(1.0, e["ref_rms"]), (k, e)
+    assert all(t["median"] <= EPE_TOL for t in traj), traj

@@ -60,8 +60,8 @@ def test_variants_construct_and_reject_out_of_scope_flags():
     CRAFT(craft_args(craft=False, use_setrans=False, f2trans="none", corr_multiplier=1))
     with pytest.raises(NotImplementedError):
         CRAFT(craft_args(f1trans="shared"))
-    with pytest.raises(NotImplementedError):
-        CRAFT(craft_args(f2_attn_mask_radius=16))
+    m = CRAFT(craft_args(f2_attn_mask_radius=16))          # --f2radius (core/setrans.py:580-584) is supported
+    assert m.f2_trans.attn_mask_radius == 16 and m.att.attn_mask_radius == -1
     with pytest.raises(NotImplementedError):
         CRAFT(craft_args(intra_pos_code_type="lsinu"))
 

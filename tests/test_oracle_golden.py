@@ -14,25 +14,40 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
-def _seeded_sd(kw):
+def _seeded_sd(kw, tweak=None):
     from craft_b200.network import CRAFT
     torch.manual_seed(1234)
-    return {k: v.clone() for k, v in CRAFT(craft_args(**kw)).state_dict().items()}
+    sd = {k: v.clone() for k, v in CRAFT(craft_args(**kw)).state_dict().items()}
+    for k, v in (tweak or {}).items():
+        sd[k].fill_(v)
+    return sd
 
 
 @pytest.mark.parametrize("name,flags", [
     ("seeded_setrans_128", dict(craft=True, use_setrans=True, f2trans=True)),
     ("seeded_gma_128", dict(craft=True, use_setrans=False, f2trans=True)),
     ("seeded_plain_128", dict(craft=False, use_setrans=False, f2trans=False)),
+    # branches the default configuration never takes: the data-dependent clamp (all three attentions / two of
+    # three), the --f2radius key mask, two modes with a negative soft-aggregation weight
+    ("seeded_clip02_128", dict(attn_clip=0.2)),
+    ("seeded_clip03_128", dict(attn_clip=0.3)),
+    ("seeded_f2radius_128", dict(f2_mask_radius=5)),
+    ("seeded_modes2_128", dict(M_inter=2, M_intra=2)),
 ])
 def test_oracle_forward_matches_golden(name, flags):
     rec = torch.load(os.path.join(GOLD, name + ".pt"), map_location="cpu")
-    sd = _seeded_sd(rec["args"])
+    sd = _seeded_sd(rec["args"], rec.get("tweak"))
     i1, i2 = synthetic_pair(rec["H"], rec["W"])
+    diag = {}
     with torch.no_grad():
-        lo, up = cpu_forward.craft_forward(sd, i1, i2, iters=rec["iters"], **flags)
+        lo, up = cpu_forward.craft_forward(sd, i1, i2, iters=rec["iters"], diag=diag, **flags)
     assert torch.allclose(lo[0], rec["flow_lo"], atol=2e-4), (lo[0] - rec["flow_lo"]).abs().max()
     assert torch.allclose(up[0], rec["flow_up"], atol=1e-3), (up[0] - rec["flow_up"]).abs().max()
+    # the reference's own diagnostics: global score maximum and whether the clamp branch was taken
+    for mod, d in rec.get("diag", {}).items():
+        assert abs(diag[mod] - d["max_attn"]) < 1e-4, (mod, diag[mod], d)
+        clip = flags.get("attn_clip", 100.0)
+        assert (diag[mod] > clip) == (d["clamp_count"] == 1), (mod, d)
 
 
 def test_oracle_seams_match_golden():
