@@ -114,6 +114,11 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     while (c > 0 && NT * c / gridDim.x > x) --c;
     return static_cast<int>(c);
   };
+  // Key tiles of a unit are visited block-COLUMN major (kt = bx * nby + by): the blocks inside the positional-
+  // bias window (|dy| <= R: ~3 of the nby block rows, all columns), which cost ~1.4x a plain tile, then occur
+  // 3 per nby everywhere in the list and every CTA's equal-length range carries the same share of them
+  // (block-row major order packed them into one contiguous run per unit: CTA finish times spread 72..86 us).
+  const int nby = p.nkt / p.nbx;
   struct Seg { int qt, mode, t0, nt; };
   auto seg_at = [&](long long lin) {
     Seg sgm;
@@ -189,7 +194,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           bool moved = false;
           if (ki < sgm.nt && mbar_test(&k_empty[ks], kph ^ 1u)) {
             const int kt = sgm.t0 + ki;
-            const int by = kt / p.nbx, bx = kt - by * p.nbx;
+            const int bx = kt / nby, by = kt - bx * nby;
             mbar_arrive_expect_tx(&k_full[ks], S::kKBytes);
             for (int a = 0; a < S::kQAtoms; ++a)
               tma_load_3d(sK + ks * S::kKBytes + a * BK * 128, &tmK, &k_full[ks], qk_col + a * 64, bx * BW, by * 8);
@@ -199,9 +204,11 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
           if (vi < sgm.nt && mbar_test(&v_empty[vs], vph ^ 1u)) {
             const int kt = sgm.t0 + vi;
+            const int vbx = kt / nby, vby = kt - vbx * nby;
+            const int vcol = (vby * p.nbx + vbx) * BK;          // V^T columns are in block-row-major block order
             mbar_arrive_expect_tx(&v_full[vs], S::kVBytes);
             for (int a = 0; a < BK / 64; ++a)
-              tma_load_2d(sV + vs * S::kVBytes + a * F * 128, &tmV, &v_full[vs], kt * BK + a * 64, sgm.mode * F);
+              tma_load_2d(sV + vs * S::kVBytes + a * F * 128, &tmV, &v_full[vs], vcol + a * 64, sgm.mode * F);
             PV_TRACE(3, g0 + vi, 1);
             if (++vs == VS) { vs = 0; vph ^= 1u; }
             ++vi; moved = true;
@@ -333,7 +340,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const int b = g % NSB;
         const uint32_t bpar = static_cast<uint32_t>(g / NSB) & 1u;
         const int kt = sgm.t0 + i;
-        const int by = kt / p.nbx, bx = kt - by * p.nbx;
+        const int bx = kt / nby, by = kt - bx * nby;
         // this thread's half block: block rows [ch*4, ch*4+4), all BW columns
         const int iy0 = by * 8 + ch * 4 - qy + R;       // table row of the first block row
         const int ix0 = bx * BW - qx + R;               // table column of the first block column
@@ -448,6 +455,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
         }
       }
+      if (trole == 1) PV_TRACE(3, g_last, 2);      // boundary: write-back (+ zero fill) done
       lin += sgm.nt;
       g0 += sgm.nt;
     }

@@ -349,6 +349,10 @@ int craft_shift_gemm(const craft_gemm_args* a, void* stream) {
     case cb::EPI_MOTION:
       if (a->Npad != 128 || !a->aux1 || !a->out_bf16) return fail("gemm: motion needs Npad=128, flow, out");
       return launch_gemm_bn<cb::EPI_MOTION>(a->BN, CL, ta, tb, p, st);
+    case cb::EPI_FLOW:
+      if (a->BN != 32 || a->Npad != 32 || !a->aux0 || !a->aux1 || !a->out_f32 || a->H <= 0)
+        return fail("gemm: flow epilogue needs BN=Npad=32, coords1, flow, an f32 delta output and a grid");
+      return launch_gemm_t<32, cb::EPI_FLOW, 1>(ta, tb, p, st);
   }
   return fail("gemm: unknown epilogue %d", a->epilogue);
 }

@@ -35,6 +35,8 @@ enum GemmEpilogue : int {
   EPI_GRU_ZR = 1,   // n<128: z=sigmoid -> Z(f32);  n>=128: r=sigmoid, (r*h) -> bf16
   EPI_GRU_Q = 2,    // q=tanh; h=(1-z)h+zq -> Hm(f32) and bf16 copy
   EPI_MOTION = 3,   // n<126: relu(acc+bias) ; n in {126,127}: flow channel copy
+  EPI_FLOW = 4,     // flow head's last conv: columns 0,1 = delta -> f32 store, and coords1 += delta,
+                    // flow = coords1 - coords0 in the same epilogue (core/network.py:247,236)
 };
 
 struct GemmParams {
@@ -73,8 +75,8 @@ struct GemmParams {
   int ldb, colb;
   float* out_f;                  // f32 destination, may be nullptr
   int ldf, colf;
-  float* aux_f0;                 // EPI_GRU_*: Z   [M,128] f32
-  float* aux_f1;                 // EPI_GRU_*: Hm  [M,128] f32 ; EPI_MOTION: flow [M,2] f32
+  float* aux_f0;                 // EPI_GRU_*: Z   [M,128] f32 ; EPI_FLOW: coords1 [M,2] f32
+  float* aux_f1;                 // EPI_GRU_*: Hm  [M,128] f32 ; EPI_MOTION / EPI_FLOW: flow [M,2] f32
 };
 
 template <int BN>
@@ -363,7 +365,18 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float v[CW];
 #pragma unroll
         for (int j = 0; j < CW; ++j) v[j] = fmaf(__uint_as_float(raw[j]), p.alpha, s_bias[nl + j]);
-        if constexpr (EPI == EPI_STORE) {
+        if constexpr (EPI == EPI_FLOW) {
+          if (n == 0) {          // this thread holds (dx, dy) of its token
+            float2* cp = reinterpret_cast<float2*>(p.aux_f0) + m;
+            float2 c1 = *cp;
+            c1.x += v[0];
+            c1.y += v[1];
+            *cp = c1;
+            const int y = m / p.Wp, x = m - y * p.Wp;
+            reinterpret_cast<float2*>(p.aux_f1)[m] = make_float2(c1.x - static_cast<float>(x), c1.y - static_cast<float>(y));
+          }
+        }
+        if constexpr (EPI == EPI_STORE || EPI == EPI_FLOW) {
           if (p.act == 1) {
 #pragma unroll
             for (int j = 0; j < CW; ++j) v[j] = fmaxf(v[j], 0.0f);

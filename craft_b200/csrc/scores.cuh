@@ -166,7 +166,7 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         for (int a = 0; a < atoms; ++a) tma_load_2d(sQ + a * 128 * 128, &tmQ, q_full, a * 64, sg.qt * 128);
         for (int i = 0; i < sg.nt; ++i) {
           const int kt = sg.t0 + i;
-          const int by = kt / p.nkt_x, bx = kt - by * p.nkt_x;
+          const int bx = kt / p.nkt_y, by = kt - bx * p.nkt_y;      // block-column major, see attn_pv.cuh
           mbar_wait(&k_empty[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&k_full[stage], k_bytes);
           uint8_t* dst = sK + stage * k_bytes;
@@ -257,7 +257,7 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const int g = g0 + i;
         const uint32_t par = (static_cast<uint32_t>(g) >> 1) & 1u;
         const int kt = sgm.t0 + i;
-        const int by = kt / p.nkt_x, bx = kt - by * p.nkt_x;
+        const int bx = kt / p.nkt_y, by = kt - bx * p.nkt_y;      // block-column major, see attn_pv.cuh
         const int ky0 = by * 8 + ch * 4, kx0 = bx * 8;          // this thread's 4 x 8 key window
         const int iy0 = ky0 - qy + R, ix0 = kx0 - qx + R;       // table coordinates of its first key
         const bool near = has_bias && (iy0 + 3 >= 0) && (iy0 <= 2 * R) && (ix0 + 7 >= 0) && (ix0 <= 2 * R);
@@ -557,13 +557,13 @@ __global__ void lse_merge_kernel(const float2* __restrict__ part, int ksplit, in
 // corr_stats_finalize: {sum, sumsq} over n elements -> {mean, rstd} (biased variance, eps 1e-12,
 // F.layer_norm semantics, core/corr.py:202) and the clamp gate: clip = (max > attn_clip) ? attn_clip : +inf.
 // sums: [2][2] -- slot 0 from the unclamped pass, slot 1 from the clamped re-pass, selected by *flag.
-__global__ void corr_stats_finalize_kernel(const double* __restrict__ sums, const int* __restrict__ flag, double n,
-                                           float* __restrict__ mean_rstd) {
+__global__ void corr_stats_finalize_kernel(const double* sums, const int* flag, double n, float* mean_rstd) {
   pdl_launch_dependents();
   pdl_wait();
-  if (flag != nullptr && *flag != 0) sums += 2;
-  const double mean = sums[0] / n;
-  double var = sums[1] / n - mean * mean;
+  if (flag != nullptr && *reinterpret_cast<const volatile int*>(flag) != 0) sums += 2;
+  const volatile double* vs = sums;          // no invariant loads: see clip_gate_kernel
+  const double mean = vs[0] / n;
+  double var = vs[1] / n - mean * mean;
   if (var < 0) var = 0;
   mean_rstd[0] = static_cast<float>(mean);
   mean_rstd[1] = static_cast<float>(1.0 / sqrt(var + 1e-12));
@@ -571,15 +571,19 @@ __global__ void corr_stats_finalize_kernel(const double* __restrict__ sums, cons
 // diag (optional, [2] f32): the module's running diagnostics {max_attn, clamp_count} that the reference
 // keeps on the host with two .item() syncs per call (core/setrans.py:520-529); here they stay on the device
 // and are read lazily.
-__global__ void clip_gate_kernel(const float* __restrict__ stat_max, float attn_clip,
-                                 float* __restrict__ clip, int* __restrict__ flag, float* __restrict__ diag) {
+// NOTE (found under CUDA-graph replay in round 2): the inputs are deliberately NOT `const __restrict__`.
+// nvcc marks loads through such pointers invariant and hoisted this kernel's only load above
+// griddepcontrol.wait, so the gate read the score maximum before the scores kernel had produced it.
+// profiles/audit_pdl_hoist.py (run by tests/test_capi_symbols.py) checks the SASS of every kernel for this.
+__global__ void clip_gate_kernel(const float* stat_max, float attn_clip, float* clip, int* flag, float* diag) {
   pdl_launch_dependents();
   pdl_wait();
-  const bool hit = stat_max[0] > attn_clip;
+  const float mx = *reinterpret_cast<const volatile float*>(stat_max);
+  const bool hit = mx > attn_clip;
   clip[0] = hit ? attn_clip : INFINITY;
   flag[0] = hit ? 1 : 0;
   if (diag) {
-    diag[0] = fmaxf(diag[0], stat_max[0]);
+    diag[0] = fmaxf(diag[0], mx);
     if (hit) diag[1] += 1.0f;
   }
 }

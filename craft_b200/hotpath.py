@@ -285,21 +285,26 @@ def sep_conv_gru(ws, uw):
     sep_conv_gru_rows(ws.grid, ws.X, ws.Hm, ws.Z, uw.gru)
 
 
-def heads(ws, uw, it=0, need_mask=True):
+def heads(ws, uw, it=0, need_mask=True, update_flow=False):
     """FlowHead core/update.py:15-16 + mask head core/update.py:124-127,161 -> DELTA[:, :2], MASKS[it & 1].
     The two second-layer convolutions are independent: the flow one runs on the side stream.
-    need_mask=False computes the flow head only (the caller discards this iteration's mask)."""
+    need_mask=False computes the flow head only (the caller discards this iteration's mask).
+    update_flow=True: the flow head's epilogue also applies coords1 += delta, flow = coords1 - coords0
+    (core/network.py:247,236) instead of a separate kernel."""
     g = ws.grid
     sg = ops.shift_gemm
+    fl = dict(M=g.Mp, Npad=32, K=256, BN=32, taps=uw.taps3, grid=g, bias=uw.fl_b, out_f=ws.DELTA)
+    if update_flow:
+        fl.update(epilogue=ops.EPI_FLOW, aux0=ws.coords1, aux1=ws.flow)
     if not need_mask:
         sg(ws.X, uw.hdf_w, M=g.Mp, Npad=256, K=128, BN=128, taps=uw.taps3, grid=g, bias=uw.hdf_b, act=1, out_b=ws.HD)
-        sg(ws.HD, uw.fl_w, M=g.Mp, Npad=32, K=256, BN=32, taps=uw.taps3, grid=g, bias=uw.fl_b, out_f=ws.DELTA)
+        sg(ws.HD, uw.fl_w, **fl)
         return
     sg(ws.X, uw.hd_w, M=g.Mp, Npad=512, K=128, BN=128, taps=uw.taps3, grid=g, bias=uw.hd_b, act=1, out_b=ws.HD)
     main, side = torch.cuda.current_stream(), ws.side
     side.wait_stream(main)
     with torch.cuda.stream(side):
-        sg(ws.HD, uw.fl_w, M=g.Mp, Npad=32, K=256, BN=32, taps=uw.taps3, grid=g, bias=uw.fl_b, out_f=ws.DELTA)
+        sg(ws.HD, uw.fl_w, **fl)
     sg(ws.HD, uw.mk_w, M=g.Mp, Npad=576, K=256, BN=64, a_koff=256, grid=g, bias=uw.mk_b, alpha=0.25,
        out_f=ws.MASKS[it & 1])
     main.wait_stream(side)

@@ -298,8 +298,8 @@ class CRAFT(nn.Module):
             for itr in range(iters):
                 need_up = not (test_mode == 1 and self.elide_dead_upsample) or itr == iters - 1
                 lookup = lambda part: corr_fn.lookup_rows(ws, ws.coords1, out_b=ws.CORR, part=part)
-                self.update_block.step(ws, att, itr, need_mask=need_up, lookup=lookup)
-                ops.flow_update(ws.coords1, ws.flow, ws.DELTA, g)
+                # coords1 += delta / flow = coords1 - coords0 (core/network.py:247,236) happen in the flow head's epilogue
+                self.update_block.step(ws, att, itr, need_mask=need_up, lookup=lookup, update_flow=True)
                 if not need_up:
                     continue
                 # the reference upsamples after every iteration (core/network.py:250-260); nothing in the next

@@ -1,8 +1,10 @@
-"""Host-side operator layer: torch tensors in, C-ABI calls out (craft_b200/_lib.py).
+"""Host-side operator layer: convenience wrappers (TokenGrid objects, keyword arguments) over the
+registered torch custom ops `torch.ops.craft_b200.*` (craft_b200/torch_ops.py), which bind the C ABI
+of libcraft_b200.so (include/craft_b200.h) one to one.
 
-torch is used here only for device memory and the current CUDA stream.  Every function launches
-hand-written sm_100a kernels from libcraft_b200.so on `torch.cuda.current_stream()` and raises if
-the library or a CUDA device is missing -- there is no fallback.
+torch is used only for device memory, the dispatcher and the current CUDA stream.  Every function
+launches hand-written sm_100a kernels on `torch.cuda.current_stream()` and raises if the library or
+a CUDA device is missing -- there is no fallback (the ops have no CPU implementation).
 """
 import ctypes as C
 import math
@@ -10,9 +12,9 @@ import math
 import torch
 
 from . import _lib
-from ._lib import DenseAttnArgs, GemmArgs, PvArgs, ScoresArgs
+from .torch_ops import OPS
 
-EPI_STORE, EPI_GRU_ZR, EPI_GRU_Q, EPI_MOTION = 0, 1, 2, 3
+EPI_STORE, EPI_GRU_ZR, EPI_GRU_Q, EPI_MOTION, EPI_FLOW = 0, 1, 2, 3, 4
 PACK_COPY, PACK_LN, PACK_TANH, PACK_RELU, PACK_RELU_LN = 0, 1, 2, 3, 4
 
 
@@ -91,24 +93,23 @@ def _ld(t):
 # ------------------------------------------------------------------------------------------------
 # layout
 # ------------------------------------------------------------------------------------------------
+def _cuda_only(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.CraftB200Error("expected CUDA tensors; craft_b200 has no CPU path")
+
+
 def pack_tokens(src, grid, mode=PACK_COPY, out_b=None, colb=0, out_f=None, colf=0):
     """src [C,H,W] f32 -> token rows (optionally LayerNorm / tanh / relu)."""
-    _chk(src, torch.float32, "src")
-    _chk(out_b, torch.bfloat16, "out_b")
-    _chk(out_f, torch.float32, "out_f")
-    Cc = src.shape[0]
-    assert src.shape[1] == grid.H and src.shape[2] == grid.W
-    _lib.call("craft_pack_tokens", _ptr(src), Cc, grid.H, grid.W, mode, _ptr(out_b), _ld(out_b), colb,
-              _ptr(out_f), _ld(out_f), colf, _stream())
+    _cuda_only(src, out_b, out_f)
+    OPS.pack_tokens(src, grid.H, grid.W, mode, out_b, colb, out_f, colf)
 
 
 def unpack_tokens(buf, col, Cc, grid, out=None):
     if out is None:
         out = torch.empty((Cc, grid.H, grid.W), dtype=torch.float32, device=buf.device)
-    is_b = 1 if buf.dtype == torch.bfloat16 else 0
-    if not is_b:
-        _chk(buf, torch.float32, "buf")
-    _lib.call("craft_unpack_tokens", _ptr(buf), is_b, _ld(buf), col, Cc, grid.H, grid.W, _ptr(out), _stream())
+    _cuda_only(buf, out)
+    OPS.unpack_tokens(buf, col, Cc, grid.H, grid.W, out)
     return out
 
 
@@ -120,36 +121,11 @@ def shift_gemm(A, Bw, *, M, Npad, K, BN, taps=(0,), a_koff=0, b_koff=0, grid=Non
                b_block_grid=None, cluster=0, stages=0, a_share=0):
     """b_block_grid: B rows are the tokens of that grid and n-tile j is its j-th 8 x BN/8 spatial block.
     a_share=1 (experimental): load the A rows of a kernel row once for all of its taps."""
-    _chk(A, torch.bfloat16, "A")
-    _chk(Bw, torch.bfloat16, "B")
-    _chk(bias, torch.float32, "bias")
-    _chk(out_b, torch.bfloat16, "out_b")
-    _chk(out_f, torch.float32, "out_f")
-    _chk(aux0, torch.float32, "aux0")
-    _chk(aux1, torch.float32, "aux1")
-    a = GemmArgs()
-    a.A, a.a_rows, a.lda, a.a_koff = A.data_ptr(), A.shape[0], A.shape[1], a_koff
-    a.B, a.b_rows, a.ldb_, a.b_koff = Bw.data_ptr(), Bw.shape[0], Bw.shape[1], b_koff
-    a.M, a.Npad, a.K, a.T, a.BN = M, Npad, K, len(taps), BN
-    a.cluster = cluster
-    a.stages = stages
-    a.a_share = a_share
-    if b_block_grid is not None:
-        a.b_blocked, a.b_H, a.b_W = 1, b_block_grid.H, b_block_grid.W
-    for i, t in enumerate(taps):
-        a.tap_off[i] = int(t)
-    a.H, a.W = (grid.H, grid.W) if grid is not None else (0, 0)
-    a.epilogue, a.alpha, a.act = epilogue, float(alpha), act
-    a.bias = bias.data_ptr() if bias is not None else None
-    a.out_bf16 = out_b.data_ptr() if out_b is not None else None
-    a.ldo_b, a.colo_b = _ld(out_b), colb
-    a.out_f32 = out_f.data_ptr() if out_f is not None else None
-    a.ldo_f, a.colo_f = _ld(out_f), colf
-    a.aux0 = aux0.data_ptr() if aux0 is not None else None
-    a.aux1 = aux1.data_ptr() if aux1 is not None else None
-    if bias is not None:
-        assert bias.numel() >= Npad
-    _lib.call("craft_shift_gemm", C.byref(a), _stream())
+    _cuda_only(A, Bw)
+    H, W = (grid.H, grid.W) if grid is not None else (0, 0)
+    bH, bW = (b_block_grid.H, b_block_grid.W) if b_block_grid is not None else (0, 0)
+    OPS.shift_gemm(A, Bw, M, Npad, K, BN, [int(t) for t in taps], a_koff, b_koff, H, W, epilogue, float(alpha), act, bias,
+                   out_b, colb, out_f, colf, aux0, aux1, bH, bW, cluster, stages, a_share)
 
 
 def conv_taps(kh, kw, grid):
@@ -211,132 +187,67 @@ def blocked_keys(grid, BK):
     return ((grid.H + 7) // 8) * ((grid.W + bw - 1) // bw) * BK
 
 
-def _scores_args(Q, K, grid, M, d, w_pos, pos_table, R, clip, run_flag, ksplit):
-    _chk(Q, torch.bfloat16, "Q")
-    _chk(K, torch.bfloat16, "K")
-    _chk(pos_table, torch.float32, "pos_table")
-    _chk(clip, torch.float32, "clip")
-    assert Q.shape == (grid.Mp, M * d) and K.shape == (grid.Mp, M * d)
-    a = ScoresArgs()
-    a.Q, a.K = Q.data_ptr(), K.data_ptr()
-    a.C, a.M, a.d = M * d, M, d
-    a.H, a.W = grid.H, grid.W
-    a.scale, a.w_pos = 1.0 / math.sqrt(d), float(w_pos)
-    a.pos_table = pos_table.data_ptr() if pos_table is not None else None
-    a.R = R
-    a.clip = clip.data_ptr()
-    a.run_flag = run_flag.data_ptr() if run_flag is not None else None
-    a.ksplit = ksplit
-    return a
-
-
 def corr_build(Q, K, grid, *, M, d, w_agg, w_pos, pos_table, R, clip, stat_sum, stat_max, levels,
                run_flag=None, ksplit=0):
     """levels: list of 4 f32 tensors [Mp, h_l*w_l] (levels[0] may be None)."""
-    a = _scores_args(Q, K, grid, M, d, w_pos, pos_table, R, clip, run_flag, ksplit)
-    a.w_agg = float(w_agg)
-    _chk(stat_sum, torch.float64, "stat_sum")
-    _chk(stat_max, torch.float32, "stat_max")
-    a.stat_sum, a.stat_max = stat_sum.data_ptr(), stat_max.data_ptr()
-    for l in range(4):
-        _chk(levels[l], torch.float32, "level")
-        a.lvl[l] = levels[l].data_ptr() if levels[l] is not None else None
-    _lib.call("craft_corr_build", C.byref(a), _stream())
+    _cuda_only(Q, K)
+    OPS.corr_build(Q, K, grid.H, grid.W, M, d, float(w_agg), float(w_pos), pos_table, R, clip, stat_sum, stat_max,
+                   levels[0], levels[1], levels[2], levels[3], run_flag, ksplit)
 
 
 def attn_lse(Q, K, grid, *, M, d, w_pos, pos_table, R, clip, stat_max, lse_part, lse2, run_flag=None, ksplit=0,
              mask_radius=-1):
-    a = _scores_args(Q, K, grid, M, d, w_pos, pos_table, R, clip, run_flag, ksplit)
-    a.mask_radius = int(mask_radius)
-    _chk(stat_max, torch.float32, "stat_max")
-    _chk(lse_part, torch.float32, "lse_part")
-    _chk(lse2, torch.float32, "lse2")
-    a.stat_max = stat_max.data_ptr()
-    a.lse_part, a.lse2 = lse_part.data_ptr(), lse2.data_ptr()
-    _lib.call("craft_attn_lse", C.byref(a), _stream())
+    _cuda_only(Q, K)
+    OPS.attn_lse(Q, K, grid.H, grid.W, M, d, float(w_pos), pos_table, R, clip, stat_max, lse_part, lse2, run_flag, ksplit,
+                 int(mask_radius))
 
 
 def corr_stats_finalize(stat_sum, n, mean_rstd, flag=None):
     """stat_sum [2,2] f64: row 0 = unclamped pass, row 1 = clamped re-pass (used when *flag != 0)."""
-    _chk(stat_sum, torch.float64, "stat_sum")
-    _lib.call("craft_corr_stats_finalize", _ptr(stat_sum), _ptr(flag), float(n), _ptr(mean_rstd), _stream())
+    OPS.corr_stats_finalize(stat_sum, flag, float(n), mean_rstd)
 
 
 def clip_gate(stat_max, attn_clip, clip, flag, diag=None):
-    _chk(diag, torch.float32, "diag")
-    _lib.call("craft_clip_gate", _ptr(stat_max), float(attn_clip), _ptr(clip), _ptr(flag), _ptr(diag), _stream())
+    OPS.clip_gate(stat_max, float(attn_clip), clip, flag, diag)
 
 
 def attn_pv(Q, K, Vt, grid, *, M, d, F, w_pos, pos_table, R, clip, lse2, out, ksplit, zero_fill=True, mask_radius=-1):
     """`out` holds `ksplit` partial-sum slots [ksplit, M, Mp, F]; zero_fill=False leaves the slots a unit does
     not use untouched (pair it with modes_finalize(pv_bk=...), which knows the schedule)."""
-    _chk(Q, torch.bfloat16, "Q")
-    _chk(K, torch.bfloat16, "K")
-    _chk(Vt, torch.bfloat16, "Vt")
-    _chk(out, torch.float32, "out")
-    _chk(lse2, torch.float32, "lse2")
-    assert Vt.shape[0] >= M * F and out.numel() >= ksplit * M * grid.Mp * F
-    a = PvArgs()
-    a.Q, a.K, a.Vt, a.ldv = Q.data_ptr(), K.data_ptr(), Vt.data_ptr(), Vt.shape[1]
-    a.C, a.M, a.d, a.F = M * d, M, d, F
-    a.H, a.W = grid.H, grid.W
-    a.scale, a.w_pos = 1.0 / math.sqrt(d), float(w_pos)
-    a.pos_table = pos_table.data_ptr() if pos_table is not None else None
-    a.R = R
-    a.clip, a.lse2, a.out = clip.data_ptr(), lse2.data_ptr(), out.data_ptr()
-    a.ksplit = ksplit
-    a.zero_fill = 1 if zero_fill else 0
-    a.mask_radius = int(mask_radius)
-    _lib.call("craft_attn_pv", C.byref(a), _stream())
+    _cuda_only(Q, K, Vt, out)
+    OPS.attn_pv(Q, K, Vt, grid.H, grid.W, M, d, F, float(w_pos), pos_table, R, clip, lse2, out, ksplit, bool(zero_fill),
+                int(mask_radius))
 
 
 def modes_finalize(O, nsum, M, F, grid, *, w_score, b_score, coeff, gma=0, x_b=None, colx=0, x_f=None, colxf=0,
                    out_b=None, colb=0, out_f=None, colf=0, pv_bk=0):
-    _chk(O, torch.float32, "O")
-    _lib.call("craft_modes_finalize", _ptr(O), nsum, M, F, _ptr(w_score), _ptr(b_score), _ptr(coeff), gma,
-              _ptr(x_b), _ld(x_b), colx, _ptr(x_f), _ld(x_f), colxf, grid.H, grid.W,
-              _ptr(out_b), _ld(out_b), colb, _ptr(out_f), _ld(out_f), colf, int(pv_bk), _stream())
+    OPS.modes_finalize(O, nsum, M, F, grid.H, grid.W, w_score, b_score, coeff, gma, x_b, colx, x_f, colxf, out_b, colb,
+                       out_f, colf, int(pv_bk))
 
 
 def soft_aggregate(x, w, b, basis=None, num_feat=1):
     """LearnedSoftAggregate on a dense f32 tensor with the group axis leading: x [M, n] (num_feat 1) or
     [M, n, F]; returns [n] / [n, F]."""
-    _chk(x, torch.float32, "x")
-    _chk(basis, torch.float32, "basis")
-    _chk(w, torch.float32, "w")
-    _chk(b, torch.float32, "b")
+    _cuda_only(x)
     M = x.shape[0]
     if num_feat == 1:
         n, F_ = x[0].numel(), 1
-        out = torch.empty(x.shape[1:], dtype=torch.float32, device=x.device)
     else:
         F_ = x.shape[-1]
         n = x[0].numel() // F_
-        out = torch.empty(x.shape[1:], dtype=torch.float32, device=x.device)
         assert w.numel() == F_
-    _lib.call("craft_soft_aggregate", _ptr(x), _ptr(basis), M, n, F_, _ptr(w), _ptr(b), _ptr(out), _stream())
+    out = torch.empty(x.shape[1:], dtype=torch.float32, device=x.device)
+    OPS.soft_aggregate(x, basis, M, n, F_, w, b, out)
     return out
 
 
 def attn_dense(Q, K, grid, *, M, d, w_pos, pos_table, R, clip, lse2=None, mask_radius=-1):
     """Dense [M, U, U] scores (lse2 None) or softmax probabilities over the REAL tokens -- small grids only."""
-    _chk(Q, torch.bfloat16, "Q")
-    _chk(K, torch.bfloat16, "K")
-    _chk(lse2, torch.float32, "lse2")
+    _cuda_only(Q, K)
     if grid.U > 4096:
         raise ValueError("attn_dense materialises [M,U,U] and is meant for small grids (U <= 4096), got U=%d" % grid.U)
     out = torch.empty((M, grid.U, grid.U), dtype=torch.float32, device=Q.device)
-    a = DenseAttnArgs()
-    a.Q, a.K = Q.data_ptr(), K.data_ptr()
-    a.C, a.M, a.d, a.H, a.W = M * d, M, d, grid.H, grid.W
-    a.scale, a.w_pos = 1.0 / math.sqrt(d), float(w_pos)
-    a.pos_table = pos_table.data_ptr() if pos_table is not None else None
-    a.R = R
-    a.clip = clip.data_ptr()
-    a.lse2 = lse2.data_ptr() if lse2 is not None else None
-    a.mask_radius = int(mask_radius)
-    a.out = out.data_ptr()
-    _lib.call("craft_attn_dense", C.byref(a), _stream())
+    OPS.attn_dense(Q, K, grid.H, grid.W, M, d, float(w_pos), pos_table, R, clip, lse2, int(mask_radius), out)
     return out
 
 
@@ -344,47 +255,33 @@ def attn_dense(Q, K, grid, *, M, d, w_pos, pos_table, R, clip, lse2=None, mask_r
 # lookup / small kernels
 # ------------------------------------------------------------------------------------------------
 def corr_lookup(levels, grid, coords, mean_rstd, out_b=None, out_nchw=None, first_level=0):
-    arr = (C.c_void_p * 4)(*[(lv.data_ptr() if lv is not None else None) for lv in levels])
-    _chk(coords, torch.float32, "coords")
-    _chk(out_b, torch.bfloat16, "out_b")
-    _chk(out_nchw, torch.float32, "out_nchw")
-    _lib.call("craft_corr_lookup", arr, grid.H, grid.W, _ptr(coords), _ptr(mean_rstd), _ptr(out_b), _ld(out_b),
-              _ptr(out_nchw), first_level, _stream())
+    OPS.corr_lookup(levels[0], levels[1], levels[2], levels[3], grid.H, grid.W, coords, mean_rstd, out_b, out_nchw,
+                    first_level)
 
 
 def corr_lookup0(Q, K, grid, *, M, d, w_agg, w_pos, pos_table, R, clip, coords, mean_rstd, out_b=None, out_nchw=None):
     """Level-0 lookup channels computed on demand from projected Q/K rows (no level-0 volume)."""
-    _chk(Q, torch.bfloat16, "Q")
-    _chk(K, torch.bfloat16, "K")
-    _chk(out_b, torch.bfloat16, "out_b")
-    _chk(out_nchw, torch.float32, "out_nchw")
-    _lib.call("craft_corr_lookup0", _ptr(Q), _ptr(K), M, d, 1.0 / math.sqrt(d), float(w_agg), float(w_pos),
-              _ptr(pos_table), R, _ptr(clip), grid.H, grid.W, _ptr(coords), _ptr(mean_rstd), _ptr(out_b), _ld(out_b),
-              _ptr(out_nchw), _stream())
+    OPS.corr_lookup0(Q, K, grid.H, grid.W, M, d, float(w_agg), float(w_pos), pos_table, R, clip, coords, mean_rstd,
+                     out_b, out_nchw)
 
 
 def convf1(flow, wt, bias, grid, out_b, colo=0):
-    _chk(flow, torch.float32, "flow")
-    _chk(wt, torch.float32, "wt")
-    _chk(out_b, torch.bfloat16, "out_b")
-    _lib.call("craft_convf1", _ptr(flow), _ptr(wt), _ptr(bias), grid.H, grid.W, _ptr(out_b), _ld(out_b), colo, _stream())
+    OPS.convf1(flow, wt, bias, grid.H, grid.W, out_b, colo)
 
 
 def flow_update(coords1, flow, delta, grid):
-    _lib.call("craft_flow_update", _ptr(coords1), _ptr(flow), _ptr(delta), _ld(delta), grid.H, grid.W, _stream())
+    OPS.flow_update(coords1, flow, delta, grid.H, grid.W)
 
 
 def init_coords(coords1, flow_init, grid):
-    _chk(flow_init, torch.float32, "flow_init")
-    _lib.call("craft_init_coords", _ptr(coords1), _ptr(flow_init), grid.H, grid.W, _stream())
+    OPS.init_coords(coords1, flow_init, grid.H, grid.W)
 
 
 def upsample_flow(mask, flow, grid, out=None):
     if out is None:
         out = torch.empty((2, 8 * grid.H, 8 * grid.W), dtype=torch.float32, device=flow.device)
-    _chk(flow, torch.float32, "flow")
-    is_b = 1 if mask.dtype == torch.bfloat16 else 0
-    _lib.call("craft_upsample_flow", _ptr(mask), is_b, _ld(mask), _ptr(flow), grid.H, grid.W, _ptr(out), _stream())
+    _cuda_only(mask, flow, out)
+    OPS.upsample_flow(mask, flow, grid.H, grid.W, out)
     return out
 
 
@@ -400,24 +297,22 @@ def _act_dtype(t, name):
 
 def instnorm_stats(x_nhwc, eps=1e-5):
     """x: [N,H,W,C] contiguous f32/f16 -> ab [N,C,2] f32 = (rstd, -mean*rstd).  Deterministic (no atomics)."""
-    half = _act_dtype(x_nhwc, "x")
+    _act_dtype(x_nhwc, "x")
     N, H, W, Cc = x_nhwc.shape
     part = torch.empty((1024 * N * Cc * 2,), dtype=torch.float32, device=x_nhwc.device)   # per-block partial sums
     ab = torch.empty((N, Cc, 2), dtype=torch.float32, device=x_nhwc.device)
-    _lib.call("craft_nhwc_instnorm_stats", _ptr(x_nhwc), half, N, H * W, Cc, float(eps), _ptr(part), part.numel(),
-              _ptr(ab), _stream())
+    OPS.nhwc_instnorm_stats(x_nhwc, N, H * W, Cc, float(eps), part, ab)
     return ab
 
 
 def nhwc_affine(v, ab=None, res=None, rab=None, relu_in=False, relu_out=False, out=None):
     """out = relu_out([ra*res+rb] + relu_in(a*v+b)); v/res/out [N,H,W,C] f32 or f16; ab/rab f32 [N or 1, C, 2]."""
-    half = _act_dtype(v, "v")
+    _act_dtype(v, "v")
     _chk(res, v.dtype, "res")
     N, H, W, Cc = v.shape
     if out is None:
         out = torch.empty_like(v)
     _chk(out, v.dtype, "out")
     st = lambda t: 0 if (t is None or t.shape[0] == 1) else 2 * Cc
-    _lib.call("craft_nhwc_affine", _ptr(v), half, _ptr(ab), st(ab), _ptr(res), _ptr(rab), st(rab), int(relu_in),
-              int(relu_out), N, H * W, Cc, _ptr(out), _stream())
+    OPS.nhwc_affine(v, ab, st(ab), res, rab, st(rab), bool(relu_in), bool(relu_out), N, H * W, Cc, out)
     return out

