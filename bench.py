@@ -1,10 +1,11 @@
 #!/usr/bin/env python
-"""bench.py -- image-pairs/sec of CRAFT.forward(test_mode=1) at 448x1024, iters=12 (BASELINE.json
-configs[1]) on N B200s, one process per GPU, pairs sharded across ranks (no data-path collective).
+"""bench.py -- image-pairs/sec of CRAFT.forward(test_mode=1) on N B200s, one process per GPU, pairs sharded
+across ranks (no data-path collective).  Default workload = BASELINE.json configs[1]: craft-sintel.pth,
+448x1024, iters=12.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config sintel|kitti|gma]
 
-Prints ONE JSON line (rank 0).  See DESIGN.md section 8 for how each field is measured.
+Prints ONE JSON line (rank 0).  DESIGN.md section 8 says how each field is measured.
 """
 import argparse
 import json
@@ -12,16 +13,25 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-H, W, ITERS = 448, 1024, 12
-WORKLOAD = "craft-sintel config (craft+f2full+setrans), %dx%d pair, iters=%d, test_mode=1, batch 1" % (H, W, ITERS)
 METRIC = "image-pairs/sec at 448x1024 iters=12"
+CONFIGS = {
+    # BASELINE.json configs[1] -- the configuration the metric is quoted on
+    "sintel": dict(H=448, W=1024, iters=12, args={}, weights="sintel", metric=METRIC,
+                   workload="craft-sintel config (craft+f2full+setrans), 448x1024 pair, iters=12, test_mode=1, batch 1"),
+    # BASELINE.json configs[4]: KITTI shape, 24 iterations (evaluate.py:180)
+    "kitti": dict(H=384, W=1248, iters=24, args={}, weights="sintel", metric="image-pairs/sec at 384x1248 iters=24",
+                  workload="craft-sintel weights, KITTI shape 384x1248 pair, iters=24, test_mode=1, batch 1"),
+    # BASELINE.json configs[2]: f2full + GMA Aggregate (no checkpoint ships for this variant: seeded init, gamma 0.5)
+    "gma": dict(H=448, W=1024, iters=12, args=dict(use_setrans=False), weights="seeded", metric=METRIC,
+                workload="CRAFT f2full + gma.Attention/Aggregate (use_setrans=False), 448x1024 pair, iters=12, "
+                         "test_mode=1, batch 1"),
+}
 
 
 def _peaks():
@@ -55,12 +65,16 @@ def _peaks():
     return out
 
 
-def _pairs(n, device=None, uint8=False):
+def _pairs(cfg, indices=None, device=None, uint8=False):
+    """Synthetic pairs: a distinct seed per GLOBAL pair index.
+    (`_pairs(n, device)` -- the form the profiling scripts use -- means the first n pairs of the default config.)"""
     import torch
-    from oracle.ref_loader import synthetic_pair
+    from craft_b200.testing import synthetic_pair
+    if isinstance(cfg, int):
+        cfg, indices, device = CONFIGS["sintel"], range(cfg), (indices if indices is not None else device)
     out = []
-    for i in range(n):
-        a, b = synthetic_pair(H, W, seed=1234 + i)
+    for i in indices:
+        a, b = synthetic_pair(cfg["H"], cfg["W"], seed=1234 + i)
         if uint8:
             a, b = a.to(torch.uint8), b.to(torch.uint8)
         if device is not None:
@@ -69,19 +83,31 @@ def _pairs(n, device=None, uint8=False):
     return out
 
 
-def _state_dict():
-    """Trained weights when the untracked local copy travelled with the snapshot, else seeded init."""
+def _build_model(cfg):
+    """craft_b200 CRAFT with the trained weights when the untracked local copy travelled with the snapshot."""
     import torch
     from craft_b200.network import CRAFT
-    from oracle.ref_loader import craft_args
+    from craft_b200.testing import craft_args
     torch.manual_seed(1234)
-    model = CRAFT(craft_args())
+    model = CRAFT(craft_args(**cfg["args"]))
     ck = os.path.join(ROOT, "tests", "golden", "_local", "craft-sintel-model.pth")
     src = "random-init (seed 1234)"
-    if os.path.isfile(ck):
+    if cfg["weights"] == "sintel" and os.path.isfile(ck):
         model.load_state_dict(torch.load(ck, map_location="cpu"), strict=True)
         src = "craft-sintel.pth"
+    elif cfg["weights"] == "seeded" and hasattr(model.update_block.aggregator, "gamma"):
+        with torch.no_grad():
+            model.update_block.aggregator.gamma.fill_(0.5)      # gamma initialises to 0: make the aggregation count
+        src += ", gamma=0.5"
     return model, src
+
+
+# names the profiling scripts under profiles/ import
+H, W, ITERS = CONFIGS["sintel"]["H"], CONFIGS["sintel"]["W"], CONFIGS["sintel"]["iters"]
+
+
+def _state_dict():
+    return _build_model(CONFIGS["sintel"])
 
 
 class ClockSampler:
@@ -131,69 +157,250 @@ class ClockSampler:
         return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
 
 
-def _cpu_port_rate(model_cpu, budget_s, threads):
-    """Oracle port (oracle/cpu_forward.py) timed on the host cores; one step = one 448x1024 pair."""
+# ------------------------------------------------------------------------------------------------
+# the reference itself (CPU and, informationally, eager CUDA)
+# ------------------------------------------------------------------------------------------------
+def _reference_model(cfg, mixed_precision=False):
+    """The UNMODIFIED reference (askerlee/craft core/network.py CRAFT) from /root/reference or, on the GPU box, from
+    the untracked copy __graft_entry__.build() staged under oracle/_ref/reference.  None when neither exists."""
+    try:
+        from oracle import ref_loader as RL
+        if not RL.reference_available():
+            return None
+        from craft_b200.testing import craft_args
+        args = craft_args(mixed_precision=mixed_precision, **cfg["args"])
+        ck = "craft-sintel.pth" if cfg["weights"] == "sintel" else None
+        model, _ = RL.build_reference_model(args, checkpoint=ck)
+        if ck is None:      # seeded variant: same weights as the craft_b200 model
+            ours, _ = _build_model(cfg)
+            model.load_state_dict(ours.state_dict(), strict=True)
+        return model
+    except Exception as e:      # a broken staging must not take the bench down: the port is the fallback
+        sys.stderr.write("reference unavailable (%r), using the oracle port\n" % (e,))
+        return None
+
+
+def _cpu_step_fn(cfg):
+    """-> (callable(pair) running ONE full-size pair on the host cores, kind)."""
     import torch
+    ref = _reference_model(cfg)
+    if ref is not None:
+        def run(pair):
+            with torch.no_grad():
+                return ref(pair[0], pair[1], iters=cfg["iters"], test_mode=1)
+        return run, "reference"
     from oracle import cpu_forward
+    model, _ = _build_model(cfg)
+    sd = {k: v for k, v in model.state_dict().items()}
+    flags = dict(use_setrans=cfg["args"].get("use_setrans", True))
+
+    def run(pair):
+        with torch.no_grad():
+            return cpu_forward.craft_forward(sd, pair[0], pair[1], iters=cfg["iters"], **flags)
+    return run, "port"
+
+
+def _cpu_rate(cfg, budget_s, threads, max_pairs=4):
+    import torch
     torch.set_num_threads(threads)
-    sd = {k: v for k, v in model_cpu.state_dict().items()}
-    pairs = _pairs(2)
+    run, kind = _cpu_step_fn(cfg)
+    pairs = _pairs(cfg, [0, 1])
     n, t_total = 0, 0.0
-    with torch.no_grad():
-        while n < 2 or (t_total < budget_s and n < 4):
-            a, b = pairs[n % len(pairs)]
-            t0 = time.time()
-            cpu_forward.craft_forward(sd, a, b, iters=ITERS)
-            t_total += time.time() - t0
-            n += 1
-            if t_total > budget_s:
-                break
-    return n / t_total, n, t_total
+    while n < max_pairs:
+        t0 = time.time()
+        run(pairs[n % 2])
+        t_total += time.time() - t0
+        n += 1
+        if n >= 2 and t_total > budget_s:
+            break
+    return n / t_total, n, t_total, kind
 
 
-def run_reference(args):
-    """`--impl reference`: the reference's CPU path.  The reference is a pure-Python tree that cannot be
-    pip-installed or shipped to the GPU box, so this arm times the oracle port (same torch ops, same
-    order) on all host threads.  Rank 0 only."""
+def run_reference(args, cfg):
+    """`--impl reference`: the reference's own CPU implementation of the path (its unmodified Python tree,
+    fp32, all host threads) on the same workload; the oracle port is the fallback when the tree is absent.
+    Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     import torch
-    model, wsrc = _state_dict()
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    from oracle import cpu_forward
-    sd = {k: v for k, v in model.state_dict().items()}
-    pairs = _pairs(2)
+    run, kind = _cpu_step_fn(cfg)
+    pairs = _pairs(cfg, [0, 1])
     steps = max(1, min(args.steps, 6))
     warm = max(0, min(args.warmup, 1))
-    with torch.no_grad():
-        for i in range(warm):
-            cpu_forward.craft_forward(sd, *pairs[i % 2], iters=ITERS)
-        t0 = time.time()
-        done = 0
-        for i in range(steps):
-            cpu_forward.craft_forward(sd, *pairs[i % 2], iters=ITERS)
-            done += 1
-            if time.time() - t0 > 150:
-                break
-        dt = time.time() - t0
+    for i in range(warm):
+        run(pairs[i % 2])
+    t0 = time.time()
+    done = 0
+    for i in range(steps):
+        run(pairs[i % 2])
+        done += 1
+        if time.time() - t0 > 150:
+            break
+    dt = time.time() - t0
     v = done / dt
-    line = dict(impl="reference", metric=METRIC, value=v, unit="pairs/s", n_gpus=args.gpus, steps=done, warmup=warm,
+    _, wsrc = _build_model(cfg)
+    line = dict(impl="reference", metric=cfg["metric"], value=v, unit="pairs/s", n_gpus=args.gpus, steps=done, warmup=warm,
                 ms_per_step=1000 * dt / done, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic integer-noise pairs, weights: " + wsrc,
-                config=dict(workload=WORKLOAD, device="host CPU"),
-                cpu_baseline=dict(value=v, unit="pairs/s", cores=threads, kind="port",
-                                  sample="%d full-size pairs (448x1024, iters=12)" % done),
+                config=dict(workload=cfg["workload"], device="host CPU"),
+                cpu_baseline=dict(value=v, unit="pairs/s", cores=threads, kind=kind,
+                                  sample="%d full-size pairs (%dx%d, iters=%d)" % (done, cfg["H"], cfg["W"], cfg["iters"])),
                 e2e=dict(value=v, unit="pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
 
-def run_ours(args):
+def _gpu_reference(cfg, dev, pairs):
+    """Informational: the unmodified reference in eager CUDA on the same B200, fp32 and
+    its own fp16 autocast (evaluate.py:1455-1456) -- the honest comparator for the kernels.  CUDA-event timed."""
+    import torch
+    out = {}
+    for tag, amp in (("fp32", False), ("fp16_autocast", True)):
+        try:
+            ref = _reference_model(cfg, mixed_precision=amp)
+            if ref is None:
+                return None
+            ref = ref.to(dev).eval()
+            with torch.no_grad():
+                for i in range(2):
+                    ref(*pairs[i % len(pairs)], iters=cfg["iters"], test_mode=1)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n = 5
+                e0.record()
+                for i in range(n):
+                    ref(*pairs[i % len(pairs)], iters=cfg["iters"], test_mode=1)
+                e1.record()
+                torch.cuda.synchronize()
+            out[tag] = dict(value=n / (e0.elapsed_time(e1) * 1e-3), unit="pairs/s", steps=n)
+            del ref
+            torch.cuda.empty_cache()
+        except Exception as e:
+            out[tag] = dict(error=repr(e)[:200])
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# per-kernel roofline table
+# ------------------------------------------------------------------------------------------------
+def _time_us(fn, reps=20):
+    import torch
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return 1000 * e0.elapsed_time(e1) / reps
+
+
+def _kernel_table(model, cfg, dev, pk):
+    """Each hot kernel of the setrans configuration timed ALONE (CUDA events on the launching stream) with the
+    arguments the model uses, against the measured peaks.  ALGORITHMIC work only:
+    QK^T = 2 U^2 C, P.V = 2 M U^2 F, conv = 2 U Cin Cout kh kw; recomputation is not credited."""
+    import torch
+    from craft_b200 import hotpath as hp, ops
+    from craft_b200.ops import TokenGrid
+    g = TokenGrid(cfg["H"] // 8, cfg["W"] // 8)
+    ws = model._workspaces.get(g, dev, model.materialize_level0)
+    U = float(g.U)
+    ub = model.update_block
+    uw = ub.weights(g)
+    att_tbl = model.att.vispos_encoder.table()
+    f2_tbl = model.f2_trans.vispos_encoder.table()
+    ks = ws.pv_split(4)
+    agg = ub.aggregator.packed()
+    rows = []
+
+    def add(name, per_pair, fn, flops=None, bytes_=None, note=None):
+        us = _time_us(fn)
+        r = dict(kernel=name, launches_per_pair=per_pair, us_per_launch=us)
+        if flops is not None:
+            ach = flops / (us * 1e-6) / 1e12
+            r.update(bound="tensor", achieved=ach, peak=pk["tf_burst"], unit="TFLOP/s", frac=ach / pk["tf_burst"],
+                     flops_per_launch=flops)
+        else:
+            ach = bytes_ / (us * 1e-6) / 1e9
+            r.update(bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"], bytes_per_launch=bytes_)
+        if note:
+            r["note"] = note
+        rows.append(r)
+        return r
+
+    it = cfg["iters"]
+    pv = add("attn_pv_kernel<32,128,128> (motion aggregator softmax.V)", it,
+             lambda: ops.attn_pv(ws.Qa, ws.Ka, ws.Vt, g, M=4, d=32, F=128, w_pos=1.0, pos_table=att_tbl, R=7, clip=ws.clip_att,
+                                 lse2=ws.lse2_att, out=ws.opart(ks, 4, 128), ksplit=ks, zero_fill=False),
+             flops=2 * U * U * 128 + 2 * 4 * U * U * 128)
+    add("attn_pv_kernel<64,256,64> (F2 transformer softmax.V)", 1,
+        lambda: ops.attn_pv(ws.Q2, ws.K2, ws.Vt, g, M=4, d=64, F=256, w_pos=0.5, pos_table=f2_tbl, R=7, clip=ws.clip_f2,
+                            lse2=ws.lse2_f2, out=ws.opart(ks, 4, 256), ksplit=ks, zero_fill=False),
+        flops=2 * U * U * 256 + 2 * 4 * U * U * 256)
+
+    def corr():
+        ws.stat_sum.zero_()
+        ops.corr_build(ws.Qc, ws.Kc, g, M=4, d=64, w_agg=ws.corr_meta["w_agg"], w_pos=0.5, pos_table=f2_tbl, R=7,
+                       clip=ws.inf_clip, stat_sum=ws.stat_sum[0], stat_max=ws.stat_max[3:4], levels=ws.levels, ksplit=ws.ks_sc)
+    add("scores_kernel<SC_CORR> (4-mode correlation volume + pyramid + LN statistics)", 1, corr, flops=2 * U * U * 256,
+        note="includes a 2 us stat_sum reset")
+    add("scores_kernel<SC_LSE> d=32 (intra-frame attention statistics)", 1,
+        lambda: ops.attn_lse(ws.Qa, ws.Ka, g, M=4, d=32, w_pos=1.0, pos_table=att_tbl, R=7, clip=ws.inf_clip,
+                             stat_max=ws.stat_max[3:4], lse_part=ws.lse_part, lse2=ws.lse2_att, ksplit=ws.ks_sc),
+        flops=2 * U * U * 128, note="includes lse_merge")
+    add("scores_kernel<SC_LSE> d=64 (F2 transformer statistics)", 1,
+        lambda: ops.attn_lse(ws.Q2, ws.K2, g, M=4, d=64, w_pos=0.5, pos_table=f2_tbl, R=7, clip=ws.inf_clip,
+                             stat_max=ws.stat_max[3:4], lse_part=ws.lse_part, lse2=ws.lse2_f2, ksplit=ws.ks_sc),
+        flops=2 * U * U * 256, note="includes lse_merge")
+    wzr, bzr, wq, bq, taps = uw.gru[0]
+    add("shift_gemm<128,GRU_ZR> (SepConvGRU z,r: 1x5 conv 512->256 + gates)", 2 * it,
+        lambda: ops.shift_gemm(ws.X, wzr, M=g.Mp, Npad=256, K=512, BN=128, taps=taps, grid=g, epilogue=ops.EPI_GRU_ZR,
+                               bias=bzr, out_b=ws.X, colb=512, aux0=ws.Z, aux1=ws.Hm),
+        flops=2 * U * 512 * 256 * 5)
+    add("shift_gemm<64,GRU_Q> (SepConvGRU q: 1x5 conv 512->128 + state update)", 2 * it,
+        lambda: ops.shift_gemm(ws.X, wq, M=g.Mp, Npad=128, K=512, BN=64, taps=taps, a_koff=128, grid=g, epilogue=ops.EPI_GRU_Q,
+                               bias=bq, out_b=ws.X, colb=0, aux0=ws.Z, aux1=ws.Hm),
+        flops=2 * U * 512 * 128 * 5)
+
+    def update_gemms():        # every tensor-core GEMM of one refinement iteration, in model order, one stream
+        hp.motion_encoder(ws, uw, None)
+        BK = ops.pv_block_keys(32, 128)
+        ops.shift_gemm(agg["w1"], ws.X, M=512, Npad=ops.blocked_keys(g, BK), K=128, BN=BK, b_koff=256, out_b=ws.Vt, b_block_grid=g)
+        hp.sep_conv_gru(ws, uw)
+        hp.heads(ws, uw, 0, need_mask=False)
+    conv = lambda cin, cout, k: 2 * U * cin * cout * k
+    gemm_flops = (conv(324, 256, 1) + conv(256, 192, 9) + conv(128, 64, 9) + conv(256, 126, 9)      # motion encoder (convf1 is FMA)
+                  + conv(128, 512, 1)                                                              # first_linear (V)
+                  + 6 * conv(512, 128, 5)                                                          # SepConvGRU
+                  + conv(128, 256, 9) + conv(256, 2, 9))                                           # flow head
+    add("shift-GEMM family, one refinement iteration (11 launches + convf1)", it, update_gemms, flops=gemm_flops,
+        note="mask head excluded (runs in the last iteration only)")
+    add("corr_lookup0_kernel (level-0 window recomputed from Q/K rows)", it,
+        lambda: ops.corr_lookup0(grid=g, coords=ws.coords1, mean_rstd=ws.mean_rstd, out_b=ws.CORR, **ws.corr_meta),
+        bytes_=2 * U * 256 * 2 + 81 * U * 2, note="algorithmic bytes = Q + K rows once + 81 bf16 outputs per query; the "
+        "kernel itself moves ~51 KB of key rows per query through L2")
+    add("corr_lookup_kernel (pooled levels 1-3)", it,
+        lambda: ops.corr_lookup(ws.levels, g, ws.coords1, ws.mean_rstd, out_b=ws.CORR, first_level=1),
+        bytes_=3 * 100 * 4 * U + 243 * U * 2)
+    add("modes_finalize_kernel<128> (mode soft-pool + skip + LayerNorm)", it,
+        lambda: ops.modes_finalize(ws.opart(ks, 4, 128), ks, 4, 128, g, w_score=agg["ws"], b_score=agg["bs"], coeff=agg["coeff"],
+                                   x_b=ws.X, colx=256, out_b=ws.X, colb=384, pv_bk=128),
+        bytes_=4 * U * 128 * 4 + U * 128 * 2 * 2)
+    add("upsample_flow_kernel (convex 8x upsampling)", 1 if True else it,
+        lambda: ops.upsample_flow(ws.MASKS[0], ws.flow, g, out=torch.empty((2, cfg["H"], cfg["W"]), device=dev)),
+        bytes_=576 * U * 4 + 2 * U * 4 + 2 * cfg["H"] * cfg["W"] * 4)
+    return pv, rows
+
+
+def run_ours(args, cfg):
+    import copy
     import torch
     import torch.distributed as dist
-    from craft_b200 import _lib, ops
-    from craft_b200.ops import TokenGrid
-    from craft_b200.setrans import get_workspace
+    from craft_b200 import _lib
+    from craft_b200.sharding import pairs_for_rank
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -209,10 +416,14 @@ def run_ours(args):
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = True
     lib = _lib.load()
-    model_cpu, wsrc = _state_dict()
-    import copy
+    model_cpu, wsrc = _build_model(cfg)
     model = copy.deepcopy(model_cpu).to(dev).eval()
-    pairs = _pairs(4, dev)
+    H, W, ITERS = cfg["H"], cfg["W"], cfg["iters"]
+    # pairs are the units of work: rank r owns global pair indices r, r+N, ... (craft_b200/sharding.py) -- every rank
+    # sees different frames
+    NPAIR = 4
+    mine = pairs_for_rank(NPAIR * world, rank, world)
+    pairs = _pairs(cfg, mine, dev)
 
     def step(i):
         a, b = pairs[i % len(pairs)]
@@ -252,7 +463,7 @@ def run_ours(args):
             launches = args.steps * int(getattr(model, "launches_last_forward", 0))
         ms = e0.elapsed_time(e1)
         # ---- end-to-end: pinned host uint8 frames -> H2D -> forward -> D2H of the full-res flow
-        host_pairs = [(a.pin_memory(), b.pin_memory()) for a, b in _pairs(4, None, uint8=True)]
+        host_pairs = [(a.pin_memory(), b.pin_memory()) for a, b in _pairs(cfg, mine, None, uint8=True)]
         out_host = torch.empty((1, 2, H, W), dtype=torch.float32).pin_memory()
 
         def e2e_step(i):
@@ -277,74 +488,56 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
 
-    # ---- roofline of the dominant kernel: the motion aggregator's flash P.V (attn_pv_kernel<32,128,...>),
-    #      12 launches per pair.  Timed alone with CUDA events on the launching stream.
-    roof = None
+    roof, gpu_ref, cpu = None, None, None
     if rank == 0:
-        g = TokenGrid(H // 8, W // 8)
-        ws = model._workspaces.get(g, dev, model.materialize_level0)
-        ks = ws.pv_split(4)
-        O = ws.opart(ks, 4, 128)
-        tbl = model.att.vispos_encoder.table()
-        def pv():   # exactly the call hotpath.value_aggregate makes 12x per pair
-            ops.attn_pv(ws.Qa, ws.Ka, ws.Vt, g, M=4, d=32, F=128, w_pos=1.0, pos_table=tbl, R=7,
-                        clip=ws.clip_att, lse2=ws.lse2_att, out=O, ksplit=ks, zero_fill=False)
-        for _ in range(3):
-            pv()
-        torch.cuda.synchronize()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 20
-        r0.record()
-        for _ in range(reps):
-            pv()
-        r1.record()
-        torch.cuda.synchronize()
-        us = 1000 * r0.elapsed_time(r1) / reps
-        U = g.U
-        flops = 2.0 * U * U * 128 + 2.0 * 4 * U * U * 128          # QK^T (C=128) + P.V (M=4, F=128), algorithmic
         pk = _peaks()
-        ach = flops / (us * 1e-6) / 1e12
-        # DRAM bytes of one launch from the committed `ncu --set full` capture (profiles/r01_pv_ncu_full.txt)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_pv_traffic.json")
-        if os.path.isfile(tpath):
-            t = json.load(open(tpath))
-            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
-        # second ceiling of this kernel: one MUFU ex2 per (query, key, mode) at 16 per clock per SM
-        mufu_us = 4.0 * U * U / (16.0 * 148 * 1.965e9) * 1e6
-        roof = dict(bound="tensor", kernel="attn_pv_kernel<32,128,128> (motion aggregator P.V, x12 per pair)",
-                    achieved=ach, peak=pk["tf_burst"], unit="TFLOP/s", frac=ach / pk["tf_burst"], traffic=traffic,
-                    us_per_launch=us, flops_per_launch=flops, peak_source=pk["src"] + " bf16 burst",
-                    note="exp-bound before tensor-bound: 4*U^2 ex2 at the measured 15.2/clk/SM MUFU rate = %.1f us "
-                         "per launch (profiles/r01_mb_exp.txt), i.e. the kernel runs at %.2f of its MUFU ceiling" % (
-                             mufu_us * 16.0 / 15.2, mufu_us * 16.0 / 15.2 / us))
-
-    if rank == 0:
-        cpu = None
+        if cfg["args"].get("use_setrans", True):
+            with torch.no_grad():
+                pv, rows = _kernel_table(model, cfg, dev, pk)
+            U = (H // 8) * (W // 8)
+            traffic = None
+            for name in ("r02_pv_traffic.json", "r01_pv_traffic.json"):
+                tpath = os.path.join(ROOT, "profiles", name)
+                if os.path.isfile(tpath):
+                    tj = json.load(open(tpath))
+                    traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                    break
+            mufu_us = 4.0 * U * U / (15.2 * 148 * 1.965e9) * 1e6
+            roof = dict(bound="tensor", kernel=pv["kernel"] + ", x%d per pair" % ITERS, achieved=pv["achieved"], peak=pv["peak"],
+                        unit="TFLOP/s", frac=pv["frac"], traffic=traffic, us_per_launch=pv["us_per_launch"],
+                        flops_per_launch=pv["flops_per_launch"], peak_source=pk["src"] + " bf16 burst (kernel timed alone)",
+                        note="second ceiling of this kernel: one exp per (query, key, mode) at the measured 15.2/clk/SM MUFU "
+                             "rate = %.1f us per launch (profiles/r01_mb_exp.txt)" % mufu_us,
+                        kernels=rows)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, n, tt = _cpu_port_rate(model_cpu, 20.0, threads)
-            cpu = dict(value=v, unit="pairs/s", cores=threads, kind="port",
-                       sample="%d full-size pairs (448x1024, iters=12), %.1f s of CPU time" % (n, tt))
+            v, n, tt, kind = _cpu_rate(cfg, 20.0, threads)
+            cpu = dict(value=v, unit="pairs/s", cores=threads, kind=kind,
+                       sample="%d full-size pairs (%dx%d, iters=%d), %.1f s of CPU time" % (n, H, W, ITERS, tt))
+        if world == 1 and args.gpu_reference:
+            gpu_ref = _gpu_reference(cfg, dev, pairs)
         total = world * args.steps
-        line = dict(metric=METRIC, value=total / (ms * 1e-3), unit="pairs/s", n_gpus=world, steps=args.steps,
+        line = dict(metric=cfg["metric"], value=total / (ms * 1e-3), unit="pairs/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
                     vs_baseline=None, dtype="bf16",
-                    data="synthetic integer-noise pairs (distinct per step), weights: " + wsrc,
-                    config=dict(workload=WORKLOAD, parallelism="pairs sharded over %d ranks, no collective" % world,
+                    data="synthetic integer-noise pairs (distinct per step and per rank), weights: " + wsrc,
+                    config=dict(workload=cfg["workload"],
+                                parallelism="pairs sharded over %d ranks (rank r owns pairs r, r+N, ...), no collective" % world,
                                 l2="inputs larger than L2: the per-step working set (68 MB pooled correlation pyramid, 30 MB "
                                    "P.V partial sums, >100 MB of encoder activations) exceeds the 126 MB L2 and every "
-                                   "buffer is rewritten each step; 4 distinct input pairs rotate",
+                                   "buffer is rewritten each step; 4 distinct input pairs rotate per rank",
                                 encoders="fnet/cnet (outside the hot path): cuDNN fp16 convolutions with fp32 accumulation "
                                          "+ craft_b200 norm/relu/residual kernels",
                                 launch="whole forward replayed as one CUDA graph; craft_b200 kernels use programmatic "
                                        "dependent launch",
                                 dead_work="test_mode=1 returns only the last upsampled flow: the mask head + convex "
-                                          "upsampling of iterations 1..11 (discarded by the reference) are elided, "
-                                          "outputs bit-identical (tests/test_gpu_e2e.py)"),
+                                          "upsampling of iterations 1..%d (discarded by the reference) are elided, "
+                                          "outputs bit-identical (tests/test_gpu_e2e.py)" % (ITERS - 1)),
                     e2e=dict(value=total / (ms_e2e * 1e-3), unit="pairs/s", h2d_bytes_per_step=2 * 3 * H * W,
                              d2h_bytes_per_step=2 * H * W * 4),
                     gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu)
+        if gpu_ref is not None:
+            line["gpu_reference"] = gpu_ref
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -356,16 +549,23 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="sintel", choices=sorted(CONFIGS),
+                    help="sintel = BASELINE configs[1] (default, the metric's configuration); kitti = configs[4] shape; "
+                         "gma = configs[2] variant")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gpu-reference", action="store_true",
+                    help="also time the unmodified reference in eager CUDA (fp32 and fp16 autocast) on the same GPU "
+                         "(informational leg `gpu_reference`, N=1 only)")
     ap.add_argument("--ncu", action="store_true",
                     help="profiling helper: warm up, then run ONE step inside a cudaProfilerStart/Stop range and exit "
                          "(use with `ncu --profile-from-start off ...`); prints no bench line")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, cfg)
     else:
-        run_ours(args)
+        run_ours(args, cfg)
 
 
 if __name__ == "__main__":

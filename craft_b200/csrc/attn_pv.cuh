@@ -107,29 +107,44 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const long long NT = static_cast<long long>(p.nqt) * p.M * p.nkt;
   const long long lin_begin = NT * blockIdx.x / gridDim.x;
   const long long lin_end = NT * (blockIdx.x + 1) / gridDim.x;
-  // CTA that owns list position x (ranges are [NT*c/G, NT*(c+1)/G))
-  auto cta_of = [&](long long x) {
-    long long c = x * gridDim.x / NT;
-    while (c + 1 < static_cast<long long>(gridDim.x) && NT * (c + 1) / gridDim.x <= x) ++c;
-    while (c > 0 && NT * c / gridDim.x > x) --c;
-    return static_cast<int>(c);
-  };
   // Key tiles of a unit are visited block-COLUMN major (kt = bx * nby + by): the blocks inside the positional-
   // bias window (|dy| <= R: ~3 of the nby block rows, all columns), which cost ~1.4x a plain tile, then occur
   // 3 per nby everywhere in the list and every CTA's equal-length range carries the same share of them
   // (block-row major order packed them into one contiguous run per unit: CTA finish times spread 72..86 us).
   const int nby = p.nkt / p.nbx;
-  struct Seg { int qt, mode, t0, nt; };
-  auto seg_at = [&](long long lin) {
-    Seg sgm;
-    const int unit = static_cast<int>(lin / p.nkt);
-    sgm.t0 = static_cast<int>(lin - static_cast<long long>(unit) * p.nkt);
-    const long long left = lin_end - lin;
-    sgm.nt = static_cast<int>(left < p.nkt - sgm.t0 ? left : p.nkt - sgm.t0);
-    sgm.qt = unit / p.M;
-    sgm.mode = unit - sgm.qt * p.M;
-    return sgm;
-  };
+  // The range is cut into segments, one per unit it touches.  ONE thread works the list out (64-bit divisions,
+  // the search for the first CTA of a shared unit) and leaves it in shared memory; every role then walks the
+  // table.  Doing this arithmetic in all 512 softmax threads at every segment boundary cost ~4000 clk per
+  // boundary (clock64 timeline, profiles/r02_pv_timeline_before.txt).
+  struct Seg { int qt, mode, t0, nt, slot, last; };
+  constexpr int kMaxSegs = 16;
+  __shared__ Seg s_segs[kMaxSegs];
+  __shared__ int s_nseg;
+  if (threadIdx.x == 32) {          // lane 0 of warp 1; thread 0 initialises the barriers meanwhile
+    // CTA that owns list position x (ranges are [NT*c/G, NT*(c+1)/G))
+    auto cta_of = [&](long long x) {
+      long long c = x * gridDim.x / NT;
+      while (c + 1 < static_cast<long long>(gridDim.x) && NT * (c + 1) / gridDim.x <= x) ++c;
+      while (c > 0 && NT * c / gridDim.x > x) --c;
+      return static_cast<int>(c);
+    };
+    int n = 0;
+    for (long long lin = lin_begin; lin < lin_end; ++n) {
+      if (n == kMaxSegs) __trap();                 // the host sizes the grid so that this cannot happen
+      Seg sg;
+      const int unit = static_cast<int>(lin / p.nkt);
+      sg.t0 = static_cast<int>(lin - static_cast<long long>(unit) * p.nkt);
+      const long long left = lin_end - lin;
+      sg.nt = static_cast<int>(left < p.nkt - sg.t0 ? left : p.nkt - sg.t0);
+      sg.qt = unit / p.M;
+      sg.mode = unit - sg.qt * p.M;
+      sg.slot = static_cast<int>(blockIdx.x) - cta_of(lin - sg.t0);      // position among the CTAs sharing the unit
+      sg.last = (sg.t0 + sg.nt == p.nkt) ? 1 : 0;
+      s_segs[n] = sg;
+      lin += sg.nt;
+    }
+    s_nseg = n;
+  }
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
@@ -162,6 +177,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int nseg = s_nseg;
 
   const bool tr = p.trace != nullptr && blockIdx.x == 0;
   auto gtime = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return static_cast<long long>(t); };
@@ -177,8 +193,8 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       int ks = 0, vs = 0;
       uint32_t kph = 0, vph = 0;
       int seg = 0, g0 = 0;
-      for (long long lin = lin_begin; lin < lin_end; ++seg) {
-        const Seg sgm = seg_at(lin);
+      for (; seg < nseg; ++seg) {
+        const Seg sgm = s_segs[seg];
         const int ch0 = sgm.mode * D;               // first channel of this mode in the Q/K rows
         const int qk_col = (ch0 >> 6) << 6;         // TMA column of the 64-channel atom holding it
         const int qb = seg & 1;
@@ -219,7 +235,6 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             if (++idle > (1u << 24)) __trap();     // protocol bug -> launch failure, never a hang
           }
         }
-        lin += sgm.nt;
         g0 += sgm.nt;
       }
     }
@@ -230,8 +245,8 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const bool leader = elect_one();
     int ks = 0, b = 0, seg = 0, g = 0;
     uint32_t kph = 0, bpar = 1;            // sp_free[b] parity for "previous use of b retired" (first use: free)
-    for (long long lin = lin_begin; lin < lin_end; ++seg) {
-      const Seg sgm = seg_at(lin);
+    for (; seg < nseg; ++seg) {
+      const Seg sgm = s_segs[seg];
       const uint32_t qk_inner = static_cast<uint32_t>((sgm.mode * D) & 63) * 2u;
       const int qb = seg & 1;
       const uint64_t dq0 = umma_desc_sw128(smem_u32(sQ + qb * S::kQBytes) + qk_inner);
@@ -262,7 +277,6 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (++ks == KS) { ks = 0; kph ^= 1u; }
         if (++b == NSB) { b = 0; bpar ^= 1u; }
       }
-      lin += sgm.nt;
     }
     __syncwarp();
   } else if (warp == 2) {
@@ -273,8 +287,8 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const bool leader = elect_one();
     int vs = 0, b = 0, seg = 0, g = 0;
     uint32_t vph = 0, bpar = 0;
-    for (long long lin = lin_begin; lin < lin_end; ++seg) {
-      const Seg sgm = seg_at(lin);
+    for (; seg < nseg; ++seg) {
+      const Seg sgm = s_segs[seg];
       // the previous segment's O must have been read back before its columns are overwritten
       mbar_wait(o_free, (static_cast<uint32_t>(seg) & 1u) ^ 1u);
       for (int i = 0; i < sgm.nt; ++i, ++g) {
@@ -304,7 +318,6 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (++vs == VS) { vs = 0; vph ^= 1u; }
         if (++b == NSB) { b = 0; bpar ^= 1u; }
       }
-      lin += sgm.nt;
     }
     __syncwarp();
   } else if (warp >= 4) {
@@ -325,13 +338,12 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
     int seg = 0, g0 = 0;                 // g = g0 + i: CTA-wide tile counter; tile g uses buffer g % NSB, group g & 1
     float lse_next = 0.f;
-    if (lin_begin < lin_end) {
-      const Seg s0 = seg_at(lin_begin);
-      const int qn = s0.qt * 128 + row;
-      lse_next = (qn < p.g.Mp) ? p.lse2[static_cast<size_t>(s0.mode) * p.g.Mp + qn] : 0.f;
+    if (nseg > 0) {
+      const int qn = s_segs[0].qt * 128 + row;
+      lse_next = (qn < p.g.Mp) ? p.lse2[static_cast<size_t>(s_segs[0].mode) * p.g.Mp + qn] : 0.f;
     }
-    for (long long lin = lin_begin; lin < lin_end; ++seg) {
-      const Seg sgm = seg_at(lin);
+    for (; seg < nseg; ++seg) {
+      const Seg sgm = s_segs[seg];
       const int q = sgm.qt * 128 + row;
       const int qy = q / p.g.Wp, qx = q - qy * p.g.Wp;
       const float lse = lse_next;
@@ -403,18 +415,16 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // -------------------------------- O write-back of this segment ------------------------
       // the four (group, half) warp sets split the F columns in quarters.  Slot = position of this
       // CTA among the CTAs that share the unit; the CTA finishing a unit zero-fills the unused slots.
-      const long long unit_lin0 = lin - sgm.t0;
-      const int slot = static_cast<int>(blockIdx.x) - cta_of(unit_lin0);
-      const bool last_part = (sgm.t0 + sgm.nt == p.nkt);
+      const int slot = sgm.slot;
+      const bool last_part = sgm.last != 0;
       const int g_last = g0 + sgm.nt - 1;
       // The next segment's log-sum-exp is fetched HERE: the 64 KB of write-back stores below take
       // ~2000 clk to drain from the load/store unit and any global load issued behind them (e.g. at the
       // top of the next segment) would stall the warp for that long; this one completes while the
       // warp waits for the last P.V anyway.
-      if (lin + sgm.nt < lin_end) {
-        const Seg nx = seg_at(lin + sgm.nt);
-        const int qn = nx.qt * 128 + row;
-        lse_next = (qn < p.g.Mp) ? p.lse2[static_cast<size_t>(nx.mode) * p.g.Mp + qn] : 0.f;
+      if (seg + 1 < nseg) {
+        const int qn = s_segs[seg + 1].qt * 128 + row;
+        lse_next = (qn < p.g.Mp) ? p.lse2[static_cast<size_t>(s_segs[seg + 1].mode) * p.g.Mp + qn] : 0.f;
       }
       if (trole < 4) PV_TRACE(trole, g_last - (g_last & 1) + (trole - 1), 5);
       mbar_wait(o_full, static_cast<uint32_t>(seg) & 1u);
@@ -456,7 +466,6 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
       }
       if (trole == 1) PV_TRACE(3, g_last, 2);      // boundary: write-back (+ zero fill) done
-      lin += sgm.nt;
       g0 += sgm.nt;
     }
   }

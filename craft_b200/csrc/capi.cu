@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "encoder.cuh"
 #include "gemm.cuh"
+#include "hostio.cuh"
 #include "pointwise.cuh"
 #include "scores.cuh"
 #include "standalone.cuh"
@@ -706,6 +707,18 @@ int craft_upsample_flow(const void* mask, int mask_is_bf16, int ldm, const float
   return check_launch("upsample_flow");
 }
 
+
+int craft_forward_interpolate(const float* flow, int H, int W, float* out, void* stream) {
+  if (!flow || !out || H < 1 || W < 1) return fail("forward_interpolate: bad arguments");
+  launch_k(cb::forward_interpolate_kernel, dim3((H * W + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream), flow, H, W, out);
+  return check_launch("forward_interpolate");
+}
+
+int craft_flow_encode(const float* flow, int H, int W, int mode, void* out, void* stream) {
+  if (!flow || !out || H < 1 || W < 1 || (mode != 0 && mode != 1)) return fail("flow_encode: bad arguments");
+  launch_k(cb::flow_encode_kernel, dim3((H * W + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream), flow, H, W, mode, out);
+  return check_launch("flow_encode");
+}
 
 int craft_nhwc_instnorm_stats(const void* x, int is_half, int N, int HW, int C, float eps, float* part,
                               long long part_capacity, float* ab, void* stream) {

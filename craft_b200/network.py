@@ -247,6 +247,10 @@ class CRAFT(nn.Module):
             ent["i1"] = image1.float().clone()
             ent["i2"] = image2.float().clone()
             ent["fi"] = flow_init.float().clone() if flow_init is not None else None
+            # warm-up and capture execute the forward three times; the attention diagnostics (max_attn / clamp_count,
+            # accumulated on the device) must count this call once
+            diags = [t for m in self.modules() if hasattr(m, "_diag") for t in m._diag.values()]
+            saved = [t.clone() for t in diags]
             side = torch.cuda.Stream(device=image1.device)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -260,6 +264,13 @@ class CRAFT(nn.Module):
             with torch.cuda.graph(g):
                 ent["out"] = self._forward_impl(ent["i1"], ent["i2"], iters, ent["fi"], test_mode)
             ent["graph"] = g
+            for m in self.modules():           # diagnostics tensors created during the warm-up start from zero
+                if hasattr(m, "_diag"):
+                    for t in m._diag.values():
+                        if not any(t is d for d in diags):
+                            t.zero_()
+            for t, sv in zip(diags, saved):
+                t.copy_(sv)
             ent["launches"] = _lib.load().craft_b200_launch_count() - n0   # craft_b200 kernels per replay
             # the graph bakes in the workspace's addresses: keep the buffers alive as long as the graph is
             g8 = TokenGrid(image1.shape[2] // 8, image1.shape[3] // 8)

@@ -279,4 +279,16 @@ def nhwc_affine(v, ab, ab_stride, res, rab, rab_stride, relu_in, relu_out, N, HW
               int(relu_out), N, HW, Cc, _ptr(out), _stream())
 
 
+@_op("forward_interpolate(Tensor flow, int H, int W, Tensor(a!) out) -> ()")
+def forward_interpolate(flow, H, W, out):
+    _chk(flow, f32, "flow"); _chk(out, f32, "out")
+    _lib.call("craft_forward_interpolate", _ptr(flow), H, W, _ptr(out), _stream())
+
+
+@_op("flow_encode(Tensor flow, int H, int W, int mode, Tensor(a!) out) -> ()")
+def flow_encode(flow, H, W, mode, out):
+    _chk(flow, f32, "flow")
+    _lib.call("craft_flow_encode", _ptr(flow), H, W, mode, _ptr(out), _stream())
+
+
 OPS = torch.ops.craft_b200

@@ -42,3 +42,25 @@ def coords_grid(batch, ht, wd, device=None):
 def upflow8(flow, mode="bilinear"):
     new_size = (8 * flow.shape[2], 8 * flow.shape[3])
     return 8 * F.interpolate(flow, size=new_size, mode=mode, align_corners=True)
+
+
+def forward_interpolate(flow):
+    """core/utils/utils.py:34-62 -- warm start between consecutive frames (evaluate.py:146-147): every
+    pixel carries its flow to where it lands, the output at a grid point is the flow of the nearest landed
+    point.  flow: [2,h,w] tensor.  The reference does this on the CPU with two scipy griddata calls per
+    frame; here it is one exact brute-force nearest-neighbour kernel (csrc/hostio.cuh) and the result stays
+    on the flow's device.  A CPU tensor is moved to the current CUDA device and back (no CPU path exists)."""
+    from .. import ops
+    if flow.dim() != 3 or flow.shape[0] != 2:
+        raise ValueError("forward_interpolate expects a [2,h,w] flow, got %s" % (list(flow.shape),))
+    src = flow.detach()
+    was_cpu = not src.is_cuda
+    if was_cpu:
+        if not torch.cuda.is_available():
+            raise RuntimeError("craft_b200.forward_interpolate needs a CUDA device: there is no CPU path")
+        src = src.cuda()
+    with torch.cuda.device(src.device):
+        src = src.float().contiguous()
+        out = torch.zeros_like(src)
+        ops.OPS.forward_interpolate(src, src.shape[1], src.shape[2], out)
+    return out.cpu() if was_cpu else out

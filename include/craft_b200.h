@@ -195,6 +195,15 @@ int craft_init_coords(float* coords1, const float* flow_init_nchw, int H, int W,
 int craft_upsample_flow(const void* mask, int mask_is_bf16, int ldm, const float* flow, int H, int W,
                         float* out_nchw, void* stream);
 
+/* ---- host I/O around the path ---------------------------------------- */
+/* forward_interpolate core/utils/utils.py:34-62 (warm start, evaluate.py:146-147): out[g] = flow of the
+ * nearest point among {p + flow(p)} that landed inside (0,W)x(0,H).  flow/out: [2,H,W] f32 planes.       */
+int craft_forward_interpolate(const float* flow, int H, int W, float* out, void* stream);
+/* byte re-packing for the writers of core/utils/frame_utils.py: mode 0 = .flo payload, interleaved f32
+ * [H][W][2] (writeFlow :70-99); mode 1 = KITTI png pixels, u16 [H][W][3] = (1, 64v+2^15, 64u+2^15) in the
+ * B,G,R order cv2.imwrite takes (writeFlowKITTI :116-120).                                              */
+int craft_flow_encode(const float* flow, int H, int W, int mode, void* out, void* stream);
+
 /* ---- encoder glue (core/extractor.py; first row outside the named hot path) ------------------- */
 /* InstanceNorm2d statistics of a channels-last tensor [N,HW,C] (f32, or f16 when is_half) ->
  * ab[N,C,2] = (rstd, -mean*rstd) (eps, biased variance, no affine: extractor.py:136-137).

@@ -16,28 +16,28 @@ import os
 import sys
 import warnings
 
-REF_ROOT = os.environ.get("CRAFT_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STAGED = os.path.join(_HERE, "_ref", "reference")      # untracked copy made by __graft_entry__.build() for the GPU box
+
+
+def _pick_root():
+    env = os.environ.get("CRAFT_REFERENCE_ROOT")
+    for cand in (env, "/root/reference", _STAGED):
+        if cand and os.path.isfile(os.path.join(cand, "core", "network.py")):
+            return cand
+    return env or "/root/reference"
+
+
+REF_ROOT = _pick_root()
 REF_CORE = os.path.join(REF_ROOT, "core")
+LOCAL_WEIGHTS = os.path.join(os.path.dirname(_HERE), "tests", "golden", "_local", "craft-sintel-model.pth")
 
 
 def reference_available() -> bool:
     return os.path.isfile(os.path.join(REF_CORE, "network.py"))
 
 
-def craft_args(**overrides) -> argparse.Namespace:
-    """Namespace matching evaluate.py's flags for the shipped checkpoints
-    (SURVEY.md section 8b / 8d config 2)."""
-    d = dict(
-        craft=True, use_setrans=True, f2trans="full", f1trans="none",
-        corr_radius=4, pos_bias_radius=7, mixed_precision=False, num_heads=1,
-        position_only=False, position_and_content=False,
-        f2_attn_mask_radius=-1, f2_num_modes=4, f2_pos_code_weight=0.5,
-        inter_num_modes=4, inter_qk_have_bias=True, inter_pos_code_type="bias",
-        inter_pos_code_weight=0.5, intra_num_modes=4, intra_pos_code_type="bias",
-        intra_pos_code_weight=1.0, dropout=0.0,
-    )
-    d.update(overrides)
-    return argparse.Namespace(**d)
+from craft_b200.testing import craft_args, smooth_pair, synthetic_pair  # noqa: E402,F401  (shared input helpers)
 
 
 @contextlib.contextmanager
@@ -55,6 +55,48 @@ def _ref_on_path():
         for n in names:
             sys.modules.pop(n, None)
         sys.modules.update(saved)
+
+
+def load_checkpoint_tensors(path):
+    """torch.load of a reference checkpoint through a RESTRICTED unpickler: the files under /root/reference
+    are untrusted public content and the checkpoints are full training states (optimizer, scheduler, the
+    trainer's Logger) in a pickle dialect torch's weights_only loader cannot parse.  Only classes from
+    torch / numpy / collections / argparse (plus builtins.getattr, which the file uses to rebuild dtypes) can
+    be instantiated; anything else -- e.g. __main__.Logger -- becomes an inert placeholder, os/subprocess/...
+    raise."""
+    import pickle
+    import torch
+
+    class _Inert:
+        def __init__(self, *a, **k):
+            pass
+
+        def __setstate__(self, st):
+            pass
+
+    ok_roots = ("torch", "numpy", "collections", "argparse", "_codecs")
+
+    class _Unpickler(pickle.Unpickler):
+        def find_class(self, module, name):
+            root = module.split(".")[0]
+            if module == "__builtin__":          # python-2 era protocol
+                module = "builtins"
+            if root in ok_roots or (module, name) in (("builtins", "getattr"), ("builtins", "set"), ("builtins", "dict"),
+                                                      ("builtins", "list"), ("builtins", "tuple"), ("builtins", "int"),
+                                                      ("builtins", "float"), ("builtins", "complex"), ("builtins", "slice")):
+                return super().find_class(module, name)
+            if root in ("__main__", "train", "train_ddp", "evaluate"):      # the trainer's own bookkeeping classes
+                return _Inert
+            raise pickle.UnpicklingError("refusing to unpickle %s.%s from an untrusted checkpoint" % (module, name))
+
+    class _Pickle:
+        __name__ = "pickle"
+        Unpickler = _Unpickler
+
+        @staticmethod
+        def load(f, **kw):
+            return _Unpickler(f, **kw).load()
+    return torch.load(path, map_location="cpu", weights_only=False, pickle_module=_Pickle)
 
 
 def load_reference_modules():
@@ -81,34 +123,15 @@ def build_reference_model(args=None, checkpoint="craft-sintel.pth", seed=1234, q
         model = mods["network"].CRAFT(args)
     if checkpoint:
         path = os.path.join(REF_ROOT, "checkpoints", checkpoint)
-        ck = torch.load(path, map_location="cpu", weights_only=False)
-        sd = ck["model"] if "model" in ck else ck
+        if os.path.isfile(path):
+            ck = load_checkpoint_tensors(path)
+            sd = ck["model"] if "model" in ck else ck
+        elif checkpoint == "craft-sintel.pth" and os.path.isfile(LOCAL_WEIGHTS):
+            sd = torch.load(LOCAL_WEIGHTS, map_location="cpu")       # the staged tree carries no checkpoints
+        else:
+            raise FileNotFoundError(path)
         sd = {k[len("module."):] if k.startswith("module.") else k: v for k, v in sd.items()}
         missing, unexpected = model.load_state_dict(sd, strict=False)
         model._load_report = (list(missing), list(unexpected))
     model.eval()
     return model, mods
-
-
-def synthetic_pair(H, W, seed=1234, B=1):
-    """SURVEY.md section 8d synthetic inputs: integer noise + (2,3) roll => true flow (3,2)."""
-    import torch
-    g = torch.Generator().manual_seed(seed)
-    image1 = torch.randint(0, 256, (B, 3, H, W), generator=g).float()
-    image2 = torch.roll(image1, shifts=(2, 3), dims=(2, 3))
-    return image1, image2
-
-
-def smooth_pair(H, W, seed=1234, B=1, blur=5):
-    """Box-blurred noise variant -- textured but smooth."""
-    import torch
-    import torch.nn.functional as F
-    g = torch.Generator().manual_seed(seed)
-    x = torch.rand((B, 3, H + 16, W + 16), generator=g)
-    k = torch.ones(3, 1, blur, blur) / (blur * blur)
-    for _ in range(2):
-        x = F.conv2d(F.pad(x, (blur // 2,) * 4, mode="reflect"), k, groups=3)
-    x = (x - x.amin()) / (x.amax() - x.amin()) * 255.0
-    image1 = x[:, :, 8:8 + H, 8:8 + W].contiguous()
-    image2 = x[:, :, 6:6 + H, 5:5 + W].contiguous()   # image2(y,x) = image1(y-2, x-3)
-    return image1, image2

@@ -128,7 +128,8 @@ def test_seams_match_reference(name):
 
     if name.startswith("seeded_clip"):
         # every gate fired: flag == 1, the clamped re-pass ran, the LN statistics are the clamped pass's
-        assert ws.flag.tolist() == [1, 1, 1] and ws.clip_corr.item() == ws.clip_f2.item() == ws.clip_att.item() == 0.2
+        assert ws.flag.tolist() == [1, 1, 1]
+        assert all(abs(c.item() - 0.2) < 1e-6 for c in (ws.clip_corr, ws.clip_f2, ws.clip_att))
         assert ws.stat_sum[1].abs().sum().item() > 0
     got = {
         "f2_out": None,
