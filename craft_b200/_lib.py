@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcraft_b200.so")
+LIB_PATH = os.path.join(_HERE, "libcraft_b200.so")              # tensor-core operands / activations in bf16
+LIB_PATH_FP16 = os.path.join(_HERE, "libcraft_b200_fp16.so")    # same sources built with fp16 operands
 MAX_TAPS = 49
 ABI_VERSION = 2
 
@@ -112,35 +113,42 @@ SIGNATURES = {
     "craft_nhwc_affine": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 
-_lib = None
+_libs = {}
 
 
-def load():
-    """Load (once) and type the shared library.  Raises CraftB200Error if it is not built."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.isfile(LIB_PATH):
+def load(fp16=False):
+    """Load (once) and type one of the two builds of the shared library.  Raises CraftB200Error if it is
+    not built."""
+    hit = _libs.get(bool(fp16))
+    if hit is not None:
+        return hit
+    path = LIB_PATH_FP16 if fp16 else LIB_PATH
+    if not os.path.isfile(path):
         raise CraftB200Error(
-            "libcraft_b200.so is not built (expected %s). Run `python -c 'import __graft_entry__ as g; "
-            "g.build()'` or `make -C craft_b200/csrc`. There is no fallback path." % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
+            "%s is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` or "
+            "`make -C craft_b200/csrc`. There is no fallback path." % path)
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)       # AttributeError here == header/library mismatch
         fn.restype = res
         fn.argtypes = args
     if lib.craft_b200_abi_version() != ABI_VERSION:
-        raise CraftB200Error("libcraft_b200.so ABI version mismatch")
-    _lib = lib
+        raise CraftB200Error("%s: ABI version mismatch" % os.path.basename(path))
+    _libs[bool(fp16)] = lib
     return lib
 
 
-def check(rc, what=""):
+def launch_count():
+    """Kernels launched so far by both builds of the library."""
+    return sum(lib.craft_b200_launch_count() for lib in _libs.values())
+
+
+def check(rc, what="", fp16=False):
     if rc != 0:
-        msg = load().craft_b200_last_error()
+        msg = load(fp16).craft_b200_last_error()
         raise CraftB200Error("%s failed: %s" % (what or "craft_b200 call", msg.decode() if msg else rc))
 
 
-def call(name, *args):
-    lib = load()
-    check(getattr(lib, name)(*args), name)
+def call(name, *args, fp16=False):
+    lib = load(fp16)
+    check(getattr(lib, name)(*args), name, fp16)

@@ -400,7 +400,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
 #pragma unroll
           for (int e = 0; e < 16; ++e)
-            pk[c / 2 + e] = pack_bf16x2(ex2_mix<POLY>(x[2 * e], 2 * e), ex2_mix<POLY>(x[2 * e + 1], 2 * e + 1));
+            pk[c / 2 + e] = pack_act2(ex2_mix<POLY>(x[2 * e], 2 * e), ex2_mix<POLY>(x[2 * e + 1], 2 * e + 1));
         }
         if (trole < 4) PV_TRACE(trole, g, 3);
         // P -> TMEM (this warp's lanes, columns it has just read), then hand the buffer to the P.V issuer

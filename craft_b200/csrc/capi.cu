@@ -238,7 +238,7 @@ int craft_pack_tokens(const float* src, int C, int H, int W, int mode, void* out
   cb::Grid2 g = make_grid(H, W);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(H * ((g.Wp + 31) / 32));
-  auto* ob = static_cast<__nv_bfloat16*>(out_b);
+  auto* ob = static_cast<cb::act_t*>(out_b);
   if (C == 128) launch_k(cb::pack_tokens_kernel<128>, dim3(grid), dim3(256), 0, st, src, g, mode, ob, ldb, colb, out_f, ldf, colf);
   else if (C == 256) launch_k(cb::pack_tokens_kernel<256>, dim3(grid), dim3(256), 0, st, src, g, mode, ob, ldb, colb, out_f, ldf, colf);
   else return fail("pack_tokens: C must be 128 or 256 (got %d)", C);
@@ -251,7 +251,7 @@ int craft_unpack_tokens(const void* src, int is_bf16, int ld, int col, int C, in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(H * ((W + 31) / 32), (C + 31) / 32);
   if (is_bf16)
-    launch_k(cb::unpack_tokens_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(src), ld, col, C, g, dst);
+    launch_k(cb::unpack_tokens_kernel<cb::act_t>, dim3(grid), dim3(256), 0, st, static_cast<const cb::act_t*>(src), ld, col, C, g, dst);
   else
     launch_k(cb::unpack_tokens_kernel<float>, dim3(grid), dim3(256), 0, st, static_cast<const float*>(src), ld, col, C, g, dst);
   return check_launch("unpack_tokens");
@@ -322,7 +322,7 @@ int craft_shift_gemm(const craft_gemm_args* a, void* stream) {
   for (int t = 0; t < a->T; ++t) p.tap_off[t] = a->tap_off[t];
   if (a->H > 0) { p.Wp = a->W + 2; p.W = a->W; p.H = a->H; } else { p.Wp = 0; p.W = 0; p.H = 0; }
   p.alpha = a->alpha; p.act = a->act; p.bias = a->bias;
-  p.out_b = static_cast<__nv_bfloat16*>(a->out_bf16); p.ldb = a->ldo_b; p.colb = a->colo_b;
+  p.out_b = static_cast<cb::act_t*>(a->out_bf16); p.ldb = a->ldo_b; p.colb = a->colo_b;
   p.out_f = a->out_f32; p.ldf = a->ldo_f; p.colf = a->colo_f;
   p.aux_f0 = a->aux0; p.aux_f1 = a->aux1;
   {
@@ -601,8 +601,8 @@ int craft_modes_finalize(const float* O, int nsum, int M, int F, const float* w_
   const long long mode_stride = static_cast<long long>(g.Mp) * F;
   const long long part_stride = mode_stride * M;
   dim3 grid((g.Mp + 7) / 8);
-  auto* xb = static_cast<const __nv_bfloat16*>(x_bf16);
-  auto* ob = static_cast<__nv_bfloat16*>(out_bf16);
+  auto* xb = static_cast<const cb::act_t*>(x_bf16);
+  auto* ob = static_cast<cb::act_t*>(out_bf16);
   if (F == 128)
     launch_k(cb::modes_finalize_kernel<128>, dim3(grid), dim3(256), 0, st, O, nsum, part_stride, M, mode_stride, w_score, b_score, coeff, gma, xb, ldx, colx, x_f32, ldxf, colxf, g, ob, ldb, colb, out_f32, ldf, colf, pv_G, pv_nkt);
   else if (F == 256)
@@ -634,7 +634,7 @@ int craft_attn_dense(const craft_dense_attn_args* a, void* stream) {
   cb::Grid2 g = make_grid(a->H, a->W);
   cb::DenseAttnParams p;
   memset(&p, 0, sizeof(p));
-  p.Q = static_cast<const __nv_bfloat16*>(a->Q); p.K = static_cast<const __nv_bfloat16*>(a->K);
+  p.Q = static_cast<const cb::act_t*>(a->Q); p.K = static_cast<const cb::act_t*>(a->K);
   p.C = a->C; p.M = a->M; p.d = a->d; p.scale = a->scale; p.w_pos = a->w_pos; p.pos_table = a->pos_table; p.R = a->R;
   p.clip = a->clip; p.lse2 = a->lse2; p.mask_radius = a->mask_radius; p.out = a->out;
   const long long units = static_cast<long long>(a->M) * a->H * a->W;
@@ -653,7 +653,7 @@ int craft_corr_lookup(const float* const* lvl, int H, int W, const float* coords
     if (l >= first_level && !lvl[l]) return fail("corr_lookup: level %d missing", l);
     h /= 2; w /= 2;
   }
-  p.coords = coords; p.stats = mean_rstd; p.out_b = static_cast<__nv_bfloat16*>(out_bf16); p.ldb = ldb;
+  p.coords = coords; p.stats = mean_rstd; p.out_b = static_cast<cb::act_t*>(out_bf16); p.ldb = ldb;
   p.out_nchw = out_nchw; p.first_level = first_level;
   launch_k(cb::corr_lookup_kernel, dim3((g.Mp + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), p, g);
   return check_launch("corr_lookup");
@@ -668,9 +668,9 @@ int craft_corr_lookup0(const void* Q, const void* K, int M, int d, float scale, 
   cb::Grid2 g = make_grid(H, W);
   cb::Lookup0Params p;
   memset(&p, 0, sizeof(p));
-  p.Q = static_cast<const __nv_bfloat16*>(Q); p.K = static_cast<const __nv_bfloat16*>(K);
+  p.Q = static_cast<const cb::act_t*>(Q); p.K = static_cast<const cb::act_t*>(K);
   p.M = M; p.d = d; p.scale = scale; p.w_agg = w_agg; p.w_pos = w_pos; p.pos_table = pos_table; p.Rb = R;
-  p.clip = clip; p.coords = coords; p.stats = mean_rstd; p.out_b = static_cast<__nv_bfloat16*>(out_bf16);
+  p.clip = clip; p.coords = coords; p.stats = mean_rstd; p.out_b = static_cast<cb::act_t*>(out_bf16);
   p.ldb = ldb; p.out_nchw = out_nchw;
   launch_k(cb::corr_lookup0_kernel, dim3((g.Mp + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), p, g);
   return check_launch("corr_lookup0");
@@ -680,7 +680,7 @@ int craft_convf1(const float* flow, const float* wt, const float* bias, int H, i
                  int colo, void* stream) {
   cb::Grid2 g = make_grid(H, W);
   dim3 grid(H * ((W + 15) / 16), 2);
-  launch_k(cb::convf1_kernel, dim3(grid), dim3(128), 0, static_cast<cudaStream_t>(stream), flow, wt, bias, g, static_cast<__nv_bfloat16*>(out_bf16), ldo, colo);
+  launch_k(cb::convf1_kernel, dim3(grid), dim3(128), 0, static_cast<cudaStream_t>(stream), flow, wt, bias, g, static_cast<cb::act_t*>(out_bf16), ldo, colo);
   return check_launch("convf1");
 }
 
@@ -701,7 +701,7 @@ int craft_upsample_flow(const void* mask, int mask_is_bf16, int ldm, const float
   dim3 grid((H * W + 3) / 4);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (mask_is_bf16)
-    launch_k(cb::upsample_flow_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(mask), ldm, flow, g, out);
+    launch_k(cb::upsample_flow_kernel<cb::act_t>, dim3(grid), dim3(256), 0, st, static_cast<const cb::act_t*>(mask), ldm, flow, g, out);
   else
     launch_k(cb::upsample_flow_kernel<float>, dim3(grid), dim3(256), 0, st, static_cast<const float*>(mask), ldm, flow, g, out);
   return check_launch("upsample_flow");

@@ -71,7 +71,7 @@ struct GemmParams {
   float alpha;
   int act;                       // 0 none, 1 relu
   const float* bias;             // [Npad] or nullptr
-  __nv_bfloat16* out_b;          // bf16 destination (row-major), may be nullptr
+  act_t* out_b;          // bf16 destination (row-major), may be nullptr
   int ldb, colb;
   float* out_f;                  // f32 destination, may be nullptr
   int ldf, colf;
@@ -386,10 +386,10 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int q = 0; q < CW / 8; ++q) {
               uint4 u;
-              u.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
-              u.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
-              u.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
-              u.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+              u.x = pack_act2(v[8 * q + 0], v[8 * q + 1]);
+              u.y = pack_act2(v[8 * q + 2], v[8 * q + 3]);
+              u.z = pack_act2(v[8 * q + 4], v[8 * q + 5]);
+              u.w = pack_act2(v[8 * q + 6], v[8 * q + 7]);
               dst[q] = u;
             }
           }
@@ -410,10 +410,10 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int q = 0; q < CW / 8; ++q) {
               uint4 u;
-              u.x = pack_bf16x2(sigmoid_fast(v[8 * q + 0]) * pre_h[c + 8 * q + 0], sigmoid_fast(v[8 * q + 1]) * pre_h[c + 8 * q + 1]);
-              u.y = pack_bf16x2(sigmoid_fast(v[8 * q + 2]) * pre_h[c + 8 * q + 2], sigmoid_fast(v[8 * q + 3]) * pre_h[c + 8 * q + 3]);
-              u.z = pack_bf16x2(sigmoid_fast(v[8 * q + 4]) * pre_h[c + 8 * q + 4], sigmoid_fast(v[8 * q + 5]) * pre_h[c + 8 * q + 5]);
-              u.w = pack_bf16x2(sigmoid_fast(v[8 * q + 6]) * pre_h[c + 8 * q + 6], sigmoid_fast(v[8 * q + 7]) * pre_h[c + 8 * q + 7]);
+              u.x = pack_act2(sigmoid_fast(v[8 * q + 0]) * pre_h[c + 8 * q + 0], sigmoid_fast(v[8 * q + 1]) * pre_h[c + 8 * q + 1]);
+              u.y = pack_act2(sigmoid_fast(v[8 * q + 2]) * pre_h[c + 8 * q + 2], sigmoid_fast(v[8 * q + 3]) * pre_h[c + 8 * q + 3]);
+              u.z = pack_act2(sigmoid_fast(v[8 * q + 4]) * pre_h[c + 8 * q + 4], sigmoid_fast(v[8 * q + 5]) * pre_h[c + 8 * q + 5]);
+              u.w = pack_act2(sigmoid_fast(v[8 * q + 6]) * pre_h[c + 8 * q + 6], sigmoid_fast(v[8 * q + 7]) * pre_h[c + 8 * q + 7]);
               dst[q] = u;
             }
           }
@@ -431,10 +431,10 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int q = 0; q < CW / 8; ++q) {
             uint4 u;
-            u.x = pack_bf16x2(hn[8 * q + 0], hn[8 * q + 1]);
-            u.y = pack_bf16x2(hn[8 * q + 2], hn[8 * q + 3]);
-            u.z = pack_bf16x2(hn[8 * q + 4], hn[8 * q + 5]);
-            u.w = pack_bf16x2(hn[8 * q + 6], hn[8 * q + 7]);
+            u.x = pack_act2(hn[8 * q + 0], hn[8 * q + 1]);
+            u.y = pack_act2(hn[8 * q + 2], hn[8 * q + 3]);
+            u.z = pack_act2(hn[8 * q + 4], hn[8 * q + 5]);
+            u.w = pack_act2(hn[8 * q + 6], hn[8 * q + 7]);
             dst[q] = u;
           }
         } else if constexpr (EPI == EPI_MOTION) {
@@ -448,10 +448,10 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int q = 0; q < CW / 8; ++q) {
             uint4 u;
-            u.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
-            u.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
-            u.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
-            u.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+            u.x = pack_act2(v[8 * q + 0], v[8 * q + 1]);
+            u.y = pack_act2(v[8 * q + 2], v[8 * q + 3]);
+            u.z = pack_act2(v[8 * q + 4], v[8 * q + 5]);
+            u.w = pack_act2(v[8 * q + 6], v[8 * q + 7]);
             dst[q] = u;
           }
           if (p.out_f) {

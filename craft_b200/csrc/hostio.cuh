@@ -62,9 +62,10 @@ __global__ void __launch_bounds__(256) flow_encode_kernel(const float* __restric
     reinterpret_cast<float2*>(out)[t] = make_float2(u, v);
   } else {
     uint16_t* o = reinterpret_cast<uint16_t*>(out) + 3 * static_cast<size_t>(t);
-    // numpy's float64 -> uint16 astype truncates toward zero (and wraps out-of-range values modulo 2^16)
-    const long long qu = static_cast<long long>(64.0 * static_cast<double>(u) + 32768.0);
-    const long long qv = static_cast<long long>(64.0 * static_cast<double>(v) + 32768.0);
+    // frame_utils.py:117 evaluates 64.0 * uv + 2**15 on the float32 array, i.e. in float32 (64 u is exact, the sum
+    // rounds to nearest); the later astype(uint16) truncates toward zero and wraps out-of-range values mod 2^16
+    const long long qu = static_cast<long long>(__fadd_rn(64.0f * u, 32768.0f));
+    const long long qv = static_cast<long long>(__fadd_rn(64.0f * v, 32768.0f));
     o[0] = 1;
     o[1] = static_cast<uint16_t>(qv);
     o[2] = static_cast<uint16_t>(qu);

@@ -23,7 +23,7 @@ struct Grid2 {
 // -------------------------------------------------------------------------------------------
 template <int C>
 __global__ void __launch_bounds__(256) pack_tokens_kernel(const float* __restrict__ src, Grid2 g,
-                                                          int mode, __nv_bfloat16* __restrict__ out_b,
+                                                          int mode, act_t* __restrict__ out_b,
                                                           int ldb, int colb, float* __restrict__ out_f,
                                                           int ldf, int colf) {
   pdl_launch_dependents();
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) pack_tokens_kernel(const float* __restric
       else if (mode == 1) v = (v - mean) * rstd;
       else if (mode == 2) v = tanhf(v);
       else if (mode == 3) v = fmaxf(v, 0.f);
-      if (out_b) out_b[p * ldb + colb + c] = __float2bfloat16_rn(v);
+      if (out_b) out_b[p * ldb + colb + c] = f2act(v);
       if (out_f) out_f[p * ldf + colf + c] = v;
     }
   }
@@ -117,7 +117,7 @@ struct LookupParams {
   long long qstride[4];  // elements between consecutive query rows
   const float* coords;   // [Mp, 2] (x, y) padded-flat
   const float* stats;    // device {mean, rstd}
-  __nv_bfloat16* out_b;  // [Mp, ldb] token-major (cols >= 4*81 left untouched)
+  act_t* out_b;  // [Mp, ldb] token-major (cols >= 4*81 left untouched)
   int ldb;
   float* out_nchw;       // [324, H, W] or nullptr
   int first_level;       // levels < first_level are skipped (handled by the on-demand kernel)
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(LookupParams p, Grid2 
       const float bot = v10 + ax * (v11 - v10);
       const float val = (top + ay * (bot - top)) * rstd;
       const int ch = l * D * D + e;
-      if (p.out_b) p.out_b[static_cast<size_t>(q) * p.ldb + ch] = __float2bfloat16_rn(val);
+      if (p.out_b) p.out_b[static_cast<size_t>(q) * p.ldb + ch] = f2act(val);
       if (p.out_nchw) p.out_nchw[(static_cast<size_t>(ch) * g.H + qy) * g.W + qx] = val;
     }
   }
@@ -179,8 +179,8 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(LookupParams p, Grid2 
 // row load (lane = 8 channels) followed by a shuffle reduction per mode.
 // -------------------------------------------------------------------------------------------
 struct Lookup0Params {
-  const __nv_bfloat16* Q;   // [Mp, 256] projected queries
-  const __nv_bfloat16* K;   // [Mp, 256] projected keys
+  const act_t* Q;   // [Mp, 256] projected queries
+  const act_t* K;   // [Mp, 256] projected keys
   int M, d;                 // modes, per-mode dim (M*d == 256)
   float scale, w_agg, w_pos;
   const float* pos_table;   // [(2R+1)^2] or nullptr
@@ -188,7 +188,7 @@ struct Lookup0Params {
   const float* clip;        // device scalar
   const float* coords;      // [Mp,2]
   const float* stats;       // {mean, rstd}
-  __nv_bfloat16* out_b;     // [Mp, ldb], channels 0..80
+  act_t* out_b;     // [Mp, ldb], channels 0..80
   int ldb;
   float* out_nchw;          // [324,H,W] (channels 0..80) or nullptr
 };
@@ -217,8 +217,9 @@ __global__ void __launch_bounds__(256) corr_lookup0_kernel(Lookup0Params p, Grid
     const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      qf[2 * k] = __uint_as_float(w[k] << 16);
-      qf[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+      const float2 v = unpack_act2(w[k]);
+      qf[2 * k] = v.x;
+      qf[2 * k + 1] = v.y;
     }
   }
   const float cx = p.coords[2 * q], cy = p.coords[2 * q + 1];
@@ -246,10 +247,9 @@ __global__ void __launch_bounds__(256) corr_lookup0_kernel(Lookup0Params p, Grid
     }
 #pragma unroll
     for (int c = 0; c < WN; ++c) {
-      float a = qf[0] * __uint_as_float(kk[c].x << 16) + qf[1] * __uint_as_float(kk[c].x & 0xffff0000u) +
-                qf[2] * __uint_as_float(kk[c].y << 16) + qf[3] * __uint_as_float(kk[c].y & 0xffff0000u) +
-                qf[4] * __uint_as_float(kk[c].z << 16) + qf[5] * __uint_as_float(kk[c].z & 0xffff0000u) +
-                qf[6] * __uint_as_float(kk[c].w << 16) + qf[7] * __uint_as_float(kk[c].w & 0xffff0000u);
+      const float2 k0 = unpack_act2(kk[c].x), k1 = unpack_act2(kk[c].y), k2 = unpack_act2(kk[c].z), k3 = unpack_act2(kk[c].w);
+      float a = qf[0] * k0.x + qf[1] * k0.y + qf[2] * k1.x + qf[3] * k1.y +
+                qf[4] * k2.x + qf[5] * k2.y + qf[6] * k3.x + qf[7] * k3.y;
       a += __shfl_xor_sync(0xffffffffu, a, 1);           // d >= 64 always (M <= 4): 8 lanes per mode at least
       a += __shfl_xor_sync(0xffffffffu, a, 2);
       a += __shfl_xor_sync(0xffffffffu, a, 4);
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(256) corr_lookup0_kernel(Lookup0Params p, Grid
     const float top = v00 + ax * (v01 - v00);
     const float bot = v10 + ax * (v11 - v10);
     const float val = (top + ay * (bot - top)) * rstd;
-    if (p.out_b) p.out_b[static_cast<size_t>(q) * p.ldb + e] = __float2bfloat16_rn(val);
+    if (p.out_b) p.out_b[static_cast<size_t>(q) * p.ldb + e] = f2act(val);
     if (p.out_nchw) p.out_nchw[(static_cast<size_t>(e) * g.H + qy) * g.W + qx] = val;
   }
 }
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(256) upsample_flow_kernel(const TM* __restrict
 __global__ void __launch_bounds__(128) convf1_kernel(const float* __restrict__ flow /*[Mp,2]*/,
                                                      const float* __restrict__ wt,
                                                      const float* __restrict__ bias, Grid2 g,
-                                                     __nv_bfloat16* __restrict__ out, int ldo, int colo) {
+                                                     act_t* __restrict__ out, int ldo, int colo) {
   pdl_launch_dependents();
   pdl_wait();
 
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(128) convf1_kernel(const float* __restrict__ f
   for (int t = 0; t < TX; ++t) {
     const int x = x0 + t;
     if (x < g.W)
-      out[(static_cast<size_t>(y) * g.Wp + x) * ldo + colo + co] = __float2bfloat16_rn(fmaxf(acc[t], 0.f));
+      out[(static_cast<size_t>(y) * g.Wp + x) * ldo + colo + co] = f2act(fmaxf(acc[t], 0.f));
   }
 }
 
@@ -471,8 +471,8 @@ __global__ void __launch_bounds__(256) modes_finalize_kernel(
     const float* __restrict__ O, int nsum, long long part_stride, int M, long long mode_stride,
     const float* __restrict__ w_score,
     const float* __restrict__ b_score, const float* __restrict__ coeff, int gma,
-    const __nv_bfloat16* __restrict__ xb, int ldx, int colx, const float* __restrict__ xf, int ldxf,
-    int colxf, Grid2 g, __nv_bfloat16* __restrict__ out_b, int ldb, int colb,
+    const act_t* __restrict__ xb, int ldx, int colx, const float* __restrict__ xf, int ldxf,
+    int colxf, Grid2 g, act_t* __restrict__ out_b, int ldb, int colb,
     float* __restrict__ out_f, int ldf, int colf, int pv_G, int pv_nkt) {
   pdl_launch_dependents();
   pdl_wait();
@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(256) modes_finalize_kernel(
     for (int m = 0; m < 4; ++m) agg += sc[m] * o[m][e];
     agg /= den;
     const float xin = xf ? xf[static_cast<size_t>(p) * ldxf + colxf + f]
-                         : __bfloat162float(xb[static_cast<size_t>(p) * ldx + colx + f]);
+                         : act2f(xb[static_cast<size_t>(p) * ldx + colx + f]);
     yv[e] = gma ? (xin + c * agg) : (c * xin + agg);
     s1 += yv[e];
   }
@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(256) modes_finalize_kernel(
 #pragma unroll
   for (int e = 0; e < PER; ++e) {
     const int f = 8 * ((lane >> 1) + 16 * (e >> 2)) + 4 * (lane & 1) + (e & 3);
-    if (out_b) out_b[static_cast<size_t>(p) * ldb + colb + f] = __float2bfloat16_rn(yv[e]);
+    if (out_b) out_b[static_cast<size_t>(p) * ldb + colb + f] = f2act(yv[e]);
     if (out_f) out_f[static_cast<size_t>(p) * ldf + colf + f] = yv[e];
   }
 }

@@ -85,8 +85,8 @@ __global__ void __launch_bounds__(256) soft_aggregate_feat_kernel(const float* _
 // the keys, lane = key.
 // -------------------------------------------------------------------------------------------
 struct DenseAttnParams {
-  const __nv_bfloat16* Q;
-  const __nv_bfloat16* K;
+  const act_t* Q;
+  const act_t* K;
   int C, M, d;
   float scale, w_pos;
   const float* pos_table;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) attn_dense_kernel(DenseAttnParams p, Grid
   const int m = static_cast<int>(unit / U), qi = static_cast<int>(unit - static_cast<long long>(m) * U);
   const int qy = qi / g.W, qx = qi - qy * g.W;
   const int qrow = qy * g.Wp + qx;
-  const __nv_bfloat16* qp = p.Q + static_cast<size_t>(qrow) * p.C + m * p.d;
+  const act_t* qp = p.Q + static_cast<size_t>(qrow) * p.C + m * p.d;
   const float clipv = *p.clip;
   const int TD = 2 * p.R + 1;
   const float lse = p.lse2 ? p.lse2[static_cast<size_t>(m) * g.Mp + qrow] : 0.f;
@@ -116,11 +116,11 @@ __global__ void __launch_bounds__(256) attn_dense_kernel(DenseAttnParams p, Grid
     const int ki = k0 + lane;
     if (ki >= U) break;
     const int ky = ki / g.W, kx = ki - ky * g.W;
-    const __nv_bfloat16* kp = p.K + static_cast<size_t>(ky * g.Wp + kx) * p.C + m * p.d;
+    const act_t* kp = p.K + static_cast<size_t>(ky * g.Wp + kx) * p.C + m * p.d;
     float acc = 0.f;
     for (int c = 0; c < p.d; c += 2) {
-      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qp + c));
-      const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(kp + c));
+      const float2 a = unpack_act2(*reinterpret_cast<const uint32_t*>(qp + c));
+      const float2 b = unpack_act2(*reinterpret_cast<const uint32_t*>(kp + c));
       acc = fmaf(a.x, b.x, acc);
       acc = fmaf(a.y, b.y, acc);
     }

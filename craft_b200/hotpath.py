@@ -28,7 +28,7 @@ class PackedWeights:
         self._store = {}
 
     def get(self, key, params, build):
-        ver = tuple((p.data_ptr(), p._version, p.device) for p in params)
+        ver = (ops.act_dtype(),) + tuple((p.data_ptr(), p._version, p.device) for p in params)
         hit = self._store.get(key)
         if hit is None or hit[0] != ver:
             with torch.no_grad():
@@ -44,7 +44,8 @@ class Workspace:
     def __init__(self, grid, device, materialize_level0=True):
         g = self.grid = grid
         self.device = device
-        z = lambda cols, dt=torch.bfloat16: torch.zeros((g.Mp, cols), dtype=dt, device=device)
+        act = self.dtype = ops.act_dtype()
+        z = lambda cols, dt=act: torch.zeros((g.Mp, cols), dtype=dt, device=device)
         f32 = torch.float32
         self.ldv = (((g.H + 7) // 8) * 8) * (((g.W + 15) // 16) * 16)     # keys in 8x16 (or 8x8) block order
         # --- feature tokens / projections
@@ -52,7 +53,7 @@ class Workspace:
         self.Qc = z(256); self.Kc = z(256)                     # corr_fn projections
         self.Q2 = z(256); self.K2 = z(256)                     # f2_trans projections
         self.Ta = z(128); self.Qa = z(128); self.Ka = z(128)   # intra-frame attention
-        self.Vt = torch.zeros((1024, self.ldv), dtype=torch.bfloat16, device=device)
+        self.Vt = torch.zeros((1024, self.ldv), dtype=act, device=device)
         self.ks_sc = ops.scores_auto_ksplit(g)
         self.lse_part = torch.zeros((self.ks_sc, 4, g.Mp, 2), dtype=f32, device=device)
         self.lse2_f2 = torch.zeros((4, g.Mp), dtype=f32, device=device)
@@ -218,7 +219,7 @@ class EncoderBuffers:
 
     def __init__(self, grid, device):
         self.grid = grid
-        z = lambda cols, dt=torch.bfloat16: torch.zeros((grid.Mp, cols), dtype=dt, device=device)
+        z = lambda cols, dt=ops.act_dtype(): torch.zeros((grid.Mp, cols), dtype=dt, device=device)
         self.X = z(640)
         self.CORR = z(384); self.C1 = z(256); self.CF = z(256); self.F1 = z(128)
         self.flow = z(2, torch.float32)

@@ -110,19 +110,38 @@ class CRAFT(nn.Module):
         self.use_cuda_graph = os.environ.get("CRAFT_B200_NO_GRAPH", "0") != "1"
         # fnet / cnet are outside the hot path; TF32 convolutions there cost ~6e-3 max abs error on
         # features of magnitude 20 and are 2.5x faster than strict fp32 (profiles/README.md).
-        self.encoder_tf32 = True
         # "fp16": encoder activations and conv operands in half precision (fp32 accumulation and fp32 norm
         # statistics) -- an 11-bit mantissa, i.e. finer than TF32's 10 bits, at half the HBM traffic.
         # The reference's own evaluation default is fp16 autocast (evaluate.py:1455-1456).
-        self.encoder_half = os.environ.get("CRAFT_B200_ENCODER", "fp16") == "fp16"
+        # (both flags are set by set_precision below)
         # test_mode=1 returns only the LAST iteration's upsampled flow (core/network.py:262-263), yet the
         # reference computes the mask head and the convex upsampling in every iteration and drops them.
         # Eliding that dead work leaves every returned value bit-identical.
         # Set False to execute the reference's schedule literally.
         self.elide_dead_upsample = True
+        # Precision tier:
+        #   "bf16"  tensor-core operands / activations in bfloat16, fp16 encoders      (north_star's 1e-2 px tier; default)
+        #   "fp16"  operands in float16 (11-bit mantissa, same speed), fp16 encoders
+        #   "fp32-parity"  float16 operands + strict-fp32 encoders: within 1e-3 px of the fp32 reference on the
+        #                  trained-weight cases (tests/test_gpu_e2e.py) -- what `--mixed_precision` off means
+        #                  in the reference's drivers (evaluate.py:1455-1456), at tensor-core speed.
+        # Accumulators, statistics, GRU state, coordinates, flow and masks are fp32 in all of them.
+        self.set_precision(os.environ.get("CRAFT_B200_PRECISION", "bf16"))
         self._graphs = collections.OrderedDict()   # LRU, bounded by max_cached_graphs
         self.max_cached_graphs = 8
         self._workspaces = WorkspaceCache(capacity=4)   # this model's own device buffers
+
+    def set_precision(self, tier):
+        if tier not in ("bf16", "fp16", "fp32-parity"):
+            raise ValueError("precision tier must be 'bf16', 'fp16' or 'fp32-parity', got %r" % (tier,))
+        self.precision = tier
+        self.act_dtype = torch.bfloat16 if tier == "bf16" else torch.float16
+        if tier == "fp32-parity":
+            self.encoder_half, self.encoder_tf32 = False, False
+        else:
+            self.encoder_half = os.environ.get("CRAFT_B200_ENCODER", "fp16") == "fp16"
+            self.encoder_tf32 = True
+        return self
 
     def freeze_bn(self):
         for m in self.modules():
@@ -224,7 +243,7 @@ class CRAFT(nn.Module):
             raise ValueError("image sides must be multiples of 8 (use InputPadder, as the reference drivers do)")
         # everything below (streams, workspaces, the library's per-device state) refers to the input's device:
         # nn.DataParallel calls each replica from its own thread with another device current
-        with torch.cuda.device(image1.device):
+        with torch.cuda.device(image1.device), ops.precision(self.act_dtype):
             savecorr = "SAVECORR" in os.environ      # core/corr.py:180-184 debugging hook: needs the stored volume
             if self.use_cuda_graph and not self.training and not torch.cuda.is_current_stream_capturing() \
                     and not savecorr:
@@ -237,7 +256,7 @@ class CRAFT(nn.Module):
 
     def _forward_graphed(self, image1, image2, iters, flow_init, test_mode):
         key = (image1.device.index, tuple(image1.shape), int(iters), int(test_mode), flow_init is not None,
-               self.materialize_level0, self.encoder_tf32, self.encoder_half, self.elide_dead_upsample)
+               self.materialize_level0, self.encoder_tf32, self.encoder_half, self.elide_dead_upsample, self.precision)
         sig = self._weights_signature()
         ent = self._graphs.get(key)
         if ent is not None:
@@ -260,7 +279,7 @@ class CRAFT(nn.Module):
             torch.cuda.synchronize(image1.device)
             g = torch.cuda.CUDAGraph()
             from . import _lib
-            n0 = _lib.load().craft_b200_launch_count()
+            n0 = _lib.launch_count()
             with torch.cuda.graph(g):
                 ent["out"] = self._forward_impl(ent["i1"], ent["i2"], iters, ent["fi"], test_mode)
             ent["graph"] = g
@@ -271,7 +290,7 @@ class CRAFT(nn.Module):
                             t.zero_()
             for t, sv in zip(diags, saved):
                 t.copy_(sv)
-            ent["launches"] = _lib.load().craft_b200_launch_count() - n0   # craft_b200 kernels per replay
+            ent["launches"] = _lib.launch_count() - n0   # craft_b200 kernels per replay
             # the graph bakes in the workspace's addresses: keep the buffers alive as long as the graph is
             g8 = TokenGrid(image1.shape[2] // 8, image1.shape[3] // 8)
             ent["ws"] = self._workspaces.get(g8, image1.device, self.materialize_level0)

@@ -14,7 +14,31 @@ import torch
 from . import _lib
 from .torch_ops import OPS
 
+import contextlib
+import contextvars
+
 EPI_STORE, EPI_GRU_ZR, EPI_GRU_Q, EPI_MOTION, EPI_FLOW = 0, 1, 2, 3, 4
+
+# Tensor-core operand / activation dtype of the current call: bfloat16 (default, libcraft_b200.so) or float16
+# (libcraft_b200_fp16.so, the fp32-parity tier).  CRAFT.forward sets it from the model's `precision`; every
+# buffer, packed weight and workspace created below follows it, and torch_ops routes each launch to the
+# matching build of the library by the dtype of its operands.
+_ACT_DTYPE = contextvars.ContextVar("craft_b200_act_dtype", default=torch.bfloat16)
+
+
+def act_dtype():
+    return _ACT_DTYPE.get()
+
+
+@contextlib.contextmanager
+def precision(dtype):
+    if dtype not in (torch.bfloat16, torch.float16):
+        raise ValueError("craft_b200 operand dtype must be torch.bfloat16 or torch.float16")
+    tok = _ACT_DTYPE.set(dtype)
+    try:
+        yield
+    finally:
+        _ACT_DTYPE.reset(tok)
 PACK_COPY, PACK_LN, PACK_TANH, PACK_RELU, PACK_RELU_LN = 0, 1, 2, 3, 4
 
 
@@ -34,8 +58,8 @@ class TokenGrid:
             h, w = h // 2, w // 2
         return out
 
-    def zeros(self, cols, dtype=torch.bfloat16, device="cuda"):
-        return torch.zeros((self.Mp, cols), dtype=dtype, device=device)
+    def zeros(self, cols, dtype=None, device="cuda"):
+        return torch.zeros((self.Mp, cols), dtype=dtype or act_dtype(), device=device)
 
 
 def _stream():
@@ -135,7 +159,7 @@ def conv_taps(kh, kw, grid):
 
 
 def pack_conv_weight(w, Npad=None, cin_perm=None, Kpad=None):
-    """[Cout,Cin,kh,kw] f32 -> bf16 [kh*kw*Npad, Kpad]: tap-major blocks of [Npad, Cin] (zero padded)."""
+    """[Cout,Cin,kh,kw] f32 -> operand dtype [kh*kw*Npad, Kpad]: tap-major blocks of [Npad, Cin] (zero padded)."""
     Cout, Cin, kh, kw = w.shape
     Npad = Npad or Cout
     Kpad = Kpad or ((Cin + 63) // 64) * 64
@@ -144,17 +168,17 @@ def pack_conv_weight(w, Npad=None, cin_perm=None, Kpad=None):
         ww = ww[:, cin_perm]
     out = torch.zeros((kh * kw, Npad, Kpad), dtype=torch.float32, device=w.device)
     out[:, :Cout, :Cin] = ww.permute(2, 3, 0, 1).reshape(kh * kw, Cout, Cin)
-    return out.reshape(kh * kw * Npad, Kpad).to(torch.bfloat16).contiguous()
+    return out.reshape(kh * kw * Npad, Kpad).to(act_dtype()).contiguous()
 
 
 def pack_linear_weight(w, Npad=None, Kpad=None):
-    """[N,K] f32 -> bf16 [Npad, Kpad]."""
+    """[N,K] f32 -> operand dtype [Npad, Kpad]."""
     N, K = w.shape
     Npad = Npad or N
     Kpad = Kpad or ((K + 63) // 64) * 64
     out = torch.zeros((Npad, Kpad), dtype=torch.float32, device=w.device)
     out[:N, :K] = w.detach().float()
-    return out.to(torch.bfloat16).contiguous()
+    return out.to(act_dtype()).contiguous()
 
 
 def pad_bias(b, Npad):

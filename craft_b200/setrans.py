@@ -254,10 +254,10 @@ class ExpandedFeatTrans(nn.Module):
         grid = handles[0].grid
         ws = get_workspace(grid, input_feat.device)
         out = torch.empty((B, U, self.feat_dim), dtype=torch.float32, device=input_feat.device)
-        xb = torch.zeros((grid.Mp, Cc), dtype=torch.bfloat16, device=input_feat.device)
+        xb = torch.zeros((grid.Mp, Cc), dtype=ops.act_dtype(), device=input_feat.device)
         yf = torch.zeros((grid.Mp, self.feat_dim), dtype=torch.float32, device=input_feat.device)
         for b in range(B):
-            xb.view(grid.H, grid.Wp, Cc)[:, :grid.W] = input_feat[b].reshape(grid.H, grid.W, Cc).to(torch.bfloat16)
+            xb.view(grid.H, grid.Wp, Cc)[:, :grid.W] = input_feat[b].reshape(grid.H, grid.W, Cc).to(xb.dtype)
             self.run(ws, handles[b], xb, 0, out_f=yf)
             out[b] = yf.view(grid.H, grid.Wp, -1)[:, :grid.W].reshape(U, -1)
         return out
@@ -442,8 +442,9 @@ class CrossAttFeatTrans(nn.Module):
         return torch.cat(outs, 0)
 
 
-def tokens_to_rows(tok, grid, dtype=torch.bfloat16):
-    """[U, C] token tensor -> padded-flat rows [Mp, C] (halo cells zero)."""
+def tokens_to_rows(tok, grid, dtype=None):
+    """[U, C] token tensor -> padded-flat rows [Mp, C] (halo cells zero) in the operand dtype."""
+    dtype = dtype or ops.act_dtype()
     Cc = tok.shape[-1]
     rows = torch.zeros((grid.H, grid.Wp, Cc), dtype=dtype, device=tok.device)
     rows[:, :grid.W] = tok.reshape(grid.H, grid.W, Cc).to(dtype)
@@ -523,7 +524,7 @@ class WorkspaceCache:
         self._lru = collections.OrderedDict()
 
     def get(self, grid, device, materialize_level0=False):
-        key = (str(device), grid.H, grid.W, bool(materialize_level0))
+        key = (str(device), grid.H, grid.W, bool(materialize_level0), ops.act_dtype())
         ws = self._lru.get(key)
         if ws is None:
             with torch.cuda.device(device):

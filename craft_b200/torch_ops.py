@@ -46,7 +46,10 @@ def _ld(t):
 def _chk(t, dtype, name):
     if t is None:
         return
-    if t.dtype != dtype:
+    if dtype == ACT:
+        if t.dtype not in (torch.bfloat16, torch.float16):
+            raise TypeError("%s: expected bfloat16 or float16, got %s" % (name, t.dtype))
+    elif t.dtype != dtype:
         raise TypeError("%s: expected %s, got %s" % (name, dtype, t.dtype))
     if not t.is_contiguous():
         raise ValueError("%s must be contiguous" % name)
@@ -66,25 +69,34 @@ def _op(schema):
     return deco
 
 
-bf16, f32, f64, i32 = torch.bfloat16, torch.float32, torch.float64, torch.int32
+bf16, f16, f32, f64, i32 = torch.bfloat16, torch.float16, torch.float32, torch.float64, torch.int32
+ACT = "act"        # placeholder dtype for _chk: either 16-bit operand type
+
+
+def _half(*ts):
+    """Which build of the library a call goes to: the fp16 one iff its 16-bit tensors are float16."""
+    kinds = {t.dtype for t in ts if t is not None and t.dtype in (bf16, f16)}
+    if len(kinds) > 1:
+        raise TypeError("mixed bf16 / fp16 operands in one call")
+    return f16 in kinds
 
 
 # ------------------------------------------------------------------------------------------------
 @_op("pack_tokens(Tensor src, int H, int W, int mode, Tensor(a!)? out_b, int colb, Tensor(b!)? out_f, int colf) -> ()")
 def pack_tokens(src, H, W, mode, out_b, colb, out_f, colf):
-    _chk(src, f32, "src"); _chk(out_b, bf16, "out_b"); _chk(out_f, f32, "out_f")
+    _chk(src, f32, "src"); _chk(out_b, ACT, "out_b"); _chk(out_f, f32, "out_f")
     assert src.shape[1] == H and src.shape[2] == W
     _lib.call("craft_pack_tokens", _ptr(src), src.shape[0], H, W, mode, _ptr(out_b), _ld(out_b), colb,
-              _ptr(out_f), _ld(out_f), colf, _stream())
+              _ptr(out_f), _ld(out_f), colf, _stream(), fp16=_half(out_b))
 
 
 @_op("unpack_tokens(Tensor buf, int col, int C, int H, int W, Tensor(a!) out) -> ()")
 def unpack_tokens(buf, col, Cc, H, W, out):
-    is_b = 1 if buf.dtype == bf16 else 0
+    is_b = 1 if buf.dtype in (bf16, f16) else 0
     if not is_b:
         _chk(buf, f32, "buf")
     _chk(out, f32, "out")
-    _lib.call("craft_unpack_tokens", _ptr(buf), is_b, _ld(buf), col, Cc, H, W, _ptr(out), _stream())
+    _lib.call("craft_unpack_tokens", _ptr(buf), is_b, _ld(buf), col, Cc, H, W, _ptr(out), _stream(), fp16=_half(buf))
 
 
 @_op("shift_gemm(Tensor A, Tensor B, int M, int Npad, int K, int BN, int[] taps, int a_koff, int b_koff, int H, int W, "
@@ -92,7 +104,7 @@ def unpack_tokens(buf, col, Cc, H, W, out):
      "Tensor(c!)? aux0, Tensor(d!)? aux1, int b_H, int b_W, int cluster, int stages, int a_share) -> ()")
 def shift_gemm(A, Bw, M, Npad, K, BN, taps, a_koff, b_koff, H, W, epilogue, alpha, act, bias, out_b, colb, out_f, colf,
                aux0, aux1, b_H, b_W, cluster, stages, a_share):
-    _chk(A, bf16, "A"); _chk(Bw, bf16, "B"); _chk(bias, f32, "bias"); _chk(out_b, bf16, "out_b")
+    _chk(A, ACT, "A"); _chk(Bw, ACT, "B"); _chk(bias, f32, "bias"); _chk(out_b, ACT, "out_b")
     _chk(out_f, f32, "out_f"); _chk(aux0, f32, "aux0"); _chk(aux1, f32, "aux1")
     a = GemmArgs()
     a.A, a.a_rows, a.lda, a.a_koff = A.data_ptr(), A.shape[0], A.shape[1], a_koff
@@ -111,11 +123,11 @@ def shift_gemm(A, Bw, M, Npad, K, BN, taps, a_koff, b_koff, H, W, epilogue, alph
     a.aux0, a.aux1 = _dp(aux0), _dp(aux1)
     if bias is not None:
         assert bias.numel() >= Npad
-    _lib.call("craft_shift_gemm", C.byref(a), _stream())
+    _lib.call("craft_shift_gemm", C.byref(a), _stream(), fp16=_half(A, Bw, out_b))
 
 
 def _scores_args(Q, K, H, W, M, d, w_pos, pos_table, R, clip, run_flag, ksplit):
-    _chk(Q, bf16, "Q"); _chk(K, bf16, "K"); _chk(pos_table, f32, "pos_table"); _chk(clip, f32, "clip")
+    _chk(Q, ACT, "Q"); _chk(K, ACT, "K"); _chk(pos_table, f32, "pos_table"); _chk(clip, f32, "clip")
     Mp = H * (W + 2)
     assert tuple(Q.shape) == (Mp, M * d) and tuple(K.shape) == (Mp, M * d)
     a = ScoresArgs()
@@ -143,7 +155,7 @@ def corr_build(Q, K, H, W, M, d, w_agg, w_pos, pos_table, R, clip, stat_sum, sta
     for l, lv in enumerate((lvl0, lvl1, lvl2, lvl3)):
         _chk(lv, f32, "level")
         a.lvl[l] = _dp(lv)
-    _lib.call("craft_corr_build", C.byref(a), _stream())
+    _lib.call("craft_corr_build", C.byref(a), _stream(), fp16=_half(Q, K))
 
 
 @_op("attn_lse(Tensor Q, Tensor K, int H, int W, int M, int d, float w_pos, Tensor? pos_table, int R, Tensor clip, "
@@ -154,13 +166,13 @@ def attn_lse(Q, K, H, W, M, d, w_pos, pos_table, R, clip, stat_max, lse_part, ls
     a.stat_max = stat_max.data_ptr()
     a.lse_part, a.lse2 = lse_part.data_ptr(), lse2.data_ptr()
     a.mask_radius = int(mask_radius)
-    _lib.call("craft_attn_lse", C.byref(a), _stream())
+    _lib.call("craft_attn_lse", C.byref(a), _stream(), fp16=_half(Q, K))
 
 
 @_op("attn_pv(Tensor Q, Tensor K, Tensor Vt, int H, int W, int M, int d, int F, float w_pos, Tensor? pos_table, int R, "
      "Tensor clip, Tensor lse2, Tensor(a!) out, int ksplit, bool zero_fill, int mask_radius) -> ()")
 def attn_pv(Q, K, Vt, H, W, M, d, F, w_pos, pos_table, R, clip, lse2, out, ksplit, zero_fill, mask_radius):
-    _chk(Q, bf16, "Q"); _chk(K, bf16, "K"); _chk(Vt, bf16, "Vt"); _chk(out, f32, "out"); _chk(lse2, f32, "lse2")
+    _chk(Q, ACT, "Q"); _chk(K, ACT, "K"); _chk(Vt, ACT, "Vt"); _chk(out, f32, "out"); _chk(lse2, f32, "lse2")
     Mp = H * (W + 2)
     assert Vt.shape[0] >= M * F and out.numel() >= ksplit * M * Mp * F
     a = PvArgs()
@@ -174,7 +186,7 @@ def attn_pv(Q, K, Vt, H, W, M, d, F, w_pos, pos_table, R, clip, lse2, out, kspli
     a.ksplit = ksplit
     a.zero_fill = 1 if zero_fill else 0
     a.mask_radius = int(mask_radius)
-    _lib.call("craft_attn_pv", C.byref(a), _stream())
+    _lib.call("craft_attn_pv", C.byref(a), _stream(), fp16=_half(Q, K, Vt))
 
 
 @_op("modes_finalize(Tensor O, int nsum, int M, int F, int H, int W, Tensor w_score, Tensor b_score, Tensor coeff, int gma, "
@@ -184,7 +196,7 @@ def modes_finalize(O, nsum, M, F, H, W, w_score, b_score, coeff, gma, x_b, colx,
     _chk(O, f32, "O")
     _lib.call("craft_modes_finalize", _ptr(O), nsum, M, F, _ptr(w_score), _ptr(b_score), _ptr(coeff), gma,
               _ptr(x_b), _ld(x_b), colx, _ptr(x_f), _ld(x_f), colxf, H, W,
-              _ptr(out_b), _ld(out_b), colb, _ptr(out_f), _ld(out_f), colf, int(pv_bk), _stream())
+              _ptr(out_b), _ld(out_b), colb, _ptr(out_f), _ld(out_f), colf, int(pv_bk), _stream(), fp16=_half(x_b, out_b))
 
 
 @_op("corr_stats_finalize(Tensor stat_sum, Tensor? flag, float n, Tensor(a!) mean_rstd) -> ()")
@@ -208,7 +220,7 @@ def soft_aggregate(x, basis, M, n, F, w, b, out):
 @_op("attn_dense(Tensor Q, Tensor K, int H, int W, int M, int d, float w_pos, Tensor? pos_table, int R, Tensor clip, "
      "Tensor? lse2, int mask_radius, Tensor(a!) out) -> ()")
 def attn_dense(Q, K, H, W, M, d, w_pos, pos_table, R, clip, lse2, mask_radius, out):
-    _chk(Q, bf16, "Q"); _chk(K, bf16, "K"); _chk(lse2, f32, "lse2"); _chk(out, f32, "out")
+    _chk(Q, ACT, "Q"); _chk(K, ACT, "K"); _chk(lse2, f32, "lse2"); _chk(out, f32, "out")
     a = DenseAttnArgs()
     a.Q, a.K = Q.data_ptr(), K.data_ptr()
     a.C, a.M, a.d, a.H, a.W = M * d, M, d, H, W
@@ -219,31 +231,31 @@ def attn_dense(Q, K, H, W, M, d, w_pos, pos_table, R, clip, lse2, mask_radius, o
     a.lse2 = _dp(lse2)
     a.mask_radius = int(mask_radius)
     a.out = out.data_ptr()
-    _lib.call("craft_attn_dense", C.byref(a), _stream())
+    _lib.call("craft_attn_dense", C.byref(a), _stream(), fp16=_half(Q, K))
 
 
 @_op("corr_lookup(Tensor? lvl0, Tensor? lvl1, Tensor? lvl2, Tensor? lvl3, int H, int W, Tensor coords, Tensor mean_rstd, "
      "Tensor(a!)? out_b, Tensor(b!)? out_nchw, int first_level) -> ()")
 def corr_lookup(lvl0, lvl1, lvl2, lvl3, H, W, coords, mean_rstd, out_b, out_nchw, first_level):
     arr = (C.c_void_p * 4)(*[_dp(lv) for lv in (lvl0, lvl1, lvl2, lvl3)])
-    _chk(coords, f32, "coords"); _chk(out_b, bf16, "out_b"); _chk(out_nchw, f32, "out_nchw")
+    _chk(coords, f32, "coords"); _chk(out_b, ACT, "out_b"); _chk(out_nchw, f32, "out_nchw")
     _lib.call("craft_corr_lookup", arr, H, W, _ptr(coords), _ptr(mean_rstd), _ptr(out_b), _ld(out_b),
-              _ptr(out_nchw), first_level, _stream())
+              _ptr(out_nchw), first_level, _stream(), fp16=_half(out_b))
 
 
 @_op("corr_lookup0(Tensor Q, Tensor K, int H, int W, int M, int d, float w_agg, float w_pos, Tensor? pos_table, int R, "
      "Tensor clip, Tensor coords, Tensor mean_rstd, Tensor(a!)? out_b, Tensor(b!)? out_nchw) -> ()")
 def corr_lookup0(Q, K, H, W, M, d, w_agg, w_pos, pos_table, R, clip, coords, mean_rstd, out_b, out_nchw):
-    _chk(Q, bf16, "Q"); _chk(K, bf16, "K"); _chk(out_b, bf16, "out_b"); _chk(out_nchw, f32, "out_nchw")
+    _chk(Q, ACT, "Q"); _chk(K, ACT, "K"); _chk(out_b, ACT, "out_b"); _chk(out_nchw, f32, "out_nchw")
     _lib.call("craft_corr_lookup0", _ptr(Q), _ptr(K), M, d, 1.0 / math.sqrt(d), float(w_agg), float(w_pos),
               _ptr(pos_table), R, _ptr(clip), H, W, _ptr(coords), _ptr(mean_rstd), _ptr(out_b), _ld(out_b),
-              _ptr(out_nchw), _stream())
+              _ptr(out_nchw), _stream(), fp16=_half(Q, K, out_b))
 
 
 @_op("convf1(Tensor flow, Tensor wt, Tensor bias, int H, int W, Tensor(a!) out_b, int colo) -> ()")
 def convf1(flow, wt, bias, H, W, out_b, colo):
-    _chk(flow, f32, "flow"); _chk(wt, f32, "wt"); _chk(out_b, bf16, "out_b")
-    _lib.call("craft_convf1", _ptr(flow), _ptr(wt), _ptr(bias), H, W, _ptr(out_b), _ld(out_b), colo, _stream())
+    _chk(flow, f32, "flow"); _chk(wt, f32, "wt"); _chk(out_b, ACT, "out_b")
+    _lib.call("craft_convf1", _ptr(flow), _ptr(wt), _ptr(bias), H, W, _ptr(out_b), _ld(out_b), colo, _stream(), fp16=_half(out_b))
 
 
 @_op("flow_update(Tensor(a!) coords1, Tensor(b!) flow, Tensor? delta, int H, int W) -> ()")
@@ -260,8 +272,8 @@ def init_coords(coords1, flow_init, H, W):
 @_op("upsample_flow(Tensor mask, Tensor flow, int H, int W, Tensor(a!) out) -> ()")
 def upsample_flow(mask, flow, H, W, out):
     _chk(flow, f32, "flow"); _chk(out, f32, "out")
-    is_b = 1 if mask.dtype == bf16 else 0
-    _lib.call("craft_upsample_flow", _ptr(mask), is_b, _ld(mask), _ptr(flow), H, W, _ptr(out), _stream())
+    is_b = 1 if mask.dtype in (bf16, f16) else 0
+    _lib.call("craft_upsample_flow", _ptr(mask), is_b, _ld(mask), _ptr(flow), H, W, _ptr(out), _stream(), fp16=_half(mask))
 
 
 @_op("nhwc_instnorm_stats(Tensor x, int N, int HW, int C, float eps, Tensor(a!) part, Tensor(b!) ab) -> ()")

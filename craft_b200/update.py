@@ -14,11 +14,11 @@ from .setrans import ExpandedFeatTrans, get_workspace, _require_inference
 
 
 def _rows_in(x_chw, grid, cols=None, col0=0):
-    """[C,h,w] fp32 -> bf16 padded-flat rows [Mp, cols] with the channels at col0 (standalone boundary only)."""
+    """[C,h,w] fp32 -> operand-dtype padded-flat rows [Mp, cols] with the channels at col0 (standalone boundary only)."""
     Cc = x_chw.shape[0]
     cols = cols or ((Cc + 63) // 64) * 64
-    buf = torch.zeros((grid.H, grid.Wp, cols), dtype=torch.bfloat16, device=x_chw.device)
-    buf[:, :grid.W, col0:col0 + Cc] = x_chw.permute(1, 2, 0).to(torch.bfloat16)
+    buf = torch.zeros((grid.H, grid.Wp, cols), dtype=ops.act_dtype(), device=x_chw.device)
+    buf[:, :grid.W, col0:col0 + Cc] = x_chw.permute(1, 2, 0).to(buf.dtype)
     return buf.view(grid.Mp, cols)
 
 
@@ -178,7 +178,7 @@ class GMAUpdateBlock(nn.Module):
         for b in range(B):
             ops.pack_tokens(net[b].float().contiguous(), g, ops.PACK_COPY, out_b=ws.X, colb=0, out_f=ws.Hm)
             ops.pack_tokens(inp[b].float().contiguous(), g, ops.PACK_COPY, out_b=ws.X, colb=128)
-            ws.CORR.view(g.H, g.Wp, 384)[:, :g.W, :324] = corr[b].permute(1, 2, 0).to(torch.bfloat16)
+            ws.CORR.view(g.H, g.Wp, 384)[:, :g.W, :324] = corr[b].permute(1, 2, 0).to(ws.CORR.dtype)
             ws.flow.view(g.H, g.Wp, 2)[:, :g.W] = flow[b].float().permute(1, 2, 0)
             self.step(ws, atts[b])
             ops.unpack_tokens(ws.Hm, 0, 128, g, out=net_o[b])

@@ -25,10 +25,11 @@ def test_library_exports_every_declared_symbol():
     if not os.path.isfile(_lib.LIB_PATH):
         import __graft_entry__ as ge
         ge.build()
-    lib = _lib.load()
-    for name in _header_functions():
-        assert hasattr(lib, name), "libcraft_b200.so does not export %s" % name
-    assert lib.craft_b200_abi_version() == _lib.ABI_VERSION
+    for fp16 in (False, True):          # both builds: bf16 operands (default) and fp16 operands (fp32-parity tier)
+        lib = _lib.load(fp16)
+        for name in _header_functions():
+            assert hasattr(lib, name), "%s does not export %s" % ("fp16 build" if fp16 else "bf16 build", name)
+        assert lib.craft_b200_abi_version() == _lib.ABI_VERSION
 
 
 def test_ctypes_mirror_matches_header():
@@ -169,5 +170,6 @@ def test_no_global_load_is_hoisted_above_the_pdl_wait():
         pytest.skip("cuobjdump not available")
     sys.path.insert(0, os.path.join(ROOT, "profiles"))
     from audit_pdl_hoist import audit
-    bad = audit(_lib.LIB_PATH)
-    assert not bad, bad
+    for path in (_lib.LIB_PATH, _lib.LIB_PATH_FP16):
+        bad = audit(path)
+        assert not bad, (path, bad)
