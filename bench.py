@@ -535,9 +535,11 @@ def run_ours(args, cfg):
         total = world * args.steps
         line = dict(metric=cfg["metric"], value=total / (ms * 1e-3), unit="pairs/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
-                    vs_baseline=None, dtype="bf16",
+                    vs_baseline=None, dtype={"bf16": "bf16", "fp16": "fp16", "fp32-parity": "fp16"}[model.precision],
                     data="synthetic integer-noise pairs (distinct per step and per rank), weights: " + wsrc,
                     config=dict(workload=cfg["workload"],
+                                precision="%s tier: tensor-core operands %s, fp32 accumulation/state (CRAFT_B200_PRECISION)"
+                                          % (model.precision, str(model.act_dtype).replace("torch.", "")),
                                 parallelism="pairs sharded over %d ranks (rank r owns pairs r, r+N, ...), no collective" % world,
                                 l2="inputs larger than L2: the per-step working set (68 MB pooled correlation pyramid, 30 MB "
                                    "P.V partial sums, >100 MB of encoder activations) exceeds the 126 MB L2 and every "

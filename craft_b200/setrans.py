@@ -519,12 +519,13 @@ class WorkspaceCache:
     module calls share the module-level one.  Bounded: KITTI-style variable input sizes would otherwise
     accumulate ~150 MB per shape."""
 
-    def __init__(self, capacity=4):
+    def __init__(self, capacity=6):
         self.capacity = capacity
         self._lru = collections.OrderedDict()
 
-    def get(self, grid, device, materialize_level0=False):
-        key = (str(device), grid.H, grid.W, bool(materialize_level0), ops.act_dtype())
+    def get(self, grid, device, materialize_level0=False, slot=0):
+        """slot: independent buffer sets for the same grid (training keeps one correlation pyramid per batch element)."""
+        key = (str(device), grid.H, grid.W, bool(materialize_level0), ops.act_dtype(), slot)
         ws = self._lru.get(key)
         if ws is None:
             with torch.cuda.device(device):

@@ -181,5 +181,58 @@ def main():
               "keys", len(rec), flush=True)
 
 
+GRAD_KEYS = ["fnet.conv1.weight", "fnet.layer3.1.conv2.weight", "cnet.conv1.weight",
+             "f2_trans.setrans.query.weight", "f2_trans.setrans.key.weight", "f2_trans.setrans.out_trans.first_linear.weight",
+             "f2_trans.setrans.out_trans.input_skip_coeff", "f2_trans.vispos_encoder.pos_coder.biases",
+             "corr_fn.setrans.query.weight", "corr_fn.setrans.query.bias", "corr_fn.setrans.attn_softaggr.feat2score.weight",
+             "corr_fn.vispos_encoder.pos_coder.biases", "att.setrans.query.weight", "att.setrans.key.weight",
+             "att.vispos_encoder.pos_coder.biases", "update_block.aggregator.first_linear.weight",
+             "update_block.aggregator.feat_softaggr.feat2score.weight", "update_block.aggregator.input_skip_coeff",
+             "update_block.encoder.convc1.weight", "update_block.gru.convz1.weight", "update_block.gru.convq2.weight",
+             "update_block.flow_head.conv2.weight", "update_block.mask.2.weight"]
+
+
+def training_loss(flow_preds, flow_gt, gamma=0.8):
+    """train.py:44-73 sequence_loss without the validity mask: exponentially weighted L1 over the iterations."""
+    n = len(flow_preds)
+    return sum(gamma ** (n - i - 1) * (flow_preds[i] - flow_gt).abs().mean() for i in range(n))
+
+
+def grad_case():
+    """Gradients of the EXECUTED reference in training mode (dropout_prob = 0 so that the run is deterministic,
+    BatchNorm frozen as train.py does after the chairs stage): the pin of craft_b200/train_path.py."""
+    kw = dict(dropout_prob=0.0)
+    H = W = 128
+    iters = 3
+    args = craft_args(**kw)
+    model, _ = build_reference_model(args, checkpoint=None)
+    sd = seeded_state(kw)
+    # seeded positional-bias tables are all-zero and gamma-like scalars sit at their init: spread the tables so
+    # that their gradient paths are exercised
+    g = torch.Generator().manual_seed(77)
+    for k in sd:
+        if k.endswith("pos_coder.biases"):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.3
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    model.freeze_bn()
+    i1, i2 = synthetic_pair(H, W)
+    flow_gt = torch.zeros(1, 2, H, W)
+    flow_gt[:, 0], flow_gt[:, 1] = 3.0, 2.0
+    preds = model(i1, i2, iters=iters, test_mode=0)
+    loss = training_loss(preds, flow_gt)
+    loss.backward()
+    named = dict(model.named_parameters())
+    rec = dict(name="seeded_setrans_128_grad", args=kw, H=H, W=W, iters=iters, loss=float(loss),
+               pos_seed=77, flow_last=preds[-1][0].detach().clone(),
+               grads={k: named[k].grad.detach().clone() for k in GRAD_KEYS},
+               grad_norms={k: float(v.grad.norm()) for k, v in named.items() if v.grad is not None})
+    torch.save(rec, os.path.join(OUT, "seeded_setrans_128_grad.pt"))
+    print("seeded_setrans_128_grad loss", float(loss), "params with grad", len(rec["grad_norms"]))
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["grad"]:
+        grad_case()
+    else:
+        main()

@@ -71,8 +71,8 @@ def test_forward_refuses_cpu_and_bad_shapes():
     with torch.no_grad():
         with pytest.raises(RuntimeError, match="no CPU path"):
             m(torch.zeros(1, 3, 64, 64), torch.zeros(1, 3, 64, 64))
-    with pytest.raises(RuntimeError, match="forward-only"):
-        m(torch.zeros(1, 3, 64, 64), torch.zeros(1, 3, 64, 64))     # grad mode + trainable params
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 3, 64, 64), torch.zeros(1, 3, 64, 64))     # grad mode (training path) is CUDA-only too
 
 
 def test_geometry_and_weight_packing():
