@@ -320,7 +320,7 @@ def _kernel_table(model, cfg, dev, pk):
     from craft_b200 import hotpath as hp, ops
     from craft_b200.ops import TokenGrid
     g = TokenGrid(cfg["H"] // 8, cfg["W"] // 8)
-    ws = model._workspaces.get(g, dev, model.materialize_level0)
+    ws = model.workspace_for(8 * g.H, 8 * g.W, dev)
     U = float(g.U)
     ub = model.update_block
     uw = ub.weights(g)

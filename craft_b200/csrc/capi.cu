@@ -672,7 +672,14 @@ int craft_corr_lookup0(const void* Q, const void* K, int M, int d, float scale, 
   p.M = M; p.d = d; p.scale = scale; p.w_agg = w_agg; p.w_pos = w_pos; p.pos_table = pos_table; p.Rb = R;
   p.clip = clip; p.coords = coords; p.stats = mean_rstd; p.out_b = static_cast<cb::act_t*>(out_bf16);
   p.ldb = ldb; p.out_nchw = out_nchw;
-  launch_k(cb::corr_lookup0_kernel, dim3((g.Mp + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), p, g);
+  static std::atomic<unsigned long long> set{0};
+  static int cap = -1;              // CRAFT_LOOKUP0_CAP: staged cells per 4x2 query patch (0 = read every row from L2)
+  if (cap < 0) { const char* e = getenv("CRAFT_LOOKUP0_CAP"); cap = e ? atoi(e) : cb::kL0Cap; if (cap > 400) cap = 400; if (cap < 0) cap = 0; }
+  const int smem = cap * 512;
+  p.cap = cap;
+  if (ensure_smem(cb::corr_lookup0_kernel, 400 * 512, set, "corr_lookup0")) return -1;
+  const int patches = ((W + cb::kL0PX - 1) / cb::kL0PX) * ((H + cb::kL0PY - 1) / cb::kL0PY);
+  launch_k(cb::corr_lookup0_kernel, dim3(patches), dim3(256), smem, static_cast<cudaStream_t>(stream), p, g);
   return check_launch("corr_lookup0");
 }
 

@@ -5,6 +5,7 @@
 // row are halo cells that always hold zeros, so a conv tap (dy,dx), |dx| <= 2, is the row offset
 // dy*Wp + dx (gemm.cuh).  Mp = h * Wp rows.
 #pragma once
+#include <limits.h>
 #include "common.cuh"
 
 namespace cb {
@@ -191,25 +192,74 @@ struct Lookup0Params {
   act_t* out_b;     // [Mp, ldb], channels 0..80
   int ldb;
   float* out_nchw;          // [324,H,W] (channels 0..80) or nullptr
+  int cap;                  // cells of shared memory available for staging a patch's bounding box (0: read from L2)
 };
+
+// Block = 8 warps = a 4 x 2 patch of queries, one warp per query.  The lookup windows of neighbouring queries
+// overlap almost completely wherever the flow is smooth (a 4 x 2 patch with locally constant flow needs
+// 13 x 11 = 143 distinct key rows, not 8 x 100), so the block first stages the BOUNDING BOX of its eight
+// windows in shared memory (one coalesced 512-byte row per cell, at most kL0Cap cells = 96 KB) and every warp
+// takes its 100 rows from there.  A patch whose windows scatter (box > kL0Cap cells: motion boundaries) falls
+// back to reading its rows straight from L2, as the round-1 kernel did for every query (51 KB per query,
+// 367 MB per launch at 448x1024 = the L2-bandwidth bound it ran at).
+constexpr int kL0Cap = 192;
+constexpr int kL0PX = 4, kL0PY = 2;
 
 __global__ void __launch_bounds__(256) corr_lookup0_kernel(Lookup0Params p, Grid2 g) {
   pdl_launch_dependents();
   pdl_wait();
 
   constexpr int R = 4, D = 2 * R + 1, WN = D + 1, C = 256, NC = WN * WN;
+  extern __shared__ uint4 s_rows[];                 // [kL0Cap][32] staged key rows
   __shared__ float win[8][NC + 4];
   __shared__ float smodes[8][NC][4];
   __shared__ float tbl[232];
+  __shared__ int s_org[8][2];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.pos_table) {
     const int n = (2 * p.Rb + 1) * (2 * p.Rb + 1);
     for (int i = threadIdx.x; i < n; i += 256) tbl[i] = p.pos_table[i] * p.w_pos;
   }
+  const int npx = (g.W + kL0PX - 1) / kL0PX;
+  const int py = blockIdx.x / npx, px = blockIdx.x - py * npx;
+  const int qx = px * kL0PX + (wib % kL0PX), qy = py * kL0PY + (wib / kL0PX);
+  const bool qvalid = qx < g.W && qy < g.H;
+  const int q = qy * g.Wp + qx;
+  float cx = 0.f, cy = 0.f;
+  if (qvalid) { cx = p.coords[2 * q]; cy = p.coords[2 * q + 1]; }
+  const float fx0 = floorf(cx), fy0 = floorf(cy);
+  const float ax = cx - fx0, ay = cy - fy0;
+  // window origin, clamped so that far-off-image coordinates cannot overflow the box arithmetic (their
+  // windows are entirely out of bounds either way)
+  const int x0 = static_cast<int>(fminf(fmaxf(fx0, -32768.f), 32768.f)) - R;
+  const int y0 = static_cast<int>(fminf(fmaxf(fy0, -32768.f), 32768.f)) - R;
+  if (lane == 0) { s_org[wib][0] = qvalid ? x0 : INT_MAX; s_org[wib][1] = qvalid ? y0 : INT_MAX; }
   __syncthreads();
-  const int q = blockIdx.x * 8 + wib;
-  const int qy = q / g.Wp, qx = q - qy * g.Wp;
-  if (q >= g.Mp || qx >= g.W) return;      // whole warp
+  int xmin = INT_MAX, ymin = INT_MAX, xmax = INT_MIN, ymax = INT_MIN;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ox = s_org[i][0], oy = s_org[i][1];
+    if (ox != INT_MAX) { xmin = min(xmin, ox); xmax = max(xmax, ox); ymin = min(ymin, oy); ymax = max(ymax, oy); }
+  }
+  if (xmin == INT_MAX) return;                      // no real query in this patch (block-uniform)
+  // only the part of the box inside the key grid is staged; cells outside it are zeros by definition
+  const int bx0 = max(xmin, 0), by0 = max(ymin, 0);
+  const int bx1 = min(xmax + WN, g.W), by1 = min(ymax + WN, g.H);     // exclusive
+  const int bw = max(bx1 - bx0, 0), bh = max(by1 - by0, 0);
+  const long long cells = static_cast<long long>(xmax - xmin + WN) * (ymax - ymin + WN);
+  const bool staged = cells <= p.cap;               // block-uniform (conservative: unclipped box); cap 0 = never
+  if (staged) {
+    // asynchronous copies (LDGSTS): all rows of a warp are in flight at once, no register round trip
+    for (int c = wib; c < bw * bh; c += 8) {
+      const int ky = by0 + c / bw, kx = bx0 + c % bw;
+      const uint4* src = reinterpret_cast<const uint4*>(p.K + (static_cast<size_t>(ky) * g.Wp + kx) * C) + lane;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&s_rows[c * 32 + lane])), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  __syncthreads();
+  if (!qvalid) return;                              // whole warp
   // this lane's 8 query channels, fp32
   float qf[8];
   {
@@ -222,28 +272,32 @@ __global__ void __launch_bounds__(256) corr_lookup0_kernel(Lookup0Params p, Grid
       qf[2 * k + 1] = v.y;
     }
   }
-  const float cx = p.coords[2 * q], cy = p.coords[2 * q + 1];
   const float mean = p.stats[0], rstd = p.stats[1];
   const float clipv = *p.clip;
-  const float fx0 = floorf(cx), fy0 = floorf(cy);
-  const float ax = cx - fx0, ay = cy - fy0;
-  const int x0 = static_cast<int>(fx0) - R, y0 = static_cast<int>(fy0) - R;
   const int lanes_per_mode = p.d >> 3;    // 8 channels per lane; 8, 16 or 32 (d = 64, 128, 256)
   const bool is_writer = (lane & (lanes_per_mode - 1)) == 0;
   const int mode_of_lane = (lanes_per_mode == 8) ? (lane >> 3) : (lanes_per_mode == 16 ? (lane >> 4) : 0);
-  // phase 1: one coalesced 512-byte key row per window cell; per-mode dot products by shuffle.
-  // The 10 loads of a window row are issued back to back (memory-level parallelism: a dependent
-  // load -> shuffle chain per cell would serialise 100 L2 round trips).
+  // phase 1: one 512-byte key row per window cell (lane = 8 channels); per-mode dot products by shuffle.
+  // The 10 rows of a window row are fetched back to back (memory-level parallelism).
 #pragma unroll 1
   for (int r = 0; r < WN; ++r) {
     const int ky = y0 + r;                  // warp-uniform
     if (ky < 0 || ky >= g.H) continue;
-    const uint4* rowbase = reinterpret_cast<const uint4*>(p.K + (static_cast<size_t>(ky) * g.Wp) * C) + lane;
     uint4 kk[WN];
+    if (staged) {
+      const int rowi = (ky - by0) * bw - bx0;      // + kx = cell index inside the staged box
 #pragma unroll
-    for (int c = 0; c < WN; ++c) {
-      const int kx = x0 + c;
-      kk[c] = (kx >= 0 && kx < g.W) ? __ldg(rowbase + static_cast<size_t>(kx) * (C / 8)) : make_uint4(0, 0, 0, 0);
+      for (int c = 0; c < WN; ++c) {
+        const int kx = x0 + c;
+        kk[c] = (kx >= 0 && kx < g.W) ? s_rows[(rowi + kx) * 32 + lane] : make_uint4(0, 0, 0, 0);
+      }
+    } else {
+      const uint4* rowbase = reinterpret_cast<const uint4*>(p.K + (static_cast<size_t>(ky) * g.Wp) * C) + lane;
+#pragma unroll
+      for (int c = 0; c < WN; ++c) {
+        const int kx = x0 + c;
+        kk[c] = (kx >= 0 && kx < g.W) ? __ldg(rowbase + static_cast<size_t>(kx) * (C / 8)) : make_uint4(0, 0, 0, 0);
+      }
     }
 #pragma unroll
     for (int c = 0; c < WN; ++c) {

@@ -146,6 +146,13 @@ class CRAFT(nn.Module):
             self.encoder_tf32 = True
         return self
 
+    def workspace_for(self, H, W, device=None):
+        """The device buffers this model uses for H x W images (token grid H/8 x W/8) at its precision tier --
+        what tests and profiling scripts inspect after a forward."""
+        device = device or next(self.parameters()).device
+        with torch.cuda.device(device), ops.precision(self.act_dtype):
+            return self._workspaces.get(TokenGrid(H // 8, W // 8), device, self.materialize_level0)
+
     def freeze_bn(self):
         for m in self.modules():
             if isinstance(m, nn.BatchNorm2d):

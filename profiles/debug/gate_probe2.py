@@ -15,7 +15,7 @@ for graph in (False, True):
     with torch.no_grad():
         lo, up = m(i1, i2, iters=4, test_mode=1)
     torch.cuda.synchronize()
-    ws = m._workspaces.get(g, torch.device("cuda", 0), False)
+    ws = m.workspace_for(8 * g.H, 8 * g.W)
     print("graph", graph, "mean flow", up.mean((0, 2, 3)).tolist(), "stat_max", ws.stat_max.tolist(), "flag", ws.flag.tolist(),
           "clips", ws.clip_corr.item(), ws.clip_f2.item(), ws.clip_att.item(),
           "diag", [(n, getattr(m, n).setrans.max_attn, getattr(m, n).setrans.clamp_count) for n in ("corr_fn", "f2_trans", "att")])

@@ -20,11 +20,11 @@ def main(which, reps):
     model, _ = _state_dict()
     model = model.to(dev).eval()
     a, b = _pairs(1, dev)[0]
-    with torch.no_grad():
+    with torch.no_grad(), ops.precision(model.act_dtype):
         model(a, b, iters=1, test_mode=1)       # fills every workspace buffer with realistic data
         torch.cuda.synchronize()
         g = TokenGrid(H // 8, W // 8)
-        ws = model._workspaces.get(g, dev, model.materialize_level0)
+        ws = model.workspace_for(8 * g.H, 8 * g.W, dev)
         ub = model.update_block
         uw = ub.weights(g)
         att_tbl = model.att.vispos_encoder.table()

@@ -121,7 +121,7 @@ def test_seams_match_reference(name):
         model(i1.cuda(), i2.cuda(), iters=1, test_mode=1)
     torch.cuda.synchronize()
     g = TokenGrid(rec["H"] // 8, rec["W"] // 8)
-    ws = model._workspaces.get(g, torch.device("cuda", 0), model.materialize_level0)
+    ws = model.workspace_for(8 * g.H, 8 * g.W)
 
     def rows(buf, c0, c1):
         return buf.float().view(g.H, g.Wp, -1)[:, :g.W, c0:c1].permute(2, 0, 1).cpu()
@@ -244,7 +244,7 @@ def test_real_frame_pair_error_trajectory_and_seams():
         model(i1, i2, iters=1, test_mode=1)
     torch.cuda.synchronize()
     g = TokenGrid(rec["H"] // 8, rec["W"] // 8)
-    ws = model._workspaces.get(g, torch.device("cuda", 0), model.materialize_level0)
+    ws = model.workspace_for(8 * g.H, 8 * g.W)
 
     def rows(buf, c0, c1):
         return buf.float().view(g.H, g.Wp, -1)[:, :g.W, c0:c1].permute(2, 0, 1)[:, ::4, ::4].cpu()

@@ -380,7 +380,8 @@ def test_fused_encoder_matches_module_path(kind):
 
 
 @pytest.mark.parametrize("H,W,M,d,clipv", [(16, 24, 4, 64, float("inf")), (17, 22, 4, 64, 2.0), (16, 16, 1, 256, float("inf"))])
-def test_corr_lookup0_on_demand(H, W, M, d, clipv):
+@pytest.mark.parametrize("spread", [5.0, 0.4, "mixed", "far"])
+def test_corr_lookup0_on_demand(H, W, M, d, clipv, spread):
     """Level-0 lookup recomputed from Q/K rows == lookup on the materialised (oracle) level-0 volume."""
     grid = TokenGrid(H, W)
     g = torch.Generator(device=DEV).manual_seed(31)
@@ -391,7 +392,18 @@ def test_corr_lookup0_on_demand(H, W, M, d, clipv):
     raw = (s * torch.softmax(s * w_agg, dim=0)).sum(0) if M > 1 else s[0]
     mean, rstd = raw.mean().item(), 1.0 / math.sqrt(raw.var(unbiased=False).item() + 1e-12)
     vol = ((raw - mean) * rstd).reshape(1, grid.U, H, W)
-    coords = R.coords_grid(1, H, W, DEV) + torch.randn((1, 2, H, W), device=DEV, generator=g) * 5
+    # spread 5: windows of a 4x2 query patch scatter (direct-from-L2 path); 0.4: smooth flow, the patch's bounding
+    # box is staged in shared memory; "mixed": smooth with a motion boundary; "far": windows partly / wholly off-image
+    noise = torch.randn((1, 2, H, W), device=DEV, generator=g)
+    if spread == "mixed":
+        flow = noise * 0.3 + torch.tensor([2.5, -1.5], device=DEV).view(1, 2, 1, 1)
+        flow[:, :, :, W // 2:] += torch.tensor([-9.0, 6.0], device=DEV).view(1, 2, 1, 1)
+    elif spread == "far":
+        flow = noise * 0.5 + torch.tensor([W - 3.0, -(H - 2.0)], device=DEV).view(1, 2, 1, 1)
+        flow[:, :, : H // 2] = noise[:, :, : H // 2] * 0.5 + torch.tensor([-6.0, 3.0], device=DEV).view(1, 2, 1, 1)
+    else:
+        flow = noise * spread
+    coords = R.coords_grid(1, H, W, DEV) + flow
     ref = R.corr_lookup([vol.reshape(grid.U, 1, H, W)], coords)[0]          # level 0 only: [81,H,W]
     Q, K = rows_from_nchw(q, grid), rows_from_nchw(k, grid)
     cbuf = rows_from_nchw(coords[0], grid, dtype=torch.float32)
