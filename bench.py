@@ -31,6 +31,12 @@ CONFIGS = {
     "gma": dict(H=448, W=1024, iters=12, args=dict(use_setrans=False), weights="seeded", metric=METRIC,
                 workload="CRAFT f2full + gma.Attention/Aggregate (use_setrans=False), 448x1024 pair, iters=12, "
                          "test_mode=1, batch 1"),
+    # BASELINE.json configs[3]: train_ddp.py FlyingThings-shape (400x720 crop, train-craft-f2full.sh:3), bs 2 per GPU,
+    # DDP gradient all-reduce the only collective.  A step = forward + backward + AdamW step on one synthetic batch.
+    "train": dict(H=400, W=720, iters=12, args={}, weights="seeded", batch=2,
+                  metric="training image-pairs/sec at 400x720 iters=12, bs 2/GPU",
+                  workload="train_ddp.py shape: CRAFT(craft+f2full+setrans) 400x720, iters=12, batch 2 per GPU, fwd+bwd+AdamW, "
+                           "DDP(find_unused_parameters=True)"),
 }
 
 
@@ -561,6 +567,87 @@ def run_ours(args, cfg):
         dist.destroy_process_group()
 
 
+def run_train(args, cfg):
+    """BASELINE configs[3]: synthetic DDP training step (train_ddp.py:185-256 wiring) -- forward through
+    craft_b200/train_path.py, backward, clip, AdamW.  --dropout-prob: the reference's training default keeps
+    token/attention dropout on (0.1 / 0.2), which forces the attention blocks onto the PyTorch restatement in
+    forward too; 0 runs their forward on the sm_100a kernels."""
+    import torch
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from craft_b200 import _lib
+    from craft_b200.network import CRAFT
+    from craft_b200.testing import craft_args, synthetic_pair
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29671")
+    if world > 1 or "RANK" in os.environ:
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+    kw = dict(cfg["args"])
+    if args.dropout_prob is not None:
+        kw["dropout_prob"] = args.dropout_prob
+    torch.manual_seed(1234)
+    model = CRAFT(craft_args(**kw)).to(dev)
+    model.train()
+    model.freeze_bn()
+    ddp = DDP(model, device_ids=[local], find_unused_parameters=True)
+    opt = torch.optim.AdamW(ddp.parameters(), lr=1.25e-4, weight_decay=1e-5, eps=1e-8)
+    B, H, W, ITERS = cfg["batch"], cfg["H"], cfg["W"], cfg["iters"]
+    batches = []
+    for i in range(2):
+        a, b = synthetic_pair(H, W, seed=1234 + 10 * rank + i, B=B)
+        batches.append((a.pin_memory(), b.pin_memory()))
+    gt = torch.zeros(B, 2, H, W, device=dev)
+    gt[:, 0], gt[:, 1] = 3.0, 2.0
+
+    def step(i):
+        a, b = batches[i % 2]
+        preds = ddp(a.to(dev, non_blocking=True), b.to(dev, non_blocking=True), iters=ITERS, test_mode=0)
+        loss = sum(0.8 ** (ITERS - k - 1) * (p - gt).abs().mean() for k, p in enumerate(preds))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(ddp.parameters(), 1.0)
+        opt.step()
+        return loss
+
+    for i in range(args.warmup):
+        step(i)
+    dist.barrier()
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step(i)
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    if rank == 0:
+        pairs = world * B * args.steps
+        dp = model.intra_trans_config.attention_probs_dropout_prob
+        line = dict(metric=cfg["metric"], value=pairs / (ms * 1e-3), unit="pairs/s", n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype=model.precision, data="synthetic integer-noise batches, random-init weights (seed 1234)",
+                    config=dict(workload=cfg["workload"], dropout_prob=dp,
+                                attention_forward="sm_100a kernels (dropout off)" if dp == 0 else
+                                "PyTorch restatement (dropout %.1f live, reference training default)" % dp,
+                                collective="DDP gradient all-reduce (NCCL) only"),
+                    e2e=dict(value=pairs / (ms * 1e-3), unit="pairs/s", h2d_bytes_per_step=2 * B * 3 * H * W * 4,
+                             d2h_bytes_per_step=0, note="host batches are uploaded inside the timed step"),
+                    gpu_launches=int(_lib.launch_count() - n0), final_loss=float(loss))
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -571,6 +658,8 @@ def main():
                     help="sintel = BASELINE configs[1] (default, the metric's configuration); kitti = configs[4] shape; "
                          "gma = configs[2] variant")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dropout-prob", type=float, default=None,
+                    help="--config train only: override the transformers' dropout (reference training default 0.1/0.2)")
     ap.add_argument("--gpu-reference", action="store_true",
                     help="also time the unmodified reference in eager CUDA (fp32 and fp16 autocast) on the same GPU "
                          "(informational leg `gpu_reference`, N=1 only)")
@@ -580,7 +669,13 @@ def main():
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.config == "train":
+        if args.impl == "reference":
+            print(json.dumps(dict(impl="reference", unavailable="the reference's training step needs CUDA + datasets; "
+                                  "the CPU arm times inference configs only")))
+        else:
+            run_train(args, cfg)
+    elif args.impl == "reference":
         run_reference(args, cfg)
     else:
         run_ours(args, cfg)

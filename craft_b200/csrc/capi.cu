@@ -673,8 +673,12 @@ int craft_corr_lookup0(const void* Q, const void* K, int M, int d, float scale, 
   p.clip = clip; p.coords = coords; p.stats = mean_rstd; p.out_b = static_cast<cb::act_t*>(out_bf16);
   p.ldb = ldb; p.out_nchw = out_nchw;
   static std::atomic<unsigned long long> set{0};
-  static int cap = -1;              // CRAFT_LOOKUP0_CAP: staged cells per 4x2 query patch (0 = read every row from L2)
-  if (cap < 0) { const char* e = getenv("CRAFT_LOOKUP0_CAP"); cap = e ? atoi(e) : cb::kL0Cap; if (cap > 400) cap = 400; if (cap < 0) cap = 0; }
+  // CRAFT_LOOKUP0_CAP: cells of shared memory for staging a 4x2 query patch's bounding box.  Default 0 = every
+  // row straight from L2: measured (profiles/r02_lookup0_cap_sweep.txt) 45.6 us, against 55 us with 144-192 staged
+  // cells (2 CTAs/SM) and 87 us with >= 256 (1 CTA/SM) -- the kernel is latency/issue bound, not L2 bound, and
+  // the staged variant pays for its shared memory with occupancy.
+  static int cap = -1;
+  if (cap < 0) { const char* e = getenv("CRAFT_LOOKUP0_CAP"); cap = e ? atoi(e) : 0; if (cap > 400) cap = 400; if (cap < 0) cap = 0; }
   const int smem = cap * 512;
   p.cap = cap;
   if (ensure_smem(cb::corr_lookup0_kernel, 400 * 512, set, "corr_lookup0")) return -1;

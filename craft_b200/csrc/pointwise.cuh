@@ -195,13 +195,14 @@ struct Lookup0Params {
   int cap;                  // cells of shared memory available for staging a patch's bounding box (0: read from L2)
 };
 
-// Block = 8 warps = a 4 x 2 patch of queries, one warp per query.  The lookup windows of neighbouring queries
-// overlap almost completely wherever the flow is smooth (a 4 x 2 patch with locally constant flow needs
-// 13 x 11 = 143 distinct key rows, not 8 x 100), so the block first stages the BOUNDING BOX of its eight
-// windows in shared memory (one coalesced 512-byte row per cell, at most kL0Cap cells = 96 KB) and every warp
-// takes its 100 rows from there.  A patch whose windows scatter (box > kL0Cap cells: motion boundaries) falls
-// back to reading its rows straight from L2, as the round-1 kernel did for every query (51 KB per query,
-// 367 MB per launch at 448x1024 = the L2-bandwidth bound it ran at).
+// Block = 8 warps = a 4 x 2 patch of queries, one warp per query; every window cell is one coalesced 512-byte
+// key row from L2 (51 KB per query, 367 MB per launch at 448x1024).
+// Optional staging (p.cap > 0, CRAFT_LOOKUP0_CAP): the windows of neighbouring queries overlap almost completely
+// wherever the flow is smooth (a 4 x 2 patch with locally constant flow needs 13 x 11 = 143 distinct key rows,
+// not 8 x 100), so the block can stage the BOUNDING BOX of its eight windows in shared memory with cp.async and
+// serve every warp from there; patches whose windows scatter fall back to L2.  Measured in round 2: bit-identical
+// and SLOWER (55 us vs 45.6 us): the shared memory costs occupancy and the kernel is bound by the latency of its
+// load -> FMA -> shuffle chains, not by L2 bandwidth.  Kept switchable, off by default.
 constexpr int kL0Cap = 192;
 constexpr int kL0PX = 4, kL0PY = 2;
 
