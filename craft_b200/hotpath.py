@@ -29,6 +29,8 @@ class PackedWeights:
 
     def get(self, key, params, build):
         ver = (ops.act_dtype(),) + tuple((p.data_ptr(), p._version, p.device) for p in params)
+        # nn.DataParallel replicas share this object (replicate() shallow-copies module __dict__s): one entry per device
+        key = (key, str(params[0].device) if params else None)
         hit = self._store.get(key)
         if hit is None or hit[0] != ver:
             with torch.no_grad():

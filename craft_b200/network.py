@@ -260,8 +260,10 @@ class CRAFT(nn.Module):
         # nn.DataParallel calls each replica from its own thread with another device current
         with torch.cuda.device(image1.device), ops.precision(self.act_dtype):
             savecorr = "SAVECORR" in os.environ      # core/corr.py:180-184 debugging hook: needs the stored volume
+            # nn.DataParallel replicas run concurrently in threads: a (global-mode) stream capture in one thread is
+            # invalidated by allocations in another, so replicas launch eagerly
             if self.use_cuda_graph and not self.training and not torch.cuda.is_current_stream_capturing() \
-                    and not savecorr:
+                    and not savecorr and not getattr(self, "_is_replica", False):
                 return self._forward_graphed(image1, image2, iters, flow_init, test_mode)
             return self._forward_impl(image1, image2, iters, flow_init, test_mode, savecorr=savecorr)
 

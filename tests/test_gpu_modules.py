@@ -341,3 +341,24 @@ def test_modules_follow_their_input_device_when_another_is_current():
         lo0, up0 = m0.to("cuda:0").eval()(i1.to("cuda:0"), i2.to("cuda:0"), iters=2, test_mode=1)
     assert up.device == dev and torch.isfinite(up).all()
     assert (up.cpu() - up0.cpu()).abs().max().item() <= 1e-3
+
+
+def test_data_parallel_on_two_gpus_matches_single_device():
+    """train.py:183 / evaluate.py:1534 wrap the model in nn.DataParallel: with a batch of two on a 2-GPU box every
+    replica (one thread per device, shared module attributes) must reproduce the single-device result."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    from oracle.ref_loader import smooth_pair, synthetic_pair
+    torch.manual_seed(1234)
+    m = CRAFT(craft_args()).cuda().eval()
+    a1, a2 = synthetic_pair(128, 128)
+    b1, b2 = smooth_pair(128, 128)
+    i1, i2 = torch.cat([a1, b1]).cuda(), torch.cat([a2, b2]).cuda()
+    dp = torch.nn.DataParallel(m, device_ids=[0, 1])
+    with torch.no_grad():
+        for _ in range(2):                       # second call: packed-weight caches of both devices are warm
+            lo, up = dp(i1, i2, iters=3, test_mode=1)
+        lo_a, up_a = m(i1[:1], i2[:1], iters=3, test_mode=1)
+        lo_b, up_b = m(i1[1:], i2[1:], iters=3, test_mode=1)
+    assert up.shape == (2, 2, 128, 128) and up.device.index == 0
+    assert (up[0] - up_a[0]).abs().max().item() <= 2e-3 and (up[1] - up_b[0]).abs().max().item() <= 2e-3
