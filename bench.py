@@ -589,9 +589,11 @@ def run_train(args, cfg):
         dist.init_process_group("nccl", device_id=dev)
     else:
         dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
-    kw = dict(cfg["args"])
+    kw = dict(cfg["args"], mixed_precision=True)      # every training script of the reference passes --mixed_precision
     if args.dropout_prob is not None:
         kw["dropout_prob"] = args.dropout_prob
+    torch.backends.cudnn.benchmark = True
+    scaler = torch.amp.GradScaler("cuda", enabled=True)       # train.py:215,231-238
     torch.manual_seed(1234)
     model = CRAFT(craft_args(**kw)).to(dev)
     model.train()
@@ -611,10 +613,12 @@ def run_train(args, cfg):
         preds = ddp(a.to(dev, non_blocking=True), b.to(dev, non_blocking=True), iters=ITERS, test_mode=0)
         loss = sum(0.8 ** (ITERS - k - 1) * (p - gt).abs().mean() for k, p in enumerate(preds))
         opt.zero_grad(set_to_none=True)
-        loss.backward()
+        scaler.scale(loss).backward()
+        scaler.unscale_(opt)
         torch.nn.utils.clip_grad_norm_(ddp.parameters(), 1.0)
-        opt.step()
-        return loss
+        scaler.step(opt)
+        scaler.update()
+        return loss.detach()
 
     for i in range(args.warmup):
         step(i)
@@ -636,7 +640,8 @@ def run_train(args, cfg):
         dp = model.intra_trans_config.attention_probs_dropout_prob
         line = dict(metric=cfg["metric"], value=pairs / (ms * 1e-3), unit="pairs/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype=model.precision, data="synthetic integer-noise batches, random-init weights (seed 1234)",
+                    dtype="fp16 autocast (--mixed_precision, GradScaler), fp32 master weights",
+                    data="synthetic integer-noise batches, random-init weights (seed 1234)",
                     config=dict(workload=cfg["workload"], dropout_prob=dp,
                                 attention_forward="sm_100a kernels (dropout off)" if dp == 0 else
                                 "PyTorch restatement (dropout %.1f live, reference training default)" % dp,

@@ -297,7 +297,9 @@ class CRAFT(nn.Module):
             g = torch.cuda.CUDAGraph()
             from . import _lib
             n0 = _lib.launch_count()
-            with torch.cuda.graph(g):
+            # an explicit capture stream: torch.cuda.graph's default one is a process-wide singleton created on
+            # whatever device was current first -- capturing a cuda:1 forward on it invalidates the capture
+            with torch.cuda.graph(g, stream=side):
                 ent["out"] = self._forward_impl(ent["i1"], ent["i2"], iters, ent["fi"], test_mode)
             ent["graph"] = g
             for m in self.modules():           # diagnostics tensors created during the warm-up start from zero

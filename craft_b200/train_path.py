@@ -352,7 +352,8 @@ def forward_train(model, image1, image2, iters=12, flow_init=None, test_mode=0):
     if a.f2trans != "none":
         f2 = model.f2_trans
         if _dropout_active(model, f2.config):
-            fmap2 = _f2_trans(f2, fmap2, True)
+            with torch.autocast("cuda", enabled=amp):          # core/network.py:185-187
+                fmap2 = _f2_trans(f2, fmap2, training).float()
         else:
             fmap2 = _KernelFwd.apply(lambda x: f2(x), lambda x: _f2_trans(f2, x, False), fmap2, *_params(f2))
 
@@ -360,7 +361,9 @@ def forward_train(model, image1, image2, iters=12, flow_init=None, test_mode=0):
     if a.craft:
         cf = model.corr_fn
         if _dropout_active(model, cf.config):
-            pyr = _pyramid(_corr_volume(cf, fmap1, fmap2, training))
+            with torch.autocast("cuda", enabled=amp):          # core/network.py:227-228
+                vol = _corr_volume(cf, fmap1, fmap2, training)
+            pyr = _pyramid(vol.float())
             lookup = lambda c: _lookup(pyr, c)
         else:
             grid = TokenGrid(h, w)
@@ -388,7 +391,8 @@ def forward_train(model, image1, image2, iters=12, flow_init=None, test_mode=0):
     if a.use_setrans:
         att = model.att
         if _dropout_active(model, att.config):
-            probs, _ = _self_att_probs(att, inp, training)
+            with torch.autocast("cuda", enabled=amp):          # core/network.py:213-214
+                probs, _ = _self_att_probs(att, inp, training)
             aggregate = lambda m3: _expanded_feat_trans(ag, m3, probs)
         else:
             per_att = []
