@@ -206,27 +206,29 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         // frees a V stage), so one thread serves both with non-blocking probes.
         int ki = 0, vi = 0;
         uint32_t idle = 0;
+        // block coordinates of the next K / V tile, advanced incrementally (no division in the loop: it would
+        // go through MUFU.RCP and queue behind the softmax warps' exponentials)
+        int bx = sgm.t0 / nby, by = sgm.t0 - bx * nby;
+        int vbx = bx, vby = by;
         while (ki < sgm.nt || vi < sgm.nt) {
           bool moved = false;
           if (ki < sgm.nt && mbar_test(&k_empty[ks], kph ^ 1u)) {
-            const int kt = sgm.t0 + ki;
-            const int bx = kt / nby, by = kt - bx * nby;
             mbar_arrive_expect_tx(&k_full[ks], S::kKBytes);
             for (int a = 0; a < S::kQAtoms; ++a)
               tma_load_3d(sK + ks * S::kKBytes + a * BK * 128, &tmK, &k_full[ks], qk_col + a * 64, bx * BW, by * 8);
             PV_TRACE(3, g0 + ki, 0);
             if (++ks == KS) { ks = 0; kph ^= 1u; }
+            if (++by == nby) { by = 0; ++bx; }
             ++ki; moved = true;
           }
           if (vi < sgm.nt && mbar_test(&v_empty[vs], vph ^ 1u)) {
-            const int kt = sgm.t0 + vi;
-            const int vbx = kt / nby, vby = kt - vbx * nby;
             const int vcol = (vby * p.nbx + vbx) * BK;          // V^T columns are in block-row-major block order
             mbar_arrive_expect_tx(&v_full[vs], S::kVBytes);
             for (int a = 0; a < BK / 64; ++a)
               tma_load_2d(sV + vs * S::kVBytes + a * F * 128, &tmV, &v_full[vs], vcol + a * 64, sgm.mode * F);
             PV_TRACE(3, g0 + vi, 1);
             if (++vs == VS) { vs = 0; vph ^= 1u; }
+            if (++vby == nby) { vby = 0; ++vbx; }
             ++vi; moved = true;
           }
           if (moved) idle = 0;
@@ -347,12 +349,15 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int q = sgm.qt * 128 + row;
       const int qy = q / p.g.Wp, qx = q - qy * p.g.Wp;
       const float lse = lse_next;
-      for (int i = (g0 & 1) ^ sg; i < sgm.nt; i += 2) {
+      // block coordinates of this group's tiles are advanced incrementally: an integer division by the runtime
+      // nby goes through MUFU.RCP, i.e. it queues behind the other group's exponentials on the same XU pipe
+      // (~450 clk per tile between a group's arrive and its next s_full wait in the clock64 timeline)
+      const int i0 = (g0 & 1) ^ sg;
+      int bx = (sgm.t0 + i0) / nby, by = (sgm.t0 + i0) - bx * nby;
+      for (int i = i0; i < sgm.nt; i += 2) {
         const int g = g0 + i;
         const int b = g % NSB;
         const uint32_t bpar = static_cast<uint32_t>(g / NSB) & 1u;
-        const int kt = sgm.t0 + i;
-        const int bx = kt / nby, by = kt - bx * nby;
         // this thread's half block: block rows [ch*4, ch*4+4), all BW columns
         const int iy0 = by * 8 + ch * 4 - qy + R;       // table row of the first block row
         const int ix0 = bx * BW - qx + R;               // table column of the first block column
@@ -410,6 +415,8 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc_fence_before();
         mbar_arrive_warp(&p_full[b]);
         if (trole < 4) PV_TRACE(trole, g, 4);
+        by += 2;
+        while (by >= nby) { by -= nby; ++bx; }
       }
 
       // -------------------------------- O write-back of this segment ------------------------

@@ -164,15 +164,17 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         mbar_wait(q_free, (static_cast<uint32_t>(seg) & 1u) ^ 1u);       // previous segment's MMAs retired
         mbar_arrive_expect_tx(q_full, q_bytes);
         for (int a = 0; a < atoms; ++a) tma_load_2d(sQ + a * 128 * 128, &tmQ, q_full, a * 64, sg.qt * 128);
+        // block-column major key tiles (see attn_pv.cuh); coordinates advanced without a division (an integer
+        // division by a runtime value goes through MUFU.RCP and queues behind the epilogue warps' exponentials)
+        int bx = sg.t0 / p.nkt_y, by = sg.t0 - bx * p.nkt_y;
         for (int i = 0; i < sg.nt; ++i) {
-          const int kt = sg.t0 + i;
-          const int bx = kt / p.nkt_y, by = kt - bx * p.nkt_y;      // block-column major, see attn_pv.cuh
           mbar_wait(&k_empty[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&k_full[stage], k_bytes);
           uint8_t* dst = sK + stage * k_bytes;
           for (int a = 0; a < atoms; ++a)
             tma_load_3d(dst + a * 64 * 128, &tmK, &k_full[stage], a * 64, bx * 8, by * 8);
           if (++stage == kScKStages) { stage = 0; phase ^= 1u; }
+          if (++by == p.nkt_y) { by = 0; ++bx; }
         }
         lin += sg.nt;
       }
@@ -253,11 +255,12 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       }
       float seg_rawmax = -INFINITY;              // merged into st_rawmax only for real query rows
 
-      for (int i = (g0 & 1) ^ eg; i < sgm.nt; i += 2) {
+      const int i0 = (g0 & 1) ^ eg;
+      int bx = (sgm.t0 + i0) / p.nkt_y, by = (sgm.t0 + i0) - bx * p.nkt_y;      // block-column major, incremental
+      auto advance = [&] { by += 2; while (by >= p.nkt_y) { by -= p.nkt_y; ++bx; } };
+      for (int i = i0; i < sgm.nt; i += 2, advance()) {
         const int g = g0 + i;
         const uint32_t par = (static_cast<uint32_t>(g) >> 1) & 1u;
-        const int kt = sgm.t0 + i;
-        const int bx = kt / p.nkt_y, by = kt - bx * p.nkt_y;      // block-column major, see attn_pv.cuh
         const int ky0 = by * 8 + ch * 4, kx0 = bx * 8;          // this thread's 4 x 8 key window
         const int iy0 = ky0 - qy + R, ix0 = kx0 - qx + R;       // table coordinates of its first key
         const bool near = has_bias && (iy0 + 3 >= 0) && (iy0 <= 2 * R) && (ix0 + 7 >= 0) && (ix0 <= 2 * R);

@@ -43,14 +43,20 @@ def _tokens_ln(feat):
 
 
 def _pos_bias(table, h, w):
-    """SlidingPosBiases2D.forward core/setrans.py:690-708 -> dense [U,U] (differentiable w.r.t. the table)."""
+    """SlidingPosBiases2D.forward core/setrans.py:690-708 -> dense [U,U], differentiable w.r.t. the table.
+    Written as two one-hot matmuls, bias[(y1,x1),(y2,x2)] = sum_ab [y2-y1+R == a] T[a,b] [x2-x1+R == b]: the
+    backward is two small GEMMs.  (A gather `table[iy, ix]` has a scatter-add backward of U^2 = 20 M atomics
+    onto 225 addresses -- measured: it dominated the training step.)"""
     R = (table.shape[0] - 1) // 2
-    ys = torch.arange(h, device=table.device)
-    xs = torch.arange(w, device=table.device)
-    dy, dx = ys[None, :] - ys[:, None], xs[None, :] - xs[:, None]
-    ok = (dy.abs() <= R)[:, None, :, None] & (dx.abs() <= R)[None, :, None, :]
-    b = table[(dy + R).clamp(0, 2 * R)[:, None, :, None], (dx + R).clamp(0, 2 * R)[None, :, None, :]]
-    return (b * ok).reshape(h * w, h * w)
+    n = 2 * R + 1
+
+    def onehot(m):
+        i = torch.arange(m, device=table.device)
+        d = i[None, :] - i[:, None] + R                       # [m1, m2]
+        return (d[..., None] == torch.arange(n, device=table.device)).to(table.dtype).reshape(m * m, n)
+    ay, ax = onehot(h), onehot(w)                              # [h*h, n], [w*w, n]
+    b = (ay @ table @ ax.t()).reshape(h, h, w, w)              # (y1, y2, x1, x2)
+    return b.permute(0, 2, 1, 3).reshape(h * w, h * w)
 
 
 def _radius_mask(h, w, radius, device):
