@@ -278,7 +278,12 @@ int craft_shift_gemm(const craft_gemm_args* a, void* stream) {
     const int mode = (a->a_share != 0 || env_mode != 0) ? 1 : 0;
     int gs = 1;
     while (gs < a->T && a->tap_off[gs] == a->tap_off[gs - 1] + 1) ++gs;
-    bool ok = mode != 0 && gs > 1 && gs <= 5 && a->T % gs == 0 && !a->b_blocked && a->cluster <= 1;
+    bool ok = mode != 0 && gs > 1 && gs <= 5 && a->T % gs == 0 && !a->b_blocked && a->cluster <= 1 && a->BN <= 128;
+    if (ok) {      // at least two grouped stages must fit
+      const int ring = a->BN == 32 ? cb::GemmSmem<32>::kRing : a->BN == 64 ? cb::GemmSmem<64>::kRing
+                     : a->BN == 96 ? cb::GemmSmem<96>::kRing : cb::GemmSmem<128>::kRing;
+      if (ring / (136 * 128 + gs * a->BN * 128) < 2) ok = false;
+    }
     for (int t = 1; ok && t < a->T; ++t)
       if (t % gs != 0 && a->tap_off[t] != a->tap_off[t - 1] + 1) ok = false;
     if (ok) { p.ashare = mode; p.gsize = gs; }
@@ -333,7 +338,14 @@ int craft_shift_gemm(const craft_gemm_args* a, void* stream) {
     p.kc = (a->K % 128 == 0) ? 2 : 1;
     if (e && atoi(e) == 1 && !p.bigbox) p.kc = 1;
     if (p.bigbox) p.kc = 2;
-    const int smax = slots / p.kc;
+    int smax = slots / p.kc;
+    if (p.ashare) {      // grouped stages: as many (A tile + gsize weight tiles) as fit in the ring
+      const int ring = a->BN == 32 ? cb::GemmSmem<32>::kRing : a->BN == 64 ? cb::GemmSmem<64>::kRing
+                     : a->BN == 96 ? cb::GemmSmem<96>::kRing : cb::GemmSmem<128>::kRing;
+      smax = ring / (136 * 128 + p.gsize * a->BN * 128);
+      if (smax > slots) smax = slots;       // barrier block holds `slots` pairs
+      if (smax < 2) { p.ashare = 0; p.gsize = 1; smax = slots / p.kc; }
+    }
     p.stages = (a->stages > 0 && a->stages < smax) ? a->stages : smax;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -85,7 +85,12 @@ struct GemmSmem {
   static constexpr int kABytes = kGemmBM * 128;
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTotal = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
+  // tap-shared ("grouped") stages: one 136-row A tile + up to 5 weight tiles under one barrier; at least two of
+  // them must fit (BN = 128: 2 x 99,328 B; BN = 256 does not use the mode)
+  static constexpr int kGroupStage5 = 136 * 128 + 5 * kBBytes;
+  static constexpr int kRing = (BN <= 128 && 2 * kGroupStage5 > kStages * kStageBytes) ? 2 * kGroupStage5 : kStages * kStageBytes;
+  static constexpr int kTotal = kRing + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
+  static_assert(kTotal <= 227 * 1024, "shift_gemm: shared memory budget");
 };
 
 __device__ __forceinline__ float sigmoid_fast(float x) {
@@ -110,23 +115,17 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   // barrier block (256 B): [acc_bar][tmem_slot][ring barriers ...]
-  uint64_t* acc_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
+  uint64_t* acc_bar = reinterpret_cast<uint64_t*>(smem + S::kRing);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
   uint64_t* full_bar = acc_bar + 2;
   uint64_t* empty_bar = full_bar + S::kStages;
-  float* s_bias = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes + 256);
-  // shared-A mode: an A ring of kAsSlots x (136 rows x 128 B) followed by a B ring of kBsSlots weight tiles
+  float* s_bias = reinterpret_cast<float*>(smem + S::kRing + 256);
+  // shared-A ("grouped") mode: a stage = one 136-row A tile (every tap of a kernel row is a row shift of it) followed
+  // by the gsize weight tiles of that kernel row, all under ONE full / empty barrier pair -- the issuing warp pays
+  // one wait + one commit per 4 * gsize MMAs, and the SM ingests 17 KB + gsize * BN * 128 B per gsize taps instead of
+  // gsize * (16 KB + BN * 128 B).  (Round 1 built this with a barrier per weight tile: exact, less ingest, slower.)
   constexpr int kAsBytes = 136 * 128;
-  constexpr int kAsSlots = 3;
-  constexpr int kBsFit = (S::kStages * S::kStageBytes - kAsSlots * kAsBytes) / S::kBBytes;
-  constexpr int kBsSlots = kBsFit < 12 ? kBsFit : 12;
-  static_assert(2 * (kAsSlots + kBsSlots) * 8 + 16 <= 256, "barrier block");
-  uint64_t* a_full = acc_bar + 2;
-  uint64_t* a_empty = a_full + kAsSlots;
-  uint64_t* b_full = a_empty + kAsSlots;
-  uint64_t* b_empty = b_full + kBsSlots;
-  uint8_t* sAs = smem;
-  uint8_t* sBs = smem + kAsSlots * kAsBytes;
+  const int g_stage_bytes = kAsBytes + p.gsize * S::kBBytes;
 
   const int warp = threadIdx.x >> 5;
   const int m0 = blockIdx.x * kGemmBM;
@@ -142,13 +141,9 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (p.ashare) {
-      for (int s = 0; s < 2 * (kAsSlots + kBsSlots); ++s) mbar_init(&a_full[s], 1);
-    } else {
-      for (int s = 0; s < S::kStages; ++s) {
-        mbar_init(&full_bar[s], p.bigbox == 2 ? 2 : 1);     // one arrive.expect_tx per producer lane
-        mbar_init(&empty_bar[s], CL);
-      }
+    for (int s = 0; s < S::kStages; ++s) {
+      mbar_init(&full_bar[s], p.bigbox == 2 ? 2 : 1);     // one arrive.expect_tx per producer lane
+      mbar_init(&empty_bar[s], CL);
     }
     mbar_init(acc_bar, 1);
     fence_mbar_init();
@@ -166,21 +161,19 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (p.ashare) {
       if (elect_one()) {
         const int GS = p.gsize, ngr = p.T / GS;
-        int as = 0, bs = 0;
-        uint32_t aph = 0, bph = 0;
+        int stage = 0;
+        uint32_t phase = 0;
         for (int gi = 0; gi < ngr; ++gi)
           for (int kc = 0; kc < kchunks; ++kc) {
-            mbar_wait(&a_empty[as], aph ^ 1u);
-            mbar_arrive_expect_tx(&a_full[as], kAsBytes);
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(g_stage_bytes));
+            uint8_t* sa = smem + stage * g_stage_bytes;
             // rows m0 + off(first tap of the group) .. +136: every tap of the group is a row shift of it
-            tma_load_2d(sAs + as * kAsBytes, &tmA, &a_full[as], p.a_koff + kc * kGemmBK, m0 + p.tap_off[gi * GS]);
-            if (++as == kAsSlots) { as = 0; aph ^= 1u; }
-            for (int j = 0; j < GS; ++j) {
-              mbar_wait(&b_empty[bs], bph ^ 1u);
-              mbar_arrive_expect_tx(&b_full[bs], S::kBBytes);
-              tma_load_2d(sBs + bs * S::kBBytes, &tmB, &b_full[bs], p.b_koff + kc * kGemmBK, (gi * GS + j) * p.Npad + n0);
-              if (++bs == kBsSlots) { bs = 0; bph ^= 1u; }
-            }
+            tma_load_2d(sa, &tmA, &full_bar[stage], p.a_koff + kc * kGemmBK, m0 + p.tap_off[gi * GS]);
+            for (int j = 0; j < GS; ++j)
+              tma_load_2d(sa + kAsBytes + j * S::kBBytes, &tmB, &full_bar[stage], p.b_koff + kc * kGemmBK,
+                          (gi * GS + j) * p.Npad + n0);
+            if (++stage == nstages) { stage = 0; phase ^= 1u; }
           }
       }
     } else if (p.bigbox) {
@@ -245,36 +238,36 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint64_t desc_base = umma_desc_sw128(smem_u32(smem));
     const bool leader = elect_one();
     if (p.ashare) {
-      const int GS = p.gsize, ngr = p.T / GS;
-      const uint64_t da_base = umma_desc_sw128(smem_u32(sAs));
-      const uint64_t db_base = umma_desc_sw128(smem_u32(sBs));
-      constexpr uint64_t kAStep = static_cast<uint64_t>(kAsBytes >> 4);
+      const int GS = p.gsize;
+      const int nst_g = (p.T / GS) * kchunks;
+      const uint64_t g_step = static_cast<uint64_t>(g_stage_bytes >> 4);
       constexpr uint64_t kBStep = static_cast<uint64_t>(S::kBBytes >> 4);
-      int as = 0, bs = 0, first = 1;
-      uint32_t aph = 0, bph = 0;
-      for (int gi = 0; gi < ngr; ++gi)
-        for (int kc = 0; kc < kchunks; ++kc) {
-          mbar_wait(&a_full[as], aph);
+      constexpr uint64_t kAOff = static_cast<uint64_t>(kAsBytes >> 4);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint64_t da = desc_base;
+      bool ready = mbar_try_wait_nohint(&full_bar[0], 0);
+      for (int it = 0; it < nst_g; ++it) {
+        if (!ready) mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (leader) {
           for (int j = 0; j < GS; ++j) {
-            mbar_wait(&b_full[bs], bph);
-            tc_fence_after();
-            if (leader) {
-              // tap j of the group reads the A rows j*128 bytes further down the same smem tile
-              const uint64_t da = da_base + static_cast<uint64_t>(as) * kAStep + static_cast<uint64_t>(j) * 8u;
-              const uint64_t db = db_base + static_cast<uint64_t>(bs) * kBStep;
-              umma_f16(tmem_base, da, db, idesc, first ? 0u : 1u);
-              umma_f16_acc(tmem_base, da + 2u, db + 2u, idesc);
-              umma_f16_acc(tmem_base, da + 4u, db + 4u, idesc);
-              umma_f16_acc(tmem_base, da + 6u, db + 6u, idesc);
-              umma_commit(&b_empty[bs]);
-              if (j == GS - 1) umma_commit(&a_empty[as]);
-              if (gi == ngr - 1 && kc == kchunks - 1 && j == GS - 1) umma_commit(acc_bar);
-            }
-            first = 0;
-            if (++bs == kBsSlots) { bs = 0; bph ^= 1u; }
+            // tap j of the group reads the A rows j * 128 bytes further down the same smem tile (the 128-byte
+            // swizzle follows the absolute smem address, so a row-shifted start needs no descriptor fix-up)
+            const uint64_t d = da + static_cast<uint64_t>(j) * 8u;
+            const uint64_t e = da + kAOff + static_cast<uint64_t>(j) * kBStep;
+            umma_f16(tmem_base, d, e, idesc, (it | j) != 0 ? 1u : 0u);
+            umma_f16_acc(tmem_base, d + 2u, e + 2u, idesc);
+            umma_f16_acc(tmem_base, d + 4u, e + 4u, idesc);
+            umma_f16_acc(tmem_base, d + 6u, e + 6u, idesc);
           }
-          if (++as == kAsSlots) { as = 0; aph ^= 1u; }
+          umma_commit(&empty_bar[stage]);
+          if (it == nst_g - 1) umma_commit(acc_bar);
         }
+        if (++stage == nstages) { stage = 0; phase ^= 1u; da = desc_base; }
+        else da += g_step;
+        ready = (it + 1 < nst_g) && mbar_try_wait_nohint(&full_bar[stage], phase);
+      }
       __syncwarp();
     } else {
     int stage = 0;

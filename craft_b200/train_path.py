@@ -124,8 +124,11 @@ def _corr_volume(cf, fmap1, fmap2, training):
     s = _scores(t1, t2, cf.setrans, bias)
     raw = _soft_aggregate(cf.setrans.attn_softaggr, s, keepdim=True) if cf.setrans.num_modes > 1 else s
     if cf.do_corr_global_norm:
-        flat = raw.reshape(B, 1, -1)
-        raw = F.layer_norm(flat, (flat.shape[2],), eps=1e-12)
+        # F.layer_norm over ONE row of U^2 = 20 M elements (core/corr.py:200-204) runs in a single thread block
+        # (34 ms forward + 44 ms backward at 400x720); the same arithmetic as parallel reductions:
+        flat = raw.float().reshape(B, -1)
+        var, mean = torch.var_mean(flat, dim=1, unbiased=False, keepdim=True)
+        raw = (flat - mean) * torch.rsqrt(var + 1e-12)
     return raw.reshape(B, h * w, h, w)
 
 
