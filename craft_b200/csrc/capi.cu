@@ -273,11 +273,14 @@ int craft_shift_gemm(const craft_gemm_args* a, void* stream) {
   memset(&p, 0, sizeof(p));
   // shared-A mode (gemm.cuh): taps in groups of consecutive row offsets, e.g. the kw taps of a conv row
   {
-    static int env_mode = -1;
-    if (env_mode < 0) { const char* e = getenv("CRAFT_GEMM_ASHARE"); env_mode = (e && atoi(e) != 0) ? 1 : 0; }
-    const int mode = (a->a_share != 0 || env_mode != 0) ? 1 : 0;
+    // CRAFT_GEMM_ASHARE: 1 = every kernel row with consecutive taps, 0 = never, unset = the 1x5 rows only --
+    // measured (profiles/r02_gemm_sweep_ashare.txt): 13.5 -> 12.1 us (GRU z/r) and 10.7 -> 8.9 us (GRU q) for five
+    // shared taps, no gain for the three of a 3x3 row.  Bit-exact either way (same MMAs, same order).
+    static int env_mode = -2;
+    if (env_mode == -2) { const char* e = getenv("CRAFT_GEMM_ASHARE"); env_mode = e ? (atoi(e) != 0 ? 1 : 0) : -1; }
     int gs = 1;
     while (gs < a->T && a->tap_off[gs] == a->tap_off[gs - 1] + 1) ++gs;
+    const int mode = (a->a_share != 0 || env_mode == 1 || (env_mode == -1 && gs == 5)) ? 1 : 0;
     bool ok = mode != 0 && gs > 1 && gs <= 5 && a->T % gs == 0 && !a->b_blocked && a->cluster <= 1 && a->BN <= 128;
     if (ok) {      // at least two grouped stages must fit
       const int ring = a->BN == 32 ? cb::GemmSmem<32>::kRing : a->BN == 64 ? cb::GemmSmem<64>::kRing

@@ -66,14 +66,19 @@ def main(which, reps):
 
         if trace:
             os.environ["CRAFT_PV_TRACE"] = trace
+        prof = os.environ.get("KO_PROFILE") == "1"      # ncu --profile-from-start off: only the measured calls are profiled
         for w in which.split(","):          # several kernels in one process: "pv,corr,lse"
             run(w)
             torch.cuda.synchronize()
+            if prof:
+                torch.cuda.profiler.start()
             e0.record()
             for _ in range(reps):
                 run(w)
             e1.record()
             torch.cuda.synchronize()
+            if prof:
+                torch.cuda.profiler.stop()
             print("%s: %.2f us per call (avg of %d)" % (w, 1000 * e0.elapsed_time(e1) / reps, reps), flush=True)
 
 
