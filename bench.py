@@ -365,9 +365,10 @@ def _kernel_table(model, cfg, dev, pk):
     def corr():
         ws.stat_sum.zero_()
         ops.corr_build(ws.Qc, ws.Kc, g, M=4, d=64, w_agg=ws.corr_meta["w_agg"], w_pos=0.5, pos_table=f2_tbl, R=7,
-                       clip=ws.inf_clip, stat_sum=ws.stat_sum[0], stat_max=ws.stat_max[3:4], levels=ws.levels, ksplit=ws.ks_sc)
+                       clip=ws.inf_clip, stat_sum=ws.stat_sum[0], stat_max=ws.stat_max[3:4], levels=ws.levels, ksplit=ws.ks_sc,
+                       level0_h16=ws.level0_h16)
     add("scores_kernel<SC_CORR> (4-mode correlation volume + pyramid + LN statistics)", 1, corr, flops=2 * U * U * 256,
-        note="includes a 2 us stat_sum reset")
+        note="includes a 2 us stat_sum reset; level 0 mode: " + ws.level0)
     add("scores_kernel<SC_LSE> d=32 (intra-frame attention statistics)", 1,
         lambda: ops.attn_lse(ws.Qa, ws.Ka, g, M=4, d=32, w_pos=1.0, pos_table=att_tbl, R=7, clip=ws.inf_clip,
                              stat_max=ws.stat_max[3:4], lse_part=ws.lse_part, lse2=ws.lse2_att, ksplit=ws.ks_sc),
@@ -399,13 +400,18 @@ def _kernel_table(model, cfg, dev, pk):
                   + conv(128, 256, 9) + conv(256, 2, 9))                                           # flow head
     add("shift-GEMM family, one refinement iteration (11 launches + convf1)", it, update_gemms, flops=gemm_flops,
         note="mask head excluded (runs in the last iteration only)")
-    add("corr_lookup0_kernel (level-0 window recomputed from Q/K rows)", it,
-        lambda: ops.corr_lookup0(grid=g, coords=ws.coords1, mean_rstd=ws.mean_rstd, out_b=ws.CORR, **ws.corr_meta),
-        bytes_=2 * U * 256 * 2 + 81 * U * 2, note="algorithmic bytes = Q + K rows once + 81 bf16 outputs per query; the "
-        "kernel itself moves ~51 KB of key rows per query through L2")
-    add("corr_lookup_kernel (pooled levels 1-3)", it,
-        lambda: ops.corr_lookup(ws.levels, g, ws.coords1, ws.mean_rstd, out_b=ws.CORR, first_level=1),
-        bytes_=3 * 100 * 4 * U + 243 * U * 2)
+    if ws.level0_h16 is not None:
+        add("corr_lookup_kernel (all 4 levels; level 0 from the fp16 block-ordered volume)", it,
+            lambda: ops.corr_lookup(ws.levels, g, ws.coords1, ws.mean_rstd, out_b=ws.CORR, level0_h16=ws.level0_h16),
+            bytes_=100 * 2 * U + 3 * 100 * 4 * U + 324 * U * 2)
+    else:
+        add("corr_lookup0_kernel (level-0 window recomputed from Q/K rows)", it,
+            lambda: ops.corr_lookup0(grid=g, coords=ws.coords1, mean_rstd=ws.mean_rstd, out_b=ws.CORR, **ws.corr_meta),
+            bytes_=2 * U * 256 * 2 + 81 * U * 2, note="algorithmic bytes = Q + K rows once + 81 bf16 outputs per query; the "
+            "kernel itself moves ~51 KB of key rows per query through L2")
+        add("corr_lookup_kernel (pooled levels 1-3)", it,
+            lambda: ops.corr_lookup(ws.levels, g, ws.coords1, ws.mean_rstd, out_b=ws.CORR, first_level=1),
+            bytes_=3 * 100 * 4 * U + 243 * U * 2)
     add("modes_finalize_kernel<128> (mode soft-pool + skip + LayerNorm)", it,
         lambda: ops.modes_finalize(ws.opart(ks, 4, 128), ks, 4, 128, g, w_score=agg["ws"], b_score=agg["bs"], coeff=agg["coeff"],
                                    x_b=ws.X, colx=256, out_b=ws.X, colb=384, pv_bk=128),

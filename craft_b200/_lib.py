@@ -51,6 +51,7 @@ class ScoresArgs(C.Structure):
         ("lvl", C.c_void_p * 4),
         ("lse_part", C.c_void_p), ("lse2", C.c_void_p),
         ("mask_radius", C.c_int),
+        ("lvl0_h16", C.c_void_p),
     ]
 
 
@@ -87,6 +88,7 @@ SIGNATURES = {
     "craft_b200_bigbox_gemm_count": (C.c_longlong, []),
     "craft_b200_device_info": (_i, [C.POINTER(_i)]),
     "craft_pack_tokens": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp]),
+    "craft_pack_tokens_nhwc": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp]),
     "craft_unpack_tokens": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "craft_shift_gemm": (_i, [C.POINTER(GemmArgs), _vp]),
     "craft_corr_build": (_i, [C.POINTER(ScoresArgs), _vp]),
@@ -101,7 +103,7 @@ SIGNATURES = {
                                   _vp, _i, _i, _vp, _i, _i, _i, _vp]),
     "craft_soft_aggregate": (_i, [_vp, _vp, _i, C.c_longlong, _i, _vp, _vp, _vp, _vp]),
     "craft_attn_dense": (_i, [C.POINTER(DenseAttnArgs), _vp]),
-    "craft_corr_lookup": (_i, [C.POINTER(_vp), _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp]),
+    "craft_corr_lookup": (_i, [C.POINTER(_vp), _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp]),
     "craft_corr_lookup0": (_i, [_vp, _vp, _i, _i, _f, _f, _f, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     "craft_convf1": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _i, _vp]),
     "craft_flow_update": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),

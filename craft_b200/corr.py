@@ -1,9 +1,10 @@
 """CorrBlock / TransCorrBlock with the reference's signatures (core/corr.py), backed by the fused
 correlation-volume kernel (scores.cuh SC_CORR) and the pyramid lookup kernel (pointwise.cuh).
 
-The U x U level-0 volume is never written to HBM (unless SAVECORR asks for it): pyramid levels 1..3
-come out of the GEMM epilogue directly and the level-0 window of each lookup is recomputed on demand
-from the projected query/key rows (pointwise.cuh corr_lookup0).
+The pyramid comes out of the GEMM epilogue directly (no pooling passes over HBM).  Level 0 is held in one of
+three ways (hotpath.level0_mode): fp16 in 8x8-key-block order (default; one lookup kernel
+for all four levels), never stored (each lookup recomputes its 10x10 window from the projected query/key rows,
+pointwise.cuh corr_lookup0), or the reference's dense fp32 volume (SAVECORR / debugging).
 The global layer-norm of the volume (core/corr.py:200-204) is applied inside the lookup as a
 deferred affine, so no second pass over the volume exists.
 """
@@ -28,7 +29,7 @@ class _LookupMixin:
         if self.radius != 4 or self.num_levels != 4:
             raise NotImplementedError("craft_b200 lookup kernel is built for radius 4, 4 levels (CRAFT default)")
         first = 0
-        if ws.levels[0] is None:      # level 0 on demand: the U x U volume was never stored
+        if ws.levels[0] is None and ws.level0_h16 is None:      # level 0 on demand: the U x U volume was never stored
             if part in ("all", "level0"):
                 ops.corr_lookup0(grid=ws.grid, coords=coords_rows, mean_rstd=ws.mean_rstd, out_b=out_b,
                                  out_nchw=out_nchw, **ws.corr_meta)
@@ -36,9 +37,9 @@ class _LookupMixin:
             if part == "level0":
                 return
         elif part == "level0":
-            return                    # materialised level 0: the single pass below covers everything
+            return                    # stored level 0 (fp16 blocks or fp32): the single pass below covers everything
         ops.corr_lookup(ws.levels, ws.grid, coords_rows, ws.mean_rstd, out_b=out_b, out_nchw=out_nchw,
-                        first_level=first)
+                        first_level=first, level0_h16=ws.level0_h16 if ws.levels[0] is None else None)
 
     def __call__(self, coords):
         """coords [B,2,h,w] (x,y) -> [B,324,h,w] fp32 (core/corr.py:47-71)."""

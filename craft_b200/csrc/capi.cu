@@ -245,6 +245,27 @@ int craft_pack_tokens(const float* src, int C, int H, int W, int mode, void* out
   return check_launch("pack_tokens");
 }
 
+int craft_pack_tokens_nhwc(const void* src, int src_is_half, int ldc, int c0, int C, int H, int W, int mode,
+                           void* out_b, int ldb, int colb, float* out_f, int ldf, int colf, void* stream) {
+  cb::Grid2 g = make_grid(H, W);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (C != 128 && C != 256) return fail("pack_tokens_nhwc: C must be 128 or 256 (got %d)", C);
+  if (c0 % 8 || ldc % 8 || c0 + C > ldc) return fail("pack_tokens_nhwc: channel window [%d, %d) of %d must be 8-aligned", c0, c0 + C, ldc);
+  if ((out_b && (ldb % 8 || colb % 8)) || (out_f && (ldf % 4 || colf % 4))) return fail("pack_tokens_nhwc: output ld/col alignment");
+  dim3 grid((g.Mp + 7) / 8);
+  auto* ob = static_cast<cb::act_t*>(out_b);
+  if (src_is_half) {
+    auto* s = static_cast<const __half*>(src);
+    if (C == 128) launch_k(cb::pack_tokens_nhwc_kernel<__half, 128>, grid, dim3(256), 0, st, s, ldc, c0, g, mode, ob, ldb, colb, out_f, ldf, colf);
+    else launch_k(cb::pack_tokens_nhwc_kernel<__half, 256>, grid, dim3(256), 0, st, s, ldc, c0, g, mode, ob, ldb, colb, out_f, ldf, colf);
+  } else {
+    auto* s = static_cast<const float*>(src);
+    if (C == 128) launch_k(cb::pack_tokens_nhwc_kernel<float, 128>, grid, dim3(256), 0, st, s, ldc, c0, g, mode, ob, ldb, colb, out_f, ldf, colf);
+    else launch_k(cb::pack_tokens_nhwc_kernel<float, 256>, grid, dim3(256), 0, st, s, ldc, c0, g, mode, ob, ldb, colb, out_f, ldf, colf);
+  }
+  return check_launch("pack_tokens_nhwc");
+}
+
 int craft_unpack_tokens(const void* src, int is_bf16, int ld, int col, int C, int H, int W, float* dst,
                         void* stream) {
   cb::Grid2 g = make_grid(H, W);
@@ -256,6 +277,9 @@ int craft_unpack_tokens(const void* src, int is_bf16, int ld, int col, int C, in
     launch_k(cb::unpack_tokens_kernel<float>, dim3(grid), dim3(256), 0, st, static_cast<const float*>(src), ld, col, C, g, dst);
   return check_launch("unpack_tokens");
 }
+
+static int launch_gemm_dispatch(const craft_gemm_args* a, int CL, const CUtensorMap& ta, const CUtensorMap& tb,
+                                const cb::GemmParams& p, cudaStream_t st);
 
 int craft_shift_gemm(const craft_gemm_args* a, void* stream) {
   if (!a || !a->A || !a->B) return fail("gemm: null operand");
@@ -352,6 +376,36 @@ int craft_shift_gemm(const craft_gemm_args* a, void* stream) {
     p.stages = (a->stages > 0 && a->stages < smax) ? a->stages : smax;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // CRAFT_GEMM_TRACE=<file> (profiling aid, eager launches only): appends one record per launch -- the clock64
+  // phase marks of CTA (0,0) and {globaltimer start, end, SM id} of every CTA.  Synchronises the stream.
+  const char* trace_path = getenv("CRAFT_GEMM_TRACE");
+  static long long* d_trace = nullptr;
+  constexpr int kTraceLen = 16 + 3 * 1024;
+  if (trace_path) {
+    if (!d_trace) cudaMalloc(&d_trace, kTraceLen * sizeof(long long));
+    cudaMemsetAsync(d_trace, 0, kTraceLen * sizeof(long long), st);
+    p.trace = d_trace;
+    const int rc = launch_gemm_dispatch(a, CL, ta, tb, p, st);
+    static long long h[kTraceLen];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(trace_path, "a")) {
+      const int nm = (a->M + cb::kGemmBM - 1) / cb::kGemmBM, nn = a->Npad / a->BN;
+      fprintf(f, "gemm BN=%d epi=%d T=%d K=%d Npad=%d ashare=%d gsize=%d stages=%d kc=%d ctas=%d\nmarks", a->BN, a->epilogue, a->T,
+              a->K, a->Npad, p.ashare, p.gsize, p.stages, p.kc, nm * nn);
+      for (int k = 0; k < 12; ++k) fprintf(f, " %lld", h[k] ? h[k] - h[0] : -1ll);
+      fprintf(f, "\n");
+      for (int c = 0; c < nm * nn && c < 1024; ++c)
+        fprintf(f, "cta %d %lld %lld %lld\n", c, h[16 + 3 * c], h[16 + 3 * c + 1], h[16 + 3 * c + 2]);
+      fclose(f);
+    }
+    return rc;
+  }
+  return launch_gemm_dispatch(a, CL, ta, tb, p, st);
+}
+
+static int launch_gemm_dispatch(const craft_gemm_args* a, int CL, const CUtensorMap& ta, const CUtensorMap& tb,
+                                const cb::GemmParams& p, cudaStream_t st) {
   switch (a->epilogue) {
     case cb::EPI_STORE: return launch_gemm_bn<cb::EPI_STORE>(a->BN, CL, ta, tb, p, st);
     case cb::EPI_GRU_ZR:
@@ -469,6 +523,9 @@ static int scores_common(const craft_scores_args* a, int mode, void* stream) {
     h /= 2; w /= 2;
   }
   p.lse_part = static_cast<float2*>(a->lse_part);
+  p.lvl0h = static_cast<__half*>(a->lvl0_h16);
+  p.l0_qstride = static_cast<long long>(p.nkt_y) * p.nkt_x * 64;
+  p.lvl0_base = p.lvl0h ? reinterpret_cast<float*>(p.lvl0h + static_cast<long long>(g.Mp) * p.l0_qstride) : nullptr;
   const int atoms = a->C / 64;
   const int smem = 1024 + atoms * 128 * 128 + cb::kScKStages * atoms * 64 * 128 + cb::kScTailBytes;
   dim3 grid(sc_grid(p.nqt, p.nkt_y * p.nkt_x));
@@ -657,19 +714,22 @@ int craft_attn_dense(const craft_dense_attn_args* a, void* stream) {
   return check_launch("attn_dense");
 }
 
-int craft_corr_lookup(const float* const* lvl, int H, int W, const float* coords, const float* mean_rstd,
-                      void* out_bf16, int ldb, float* out_nchw, int first_level, void* stream) {
+int craft_corr_lookup(const float* const* lvl, const void* lvl0_h16, int H, int W, const float* coords,
+                      const float* mean_rstd, void* out_bf16, int ldb, float* out_nchw, int first_level, void* stream) {
   cb::Grid2 g = make_grid(H, W);
   cb::LookupParams p;
   memset(&p, 0, sizeof(p));
   int h = H, w = W;
   for (int l = 0; l < 4; ++l) {
     p.lvl[l] = lvl[l]; p.hl[l] = h; p.wl[l] = w; p.qstride[l] = static_cast<long long>(h) * w;
-    if (l >= first_level && !lvl[l]) return fail("corr_lookup: level %d missing", l);
+    if (l >= first_level && !lvl[l] && !(l == 0 && lvl0_h16)) return fail("corr_lookup: level %d missing", l);
     h /= 2; w /= 2;
   }
   p.coords = coords; p.stats = mean_rstd; p.out_b = static_cast<cb::act_t*>(out_bf16); p.ldb = ldb;
   p.out_nchw = out_nchw; p.first_level = first_level;
+  p.lvl0h = static_cast<const __half*>(lvl0_h16); p.nbx0 = (W + 7) / 8;
+  p.qstride0h = static_cast<long long>((H + 7) / 8) * p.nbx0 * 64;
+  p.lvl0_base = p.lvl0h ? reinterpret_cast<const float*>(p.lvl0h + static_cast<long long>(g.Mp) * p.qstride0h) : nullptr;
   launch_k(cb::corr_lookup_kernel, dim3((g.Mp + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), p, g);
   return check_launch("corr_lookup");
 }

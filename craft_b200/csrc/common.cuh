@@ -396,7 +396,7 @@ __device__ __forceinline__ float sigmoidf_fast(float x) {
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 // 256-bit global store (sm_100): eight floats, 32-byte aligned -- one whole sector per lane
-__device__ __forceinline__ void st_global_v8(float* p, const uint32_t (&r)[8]) {
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&r)[8]) {
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
                "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");

@@ -77,6 +77,8 @@ struct GemmParams {
   int ldf, colf;
   float* aux_f0;                 // EPI_GRU_*: Z   [M,128] f32 ; EPI_FLOW: coords1 [M,2] f32
   float* aux_f1;                 // EPI_GRU_*: Hm  [M,128] f32 ; EPI_MOTION / EPI_FLOW: flow [M,2] f32
+  // CRAFT_GEMM_TRACE (profiling): clock64 of CTA (0,0)'s phases in [0,16), then per CTA {globaltimer start, end, smid}
+  long long* trace;
 };
 
 template <int BN>
@@ -108,6 +110,14 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   using S = GemmSmem<BN>;
   static_assert(BN % (8 * CL) == 0, "weight slice per CTA must be whole 8-row swizzle groups");
   pdl_launch_dependents();
+  const bool tr0 = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0;
+#define G_TRACE(slot) do { if (tr0) p.trace[slot] = clock64(); } while (0)
+  // marks taken before griddepcontrol.wait stay in registers until after it (no global access may precede the wait)
+  long long tr_c0 = 0, tr_c1 = 0, tr_g0 = 0;
+  if (p.trace != nullptr && threadIdx.x == 0) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_g0));
+    tr_c0 = clock64();
+  }
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms.  The dynamic smem window starts at
   // the same offset in every CTA of the cluster, so the aligned addresses agree too (multicast
@@ -149,11 +159,20 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  if (p.trace != nullptr && threadIdx.x == 0) tr_c1 = clock64();
   pdl_wait();                                    // A, bias and the GRU state come from earlier kernels
+  if (p.trace != nullptr && threadIdx.x == 0) {
+    unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    long long* e = p.trace + 16 + 3 * (blockIdx.y * gridDim.x + blockIdx.x);
+    e[0] = tr_g0; e[2] = sm;
+    if (tr0) { p.trace[0] = tr_c0; p.trace[1] = tr_c1; }
+  }
+  if (threadIdx.x == 0) G_TRACE(2);
   tc_fence_before();
   if constexpr (CL > 1) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) G_TRACE(3);
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -173,8 +192,10 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int j = 0; j < GS; ++j)
               tma_load_2d(sa + kAsBytes + j * S::kBBytes, &tmB, &full_bar[stage], p.b_koff + kc * kGemmBK,
                           (gi * GS + j) * p.Npad + n0);
+            if (gi == 0 && kc == 0) G_TRACE(4);
             if (++stage == nstages) { stage = 0; phase ^= 1u; }
           }
+        G_TRACE(5);
       }
     } else if (p.bigbox) {
       const uint32_t lane = lane_id();
@@ -221,8 +242,10 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           if (++kc == kchunks) { kc = 0; ++t; }
         }
+        if (it == 0) G_TRACE(4);
         if (++stage == nstages) { stage = 0; phase ^= 1u; }
       }
+      G_TRACE(5);
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
@@ -249,6 +272,7 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       bool ready = mbar_try_wait_nohint(&full_bar[0], 0);
       for (int it = 0; it < nst_g; ++it) {
         if (!ready) mbar_wait(&full_bar[stage], phase);
+        if (it == 0) G_TRACE(6);
         tc_fence_after();
         if (leader) {
           for (int j = 0; j < GS; ++j) {
@@ -268,6 +292,7 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         else da += g_step;
         ready = (it + 1 < nst_g) && mbar_try_wait_nohint(&full_bar[stage], phase);
       }
+      G_TRACE(7);
       __syncwarp();
     } else {
     int stage = 0;
@@ -276,6 +301,7 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     bool ready = mbar_try_wait_nohint(&full_bar[0], 0);
     for (int it = 0; it < nst; ++it) {
       if (!ready) mbar_wait(&full_bar[stage], phase);
+      if (it == 0) G_TRACE(6);
       tc_fence_after();
       if (leader) {
         for (int a = 0; a < KC; ++a) {
@@ -298,6 +324,7 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       else da += static_cast<uint64_t>(KC) * kSlotStep;
       ready = (it + 1 < nst) && mbar_try_wait_nohint(&full_bar[stage], phase);
     }
+    G_TRACE(7);
     __syncwarp();
     }
   } else {
@@ -343,8 +370,10 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
     asm volatile("bar.sync 1, 256;");                  // s_bias visible to all epilogue warps
+    if (warp == 2) G_TRACE(8);
 
     mbar_wait(acc_bar, 0);
+    if (warp == 2) G_TRACE(9);
     tc_fence_after();
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + half * HALF;
 #pragma unroll
@@ -456,11 +485,18 @@ shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       __syncwarp();
     }
+    if (warp == 2) G_TRACE(10);
     tc_fence_before();
   }
 
   // No CTA may leave while a peer can still multicast into its smem or arrive on its barriers.
   if constexpr (CL > 1) cluster_sync(); else __syncthreads();
+  if (threadIdx.x == 0) G_TRACE(11);
+  if (p.trace != nullptr && threadIdx.x == 0) {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[16 + 3 * (blockIdx.y * gridDim.x + blockIdx.x) + 1] = static_cast<long long>(t);
+  }
+#undef G_TRACE
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);

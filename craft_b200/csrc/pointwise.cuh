@@ -6,6 +6,7 @@
 // dy*Wp + dx (gemm.cuh).  Mp = h * Wp rows.
 #pragma once
 #include <limits.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace cb {
@@ -74,6 +75,84 @@ __global__ void __launch_bounds__(256) pack_tokens_kernel(const float* __restric
   }
 }
 
+// pack_tokens_nhwc: the same token packer for a channels-last source [H][W][ldc] (f16 or f32, the layout the
+// fused encoders produce): a token's channels are already contiguous, so this is one warp per token with
+// 16-byte loads -- no transpose through shared memory and no NHWC -> NCHW -> token round trip
+// (core/extractor.py output -> core/setrans.py:791-795 / core/network.py:209-211).
+// Channels [c0, c0 + C) of every token are packed; C in {128, 256}; modes as in pack_tokens_kernel.
+template <typename TS, int C>
+__global__ void __launch_bounds__(256) pack_tokens_nhwc_kernel(const TS* __restrict__ src, int ldc, int c0, Grid2 g,
+                                                               int mode, act_t* __restrict__ out_b, int ldb, int colb,
+                                                               float* __restrict__ out_f, int ldf, int colf) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int PER = C / 32;                 // channels per lane: 4 or 8, contiguous
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (p >= g.Mp) return;
+  const int y = p / g.Wp, x = p - y * g.Wp;
+  float v[PER];
+  if (x < g.W) {
+    const TS* s = src + (static_cast<size_t>(y) * g.W + x) * ldc + c0 + lane * PER;
+    if constexpr (sizeof(TS) == 2) {          // PER halves = 8 or 16 bytes, aligned (c0, ldc multiples of 8)
+      uint32_t w[PER / 2];
+      if constexpr (PER == 8) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(s));
+        w[0] = u.x; w[1] = u.y; w[2] = u.z; w[3] = u.w;
+      } else {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(s));
+        w[0] = u.x; w[1] = u.y;
+      }
+#pragma unroll
+      for (int k = 0; k < PER / 2; ++k) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+        v[2 * k] = f.x; v[2 * k + 1] = f.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < PER; k += 4) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(s + k));
+        v[k] = f.x; v[k + 1] = f.y; v[k + 2] = f.z; v[k + 3] = f.w;
+      }
+    }
+    if (mode == 4) {
+#pragma unroll
+      for (int k = 0; k < PER; ++k) v[k] = fmaxf(v[k], 0.f);
+    }
+    if (mode == 1 || mode == 4) {
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < PER; ++k) sum += v[k];
+      const float mean = warp_sum(sum) * (1.0f / C);
+      float var = 0.f;
+#pragma unroll
+      for (int k = 0; k < PER; ++k) { const float d = v[k] - mean; var += d * d; }
+      const float rstd = rsqrtf(warp_sum(var) * (1.0f / C) + 1e-12f);
+#pragma unroll
+      for (int k = 0; k < PER; ++k) v[k] = (v[k] - mean) * rstd;
+    } else if (mode == 2) {
+#pragma unroll
+      for (int k = 0; k < PER; ++k) v[k] = tanhf(v[k]);
+    } else if (mode == 3) {
+#pragma unroll
+      for (int k = 0; k < PER; ++k) v[k] = fmaxf(v[k], 0.f);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < PER; ++k) v[k] = 0.f;                           // halo cell
+  }
+  if (out_b) {
+    act_t* d = out_b + static_cast<size_t>(p) * ldb + colb + lane * PER;
+#pragma unroll
+    for (int k = 0; k < PER; k += 2) *reinterpret_cast<uint32_t*>(d + k) = pack_act2(v[k], v[k + 1]);
+  }
+  if (out_f) {
+    float* d = out_f + static_cast<size_t>(p) * ldf + colf + lane * PER;
+#pragma unroll
+    for (int k = 0; k < PER; k += 4) *reinterpret_cast<float4*>(d + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+  }
+}
+
 // unpack_tokens: token-major rows (bf16 or f32) -> NCHW fp32.
 template <typename T>
 __global__ void __launch_bounds__(256) unpack_tokens_kernel(const T* __restrict__ src, int ld, int col,
@@ -122,6 +201,11 @@ struct LookupParams {
   int ldb;
   float* out_nchw;       // [324, H, W] or nullptr
   int first_level;       // levels < first_level are skipped (handled by the on-demand kernel)
+  // level 0 stored in 16 bits, blocked [Mp][nby*nbx][64] (scores.cuh lvl0h); used instead of lvl[0] when non-null
+  const __half* lvl0h;
+  const float* lvl0_base;   // [Mp][nblk][2] fp32 mean of each 4x8 half block; lvl0h holds fp16 deltas against it
+  int nbx0;              // 8x8 blocks per block row
+  long long qstride0h;
 };
 
 __global__ void __launch_bounds__(256) corr_lookup_kernel(LookupParams p, Grid2 g) {
@@ -145,14 +229,29 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(LookupParams p, Grid2 
     const float ax = px - fx0, ay = py - fy0;
     const int x0 = static_cast<int>(fx0) - R, y0 = static_cast<int>(fy0) - R;
     const int hl = p.hl[l], wl = p.wl[l];
-    const float* vol = p.lvl[l] + static_cast<long long>(q) * p.qstride[l];
     __syncwarp();
-    for (int e = lane; e < WN * WN; e += 32) {
-      const int r = e / WN, c = e - r * WN;
-      const int yy = y0 + r, xx = x0 + c;
-      float v = 0.f;
-      if (yy >= 0 && yy < hl && xx >= 0 && xx < wl) v = __ldg(vol + yy * wl + xx) - mean;
-      wv[e] = v;   // (value - mean) inside bounds, 0 outside == deferred-LN numerator
+    if (l == 0 && p.lvl0h != nullptr) {
+      const __half* vol = p.lvl0h + static_cast<long long>(q) * p.qstride0h;
+      const float* bases = p.lvl0_base + static_cast<long long>(q) * (p.qstride0h >> 5);
+      for (int e = lane; e < WN * WN; e += 32) {
+        const int r = e / WN, c = e - r * WN;
+        const int yy = y0 + r, xx = x0 + c;
+        float v = 0.f;
+        if (yy >= 0 && yy < hl && xx >= 0 && xx < wl) {
+          const int blk = (yy >> 3) * p.nbx0 + (xx >> 3);
+          v = (__ldg(bases + 2 * blk + ((yy >> 2) & 1)) - mean) + __half2float(__ldg(vol + (blk << 6) + ((yy & 7) << 3) + (xx & 7)));
+        }
+        wv[e] = v;
+      }
+    } else {
+      const float* vol = p.lvl[l] + static_cast<long long>(q) * p.qstride[l];
+      for (int e = lane; e < WN * WN; e += 32) {
+        const int r = e / WN, c = e - r * WN;
+        const int yy = y0 + r, xx = x0 + c;
+        float v = 0.f;
+        if (yy >= 0 && yy < hl && xx >= 0 && xx < wl) v = __ldg(vol + yy * wl + xx) - mean;
+        wv[e] = v;   // (value - mean) inside bounds, 0 outside == deferred-LN numerator
+      }
     }
     __syncwarp();
     for (int e = lane; e < D * D; e += 32) {

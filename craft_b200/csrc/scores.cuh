@@ -56,6 +56,15 @@ struct ScoreParams {
   float* stat_max;         // [1]: global max of raw scaled scores (pre-bias)
   float* lvl[4];           // pooled volumes [Mp][h_l*w_l]; lvl[0] optional
   int hl[4], wl[4];
+  // level 0 in 16 bits, BLOCKED: [Mp][nkt_y*nkt_x][64] fp16 (both precision tiers), block (by, bx) = the 8x8 key
+  // block of one tile, cell (y&7)*8 + (x&7) -- a thread's half block is 64 contiguous bytes (two 256-bit stores,
+  // whole sectors), and a lookup window row inside a block is one 16-byte run.  104 MB at 448x1024.
+  // The halves are DELTAS against the fp32 mean of their 4x8 half block (lvl0_base [Mp][nkt][2], 6.5 MB): the
+  // rounding error is then relative to the local variation of the volume, not to its magnitude -- a volume
+  // whose mean is 100x its standard deviation (a saturated clamp) loses nothing under the global layer-norm.
+  __half* lvl0h;
+  float* lvl0_base;
+  long long l0_qstride;    // halves between consecutive query rows (nkt_y*nkt_x*64)
   // SC_LSE
   float2* lse_part;        // [nslots][M][Mp] (max, sumexp) natural-exp domain
 };
@@ -341,7 +350,24 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 if ((ky0 + (e >> 3) < p.g.H) && (kx0 + (e & 7) < p.g.W)) { st_sum += agg[e]; st_sq = fmaf(agg[e], agg[e], st_sq); }
               }
             }
-            // level 0 (optional, debugging / SAVECORR)
+            if (p.lvl0h) {
+              float base = 0.f;
+#pragma unroll
+              for (int e = 0; e < 32; ++e) base += agg[e];
+              base *= (1.0f / 32.0f);
+              uint32_t w16[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const __half2 h2 = __floats2half2_rn(agg[2 * e] - base, agg[2 * e + 1] - base);
+                w16[e] = *reinterpret_cast<const uint32_t*>(&h2);
+              }
+              const size_t blk = static_cast<size_t>(by * p.nkt_x + bx);
+              __half* dst = p.lvl0h + static_cast<size_t>(q) * p.l0_qstride + (blk * 64 + ch * 32);
+              st_global_v8(dst, *reinterpret_cast<const uint32_t(*)[8]>(&w16[0]));
+              st_global_v8(dst + 16, *reinterpret_cast<const uint32_t(*)[8]>(&w16[8]));
+              p.lvl0_base[(static_cast<size_t>(q) * (p.l0_qstride >> 6) + blk) * 2 + ch] = base;
+            }
+            // level 0 in fp32, row-major (optional, debugging / SAVECORR)
             if (p.lvl[0]) {
               float* dst = p.lvl[0] + static_cast<size_t>(q) * (p.hl[0] * p.wl[0]);
 #pragma unroll

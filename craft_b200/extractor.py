@@ -127,22 +127,32 @@ class BasicEncoder(nn.Module):
                 and self.norm_fn in ("instance", "batch") and not torch.is_autocast_enabled()
                 and getattr(self, "use_fused", True))
 
+    def _forward_fused(self, x):
+        """[N,3,H,W] fp32 -> conv2 output as a channels-last tensor (NCHW shape, NHWC memory), f16 or f32."""
+        half = bool(getattr(self, "fused_half", False))
+        if getattr(self, "_fz", None) is None or self._fz.kind != self.norm_fn or self._fz.half != half:
+            self._fz = _Fused(self.norm_fn, half)
+        fz = self._fz
+        x = x.to(fz.dtype).contiguous(memory_format=torch.channels_last)
+        x = fz.norm_act(self.norm1, fz.conv(self.conv1, x), self.conv1, relu=True)
+        for layer in (self.layer1, self.layer2, self.layer3):
+            for blk in layer:
+                x = blk.forward_fused(x, fz)
+        return fz.conv(self.conv2, x, bias=True)
+
+    def forward_nhwc(self, x):
+        """Inference fast path: [N,3,H,W] -> [N, H/8, W/8, C] contiguous (channels-last), in the encoder's
+        activation type.  Callers check _can_fuse first."""
+        y = self._forward_fused(x).permute(0, 2, 3, 1)
+        return y if y.is_contiguous() else y.contiguous()
+
     def forward(self, x):
         is_list = isinstance(x, (tuple, list))
         if is_list:
             batch_dim = x[0].shape[0]
             x = torch.cat(x, dim=0)
         if self._can_fuse(x):
-            half = bool(getattr(self, "fused_half", False))
-            if getattr(self, "_fz", None) is None or self._fz.kind != self.norm_fn or self._fz.half != half:
-                self._fz = _Fused(self.norm_fn, half)
-            fz = self._fz
-            x = x.to(fz.dtype).contiguous(memory_format=torch.channels_last)
-            x = fz.norm_act(self.norm1, fz.conv(self.conv1, x), self.conv1, relu=True)
-            for layer in (self.layer1, self.layer2, self.layer3):
-                for blk in layer:
-                    x = blk.forward_fused(x, fz)
-            x = fz.conv(self.conv2, x, bias=True).float().contiguous()      # back to NCHW fp32 for the token packer
+            x = self._forward_fused(x).float().contiguous()      # NCHW fp32, the reference's output format
             if is_list:
                 x = torch.split(x, [batch_dim, batch_dim], dim=0)
             return x

@@ -12,6 +12,7 @@ padded-flat token grid; the update block's GRU input lives in ONE 640-column bf1
 so that torch.cat never happens: each producer kernel writes its column slice in place.
 """
 import math
+import os
 
 import torch
 
@@ -39,13 +40,30 @@ class PackedWeights:
         return hit[1]
 
 
+def level0_mode(x=None):
+    """How level 0 of the correlation pyramid is held:
+      "h16"      (default) the build kernel stores it in 8x8-key-block order as fp16 deltas against the fp32 mean
+                 of each 4x8 half block (110 MB at 448x1024) and ONE lookup kernel serves all four levels;
+      "ondemand" never stored: each lookup recomputes its 10x10 window from the projected Q/K rows;
+      "f32"      the reference's dense fp32 [U,U] volume (SAVECORR / debugging / standalone scores-only calls).
+    True -> "f32"; None / False -> $CRAFT_B200_LEVEL0 or "h16"."""
+    if x is True:
+        return "f32"
+    if x is None or x is False:
+        x = os.environ.get("CRAFT_B200_LEVEL0", "h16")
+    if x not in ("h16", "ondemand", "f32"):
+        raise ValueError("level-0 mode must be h16, ondemand or f32 (got %r)" % (x,))
+    return x
+
+
 class Workspace:
     """All device buffers for one (H, W) token grid on one device.  Allocated once and reused, so the
     addresses baked into TMA descriptors stay valid and the whole schedule can live in a CUDA graph."""
 
-    def __init__(self, grid, device, materialize_level0=True):
+    def __init__(self, grid, device, materialize_level0=None):
         g = self.grid = grid
         self.device = device
+        self.level0 = level0_mode(materialize_level0)
         act = self.dtype = ops.act_dtype()
         z = lambda cols, dt=act: torch.zeros((g.Mp, cols), dtype=dt, device=device)
         f32 = torch.float32
@@ -80,9 +98,11 @@ class Workspace:
         shapes = g.level_shapes()
         self.levels = [None] * 4
         for l, (h, w) in enumerate(shapes):
-            if l == 0 and not materialize_level0:
+            if l == 0 and self.level0 != "f32":
                 continue
             self.levels[l] = torch.zeros((g.Mp, max(h * w, 1)), dtype=f32, device=device)
+        self.level0_h16 = None      # fp16 level 0, allocated by the first build_correlation (standalone attention
+                                    # calls on the shared workspace never need its 100 MB)
         # --- update block
         self.X = z(640)
         self.Hm = z(128, f32); self.Z = z(128, f32)
@@ -96,6 +116,16 @@ class Workspace:
         self.side = torch.cuda.Stream(device=device)    # second lane for independent branches (captured too)
         self.ev_lookup = torch.cuda.Event()
         self.coords1 = z(2, f32); self.flow = z(2, f32)
+
+    def ensure_level0(self):
+        if self.level0 == "h16" and self.level0_h16 is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("the fp16 level-0 volume must be allocated before CUDA-graph capture (run one eager forward)")
+            g = self.grid
+            nblk = ((g.H + 7) // 8) * ((g.W + 7) // 8)
+            # [Mp][nblk][64] fp16 deltas, then [Mp][nblk][2] fp32 half-block means (include/craft_b200.h)
+            self.level0_h16 = torch.zeros((g.Mp * nblk * 68,), dtype=torch.float16, device=self.device)
+        return self.level0_h16
 
     def opart(self, ks, M, F):
         if ks * M * self.grid.Mp * F > self.Opart.numel():
@@ -169,7 +199,7 @@ def build_correlation(ws, Q, K, *, M, d, w_agg, table, w_pos, global_norm, attn_
     smax.fill_(-_INF)
     flag = ws.flag[0:1]
     kw = dict(M=M, d=d, w_agg=w_agg, w_pos=w_pos, pos_table=table, R=7, clip=clip, levels=ws.levels,
-              ksplit=ws.ks_sc)
+              ksplit=ws.ks_sc, level0_h16=ws.ensure_level0())
     ops.corr_build(Q, K, g, stat_sum=ws.stat_sum[0], stat_max=smax, **kw)
     if M > 1:   # the clamp exists only on the transformer path
         ops.clip_gate(smax, attn_clip, clip, flag, diag)
@@ -249,24 +279,27 @@ class UpdateWeights(EncoderWeights):
 def motion_encoder(ws, uw, lookup=None):
     """BasicMotionEncoder.forward core/update.py:79-87 -> X[:, 256:384] (126 features + the flow).
 
-    `lookup(part)` (optional) is the correlation lookup of this iteration (core/corr.py:47-71).  Its
-    level-0 part runs on the main stream; the pooled levels and the flow branch (convf1 -> convf2), all
-    of which depend only on the current coordinates, run on the side stream next to it; the
-    correlation branch (convc1 -> convc2) starts as soon as both lookup halves are in."""
+    `lookup(part)` (optional) is the correlation lookup of this iteration (core/corr.py:47-71).  The flow
+    branch (convf1 -> convf2) depends only on the current flow and runs on the side stream next to the
+    lookup and the correlation branch (convc1 -> convc2).  When level 0 is computed on demand the lookup
+    is two kernels: the level-0 part runs on the main stream, the pooled levels on the side stream."""
     g = ws.grid
     sg = ops.shift_gemm
     main, side = torch.cuda.current_stream(), ws.side
+    split = lookup is not None and getattr(ws, "level0", "f32") == "ondemand"
     side.wait_stream(main)
     with torch.cuda.stream(side):
-        if lookup is not None:
+        if split:
             lookup("pooled")
             ws.ev_lookup.record(side)
         ops.convf1(ws.flow, uw.f1_w, uw.f1_b, g, ws.F1)
         sg(ws.F1, uw.f2_w, M=g.Mp, Npad=64, K=128, BN=64, taps=uw.taps3, grid=g, bias=uw.f2_b, act=1, out_b=ws.CF,
            colb=192)
-    if lookup is not None:
+    if split:
         lookup("level0")
         main.wait_event(ws.ev_lookup)
+    elif lookup is not None:
+        lookup("all")
     sg(ws.CORR, uw.c1_w, M=g.Mp, Npad=256, K=384, BN=128, grid=g, bias=uw.c1_b, act=1, out_b=ws.C1)
     # N = 192 as two 96-wide tiles: 114 CTAs = one wave (three 64-wide tiles would need 171 CTAs = two waves)
     sg(ws.C1, uw.c2_w, M=g.Mp, Npad=192, K=256, BN=96, taps=uw.taps3, grid=g, bias=uw.c2_b, act=1, out_b=ws.CF)

@@ -103,7 +103,9 @@ class CRAFT(nn.Module):
 
         self.update_block = GMAUpdateBlock(self.args, hidden_dim=hdim)
         self.call_counter = 0
-        self.materialize_level0 = False    # True only for debugging / SAVECORR: writes the 205 MB level-0 volume
+        self.materialize_level0 = False    # True only for debugging / SAVECORR: writes the 205 MB fp32 level-0 volume
+        self.encoder_nhwc = os.environ.get("CRAFT_B200_ENCODER_NHWC", "1") != "0"   # fused encoders -> token packer directly
+        self.level0 = None                 # None: $CRAFT_B200_LEVEL0 or "h16"; "ondemand": level 0 is never stored
         # Inference calls are captured into one CUDA graph per (shape, iters, test_mode) and replayed:
         # the ~250 launches of a forward then cost no host time.  Set False (or CRAFT_B200_NO_GRAPH=1)
         # to launch eagerly.
@@ -151,7 +153,7 @@ class CRAFT(nn.Module):
         what tests and profiling scripts inspect after a forward."""
         device = device or next(self.parameters()).device
         with torch.cuda.device(device), ops.precision(self.act_dtype):
-            return self._workspaces.get(TokenGrid(H // 8, W // 8), device, self.materialize_level0)
+            return self._workspaces.get(TokenGrid(H // 8, W // 8), device, self.materialize_level0 or self.level0)
 
     def freeze_bn(self):
         for m in self.modules():
@@ -191,6 +193,17 @@ class CRAFT(nn.Module):
         with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark,
                                         deterministic=False, allow_tf32=self.encoder_tf32), \
                 torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+            if self.encoder_nhwc and not amp and self.fnet._can_fuse(image1) and self.cnet._can_fuse(image1):
+                # fused encoders: the channels-last 16-bit output of the last convolution goes straight to the
+                # token packers (one LN-and-pack kernel; no NHWC -> NCHW fp32 conversion passes)
+                with torch.cuda.stream(side):
+                    cn = self.cnet.forward_nhwc(image1)
+                fm = self.fnet.forward_nhwc(torch.cat([image1, image2], dim=0))
+                main.wait_stream(side)
+                cn.record_stream(main)
+                B = image1.shape[0]
+                return ([ops.NhwcFeat(fm[b]) for b in range(B)], [ops.NhwcFeat(fm[B + b]) for b in range(B)],
+                        [ops.NhwcFeat(cn[b]) for b in range(B)])
             with torch.cuda.stream(side):
                 cnet_feat = self.cnet(image1).float().contiguous()
             fmap1, fmap2 = self.fnet([image1, image2])
@@ -230,14 +243,17 @@ class CRAFT(nn.Module):
             else:
                 ops.pack_tokens(fmap2, g, ops.PACK_COPY, out_b=ws.Kc)
             hp.build_correlation(ws, ws.Qc, ws.Kc, M=1, d=256, w_agg=0.0, table=None, w_pos=0.0, global_norm=False)
-        net, inp = cnet_feat[:128], cnet_feat[128:]
-        ops.pack_tokens(net.contiguous(), g, ops.PACK_TANH, out_b=ws.X, colb=0, out_f=ws.Hm)
-        ops.pack_tokens(inp.contiguous(), g, ops.PACK_RELU, out_b=ws.X, colb=128)
+        if isinstance(cnet_feat, ops.NhwcFeat):
+            net, inp = cnet_feat.window(0, 128), cnet_feat.window(128, 128)
+        else:
+            net, inp = cnet_feat[:128].contiguous(), cnet_feat[128:].contiguous()
+        ops.pack_tokens(net, g, ops.PACK_TANH, out_b=ws.X, colb=0, out_f=ws.Hm)
+        ops.pack_tokens(inp, g, ops.PACK_RELU, out_b=ws.X, colb=128)
         if a.use_setrans:
-            att = self.att.attend(ws, inp.contiguous(), ws.Ta, ws.Qa, ws.Ka, ws.lse2_att, ws.clip_att, slot=2,
+            att = self.att.attend(ws, inp, ws.Ta, ws.Qa, ws.Ka, ws.lse2_att, ws.clip_att, slot=2,
                                   pack_mode=ops.PACK_RELU_LN)
         else:
-            ops.pack_tokens(inp.contiguous(), g, ops.PACK_RELU, out_b=ws.Ta)
+            ops.pack_tokens(inp, g, ops.PACK_RELU, out_b=ws.Ta)
             att = self.att.attend(ws, ws.Ta, ws.Qa, ws.Ka, ws.lse2_att, ws.clip_att)
         ops.init_coords(ws.coords1, flow_init, g)
         ops.flow_update(ws.coords1, ws.flow, None, g)
@@ -273,7 +289,7 @@ class CRAFT(nn.Module):
 
     def _forward_graphed(self, image1, image2, iters, flow_init, test_mode):
         key = (image1.device.index, tuple(image1.shape), int(iters), int(test_mode), flow_init is not None,
-               self.materialize_level0, self.encoder_tf32, self.encoder_half, self.elide_dead_upsample, self.precision)
+               self.materialize_level0, hp.level0_mode(self.level0), self.encoder_tf32, self.encoder_half, self.elide_dead_upsample, self.precision)
         sig = self._weights_signature()
         ent = self._graphs.get(key)
         if ent is not None:
@@ -312,7 +328,7 @@ class CRAFT(nn.Module):
             ent["launches"] = _lib.launch_count() - n0   # craft_b200 kernels per replay
             # the graph bakes in the workspace's addresses: keep the buffers alive as long as the graph is
             g8 = TokenGrid(image1.shape[2] // 8, image1.shape[3] // 8)
-            ent["ws"] = self._workspaces.get(g8, image1.device, self.materialize_level0)
+            ent["ws"] = self._workspaces.get(g8, image1.device, self.materialize_level0 or self.level0)
             self._graphs[key] = ent
             while len(self._graphs) > self.max_cached_graphs:
                 self._graphs.popitem(last=False)
@@ -332,7 +348,7 @@ class CRAFT(nn.Module):
         B, _, H, W = image1.shape
         fmap1, fmap2, cnet_feat = self._encoders(image1.float(), image2.float())
         g = TokenGrid(H // 8, W // 8)
-        ws = self._workspaces.get(g, image1.device, self.materialize_level0 or savecorr)
+        ws = self._workspaces.get(g, image1.device, self.materialize_level0 or savecorr or self.level0)
         dev = image1.device
         flow_lo = torch.empty((B, 2, g.H, g.W), dtype=torch.float32, device=dev)
         n_up = iters if test_mode != 1 else 1

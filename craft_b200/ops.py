@@ -123,10 +123,36 @@ def _cuda_only(*ts):
             raise _lib.CraftB200Error("expected CUDA tensors; craft_b200 has no CPU path")
 
 
+class NhwcFeat:
+    """A channels-last feature map [H, W, ldc] (f16 or f32, contiguous) with a channel window [c0, c0 + C): what the
+    fused encoders hand to the token packer, so that the NHWC -> NCHW fp32 -> token round trip
+    (core/extractor.py output -> core/setrans.py:791-795 / core/network.py:209-211) never happens."""
+
+    def __init__(self, t, c0=0, C=None):
+        assert t.dim() == 3 and t.is_contiguous()
+        self.t, self.c0, self.C = t, c0, (t.shape[2] - c0 if C is None else C)
+
+    def window(self, c0, C):
+        assert c0 + C <= self.C
+        return NhwcFeat(self.t, self.c0 + c0, C)
+
+    def nchw(self):
+        """[C, H, W] fp32 (tests / debugging)."""
+        return self.t[:, :, self.c0:self.c0 + self.C].permute(2, 0, 1).float().contiguous()
+
+
 def pack_tokens(src, grid, mode=PACK_COPY, out_b=None, colb=0, out_f=None, colf=0):
-    """src [C,H,W] f32 -> token rows (optionally LayerNorm / tanh / relu)."""
+    """src [C,H,W] f32 (or an NhwcFeat) -> token rows (optionally LayerNorm / tanh / relu)."""
+    if isinstance(src, NhwcFeat):
+        return pack_tokens_nhwc(src.t, grid, mode, c0=src.c0, C=src.C, out_b=out_b, colb=colb, out_f=out_f, colf=colf)
     _cuda_only(src, out_b, out_f)
     OPS.pack_tokens(src, grid.H, grid.W, mode, out_b, colb, out_f, colf)
+
+
+def pack_tokens_nhwc(src, grid, mode=PACK_COPY, c0=0, C=None, out_b=None, colb=0, out_f=None, colf=0):
+    """src [H,W,ldc] channels-last f16/f32 -> token rows of channels [c0, c0+C) (LayerNorm / tanh / relu as pack_tokens)."""
+    _cuda_only(src, out_b, out_f)
+    OPS.pack_tokens_nhwc(src, c0, C or src.shape[2], grid.H, grid.W, mode, out_b, colb, out_f, colf)
 
 
 def unpack_tokens(buf, col, Cc, grid, out=None):
@@ -212,11 +238,12 @@ def blocked_keys(grid, BK):
 
 
 def corr_build(Q, K, grid, *, M, d, w_agg, w_pos, pos_table, R, clip, stat_sum, stat_max, levels,
-               run_flag=None, ksplit=0):
-    """levels: list of 4 f32 tensors [Mp, h_l*w_l] (levels[0] may be None)."""
+               run_flag=None, ksplit=0, level0_h16=None):
+    """levels: list of 4 f32 tensors [Mp, h_l*w_l] (levels[0] may be None); level0_h16: optional fp16
+    [Mp, nblocks*64] level 0 in 8x8 key-block order (see include/craft_b200.h)."""
     _cuda_only(Q, K)
     OPS.corr_build(Q, K, grid.H, grid.W, M, d, float(w_agg), float(w_pos), pos_table, R, clip, stat_sum, stat_max,
-                   levels[0], levels[1], levels[2], levels[3], run_flag, ksplit)
+                   levels[0], levels[1], levels[2], levels[3], run_flag, ksplit, level0_h16)
 
 
 def attn_lse(Q, K, grid, *, M, d, w_pos, pos_table, R, clip, stat_max, lse_part, lse2, run_flag=None, ksplit=0,
@@ -278,9 +305,10 @@ def attn_dense(Q, K, grid, *, M, d, w_pos, pos_table, R, clip, lse2=None, mask_r
 # ------------------------------------------------------------------------------------------------
 # lookup / small kernels
 # ------------------------------------------------------------------------------------------------
-def corr_lookup(levels, grid, coords, mean_rstd, out_b=None, out_nchw=None, first_level=0):
+def corr_lookup(levels, grid, coords, mean_rstd, out_b=None, out_nchw=None, first_level=0, level0_h16=None):
+    """level0_h16: level 0 in blocked fp16 (corr_build(level0_h16=...)), read instead of levels[0]."""
     OPS.corr_lookup(levels[0], levels[1], levels[2], levels[3], grid.H, grid.W, coords, mean_rstd, out_b, out_nchw,
-                    first_level)
+                    first_level, level0_h16)
 
 
 def corr_lookup0(Q, K, grid, *, M, d, w_agg, w_pos, pos_table, R, clip, coords, mean_rstd, out_b=None, out_nchw=None):

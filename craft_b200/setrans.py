@@ -514,7 +514,7 @@ class SelfAttVisPosTrans(nn.Module):
 
 
 class WorkspaceCache:
-    """LRU of hotpath.Workspace objects keyed by (device, H, W, materialize_level0).  Each CRAFT instance
+    """LRU of hotpath.Workspace objects keyed by (device, H, W, level-0 mode).  Each CRAFT instance
     owns one (so that two models never share buffers a captured CUDA graph has baked in); standalone
     module calls share the module-level one.  Bounded: KITTI-style variable input sizes would otherwise
     accumulate ~150 MB per shape."""
@@ -525,7 +525,8 @@ class WorkspaceCache:
 
     def get(self, grid, device, materialize_level0=False, slot=0):
         """slot: independent buffer sets for the same grid (training keeps one correlation pyramid per batch element)."""
-        key = (str(device), grid.H, grid.W, bool(materialize_level0), ops.act_dtype(), slot)
+        materialize_level0 = hp.level0_mode(materialize_level0)
+        key = (str(device), grid.H, grid.W, materialize_level0, ops.act_dtype(), slot)
         ws = self._lru.get(key)
         if ws is None:
             with torch.cuda.device(device):
@@ -545,4 +546,4 @@ _SHARED_WORKSPACES = WorkspaceCache()
 
 
 def get_workspace(grid, device, materialize_level0=None, cache=None):
-    return (cache or _SHARED_WORKSPACES).get(grid, device, bool(materialize_level0))
+    return (cache or _SHARED_WORKSPACES).get(grid, device, materialize_level0)

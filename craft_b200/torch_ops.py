@@ -90,6 +90,17 @@ def pack_tokens(src, H, W, mode, out_b, colb, out_f, colf):
               _ptr(out_f), _ld(out_f), colf, _stream(), fp16=_half(out_b))
 
 
+@_op("pack_tokens_nhwc(Tensor src, int c0, int C, int H, int W, int mode, Tensor(a!)? out_b, int colb, Tensor(b!)? out_f, int colf) -> ()")
+def pack_tokens_nhwc(src, c0, Cc, H, W, mode, out_b, colb, out_f, colf):
+    """src [H, W, ldc] channels-last, f16 or f32, contiguous."""
+    if src.dtype not in (f16, f32):
+        raise TypeError("src: expected float16 or float32, got %s" % src.dtype)
+    _chk(src, src.dtype, "src"); _chk(out_b, ACT, "out_b"); _chk(out_f, f32, "out_f")
+    assert src.shape[0] == H and src.shape[1] == W
+    _lib.call("craft_pack_tokens_nhwc", _ptr(src), 1 if src.dtype == f16 else 0, src.shape[2], c0, Cc, H, W, mode,
+              _ptr(out_b), _ld(out_b), colb, _ptr(out_f), _ld(out_f), colf, _stream(), fp16=_half(out_b))
+
+
 @_op("unpack_tokens(Tensor buf, int col, int C, int H, int W, Tensor(a!) out) -> ()")
 def unpack_tokens(buf, col, Cc, H, W, out):
     is_b = 1 if buf.dtype in (bf16, f16) else 0
@@ -145,9 +156,9 @@ def _scores_args(Q, K, H, W, M, d, w_pos, pos_table, R, clip, run_flag, ksplit):
 
 @_op("corr_build(Tensor Q, Tensor K, int H, int W, int M, int d, float w_agg, float w_pos, Tensor? pos_table, int R, "
      "Tensor clip, Tensor(a!) stat_sum, Tensor(b!) stat_max, Tensor(c!)? lvl0, Tensor(d!) lvl1, Tensor(e!) lvl2, "
-     "Tensor(f!) lvl3, Tensor? run_flag, int ksplit) -> ()")
+     "Tensor(f!) lvl3, Tensor? run_flag, int ksplit, Tensor(g!)? lvl0_h16) -> ()")
 def corr_build(Q, K, H, W, M, d, w_agg, w_pos, pos_table, R, clip, stat_sum, stat_max, lvl0, lvl1, lvl2, lvl3, run_flag,
-               ksplit):
+               ksplit, lvl0_h16):
     a = _scores_args(Q, K, H, W, M, d, w_pos, pos_table, R, clip, run_flag, ksplit)
     a.w_agg = float(w_agg)
     _chk(stat_sum, f64, "stat_sum"); _chk(stat_max, f32, "stat_max")
@@ -155,6 +166,10 @@ def corr_build(Q, K, H, W, M, d, w_agg, w_pos, pos_table, R, clip, stat_sum, sta
     for l, lv in enumerate((lvl0, lvl1, lvl2, lvl3)):
         _chk(lv, f32, "level")
         a.lvl[l] = _dp(lv)
+    if lvl0_h16 is not None:
+        _chk(lvl0_h16, f16, "lvl0_h16")
+        assert lvl0_h16.numel() >= H * (W + 2) * ((H + 7) // 8) * ((W + 7) // 8) * 68   # fp16 deltas + fp32 half-block means
+    a.lvl0_h16 = _dp(lvl0_h16)
     _lib.call("craft_corr_build", C.byref(a), _stream(), fp16=_half(Q, K))
 
 
@@ -235,11 +250,14 @@ def attn_dense(Q, K, H, W, M, d, w_pos, pos_table, R, clip, lse2, mask_radius, o
 
 
 @_op("corr_lookup(Tensor? lvl0, Tensor? lvl1, Tensor? lvl2, Tensor? lvl3, int H, int W, Tensor coords, Tensor mean_rstd, "
-     "Tensor(a!)? out_b, Tensor(b!)? out_nchw, int first_level) -> ()")
-def corr_lookup(lvl0, lvl1, lvl2, lvl3, H, W, coords, mean_rstd, out_b, out_nchw, first_level):
+     "Tensor(a!)? out_b, Tensor(b!)? out_nchw, int first_level, Tensor? lvl0_h16) -> ()")
+def corr_lookup(lvl0, lvl1, lvl2, lvl3, H, W, coords, mean_rstd, out_b, out_nchw, first_level, lvl0_h16):
     arr = (C.c_void_p * 4)(*[_dp(lv) for lv in (lvl0, lvl1, lvl2, lvl3)])
     _chk(coords, f32, "coords"); _chk(out_b, ACT, "out_b"); _chk(out_nchw, f32, "out_nchw")
-    _lib.call("craft_corr_lookup", arr, H, W, _ptr(coords), _ptr(mean_rstd), _ptr(out_b), _ld(out_b),
+    _chk(lvl0_h16, f16, "lvl0_h16")
+    for lv in (lvl0, lvl1, lvl2, lvl3):
+        _chk(lv, f32, "level")
+    _lib.call("craft_corr_lookup", arr, _ptr(lvl0_h16), H, W, _ptr(coords), _ptr(mean_rstd), _ptr(out_b), _ld(out_b),
               _ptr(out_nchw), first_level, _stream(), fp16=_half(out_b))
 
 

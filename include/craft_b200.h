@@ -37,6 +37,10 @@ int craft_b200_device_info(int* out3);
  * core/setrans.py:791-795 (mode 1) and the tanh/relu split core/network.py:209-211.       */
 int craft_pack_tokens(const float* src_nchw, int C, int H, int W, int mode, void* out_bf16,
                       int ldb, int colb, float* out_f32, int ldf, int colf, void* stream);
+/* Same packer for a channels-last source [H][W][ldc] (f16 if src_is_half else f32 -- what the fused encoders
+ * produce): channels [c0, c0+C) of every token, C in {128, 256}; mode 4 = relu then LayerNorm.             */
+int craft_pack_tokens_nhwc(const void* src, int src_is_half, int ldc, int c0, int C, int H, int W, int mode,
+                           void* out_16, int ldb, int colb, float* out_f32, int ldf, int colf, void* stream);
 /* token rows (bf16 if is_bf16 else f32) -> NCHW f32 */
 int craft_unpack_tokens(const void* src, int is_bf16, int ld, int col, int C, int H, int W,
                         float* dst_nchw, void* stream);
@@ -98,6 +102,11 @@ typedef struct craft_scores_args {
   float* lse2;        /* [M][Mp] out                                                          */
   int mask_radius;    /* attn_lse only; > 0: keys with max(|dy|,|dx|) > mask_radius are masked out
                          (--f2radius, SelfAttVisPosTrans.forward core/setrans.py:580-584); <= 0: off */
+  void* lvl0_h16;     /* corr build, optional: level 0 in 16 bits.  Mp*nblk*64 IEEE fp16 (both precision tiers)
+                         [Mp][nblk = ceil(H/8)*ceil(W/8)][64]: 8x8 key block (by,bx) -> block by*ceil(W/8)+bx,
+                         cell (y%8)*8 + x%8, each value a DELTA against the fp32 mean of its 4x8 half block;
+                         followed (same allocation, at fp16 element Mp*nblk*64) by those means, f32
+                         [Mp][nblk][2].  Mp*nblk*136 bytes.  Read back by craft_corr_lookup(lvl0_h16). */
 } craft_scores_args;
 /* TransCorrBlock.update core/corr.py:148-207 (+ CorrBlock.__init__ :16-45 with M=1).         */
 int craft_corr_build(const craft_scores_args* a, void* stream);
@@ -171,7 +180,8 @@ typedef struct craft_dense_attn_args {
 int craft_attn_dense(const craft_dense_attn_args* a, void* stream);
 
 /* ---- correlation lookup (CorrBlock.__call__ core/corr.py:47-71) --------------------------- */
-int craft_corr_lookup(const float* const* lvl /*host array of 4 device ptrs*/, int H, int W,
+/* lvl0_h16 (optional): level 0 as written by craft_corr_build(lvl0_h16) -- used instead of lvl[0].   */
+int craft_corr_lookup(const float* const* lvl /*host array of 4 device ptrs*/, const void* lvl0_h16, int H, int W,
                       const float* coords /*[Mp,2]*/, const float* mean_rstd, void* out_bf16,
                       int ldb, float* out_nchw, int first_level, void* stream);
 

@@ -16,6 +16,7 @@ from craft_b200.setrans import get_workspace  # noqa: E402
 
 def main(which, reps):
     trace = os.environ.pop("CRAFT_PV_TRACE", None)     # only the kernel under test is traced, not the warm-up forward
+    gtrace = os.environ.pop("CRAFT_GEMM_TRACE", None)
     dev = torch.device("cuda", 0)
     model, _ = _state_dict()
     model = model.to(dev).eval()
@@ -46,7 +47,7 @@ def main(which, reps):
                 ws.stat_sum.zero_()
                 ops.corr_build(ws.Qc, ws.Kc, g, M=4, d=64, w_agg=0.1285, w_pos=0.5, pos_table=f2_tbl, R=7,
                                clip=ws.inf_clip, stat_sum=ws.stat_sum[0], stat_max=ws.stat_max[0:1], levels=ws.levels,
-                               ksplit=ws.ks_sc)
+                               ksplit=ws.ks_sc, level0_h16=ws.level0_h16)
             elif which == "lse_f2":
                 ops.attn_lse(ws.Q2, ws.K2, g, M=4, d=64, w_pos=0.5, pos_table=f2_tbl, R=7, clip=ws.inf_clip,
                              stat_max=ws.stat_max[1:2], lse_part=ws.lse_part, lse2=ws.lse2_f2, ksplit=ws.ks_sc)
@@ -59,13 +60,21 @@ def main(which, reps):
                 ops.corr_lookup0(grid=g, coords=ws.coords1, mean_rstd=ws.mean_rstd, out_b=ws.CORR, **ws.corr_meta)
             elif which == "lookup":
                 ops.corr_lookup(ws.levels, g, ws.coords1, ws.mean_rstd, out_b=ws.CORR, first_level=1)
+            elif which == "lookup_all":
+                ops.corr_lookup(ws.levels, g, ws.coords1, ws.mean_rstd, out_b=ws.CORR, level0_h16=ws.level0_h16)
             elif which == "heads":
                 hp.heads(ws, uw)
+            elif which == "iter_gemms":     # every tensor-core GEMM of one refinement iteration but the V^T one
+                hp.motion_encoder(ws, uw, None)
+                hp.sep_conv_gru(ws, uw)
+                hp.heads(ws, uw, 0, need_mask=False)
             else:
                 raise SystemExit("unknown kernel " + which)
 
         if trace:
             os.environ["CRAFT_PV_TRACE"] = trace
+        if gtrace:
+            os.environ["CRAFT_GEMM_TRACE"] = gtrace
         prof = os.environ.get("KO_PROFILE") == "1"      # ncu --profile-from-start off: only the measured calls are profiled
         for w in which.split(","):          # several kernels in one process: "pv,corr,lse"
             run(w)

@@ -203,19 +203,28 @@ def test_batch_of_two_equals_two_single_pairs():
     assert _epe(up[0].cpu(), up[1].cpu()) > 10 * max(errs)          # the two pairs really are different problems
 
 
-def test_stored_level0_volume_agrees_with_on_demand_lookup():
-    """materialize_level0=True (the SAVECORR / debugging path) writes the U x U level-0 volume from the
-    build kernel's tensor-core tiles; the default path recomputes each 10x10 window from the Q/K rows.
-    Same bf16 products, different fp32 summation order: the flows must agree far inside the parity bound."""
+def test_three_ways_of_holding_level0_agree():
+    """Level 0 of the pyramid is held as fp16 key blocks (default: one lookup kernel for all levels), not at all
+    ("ondemand": every lookup recomputes its 10x10 window from the Q/K rows) or as the reference's dense fp32
+    volume (materialize_level0 / SAVECORR).  Same tensor-core products; fp16 rounding of the stored value or a
+    different fp32 summation order: the flows must agree far inside the parity bound, and each must meet the
+    golden flow on its own."""
     rec = torch.load(os.path.join(GOLD, "seeded_setrans_128.pt"), map_location="cpu")
     model = _model(rec)
     i1, i2 = (t.cuda() for t in _inputs(rec))
+    ups = {}
     with torch.no_grad():
-        _, up_a = model(i1, i2, iters=4, test_mode=1)
-        model.materialize_level0 = True
-        _, up_b = model(i1, i2, iters=4, test_mode=1)
-    torch.cuda.synchronize()
-    assert _epe(up_a[0].cpu(), up_b[0].cpu()) <= 2e-3
+        for mode in ("h16", "ondemand", "f32"):
+            model.level0 = mode if mode != "f32" else None
+            model.materialize_level0 = mode == "f32"
+            _, up = model(i1, i2, iters=rec["iters"], test_mode=1)
+            torch.cuda.synchronize()
+            assert model.workspace_for(*i1.shape[-2:]).level0 == mode
+            ups[mode] = up[0].cpu()
+    errs = {m: _epe(u, rec["flow_up"]) for m, u in ups.items()}
+    _report("level0_modes", **errs, h16_vs_f32=_epe(ups["h16"], ups["f32"]), ondemand_vs_f32=_epe(ups["ondemand"], ups["f32"]))
+    assert _epe(ups["h16"], ups["f32"]) <= 2e-3 and _epe(ups["ondemand"], ups["f32"]) <= 2e-3
+    assert max(errs.values()) <= EPE_TOL, errs
 
 
 def test_real_frame_pair_error_trajectory_and_seams():
@@ -320,3 +329,29 @@ def test_fp16_tier_on_seeded_and_real_frames_is_no_worse_than_bf16():
             out[tier] = _epe(up[0].cpu(), rec["flow_up"])
         _report(name + ":tiers", **out)
         assert out["fp32-parity"] <= max(out["bf16"], 2e-3), out
+
+
+def test_savecorr_hook_writes_the_normalised_volume(tmp_path, monkeypatch):
+    """The reference's SAVECORR debugging hook (core/corr.py:180-184) dumps the normalised level-0 volume
+    [B,h,w,h,w]; here it forces the materialising path (the default never stores that volume)."""
+    from oracle import restate as R
+    rec = torch.load(os.path.join(GOLD, "seeded_setrans_128.pt"), map_location="cpu")
+    model = _model(rec)
+    i1, i2 = (t.cuda() for t in _inputs(rec))
+    path = str(tmp_path / "corr.pt")
+    monkeypatch.setenv("SAVECORR", path)
+    fn, cn = rec["fnet_out"].cuda(), rec["cnet_out"].cuda()
+    model._encoders = lambda a, b: (fn[0:1].contiguous(), fn[1:2].contiguous(), cn.contiguous())
+    with torch.no_grad():
+        model(i1, i2, iters=1, test_mode=1)
+    torch.cuda.synchronize()
+    monkeypatch.delenv("SAVECORR")
+    vol = torch.load(path)
+    assert tuple(vol.shape) == (1, 16, 16, 16, 16)
+    sd = {k: v.cpu() for k, v in model.state_dict().items()}
+    ref, _, _ = R.trans_corr_volume(rec["fnet_out"][0:1], rec["f2_out"], sd["corr_fn.setrans.query.weight"],
+                                    sd["corr_fn.setrans.query.bias"],
+                                    sd["corr_fn.setrans.attn_softaggr.feat2score.weight"].reshape(()),
+                                    sd["corr_fn.setrans.attn_softaggr.feat2score.bias"].reshape(()),
+                                    sd["corr_fn.vispos_encoder.pos_coder.biases"], 4, 0.5)
+    assert (vol.reshape(1, 256, 16, 16) - ref).abs().mean().item() <= 5e-3

@@ -132,6 +132,30 @@ def test_pack_unpack(Cc, mode):
     assert of.reshape(grid.H, grid.Wp, -1)[:, grid.W:].abs().max() == 0
 
 
+def _level0_encode(vol):
+    """[Mp, H, W] fp32 -> the 16-bit level-0 format of include/craft_b200.h (craft_scores_args.lvl0_h16): fp16 deltas in
+    8x8-key-block order followed by the fp32 means of the 4x8 half blocks."""
+    Mp, H, W = vol.shape
+    nby, nbx = (H + 7) // 8, (W + 7) // 8
+    pad = torch.zeros((Mp, nby * 8, nbx * 8), device=vol.device)
+    pad[:, :H, :W] = vol
+    blk = pad.reshape(Mp, nby, 2, 4, nbx, 8).permute(0, 1, 4, 2, 3, 5)          # [Mp, by, bx, half, 4, 8]
+    base = blk.mean(dim=(4, 5))                                                  # [Mp, by, bx, 2]
+    delta = (blk - base[..., None, None]).half()
+    return torch.cat([delta.reshape(-1), base.contiguous().reshape(-1).view(torch.float16)]).contiguous()
+
+
+def _level0_decode(buf, grid):
+    """-> [Mp, H, W] fp32 volume held by a lvl0_h16 buffer."""
+    Mp, H, W = grid.Mp, grid.H, grid.W
+    nby, nbx = (H + 7) // 8, (W + 7) // 8
+    n = Mp * nby * nbx * 64
+    delta = buf[:n].reshape(Mp, nby, nbx, 2, 4, 8).float()
+    base = buf[n:n + Mp * nby * nbx * 4].view(torch.float32).reshape(Mp, nby, nbx, 2)
+    v = (delta + base[..., None, None]).permute(0, 1, 3, 4, 2, 5).reshape(Mp, nby * 8, nbx * 8)
+    return v[:, :H, :W]
+
+
 @pytest.mark.parametrize("H,W", [(16, 24), (17, 22)])
 def test_corr_lookup(H, W):
     grid = TokenGrid(H, W)
@@ -159,6 +183,16 @@ def test_corr_lookup(H, W):
     assert torch.allclose(out_n, ref, atol=2e-4, rtol=1e-4), (out_n - ref).abs().max()
     got_b = nchw_from_rows(out_b, grid, 324)
     assert torch.allclose(got_b, ref, atol=5e-2, rtol=1e-2)
+    # the same lookup with level 0 held as fp16 8x8-key blocks (the default model path): bit-identical to the
+    # fp32 lookup of the fp16-rounded volume
+    l0h = _level0_encode(levels[0].reshape(grid.Mp, H, W))
+    out_h = torch.zeros((324, H, W), device=DEV)
+    ops.corr_lookup([None] + levels[1:], grid, cbuf, stats, out_nchw=out_h, level0_h16=l0h)
+    out_r = torch.zeros((324, H, W), device=DEV)
+    ops.corr_lookup([_level0_decode(l0h, grid).reshape(grid.Mp, H * W).contiguous()] + levels[1:], grid, cbuf, stats, out_nchw=out_r)
+    torch.cuda.synchronize()
+    assert torch.allclose(out_h, out_r, atol=1e-5, rtol=1e-5)      # same values, the subtraction of the mean re-associated
+    assert torch.allclose(out_h, ref, atol=3e-3, rtol=1e-3), (out_h - ref).abs().max()
 
 
 def test_upsample_and_small_kernels():
@@ -237,8 +271,10 @@ def test_corr_build(H, W, M, d, clipv):
     stat_sum = torch.zeros(2, dtype=torch.float64, device=DEV)
     stat_max = torch.full((1,), -float("inf"), device=DEV)
     clip = torch.tensor([clipv], device=DEV)
+    nby, nbx = (H + 7) // 8, (W + 7) // 8
+    l0h = torch.full((grid.Mp * nby * nbx * 68,), float("nan"), dtype=torch.float16, device=DEV)
     ops.corr_build(Q, K, grid, M=M, d=d, w_agg=w_agg, w_pos=w_pos, pos_table=table, R=7, clip=clip,
-                   stat_sum=stat_sum, stat_max=stat_max, levels=levels)
+                   stat_sum=stat_sum, stat_max=stat_max, levels=levels, level0_h16=l0h)
     mr = torch.zeros(2, device=DEV)
     ops.corr_stats_finalize(stat_sum, grid.U * grid.U, mr)
     torch.cuda.synchronize()
@@ -252,6 +288,11 @@ def test_corr_build(H, W, M, d, clipv):
         got = lv.reshape(grid.H, grid.Wp, h * w)[:, :W].reshape(grid.U, h, w)
         ref = pyr[l].reshape(grid.U, h, w)
         assert torch.allclose(got, ref, atol=2e-3, rtol=1e-3), (l, (got - ref).abs().max())
+    # level 0 again, as the 16-bit block-ordered copy the default lookup reads (fp16 deltas against fp32 half-block
+    # means): within fp16 rounding of the LOCAL variation of the fp32 level 0
+    got0 = _level0_decode(l0h, grid).reshape(grid.H, grid.Wp, H, W)[:, :W].reshape(grid.U, H, W)
+    f32_0 = levels[0].reshape(grid.H, grid.Wp, H, W)[:, :W].reshape(grid.U, H, W)
+    assert torch.allclose(got0, f32_0, atol=3e-3 * float(f32_0.std()), rtol=0), (got0 - f32_0).abs().max()
 
 
 @pytest.mark.parametrize("H,W,M,d,F_", [(16, 24, 4, 32, 128), (13, 22, 4, 64, 256), (12, 20, 1, 128, 128)])
