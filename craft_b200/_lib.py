@@ -112,6 +112,7 @@ SIGNATURES = {
     "craft_forward_interpolate": (_i, [_vp, _i, _i, _vp, _vp]),
     "craft_flow_encode": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "craft_nhwc_instnorm_stats": (_i, [_vp, _i, _i, _i, _i, _f, _vp, C.c_longlong, _vp, _vp]),
+    "craft_image_s2d": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
     "craft_nhwc_affine": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 

@@ -64,7 +64,9 @@ struct PvSmem {
   static_assert(kTotal <= 227 * 1024, "attn_pv: shared memory budget");
 };
 
-template <int D, int F, int BK, int KS, int VS, int POLY = 0, bool MASKED = false>
+// TRACE: the clock64 timeline instrumentation (CRAFT_PV_TRACE) is a separate instantiation -- even predicated off,
+// its ~30 instructions per tile and the registers they pin sit in the issue slots of the loops being measured.
+template <int D, int F, int BK, int KS, int VS, int POLY = 0, bool MASKED = false, bool TRACE = false>
 __global__ void __launch_bounds__(kPvThreads, 1)
 attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ PvParams p) {
@@ -179,12 +181,16 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   const int nseg = s_nseg;
 
-  const bool tr = p.trace != nullptr && blockIdx.x == 0;
+  const bool tr = TRACE && p.trace != nullptr && blockIdx.x == 0;
   auto gtime = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return static_cast<long long>(t); };
-  if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 256) p.trace[2048 + 2 * blockIdx.x] = gtime();
+  if constexpr (TRACE) {
+    if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 256) p.trace[2048 + 2 * blockIdx.x] = gtime();
+  }
 #define PV_TRACE(role, tile, slot)                                                              \
   do {                                                                                          \
-    if (tr && (threadIdx.x & 31) == 0 && (tile) < 64) p.trace[((role) * 64 + (tile)) * 8 + (slot)] = clock64(); \
+    if constexpr (TRACE) {                                                                      \
+      if (tr && (threadIdx.x & 31) == 0 && (tile) < 64) p.trace[((role) * 64 + (tile)) * 8 + (slot)] = clock64(); \
+    }                                                                                           \
   } while (0)
 
   if (warp == 0) {
@@ -336,7 +342,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16);
     const int R = p.R;
     const bool has_bias = p.pos_table != nullptr;
-    const int trole = (warp == 4 || warp == 8) ? 1 + sg : 99;
+    const int trole = TRACE ? ((warp == 4 || warp == 8) ? 1 + sg : 99) : 99;
 
     int seg = 0, g0 = 0;                 // g = g0 + i: CTA-wide tile counter; tile g uses buffer g % NSB, group g & 1
     float lse_next = 0.f;
@@ -354,10 +360,11 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // (~450 clk per tile between a group's arrive and its next s_full wait in the clock64 timeline)
       const int i0 = (g0 & 1) ^ sg;
       int bx = (sgm.t0 + i0) / nby, by = (sgm.t0 + i0) - bx * nby;
+      // S/P buffer and its phase for this group's next tile, advanced by two tiles per iteration
+      int b = (g0 + i0) % NSB;
+      uint32_t bpar = static_cast<uint32_t>((g0 + i0) / NSB) & 1u;
       for (int i = i0; i < sgm.nt; i += 2) {
         const int g = g0 + i;
-        const int b = g % NSB;
-        const uint32_t bpar = static_cast<uint32_t>(g / NSB) & 1u;
         // this thread's half block: block rows [ch*4, ch*4+4), all BW columns
         const int iy0 = by * 8 + ch * 4 - qy + R;       // table row of the first block row
         const int ix0 = bx * BW - qx + R;               // table column of the first block column
@@ -417,6 +424,8 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (trole < 4) PV_TRACE(trole, g, 4);
         by += 2;
         while (by >= nby) { by -= nby; ++bx; }
+        b += 2;
+        if (b >= NSB) { b -= NSB; bpar ^= 1u; }
       }
 
       // -------------------------------- O write-back of this segment ------------------------
@@ -479,7 +488,9 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #undef PV_TRACE
 
   __syncthreads();
-  if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 256) p.trace[2048 + 2 * blockIdx.x + 1] = gtime();
+  if constexpr (TRACE) {
+    if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 256) p.trace[2048 + 2 * blockIdx.x + 1] = gtime();
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);

@@ -297,14 +297,15 @@ int craft_shift_gemm(const craft_gemm_args* a, void* stream) {
   memset(&p, 0, sizeof(p));
   // shared-A mode (gemm.cuh): taps in groups of consecutive row offsets, e.g. the kw taps of a conv row
   {
-    // CRAFT_GEMM_ASHARE: 1 = every kernel row with consecutive taps, 0 = never, unset = the 1x5 rows only --
-    // measured (profiles/r02_gemm_sweep_ashare.txt): 13.5 -> 12.1 us (GRU z/r) and 10.7 -> 8.9 us (GRU q) for five
-    // shared taps, no gain for the three of a 3x3 row.  Bit-exact either way (same MMAs, same order).
+    // CRAFT_GEMM_ASHARE: 0 = never, otherwise every kernel row of consecutive taps (1x5 and 3x3) -- measured
+    // (profiles/r02_gemm_sweep_ashare.txt, r02_gemm_trace*.txt): 13.5 -> 12.1 us (GRU z/r), 10.7 -> 8.9 us (GRU q) for
+    // five shared taps; the single-wave 3x3 convolutions 10.4 -> 8.9, 9.4 -> 7.8, 8.1 -> 6.8, 7.3 -> 6.6, 5.4 -> 4.6 us
+    // (CTA durations).  Bit-exact either way (same MMAs, same order).
     static int env_mode = -2;
     if (env_mode == -2) { const char* e = getenv("CRAFT_GEMM_ASHARE"); env_mode = e ? (atoi(e) != 0 ? 1 : 0) : -1; }
     int gs = 1;
     while (gs < a->T && a->tap_off[gs] == a->tap_off[gs - 1] + 1) ++gs;
-    const int mode = (a->a_share != 0 || env_mode == 1 || (env_mode == -1 && gs == 5)) ? 1 : 0;
+    const int mode = (a->a_share != 0 || env_mode != 0) ? 1 : 0;
     bool ok = mode != 0 && gs > 1 && gs <= 5 && a->T % gs == 0 && !a->b_blocked && a->cluster <= 1 && a->BN <= 128;
     if (ok) {      // at least two grouped stages must fit
       const int ring = a->BN == 32 ? cb::GemmSmem<32>::kRing : a->BN == 64 ? cb::GemmSmem<64>::kRing
@@ -571,7 +572,7 @@ int craft_clip_gate(const float* stat_max, float attn_clip, float* clip, int* fl
 }
 
 }  // extern "C" (pause)
-template <int D, int F, int BK, int KS, int VS, int POLY = 0, bool MASKED = false>
+template <int D, int F, int BK, int KS, int VS, int POLY = 0, bool MASKED = false, bool TRACE = false>
 static int launch_pv(const craft_pv_args* a, const cb::Grid2& g, cudaStream_t st) {
   using S = cb::PvSmem<D, F, BK, KS, VS>;
   CUtensorMap tq, tk, tv;
@@ -591,12 +592,12 @@ static int launch_pv(const craft_pv_args* a, const cb::Grid2& g, cudaStream_t st
   p.g = g; p.M = a->M; p.nslots = a->ksplit; p.zero_fill = a->zero_fill; p.nqt = nqt; p.scale = a->scale; p.w_pos = a->w_pos;
   p.pos_table = a->pos_table; p.R = a->R; p.clip = a->clip; p.lse2 = a->lse2; p.out = a->out;
   p.nkt = nkt; p.nbx = nbx; p.mask_radius = a->mask_radius;
-  auto kern = cb::attn_pv_kernel<D, F, BK, KS, VS, POLY, MASKED>;
+  auto kern = cb::attn_pv_kernel<D, F, BK, KS, VS, POLY, MASKED, TRACE>;
   static std::atomic<unsigned long long> set{0};
   if (ensure_smem(kern, S::kTotal, set, "attn_pv")) return -1;
   dim3 grid(pv_grid(nqt, a->M, nkt));
   static long long* d_trace = nullptr;
-  const char* trace_path = getenv("CRAFT_PV_TRACE");     // profiling aid: dumps CTA 0's clock64 timeline
+  const char* trace_path = TRACE ? getenv("CRAFT_PV_TRACE") : nullptr;     // profiling aid: dumps CTA 0's clock64 timeline
   if (trace_path) {
     if (!d_trace) cudaMalloc(&d_trace, (4 * 64 * 8 + 512) * sizeof(long long));
     cudaMemsetAsync(d_trace, 0, (4 * 64 * 8 + 512) * sizeof(long long), st);
@@ -641,7 +642,9 @@ int craft_attn_pv(const craft_pv_args* a, void* stream) {
       case 3: return launch_pv<32, 128, 128, 3, 4, 3>(a, g, st);
       case 4: return launch_pv<32, 128, 128, 3, 4, 4>(a, g, st);
       case 8: return launch_pv<32, 128, 128, 3, 4, 8>(a, g, st);
-      default: return launch_pv<32, 128, 128, 3, 4>(a, g, st);
+      default:
+        if (getenv("CRAFT_PV_TRACE")) return launch_pv<32, 128, 128, 3, 4, 0, false, true>(a, g, st);   // instrumented build
+        return launch_pv<32, 128, 128, 3, 4>(a, g, st);
     }
   }
   if (a->mask_radius > 0) {
@@ -804,6 +807,17 @@ int craft_flow_encode(const float* flow, int H, int W, int mode, void* out, void
   if (!flow || !out || H < 1 || W < 1 || (mode != 0 && mode != 1)) return fail("flow_encode: bad arguments");
   launch_k(cb::flow_encode_kernel, dim3((H * W + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream), flow, H, W, mode, out);
   return check_launch("flow_encode");
+}
+
+int craft_image_s2d(const float* img, int N, int H, int W, void* out, int out_is_half, void* stream) {
+  if (!img || !out) return fail("image_s2d: null operand");
+  if (N < 1 || H < 2 || W < 2 || H % 2 || W % 2) return fail("image_s2d: H, W must be even (got %d x %d)", H, W);
+  const long long cells = static_cast<long long>(N) * (H / 2 + 3) * (W / 2 + 3);
+  const dim3 grid(static_cast<unsigned>((cells + 255) / 256));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (out_is_half) launch_k(cb::image_s2d_kernel<__half>, grid, dim3(256), 0, st, img, N, H, W, static_cast<__half*>(out));
+  else launch_k(cb::image_s2d_kernel<float>, grid, dim3(256), 0, st, img, N, H, W, static_cast<float*>(out));
+  return check_launch("image_s2d");
 }
 
 int craft_nhwc_instnorm_stats(const void* x, int is_half, int N, int HW, int C, float eps, float* part,

@@ -52,6 +52,8 @@ template <> struct ActVec<__half> {
 // x: [N, HW, C] channels-last (f32 or f16).  part: [chunks][N][C][2] f32 partial (sum, sum of squares);
 // every block owns one slot, so the reduction order -- and therefore the result -- is fixed
 // (no atomics).  grid = (chunks, N); block = 256 threads = (C/VEC channel groups) x rows in flight.
+// (Folding the reduction of the partials into this kernel -- "last block done" -- was tried in round 2: one block
+// summing ~300 partials per channel is L2-latency bound and made the pass 4x slower; it stays a second launch.)
 template <typename T>
 __global__ void __launch_bounds__(256) nhwc_stats_kernel(const T* __restrict__ x, int HW, int C,
                                                          int rows_per_block, float* __restrict__ part) {
@@ -114,6 +116,53 @@ __global__ void __launch_bounds__(256) instnorm_finalize_kernel(const float* __r
     const float rstd = rsqrtf(var + eps);
     ab[2 * i] = rstd;
     ab[2 * i + 1] = -mean * rstd;
+  }
+}
+
+// image_s2d: the encoders' input transform.  [N,3,H,W] f32 frames in 0..255 -> 2*(x/255)-1 (core/network.py:170-171),
+// 2x2 space-to-depth, channels-last, zero border of (2 before, 1 after) cells: out [N, H/2+3, W/2+3, 16], channel
+// (py*2 + px)*3 + c, channels 12..15 zero.  The 7x7 stride-2 first convolution (core/extractor.py:129) is then a
+// 4x4 stride-1 convolution over 16 channels with no padding -- a shape cuDNN runs on the sm_100 tensor-op kernels
+// instead of the sm_80 fallback it picks for 3 input channels (105 us -> see profiles/).
+template <typename T>
+__global__ void __launch_bounds__(256) image_s2d_kernel(const float* __restrict__ img, int N, int H, int W,
+                                                        T* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int Hs = H / 2 + 3, Ws = W / 2 + 3;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(N) * Hs * Ws) return;
+  const int xs = static_cast<int>(idx % Ws);
+  const int ys = static_cast<int>((idx / Ws) % Hs);
+  const int n = static_cast<int>(idx / (static_cast<long long>(Ws) * Hs));
+  const int Y = ys - 2, X = xs - 2;
+  float v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = 0.f;
+  if (Y >= 0 && Y < H / 2 && X >= 0 && X < W / 2) {
+    const float* base = img + static_cast<size_t>(n) * 3 * H * W;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int py = 0; py < 2; ++py) {
+        const float2 two = __ldg(reinterpret_cast<const float2*>(base + (static_cast<size_t>(c) * H + 2 * Y + py) * W + 2 * X));
+        v[(py * 2 + 0) * 3 + c] = 2.0f * (two.x / 255.0f) - 1.0f;      // the reference's rounding order
+        v[(py * 2 + 1) * 3 + c] = 2.0f * (two.y / 255.0f) - 1.0f;
+      }
+  }
+  T* dst = out + idx * 16;
+  if constexpr (sizeof(T) == 2) {
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const __half2 h = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+      w[k] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    reinterpret_cast<uint4*>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    reinterpret_cast<uint4*>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) reinterpret_cast<float4*>(dst)[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
   }
 }
 

@@ -93,6 +93,29 @@ class _Fused:
     def norm_act(self, norm, y, conv, relu=True):
         return self.affine(y, self.scale_shift(norm, y, conv), relu_in=relu)
 
+    def conv1_s2d(self, m, s):
+        """The 7x7 stride-2 first convolution (core/extractor.py:129) on the space-to-depth input of
+        ops.image_s2d: a 4x4 stride-1 convolution over 16 channels, no padding.  Row 2y + ky - 3 of the image is
+        row y + a of the s2d grid with parity py, ky = 2a + py + 3, a in [-2, 1]; the same along x."""
+        def build():
+            w = m.weight.detach().float()                       # [O, 3, 7, 7]
+            O = w.shape[0]
+            w4 = torch.zeros((O, 16, 4, 4), dtype=torch.float32, device=w.device)
+            for a in range(-2, 2):
+                for py in range(2):
+                    ky = 2 * a + py + 3
+                    if not 0 <= ky <= 6:
+                        continue
+                    for b in range(-2, 2):
+                        for px in range(2):
+                            kx = 2 * b + px + 3
+                            if 0 <= kx <= 6:
+                                c0 = (py * 2 + px) * 3
+                                w4[:, c0:c0 + 3, a + 2, b + 2] = w[:, :, ky, kx]
+            return w4.to(self.dtype).contiguous(memory_format=torch.channels_last)
+        w4 = self.cache.get(("w_s2d", id(m)), [m.weight], build)
+        return F.conv2d(s.permute(0, 3, 1, 2), w4)              # NCHW view of the channels-last buffer
+
 
 class BasicEncoder(nn.Module):
     def __init__(self, output_dim=128, norm_fn="batch", dropout=0.0):
@@ -127,24 +150,31 @@ class BasicEncoder(nn.Module):
                 and self.norm_fn in ("instance", "batch") and not torch.is_autocast_enabled()
                 and getattr(self, "use_fused", True))
 
-    def _forward_fused(self, x):
+    def _forward_fused(self, x, s2d=None):
         """[N,3,H,W] fp32 -> conv2 output as a channels-last tensor (NCHW shape, NHWC memory), f16 or f32."""
         half = bool(getattr(self, "fused_half", False))
         if getattr(self, "_fz", None) is None or self._fz.kind != self.norm_fn or self._fz.half != half:
             self._fz = _Fused(self.norm_fn, half)
         fz = self._fz
-        x = x.to(fz.dtype).contiguous(memory_format=torch.channels_last)
-        x = fz.norm_act(self.norm1, fz.conv(self.conv1, x), self.conv1, relu=True)
+        if s2d is not None:
+            x = fz.conv1_s2d(self.conv1, s2d)
+        else:
+            x = fz.conv(self.conv1, x.to(fz.dtype).contiguous(memory_format=torch.channels_last))
+        x = fz.norm_act(self.norm1, x, self.conv1, relu=True)
         for layer in (self.layer1, self.layer2, self.layer3):
             for blk in layer:
                 x = blk.forward_fused(x, fz)
         return fz.conv(self.conv2, x, bias=True)
 
-    def forward_nhwc(self, x):
-        """Inference fast path: [N,3,H,W] -> [N, H/8, W/8, C] contiguous (channels-last), in the encoder's
-        activation type.  Callers check _can_fuse first."""
-        y = self._forward_fused(x).permute(0, 2, 3, 1)
+    def forward_nhwc(self, x=None, s2d=None):
+        """Inference fast path: [N,3,H,W] normalised frames -- or `s2d`, the output of ops.image_s2d on the RAW
+        frames (normalisation, space-to-depth and padding of the first convolution in one kernel) -- to
+        [N, H/8, W/8, C] contiguous (channels-last), in the encoder's activation type.  Callers check _can_fuse."""
+        y = self._forward_fused(x, s2d).permute(0, 2, 3, 1)
         return y if y.is_contiguous() else y.contiguous()
+
+    def fused_dtype(self):
+        return torch.float16 if bool(getattr(self, "fused_half", False)) else torch.float32
 
     def forward(self, x):
         is_list = isinstance(x, (tuple, list))

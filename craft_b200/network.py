@@ -181,10 +181,12 @@ class CRAFT(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def _encoders(self, image1, image2):
-        image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
-        image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
         amp = bool(getattr(self.args, "mixed_precision", False))
         self.fnet.fused_half = self.cnet.fused_half = bool(self.encoder_half)
+        if self.encoder_nhwc and not amp and self.fnet._can_fuse(image1) and self.cnet._can_fuse(image1):
+            return self._encoders_fused(image1, image2)
+        image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
+        image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
         # fnet (two frames) and cnet (frame 1) are independent: run cnet on a side stream so their
         # many small, latency-bound kernels overlap (fork/join is captured into the CUDA graph too).
         main = torch.cuda.current_stream()
@@ -193,23 +195,32 @@ class CRAFT(nn.Module):
         with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark,
                                         deterministic=False, allow_tf32=self.encoder_tf32), \
                 torch.autocast("cuda", dtype=torch.float16, enabled=amp):
-            if self.encoder_nhwc and not amp and self.fnet._can_fuse(image1) and self.cnet._can_fuse(image1):
-                # fused encoders: the channels-last 16-bit output of the last convolution goes straight to the
-                # token packers (one LN-and-pack kernel; no NHWC -> NCHW fp32 conversion passes)
-                with torch.cuda.stream(side):
-                    cn = self.cnet.forward_nhwc(image1)
-                fm = self.fnet.forward_nhwc(torch.cat([image1, image2], dim=0))
-                main.wait_stream(side)
-                cn.record_stream(main)
-                B = image1.shape[0]
-                return ([ops.NhwcFeat(fm[b]) for b in range(B)], [ops.NhwcFeat(fm[B + b]) for b in range(B)],
-                        [ops.NhwcFeat(cn[b]) for b in range(B)])
             with torch.cuda.stream(side):
                 cnet_feat = self.cnet(image1).float().contiguous()
             fmap1, fmap2 = self.fnet([image1, image2])
         main.wait_stream(side)
         cnet_feat.record_stream(main)
         return fmap1.float().contiguous(), fmap2.float().contiguous(), cnet_feat
+
+    def _encoders_fused(self, image1, image2):
+        """Inference fast path of both encoders: ONE input kernel (normalisation, 2x2
+        space-to-depth, channels-last, the first convolution's zero border) for all three encoder inputs; cuDNN
+        convolutions on channels-last tensors (the 7x7/2 one as a 4x4/1 over 16 channels); craft_b200 norm / ReLU /
+        residual kernels; the channels-last output of the last convolution goes straight to the token packers."""
+        B = image1.shape[0]
+        s = ops.image_s2d(torch.cat([image1, image2], dim=0), dtype=self.fnet.fused_dtype())
+        main = torch.cuda.current_stream()
+        side = self._side_stream(image1.device)
+        side.wait_stream(main)
+        with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark,
+                                        deterministic=False, allow_tf32=self.encoder_tf32):
+            with torch.cuda.stream(side):      # fnet (two frames) and cnet (frame 1) are independent
+                cn = self.cnet.forward_nhwc(s2d=s[:B])
+            fm = self.fnet.forward_nhwc(s2d=s)
+        main.wait_stream(side)
+        cn.record_stream(main)
+        return ([ops.NhwcFeat(fm[b]) for b in range(B)], [ops.NhwcFeat(fm[B + b]) for b in range(B)],
+                [ops.NhwcFeat(cn[b]) for b in range(B)])
 
     def _side_stream(self, device):
         key = str(device)

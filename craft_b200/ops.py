@@ -357,6 +357,16 @@ def instnorm_stats(x_nhwc, eps=1e-5):
     return ab
 
 
+def image_s2d(img, dtype=torch.float16):
+    """[N,3,H,W] f32 frames (0..255) -> normalised, 2x2 space-to-depth, channels-last, zero-bordered input of the
+    encoders' first convolution: [N, H/2+3, W/2+3, 16] (include/craft_b200.h craft_image_s2d)."""
+    _cuda_only(img)
+    N, _, H, W = img.shape
+    out = torch.empty((N, H // 2 + 3, W // 2 + 3, 16), dtype=dtype, device=img.device)
+    OPS.image_s2d(img.contiguous(), out)
+    return out
+
+
 def nhwc_affine(v, ab=None, res=None, rab=None, relu_in=False, relu_out=False, out=None):
     """out = relu_out([ra*res+rb] + relu_in(a*v+b)); v/res/out [N,H,W,C] f32 or f16; ab/rab f32 [N or 1, C, 2]."""
     _act_dtype(v, "v")

@@ -301,6 +301,18 @@ def nhwc_instnorm_stats(x, N, HW, Cc, eps, part, ab):
               _stream())
 
 
+@_op("image_s2d(Tensor img, Tensor(a!) out) -> ()")
+def image_s2d(img, out):
+    """img [N,3,H,W] f32 (0..255) -> out [N, H/2+3, W/2+3, 16] f16/f32 (see include/craft_b200.h)."""
+    _chk(img, f32, "img")
+    if out.dtype not in (f16, f32):
+        raise TypeError("out: expected float16 or float32, got %s" % out.dtype)
+    _chk(out, out.dtype, "out")
+    N, _, H, W = img.shape
+    assert img.shape[1] == 3 and tuple(out.shape) == (N, H // 2 + 3, W // 2 + 3, 16)
+    _lib.call("craft_image_s2d", _ptr(img), N, H, W, _ptr(out), 1 if out.dtype == f16 else 0, _stream())
+
+
 @_op("nhwc_affine(Tensor v, Tensor? ab, int ab_stride, Tensor? res, Tensor? rab, int rab_stride, bool relu_in, bool relu_out, "
      "int N, int HW, int C, Tensor(a!) out) -> ()")
 def nhwc_affine(v, ab, ab_stride, res, rab, rab_stride, relu_in, relu_out, N, HW, Cc, out):

@@ -221,6 +221,11 @@ int craft_flow_encode(const float* flow, int H, int W, int mode, void* out, void
  * enough); the partials are reduced in a fixed order, so the result is run-to-run deterministic. */
 int craft_nhwc_instnorm_stats(const void* x, int is_half, int N, int HW, int C, float eps, float* part,
                               long long part_capacity, float* ab, void* stream);
+/* Input transform of both encoders: f32 frames [N,3,H,W] in 0..255 -> 2*(x/255)-1 (core/network.py:170-171), 2x2
+ * space-to-depth, channels-last, zero border (2 cells before, 1 after): out [N][H/2+3][W/2+3][16] (f16 if
+ * out_is_half else f32), channel (py*2+px)*3 + c, channels 12..15 zero.  The 7x7 stride-2 convolution
+ * core/extractor.py:129 becomes a 4x4 stride-1 convolution over it with no padding.                       */
+int craft_image_s2d(const float* img, int N, int H, int W, void* out, int out_is_half, void* stream);
 /* out = relu_out( [ra*res+rb] + relu_in(a*v+b) ): norm + ReLU + residual of ResidualBlock.forward
  * (extractor.py:55-64).  v/res/out: f32 or f16 (is_half); ab / rab: f32 [N or 1][C][2];
  * *_nstride = 2*C per image or 0 when shared.                                                       */

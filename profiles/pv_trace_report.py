@@ -6,15 +6,15 @@ rows = [r for r in allrows if r[0] < 4]
 spans = [r for r in allrows if r[0] == 9]
 t0 = min(v for r in rows for v in r[2:] if v > 0)
 names = {0: "MMA  [S(j) issued by S-warp, -, PV-warp: p_full, v_full, PV issued]",
-         1: "SM g0 [top, s_full, p_empty, S loaded, P stored, p_full arrived]",
-         2: "SM g1 [top, s_full, p_empty, S loaded, P stored, p_full arrived]",
+         1: "SM g0 [loop top, s_full acquired, S loaded, P computed, P stored + arrived, o_full wait, o_full acquired, O written]",
+         2: "SM g1 [loop top, s_full acquired, S loaded, P computed, P stored + arrived, o_full wait, o_full acquired, O written]",
          3: "TMA  [K issued, V issued]"}
 for role in range(4):
     print(names[role])
     for r in rows:
         if r[0] != role or not any(r[2:]):
             continue
-        print("  tile %2d: " % r[1] + " ".join("%7d" % (v - t0) if v else "      -" for v in r[2:8]))
+        print("  tile %2d: " % r[1] + " ".join("%7d" % (v - t0) if v else "      -" for v in r[2:10]))
 if spans:
     s0 = min(r[2] for r in spans)
     ends = sorted(r[3] - s0 for r in spans)

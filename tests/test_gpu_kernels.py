@@ -420,6 +420,51 @@ def test_fused_encoder_matches_module_path(kind):
     assert (got_h - ref).abs().mean() <= 4e-3 * max(1.0, ref.abs().mean().item()), (got_h - ref).abs().mean()
 
 
+@pytest.mark.parametrize("kind", ["instance", "batch"])
+def test_s2d_first_convolution_and_direct_token_packing(kind):
+    """The inference fast path of the encoders: raw 0..255 frames -> image_s2d (normalise + 2x2 space-to-depth +
+    zero border) -> the 7x7/2 convolution as a 4x4/1 one -> ... -> channels-last features handed to the token
+    packer.  Checked against the plain module path on the normalised frames (core/network.py:170-171,
+    core/extractor.py:173-196) and the NCHW packer."""
+    from craft_b200.extractor import BasicEncoder
+    torch.manual_seed(5)
+    enc = BasicEncoder(output_dim=256, norm_fn=kind).to(DEV).eval()
+    img = torch.randint(0, 256, (2, 3, 96, 160), device=DEV).float()
+    xn = 2 * (img / 255.0) - 1.0
+    torch.backends.cudnn.allow_tf32 = False
+    with torch.no_grad():
+        # the input transform alone, against pixel_unshuffle of the normalised frames
+        s = ops.image_s2d(img, dtype=torch.float32)
+        assert tuple(s.shape) == (2, 96 // 2 + 3, 160 // 2 + 3, 16)
+        inner = s[:, 2:-1, 2:-1, :12].reshape(2, 48, 80, 2, 2, 3)            # [n, Y, X, py, px, c]
+        back = inner.permute(0, 5, 1, 3, 2, 4).reshape(2, 3, 96, 160)
+        assert torch.allclose(back, xn, atol=2.5e-7, rtol=0)      # (torch's CUDA x/255 multiplies by the rounded reciprocal)
+        assert s[:, :2].abs().max() == 0 and s[:, -1].abs().max() == 0 and s[:, :, :2].abs().max() == 0
+        assert s[:, :, -1].abs().max() == 0 and s[..., 12:].abs().max() == 0
+        enc.use_fused = False
+        ref = enc(xn)
+        enc.use_fused = True
+        for half, atol_max, atol_mean in ((False, 2e-3, 2e-4), (True, 2e-2, 4e-3)):
+            enc.fused_half = half
+            y = enc.forward_nhwc(s2d=ops.image_s2d(img, dtype=enc.fused_dtype()))       # [N, h, w, 256]
+            assert y.is_contiguous() and y.dtype == enc.fused_dtype()
+            got = y.permute(0, 3, 1, 2).float()
+            scale = max(1.0, ref.abs().max().item())
+            assert (got - ref).abs().max() <= atol_max * scale, (half, (got - ref).abs().max())
+            assert (got - ref).abs().mean() <= atol_mean * max(1.0, ref.abs().mean().item())
+            # channels-last features -> token rows, against the NCHW packer on the same values
+            grid = TokenGrid(y.shape[1], y.shape[2])
+            for mode, c0, Cc in ((ops.PACK_LN, 0, 256), (ops.PACK_TANH, 0, 128), (ops.PACK_RELU_LN, 128, 128), (ops.PACK_RELU, 128, 128)):
+                a_b, a_f = grid.zeros(Cc + 64), grid.zeros(Cc, dtype=torch.float32)
+                b_b, b_f = grid.zeros(Cc + 64), grid.zeros(Cc, dtype=torch.float32)
+                ops.pack_tokens(ops.NhwcFeat(y[0]).window(c0, Cc), grid, mode, out_b=a_b, colb=64, out_f=a_f)
+                ops.pack_tokens(got[0, c0:c0 + Cc].contiguous(), grid, mode, out_b=b_b, colb=64, out_f=b_f)
+                torch.cuda.synchronize()
+                assert torch.allclose(a_f, b_f, atol=2e-5, rtol=1e-5), (mode, (a_f - b_f).abs().max())
+                assert torch.allclose(a_b.float(), b_b.float(), atol=2e-2, rtol=1e-2)
+                assert a_f.reshape(grid.H, grid.Wp, -1)[:, grid.W:].abs().max() == 0
+
+
 @pytest.mark.parametrize("H,W,M,d,clipv", [(16, 24, 4, 64, float("inf")), (17, 22, 4, 64, 2.0), (16, 16, 1, 256, float("inf"))])
 @pytest.mark.parametrize("spread", [5.0, 0.4, "mixed", "far"])
 def test_corr_lookup0_on_demand(H, W, M, d, clipv, spread):
