@@ -18,16 +18,24 @@
 // other block takes the 3-instruction fast path.  V^T arrives in the same block order
 // (gemm.cuh b_blocked).
 //
-// Data flow per key tile j (TMEM buffer b = j mod NSB):
-//     warp 1   : S[b] = Q K_j^T                     tcgen05.mma SS, fp32 accumulator in TMEM
-//     softmax  : P[b] = exp2(S[b]*c - lse) as bf16  written back into the SAME TMEM columns (tcgen05.st)
-//     warp 2   : O += P[b] V_j                       tcgen05.mma with the A operand read from TMEM
+// Data flow per key tile j (two softmax groups alternate tiles):
+//     warp 1   : S = Q K_j^T                        tcgen05.mma SS, fp32 accumulator in TMEM
+//     softmax  : P = exp2(S*c - lse) as bf16        written back to TMEM (tcgen05.st)
+//     warp 2   : O += P V_j                          tcgen05.mma with the A operand read from TMEM
 // P never touches shared memory: no 32 KB/tile of st.shared, no proxy fence, and the P.V MMA reads
-// only V from smem.  With NSB = 3 S/P buffers and two softmax groups alternating tiles, S runs up to
-// three tiles ahead and neither the softmax groups nor the two MMA-issuing warps wait on each other
-// in steady state.  The two MMA streams are issued by different warps because the instruction
-// latency of an issuing warp (barrier probes, descriptor arithmetic, one UTCHMMA per 16 K columns)
-// -- not the tensor pipe -- is what paces a tile (profiles/README.md, "attn_pv timeline").
+// only V from smem.  Two TMEM layouts (template SPLIT), chosen per shape by measurement:
+//   ring  (SPLIT = false): three S/P buffers, P overwrites columns of the S it came from; S(j+3) waits for
+//         P.V(j) to retire.  The ring S issue -> softmax -> arrival skew -> P.V issue -> retire (~4300 clk for
+//         3 tiles) staggers the two groups, which is what the 128-key tiles of the aggregator want (83 us
+//         against 89 us): a lone group reaches only ~73 % of the MUFU rate, two groups in step idle together.
+//   split (SPLIT = true):  S 2 x BK columns | P 2 x BK/2 | O; group g owns S[g] and P[g].  S[g] is handed back
+//         as soon as the group has LOADED it, so S(j+2) is computed under tile j, and P[g] is free long before
+//         it is needed.  Wins for the 64-key tiles of the F2 transformer (118 -> 104 us), whose per-tile
+//         hand-offs weigh twice as much.
+// (Also tried on the split layout: an "exponential token" that makes the groups take turns on the MUFU unit --
+//  115 us: exclusive access runs at the lone-group rate.  profiles/r02_pv_split_token.txt.)
+// The two MMA streams are issued by different warps because the instruction latency of an issuing warp
+// (barrier probes, descriptor arithmetic, one UTCHMMA per 16 K columns) is what paces a tile.
 #pragma once
 #include "common.cuh"
 #include "pointwise.cuh"
@@ -66,7 +74,7 @@ struct PvSmem {
 
 // TRACE: the clock64 timeline instrumentation (CRAFT_PV_TRACE) is a separate instantiation -- even predicated off,
 // its ~30 instructions per tile and the registers they pin sit in the issue slots of the loops being measured.
-template <int D, int F, int BK, int KS, int VS, int POLY = 0, bool MASKED = false, bool TRACE = false>
+template <int D, int F, int BK, int KS, int VS, int POLY = 0, bool MASKED = false, bool TRACE = false, bool SPLIT = false>
 __global__ void __launch_bounds__(kPvThreads, 1)
 attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ PvParams p) {
@@ -74,10 +82,11 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   constexpr int BW = BK / 8;             // block width in tokens (block height is 8)
   constexpr int HALF = BK / 2;           // S columns per softmax thread
   constexpr int PW = BK / 4;             // packed P columns (2 bf16 each) per softmax thread
-  constexpr int NSB = 3;                 // S/P buffers in TMEM
-  constexpr uint32_t kTmemO = NSB * BK;  // O accumulator starts after the S/P buffers
-  constexpr uint32_t kPOff = BK / 4;     // P sits at S + BK/4: every warp overwrites only columns it has read itself
-  static_assert(NSB * BK + F <= 512, "attn_pv: TMEM budget");
+  constexpr int NSB = SPLIT ? 2 : 3;     // S buffers in TMEM (split: one S and one P buffer per softmax group)
+  constexpr uint32_t kTmemP = NSB * BK;  // split: P buffers (BK/2 packed columns each) follow the S buffers
+  constexpr uint32_t kPOff = BK / 4;     // ring: P sits at S + BK/4: every warp overwrites only columns it has read itself
+  constexpr uint32_t kTmemO = SPLIT ? NSB * BK + NSB * (BK / 2) : NSB * BK;   // O accumulator
+  static_assert(kTmemO + F <= 512, "attn_pv: TMEM budget");
   static_assert(HALF == 32 || HALF == 64, "attn_pv: BK must be 64 or 128");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -92,10 +101,12 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t* k_empty = k_full + KS;
   uint64_t* v_full = k_empty + KS;
   uint64_t* v_empty = v_full + VS;
-  uint64_t* s_full = v_empty + VS;       // [NSB] S(j) complete in TMEM            (tcgen05.commit, count 1)
-  uint64_t* p_full = s_full + NSB;       // [NSB] P(j) stored to TMEM              (8 softmax warps)
-  uint64_t* sp_free = p_full + NSB;      // [NSB] P.V(j) retired: buffer reusable   (tcgen05.commit, count 1)
-  uint64_t* o_full = sp_free + NSB;      // O of the current segment complete           (tcgen05.commit)
+  uint64_t* s_full = v_empty + VS;       // [NSB] S(j) complete in TMEM                      (tcgen05.commit, count 1)
+  uint64_t* s_free = s_full + NSB;       // [NSB] S buffer reusable -- split: S(j) loaded into registers (8 softmax
+                                         //       warps); ring: P.V(j) retired (tcgen05.commit, count 1)
+  uint64_t* p_full = s_free + NSB;       // [NSB] P(j) stored to TMEM                        (8 softmax warps)
+  uint64_t* p_free = p_full + NSB;       // [NSB] split only: P.V(j) retired, P buffer reusable (tcgen05.commit, count 1)
+  uint64_t* o_full = p_free + NSB;       // O of the current segment complete                 (tcgen05.commit)
   uint64_t* o_free = o_full + 1;         // O read back by the 16 epilogue warps         (count 16)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
   // positional-bias table, zero padded so that a thread's 4 x BW window can be read without range
@@ -157,8 +168,9 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     for (int s = 0; s < VS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
     for (int b = 0; b < NSB; ++b) {
       mbar_init(&s_full[b], 1);
+      mbar_init(&s_free[b], SPLIT ? 8 : 1);
       mbar_init(&p_full[b], 8);      // one arrival per softmax warp of the group
-      mbar_init(&sp_free[b], 1);
+      mbar_init(&p_free[b], 1);
     }
     mbar_init(o_full, 1);
     mbar_init(o_free, 16);
@@ -252,7 +264,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     constexpr uint64_t kKStep = static_cast<uint64_t>(S::kKBytes >> 4);
     const bool leader = elect_one();
     int ks = 0, b = 0, seg = 0, g = 0;
-    uint32_t kph = 0, bpar = 1;            // sp_free[b] parity for "previous use of b retired" (first use: free)
+    uint32_t kph = 0, bpar = 1;            // s_free[b] parity for "buffer b is reusable" (first use: free)
     for (; seg < nseg; ++seg) {
       const Seg sgm = s_segs[seg];
       const uint32_t qk_inner = static_cast<uint32_t>((sgm.mode * D) & 63) * 2u;
@@ -262,9 +274,9 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       mbar_wait(&q_full[qb], (static_cast<uint32_t>(seg) >> 1) & 1u);
       for (int i = 0; i < sgm.nt; ++i, ++g) {
         const bool r1 = mbar_try_wait_nohint(&k_full[ks], kph);
-        const bool r2 = mbar_try_wait_nohint(&sp_free[b], bpar);
+        const bool r2 = mbar_try_wait_nohint(&s_free[b], bpar);
         if (!r1) mbar_wait(&k_full[ks], kph);
-        if (!r2) mbar_wait(&sp_free[b], bpar);
+        if (!r2) mbar_wait(&s_free[b], bpar);
         tc_fence_after();
         if (leader) {
           const uint32_t ts = tmem_base + static_cast<uint32_t>(b * BK);
@@ -308,7 +320,8 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         PV_TRACE(0, g, 3);
         tc_fence_after();
         if (leader) {
-          const uint32_t tp = tmem_base + static_cast<uint32_t>(b * BK) + kPOff;
+          const uint32_t tp = SPLIT ? tmem_base + kTmemP + static_cast<uint32_t>(b * (BK / 2))
+                                    : tmem_base + static_cast<uint32_t>(b * BK) + kPOff;
           const uint64_t dv = dv0 + static_cast<uint64_t>(vs) * kVStep;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
@@ -318,7 +331,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             if (k == 0) umma_f16_ts(tmem_base + kTmemO, tp, dv + ov, idesc_o, i != 0 ? 1u : 0u);
             else umma_f16_ts(tmem_base + kTmemO, tp + 8u * k, dv + ov, idesc_o, 1u);
           }
-          umma_commit(&sp_free[b]);
+          umma_commit(SPLIT ? &p_free[b] : &s_free[b]);
           umma_commit(&v_empty[vs]);
           if (i == sgm.nt - 1) umma_commit(o_full);
         }
@@ -350,8 +363,9 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int qn = s_segs[0].qt * 128 + row;
       lse_next = (qn < p.g.Mp) ? p.lse2[static_cast<size_t>(s_segs[0].mode) * p.g.Mp + qn] : 0.f;
     }
+    Seg sg_next = s_segs[0];
     for (; seg < nseg; ++seg) {
-      const Seg sgm = s_segs[seg];
+      const Seg sgm = sg_next;
       const int q = sgm.qt * 128 + row;
       const int qy = q / p.g.Wp, qx = q - qy * p.g.Wp;
       const float lse = lse_next;
@@ -360,9 +374,10 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // (~450 clk per tile between a group's arrive and its next s_full wait in the clock64 timeline)
       const int i0 = (g0 & 1) ^ sg;
       int bx = (sgm.t0 + i0) / nby, by = (sgm.t0 + i0) - bx * nby;
-      // S/P buffer and its phase for this group's next tile, advanced by two tiles per iteration
-      int b = (g0 + i0) % NSB;
-      uint32_t bpar = static_cast<uint32_t>((g0 + i0) / NSB) & 1u;
+      // this group's tiles are the ones with CTA-wide index g == sg (mod 2).  split: buffers S[sg], P[sg], whose
+      // phase flips with every tile of the group; ring: buffer g % 3, advanced by two tiles per iteration
+      int b = SPLIT ? sg : (g0 + i0) % NSB;
+      uint32_t bpar = static_cast<uint32_t>(SPLIT ? (g0 + i0) >> 1 : (g0 + i0) / NSB) & 1u;
       for (int i = i0; i < sgm.nt; i += 2) {
         const int g = g0 + i;
         // this thread's half block: block rows [ch*4, ch*4+4), all BW columns
@@ -374,12 +389,18 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (trole < 4) PV_TRACE(trole, g, 1);
         tc_fence_after();
         const uint32_t tS = tlane + static_cast<uint32_t>(b * BK + ch * HALF);
-        const uint32_t tP = tlane + static_cast<uint32_t>(b * BK) + kPOff + static_cast<uint32_t>(ch * PW);
+        const uint32_t tP = SPLIT ? tlane + kTmemP + static_cast<uint32_t>(b * (BK / 2) + ch * PW)
+                                  : tlane + static_cast<uint32_t>(b * BK) + kPOff + static_cast<uint32_t>(ch * PW);
         uint32_t raw_all[HALF];
 #pragma unroll
         for (int c = 0; c < HALF; c += 32)
           tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&raw_all[c]));
         tmem_ld_wait();
+        if constexpr (SPLIT) {
+          // S is in registers: hand the buffer back, so that S of this group's NEXT tile is computed under this one
+          tc_fence_before();
+          mbar_arrive_warp(&s_free[b]);
+        }
         if (trole < 4) PV_TRACE(trole, g, 2);
         uint32_t pk[PW];
 #pragma unroll
@@ -415,7 +436,12 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             pk[c / 2 + e] = pack_act2(ex2_mix<POLY>(x[2 * e], 2 * e), ex2_mix<POLY>(x[2 * e + 1], 2 * e + 1));
         }
         if (trole < 4) PV_TRACE(trole, g, 3);
-        // P -> TMEM (this warp's lanes, columns it has just read), then hand the buffer to the P.V issuer
+        // P -> TMEM, then hand it to the P.V issuer.  split: the group's P buffer is free once the P.V of its
+        // previous tile has retired -- a whole tile ago; ring: the columns of S this warp has just read
+        if constexpr (SPLIT) {
+          mbar_wait(&p_free[b], bpar ^ 1u);
+          tc_fence_after();
+        }
         if constexpr (PW == 32) tmem_st32(tP, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
         else tmem_st16(tP, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
         tmem_st_wait();
@@ -424,8 +450,8 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (trole < 4) PV_TRACE(trole, g, 4);
         by += 2;
         while (by >= nby) { by -= nby; ++bx; }
-        b += 2;
-        if (b >= NSB) { b -= NSB; bpar ^= 1u; }
+        if constexpr (SPLIT) bpar ^= 1u;
+        else { b += 2; if (b >= NSB) { b -= NSB; bpar ^= 1u; } }
       }
 
       // -------------------------------- O write-back of this segment ------------------------
@@ -434,13 +460,14 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int slot = sgm.slot;
       const bool last_part = sgm.last != 0;
       const int g_last = g0 + sgm.nt - 1;
-      // The next segment's log-sum-exp is fetched HERE: the 64 KB of write-back stores below take
-      // ~2000 clk to drain from the load/store unit and any global load issued behind them (e.g. at the
-      // top of the next segment) would stall the warp for that long; this one completes while the
-      // warp waits for the last P.V anyway.
+      // The next segment's table entry and log-sum-exp are fetched HERE: the 64 KB of write-back stores below
+      // take ~2000 clk to drain from the load/store unit and any load issued behind them -- global OR shared
+      // (the timeline showed ~2200 clk between "O written" and the next loop top, spent on the s_segs read) --
+      // stalls the warp for that long; these complete while the warp waits for the last P.V anyway.
       if (seg + 1 < nseg) {
-        const int qn = s_segs[seg + 1].qt * 128 + row;
-        lse_next = (qn < p.g.Mp) ? p.lse2[static_cast<size_t>(s_segs[seg + 1].mode) * p.g.Mp + qn] : 0.f;
+        sg_next = s_segs[seg + 1];
+        const int qn = sg_next.qt * 128 + row;
+        lse_next = (qn < p.g.Mp) ? p.lse2[static_cast<size_t>(sg_next.mode) * p.g.Mp + qn] : 0.f;
       }
       if (trole < 4) PV_TRACE(trole, g_last - (g_last & 1) + (trole - 1), 5);
       mbar_wait(o_full, static_cast<uint32_t>(seg) & 1u);

@@ -572,7 +572,7 @@ int craft_clip_gate(const float* stat_max, float attn_clip, float* clip, int* fl
 }
 
 }  // extern "C" (pause)
-template <int D, int F, int BK, int KS, int VS, int POLY = 0, bool MASKED = false, bool TRACE = false>
+template <int D, int F, int BK, int KS, int VS, int POLY = 0, bool MASKED = false, bool TRACE = false, bool SPLIT = false>
 static int launch_pv(const craft_pv_args* a, const cb::Grid2& g, cudaStream_t st) {
   using S = cb::PvSmem<D, F, BK, KS, VS>;
   CUtensorMap tq, tk, tv;
@@ -592,7 +592,8 @@ static int launch_pv(const craft_pv_args* a, const cb::Grid2& g, cudaStream_t st
   p.g = g; p.M = a->M; p.nslots = a->ksplit; p.zero_fill = a->zero_fill; p.nqt = nqt; p.scale = a->scale; p.w_pos = a->w_pos;
   p.pos_table = a->pos_table; p.R = a->R; p.clip = a->clip; p.lse2 = a->lse2; p.out = a->out;
   p.nkt = nkt; p.nbx = nbx; p.mask_radius = a->mask_radius;
-  auto kern = cb::attn_pv_kernel<D, F, BK, KS, VS, POLY, MASKED, TRACE>;
+
+  auto kern = cb::attn_pv_kernel<D, F, BK, KS, VS, POLY, MASKED, TRACE, SPLIT>;
   static std::atomic<unsigned long long> set{0};
   if (ensure_smem(kern, S::kTotal, set, "attn_pv")) return -1;
   dim3 grid(pv_grid(nqt, a->M, nkt));
@@ -648,11 +649,12 @@ int craft_attn_pv(const craft_pv_args* a, void* stream) {
     }
   }
   if (a->mask_radius > 0) {
-    if (a->d == 64 && a->F == 256) return launch_pv<64, 256, 64, 4, 4, 0, true>(a, g, st);
+    if (a->d == 64 && a->F == 256) return launch_pv<64, 256, 64, 4, 4, 0, true, false, true>(a, g, st);
     return fail("attn_pv: the --f2radius key mask is built for the F2 transformer shape (d=64, F=256) only");
   }
-  if (a->d == 64 && a->F == 256) return launch_pv<64, 256, 64, 4, 4>(a, g, st);
-  if (a->d == 128 && a->F == 128) return launch_pv<128, 128, 64, 3, 4>(a, g, st);
+  // 64-key tiles: the split TMEM layout (attn_pv.cuh; F2 transformer 118 -> 104 us); 128-key tiles: the ring
+  if (a->d == 64 && a->F == 256) return launch_pv<64, 256, 64, 4, 4, 0, false, false, true>(a, g, st);
+  if (a->d == 128 && a->F == 128) return launch_pv<128, 128, 64, 3, 4, 0, false, false, true>(a, g, st);
   if (a->d == 64 && a->F == 128) return launch_pv<64, 128, 128, 3, 4>(a, g, st);
   return fail("attn_pv: unsupported (d=%d, F=%d)", a->d, a->F);
 }
