@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(LookupParams p, Grid2 
   pdl_wait();
 
   constexpr int R = 4, D = 2 * R + 1, WN = D + 1;   // 9 taps, 10 cells
-  __shared__ float win[8][WN * WN + 4];
+  constexpr int NC = WN * WN, NCP = NC + 4;
+  __shared__ float win[8][4][NCP];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * 8 + wib;   // padded-flat query index
   if (q >= g.Mp) return;
@@ -221,46 +222,66 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(LookupParams p, Grid2 
   if (qx >= g.W) return;                // halo token: leave zeros
   const float cx = p.coords[2 * q], cy = p.coords[2 * q + 1];
   const float mean = p.stats[0], rstd = p.stats[1];
-  float* wv = win[wib];
-  for (int l = p.first_level; l < 4; ++l) {
+  // phase 1: the 10x10 windows of ALL levels are gathered first -- every lane has its 13-16 independent loads in
+  // flight at once (one level at a time, each gather paid the full L2 / HBM latency: 12.6 us per call)
+  float ax[4], ay[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
     const float inv = 1.0f / static_cast<float>(1 << l);
     const float px = cx * inv, py = cy * inv;
     const float fx0 = floorf(px), fy0 = floorf(py);
-    const float ax = px - fx0, ay = py - fy0;
+    ax[l] = px - fx0;
+    ay[l] = py - fy0;
+    if (l < p.first_level) continue;
     const int x0 = static_cast<int>(fx0) - R, y0 = static_cast<int>(fy0) - R;
     const int hl = p.hl[l], wl = p.wl[l];
-    __syncwarp();
+    float* wv = win[wib][l];
     if (l == 0 && p.lvl0h != nullptr) {
       const __half* vol = p.lvl0h + static_cast<long long>(q) * p.qstride0h;
       const float* bases = p.lvl0_base + static_cast<long long>(q) * (p.qstride0h >> 5);
-      for (int e = lane; e < WN * WN; e += 32) {
-        const int r = e / WN, c = e - r * WN;
-        const int yy = y0 + r, xx = x0 + c;
-        float v = 0.f;
-        if (yy >= 0 && yy < hl && xx >= 0 && xx < wl) {
-          const int blk = (yy >> 3) * p.nbx0 + (xx >> 3);
-          v = (__ldg(bases + 2 * blk + ((yy >> 2) & 1)) - mean) + __half2float(__ldg(vol + (blk << 6) + ((yy & 7) << 3) + (xx & 7)));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = lane + 32 * k;
+        if (e < NC) {
+          const int r = e / WN, c = e - r * WN;
+          const int yy = y0 + r, xx = x0 + c;
+          float v = 0.f;
+          if (yy >= 0 && yy < hl && xx >= 0 && xx < wl) {
+            const int blk = (yy >> 3) * p.nbx0 + (xx >> 3);
+            v = (__ldg(bases + 2 * blk + ((yy >> 2) & 1)) - mean) + __half2float(__ldg(vol + (blk << 6) + ((yy & 7) << 3) + (xx & 7)));
+          }
+          wv[e] = v;
         }
-        wv[e] = v;
       }
     } else {
       const float* vol = p.lvl[l] + static_cast<long long>(q) * p.qstride[l];
-      for (int e = lane; e < WN * WN; e += 32) {
-        const int r = e / WN, c = e - r * WN;
-        const int yy = y0 + r, xx = x0 + c;
-        float v = 0.f;
-        if (yy >= 0 && yy < hl && xx >= 0 && xx < wl) v = __ldg(vol + yy * wl + xx) - mean;
-        wv[e] = v;   // (value - mean) inside bounds, 0 outside == deferred-LN numerator
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = lane + 32 * k;
+        if (e < NC) {
+          const int r = e / WN, c = e - r * WN;
+          const int yy = y0 + r, xx = x0 + c;
+          float v = 0.f;
+          if (yy >= 0 && yy < hl && xx >= 0 && xx < wl) v = __ldg(vol + yy * wl + xx) - mean;
+          wv[e] = v;   // (value - mean) inside bounds, 0 outside == deferred-LN numerator
+        }
       }
     }
-    __syncwarp();
+  }
+  __syncwarp();
+  // phase 2: 4 x 81 bilinear taps
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    if (l < p.first_level) continue;
+    const float* wv = win[wib][l];
+    const float axl = ax[l], ayl = ay[l];
     for (int e = lane; e < D * D; e += 32) {
       const int i = e / D, j = e - i * D;   // i: x offset index, j: y offset index
       const float v00 = wv[j * WN + i], v01 = wv[j * WN + i + 1];
       const float v10 = wv[(j + 1) * WN + i], v11 = wv[(j + 1) * WN + i + 1];
-      const float top = v00 + ax * (v01 - v00);
-      const float bot = v10 + ax * (v11 - v10);
-      const float val = (top + ay * (bot - top)) * rstd;
+      const float top = v00 + axl * (v01 - v00);
+      const float bot = v10 + axl * (v11 - v10);
+      const float val = (top + ayl * (bot - top)) * rstd;
       const int ch = l * D * D + e;
       if (p.out_b) p.out_b[static_cast<size_t>(q) * p.ldb + ch] = f2act(val);
       if (p.out_nchw) p.out_nchw[(static_cast<size_t>(ch) * g.H + qy) * g.W + qx] = val;
