@@ -493,19 +493,34 @@ def run_ours(args, cfg):
         host_pairs = [(a.pin_memory(), b.pin_memory()) for a, b in _pairs(cfg, mine, None, uint8=True)]
         out_host = torch.empty((1, 2, H, W), dtype=torch.float32).pin_memory()
 
-        def e2e_step(i):
-            a, b = host_pairs[i % len(host_pairs)]
-            _, up = model(a.to(dev, non_blocking=True).float(), b.to(dev, non_blocking=True).float(),
-                          iters=ITERS, test_mode=1)
-            out_host.copy_(up, non_blocking=True)
+        if args.e2e_serial:
+            # one pair at a time on one stream, as evaluate.py's loops do
+            def e2e_step(i):
+                a, b = host_pairs[i % len(host_pairs)]
+                _, up = model(a.to(dev, non_blocking=True).float(), b.to(dev, non_blocking=True).float(),
+                              iters=ITERS, test_mode=1)
+                out_host.copy_(up, non_blocking=True)
 
-        for i in range(2):
-            e2e_step(i)
+            def e2e_run(n):
+                for i in range(n):
+                    e2e_step(i)
+        else:
+            # craft_b200.pipeline.PairStream: the same per-pair traffic (every pair's frames H2D, its flow D2H, all
+            # inside the timed region) with the copies of neighbouring pairs on a second stream under the forward
+            from craft_b200.pipeline import PairStream
+            ps = PairStream(model, iters=ITERS)
+
+            def e2e_run(n):
+                got = 0
+                for flow in ps.map(host_pairs[i % len(host_pairs)] for i in range(n)):
+                    got += 1
+                assert got == n
+
+        e2e_run(2)
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        for i in range(args.steps):
-            e2e_step(i)
+        e2e_run(args.steps)
         f1.record()
         barrier()
         ms_e2e = f0.elapsed_time(f1)
@@ -564,7 +579,10 @@ def run_ours(args, cfg):
                                           "upsampling of iterations 1..%d (discarded by the reference) are elided, "
                                           "outputs bit-identical (tests/test_gpu_e2e.py)" % (ITERS - 1)),
                     e2e=dict(value=total / (ms_e2e * 1e-3), unit="pairs/s", h2d_bytes_per_step=2 * 3 * H * W,
-                             d2h_bytes_per_step=2 * H * W * 4),
+                             d2h_bytes_per_step=2 * H * W * 4,
+                             mode=("serial: H2D -> CRAFT.forward -> D2H on one stream" if args.e2e_serial else
+                                   "craft_b200.pipeline.PairStream: every pair's uint8 frames H2D and its flow D2H inside the "
+                                   "timed region, the copies of neighbouring pairs on a second stream under the forward")),
                     gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu)
         if gpu_ref is not None:
             line["gpu_reference"] = gpu_ref
@@ -669,6 +687,7 @@ def main():
                     help="sintel = BASELINE configs[1] (default, the metric's configuration); kitti = configs[4] shape; "
                          "gma = configs[2] variant")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-serial", action="store_true", help="e2e leg: one pair at a time on one stream (no PairStream overlap)")
     ap.add_argument("--dropout-prob", type=float, default=None,
                     help="--config train only: override the transformers' dropout (reference training default 0.1/0.2)")
     ap.add_argument("--gpu-reference", action="store_true",

@@ -62,6 +62,11 @@ def main(which, reps):
                 ops.corr_lookup(ws.levels, g, ws.coords1, ws.mean_rstd, out_b=ws.CORR, first_level=1)
             elif which == "lookup_all":
                 ops.corr_lookup(ws.levels, g, ws.coords1, ws.mean_rstd, out_b=ws.CORR, level0_h16=ws.level0_h16)
+            elif which == "finalize":
+                agg = ub.aggregator.packed()
+                ks = ws.pv_split(4)
+                ops.modes_finalize(ws.opart(ks, 4, 128), ks, 4, 128, g, w_score=agg["ws"], b_score=agg["bs"], coeff=agg["coeff"],
+                                   x_b=ws.X, colx=256, out_b=ws.X, colb=384, pv_bk=ops.pv_block_keys(32, 128))
             elif which == "heads":
                 hp.heads(ws, uw)
             elif which == "iter_gemms":     # every tensor-core GEMM of one refinement iteration but the V^T one

@@ -355,3 +355,25 @@ def test_savecorr_hook_writes_the_normalised_volume(tmp_path, monkeypatch):
                                     sd["corr_fn.setrans.attn_softaggr.feat2score.bias"].reshape(()),
                                     sd["corr_fn.vispos_encoder.pos_coder.biases"], 4, 0.5)
     assert (vol.reshape(1, 256, 16, 16) - ref).abs().mean().item() <= 5e-3
+
+
+def test_pair_stream_matches_direct_calls():
+    """craft_b200.pipeline.PairStream (copies on a second stream, double-buffered staging) returns, pair by pair and
+    in order, exactly what `model(image1.cuda(), image2.cuda())` followed by `.cpu()` returns."""
+    from craft_b200.pipeline import PairStream
+    rec = torch.load(os.path.join(GOLD, "seeded_setrans_128.pt"), map_location="cpu")
+    model = _model(rec)
+    g = torch.Generator().manual_seed(7)
+    pairs = [(torch.randint(0, 256, (1, 3, 128, 128), generator=g, dtype=torch.uint8).pin_memory(),
+              torch.randint(0, 256, (1, 3, 128, 128), generator=g, dtype=torch.uint8).pin_memory()) for _ in range(5)]
+    with torch.no_grad():
+        direct = [model(a.cuda().float(), b.cuda().float(), iters=4, test_mode=1)[1].cpu() for a, b in pairs]
+    ps = PairStream(model, iters=4)
+    streamed = [f.clone() for f in ps.map(pairs)]
+    assert len(streamed) == len(pairs)
+    for d, s_ in zip(direct, streamed):
+        assert (d - s_).abs().max().item() <= 1e-3          # (the LN statistics use fp64 atomics: not bit-reproducible)
+    assert _epe(direct[0][0], direct[1][0]) > 1e-3          # the pairs really differ
+    # a second pass over the same stream object reuses its staging buffers
+    again = [f.clone() for f in ps.map(pairs[:2])]
+    assert (again[0] - direct[0]).abs().max().item() <= 1e-3 and (again[1] - direct[1]).abs().max().item() <= 1e-3
