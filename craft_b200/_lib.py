@@ -113,6 +113,7 @@ SIGNATURES = {
     "craft_flow_encode": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "craft_nhwc_instnorm_stats": (_i, [_vp, _i, _i, _i, _i, _f, _vp, C.c_longlong, _vp, _vp]),
     "craft_image_s2d": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
+    "craft_nhwc_instnorm_apply": (_i, [_vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _i, _i, _vp, C.c_longlong, _vp, _vp, _vp]),
     "craft_nhwc_affine": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 

@@ -59,26 +59,31 @@ struct PvParams {
   float* out;              // [nslots][M][F/8][Mp][8] f32 partial sums (8-column chunks, see the write-back)
   int nkt, nbx;            // key tiles (blocks) in total / per block-row
   int mask_radius;         // > 0: keys farther than this (Chebyshev) from the query get probability 0 (--f2radius)
+  int nostore;             // timing experiment only (CRAFT_PV_NOSTORE=1): skip the O write-back stores -- WRONG results
   long long* trace;        // CRAFT_PV_TRACE: clock64 timeline of CTA 0: [role 4][tile 64][slot 8], then globaltimer (start, end) of every CTA
 };
 
-template <int D, int F, int BK, int KS, int VS>
+// BULK: 32 KB of shared memory through which the O write-back goes (see the write-back below)
+template <int D, int F, int BK, int KS, int VS, bool BULK = false>
 struct PvSmem {
   static constexpr int kQAtoms = D > 64 ? D / 64 : 1;
   static constexpr int kQBytes = kQAtoms * 128 * 128;
   static constexpr int kKBytes = kQAtoms * BK * 128;
   static constexpr int kVBytes = (BK / 64) * F * 128;
-  static constexpr int kTotal = 2 * kQBytes + KS * kKBytes + VS * kVBytes + 1024 + 512 + 4096;   // + align, barriers, bias table
+  static constexpr int kStageBytes = BULK ? 8 * 128 * 32 : 0;       // 8 chunks x 128 rows x 8 floats
+  static constexpr int kTotal = 2 * kQBytes + KS * kKBytes + VS * kVBytes + kStageBytes + 1024 + 512 + 4096;   // + align, barriers, bias table
   static_assert(kTotal <= 227 * 1024, "attn_pv: shared memory budget");
 };
 
 // TRACE: the clock64 timeline instrumentation (CRAFT_PV_TRACE) is a separate instantiation -- even predicated off,
 // its ~30 instructions per tile and the registers they pin sit in the issue slots of the loops being measured.
-template <int D, int F, int BK, int KS, int VS, int POLY = 0, bool MASKED = false, bool TRACE = false, bool SPLIT = false>
+template <int D, int F, int BK, int KS, int VS, int POLY = 0, bool MASKED = false, bool TRACE = false, bool SPLIT = false,
+          bool BULK = false>
 __global__ void __launch_bounds__(kPvThreads, 1)
 attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ PvParams p) {
-  using S = PvSmem<D, F, BK, KS, VS>;
+  using S = PvSmem<D, F, BK, KS, VS, BULK>;
+  static_assert(!BULK || F == 128, "attn_pv: the bulk write-back is built for F = 128 (one 32-column quarter per warp)");
   constexpr int BW = BK / 8;             // block width in tokens (block height is 8)
   constexpr int HALF = BK / 2;           // S columns per softmax thread
   constexpr int PW = BK / 4;             // packed P columns (2 bf16 each) per softmax thread
@@ -94,7 +99,8 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + 2 * S::kQBytes;
   uint8_t* sV = sK + KS * S::kKBytes;
-  uint8_t* tail = sV + VS * S::kVBytes;
+  uint8_t* sStage = sV + VS * S::kVBytes;                 // BULK: O staging, [8 chunks][128 rows][8 floats]
+  uint8_t* tail = sStage + S::kStageBytes;
   uint64_t* q_full = reinterpret_cast<uint64_t*>(tail);   // [2] Q of segment s lives in buffer s & 1
   uint64_t* q_free = q_full + 2;                           // [2] all S MMAs of that segment retired
   uint64_t* k_full = q_free + 2;
@@ -108,7 +114,8 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t* p_free = p_full + NSB;       // [NSB] split only: P.V(j) retired, P buffer reusable (tcgen05.commit, count 1)
   uint64_t* o_full = p_free + NSB;       // O of the current segment complete                 (tcgen05.commit)
   uint64_t* o_free = o_full + 1;         // O read back by the 16 epilogue warps         (count 16)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
+  uint64_t* stage_free = o_free + 1;     // BULK: the previous user's bulk copies have read the staging buffer (count 1)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_free + 1);
   // positional-bias table, zero padded so that a thread's 4 x BW window can be read without range
   // checks: row iy+3 (iy in [-3, 2R+3]), column ix+BW-1 (ix in [-(BW-1), 2R+BW-1]); log2 domain
   float* s_table = reinterpret_cast<float*>(tail + 512);
@@ -174,6 +181,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     mbar_init(o_full, 1);
     mbar_init(o_free, 16);
+    mbar_init(stage_free, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -482,12 +490,56 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       float* dst = p.out + (static_cast<size_t>(slot) * p.M + sgm.mode) * p.g.Mp * F + static_cast<size_t>(q) * 8;
       constexpr int kQuarter = F / 4;
       const int c_begin = (sg * 2 + ch) * kQuarter;
+      if constexpr (BULK) {
+        // Write-back through shared memory and the bulk-copy engine.  Stored straight from registers, the 64 KB of
+        // a segment keep the load/store unit busy for ~4400 clk (2200 to issue, 2200 more to drain, during which
+        // the next barrier operation of these warps cannot issue: ~5900 clk from the last P of a segment to the
+        // first tile of the next, 2.5 times per CTA -- profiles/r02_pv_timeline_ring.txt).  Here a warp reads its
+        // 32 O columns (the accumulator is free again as soon as they are in registers), parks them in a 32 KB
+        // staging buffer in the layout of `out` ([chunk][row][8]: 4 KB contiguous per chunk) and one thread per
+        // group hands the eight chunks to cp.async.bulk.  The two groups use the buffer in turn.
+        uint32_t raw[32];
+        tmem_ld32(tlane + kTmemO + c_begin, raw);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive_warp(o_free);
+        if (trole < 4) PV_TRACE(trole, g_last - (g_last & 1) + (trole - 1), 7);
+        // use u = 2*seg + sg of the staging buffer waits for use u-1 to have been read out
+        if (sg == 1) mbar_wait(stage_free, 0u);
+        else if (seg > 0) mbar_wait(stage_free, 1u);
+        float4* srow = reinterpret_cast<float4*>(sStage) + (static_cast<size_t>(ch * 4) * 128 + row) * 2;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          srow[static_cast<size_t>(e) * 256] = make_float4(__uint_as_float(raw[8 * e]), __uint_as_float(raw[8 * e + 1]),
+                                                           __uint_as_float(raw[8 * e + 2]), __uint_as_float(raw[8 * e + 3]));
+          srow[static_cast<size_t>(e) * 256 + 1] = make_float4(__uint_as_float(raw[8 * e + 4]), __uint_as_float(raw[8 * e + 5]),
+                                                               __uint_as_float(raw[8 * e + 6]), __uint_as_float(raw[8 * e + 7]));
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + sg) : "memory");
+        if (ch == 0 && lane_grp == 0 && (threadIdx.x & 31) == 0) {
+          const int q0 = sgm.qt * 128;
+          const int rows = min(128, p.g.Mp - q0);
+          if (rows > 0 && !p.nostore) {
+            float* gdst = p.out + (static_cast<size_t>(slot) * p.M + sgm.mode) * p.g.Mp * F + static_cast<size_t>(q0) * 8;
+#pragma unroll 1
+            for (int cg = 0; cg < 8; ++cg)
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
+                               gdst + static_cast<size_t>(sg * 8 + cg) * p.g.Mp * 8),
+                           "r"(smem_u32(sStage + cg * 4096)), "r"(rows * 32)
+                           : "memory");
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive(stage_free);
+        }
+      } else {
 #pragma unroll
       for (int c = 0; c < kQuarter; c += 32) {
         uint32_t raw[32];
         tmem_ld32(tlane + kTmemO + c_begin + c, raw);
         tmem_ld_wait();
-        if (q < p.g.Mp) {
+        if (q < p.g.Mp && !p.nostore) {
 #pragma unroll
           for (int e = 0; e < 4; ++e)      // one 256-bit store per chunk: consecutive lanes -> 1 KB contiguous
             st_global_v8(dst + static_cast<size_t>((c_begin + c) / 8 + e) * p.g.Mp * 8,
@@ -497,6 +549,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc_fence_before();
       mbar_arrive_warp(o_free);
       if (trole < 4) PV_TRACE(trole, g_last - (g_last & 1) + (trole - 1), 7);
+      }
       if (p.zero_fill && last_part && q < p.g.Mp) {
         for (int sl = slot + 1; sl < p.nslots; ++sl) {
 #pragma unroll
@@ -510,6 +563,9 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       if (trole == 1) PV_TRACE(3, g_last, 2);      // boundary: write-back (+ zero fill) done
       g0 += sgm.nt;
+    }
+    if constexpr (BULK) {      // the bulk copies must have completed (writes performed) before the CTA exits
+      if (ch == 0 && lane_grp == 0 && (threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   }
 #undef PV_TRACE

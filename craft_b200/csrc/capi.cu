@@ -572,9 +572,10 @@ int craft_clip_gate(const float* stat_max, float attn_clip, float* clip, int* fl
 }
 
 }  // extern "C" (pause)
-template <int D, int F, int BK, int KS, int VS, int POLY = 0, bool MASKED = false, bool TRACE = false, bool SPLIT = false>
+template <int D, int F, int BK, int KS, int VS, int POLY = 0, bool MASKED = false, bool TRACE = false, bool SPLIT = false,
+          bool BULK = false>
 static int launch_pv(const craft_pv_args* a, const cb::Grid2& g, cudaStream_t st) {
-  using S = cb::PvSmem<D, F, BK, KS, VS>;
+  using S = cb::PvSmem<D, F, BK, KS, VS, BULK>;
   CUtensorMap tq, tk, tv;
   if (make_map_2d(&tq, a->Q, g.Mp, a->C, a->C, 128)) return -1;
   constexpr int BW = BK / 8;
@@ -592,8 +593,9 @@ static int launch_pv(const craft_pv_args* a, const cb::Grid2& g, cudaStream_t st
   p.g = g; p.M = a->M; p.nslots = a->ksplit; p.zero_fill = a->zero_fill; p.nqt = nqt; p.scale = a->scale; p.w_pos = a->w_pos;
   p.pos_table = a->pos_table; p.R = a->R; p.clip = a->clip; p.lse2 = a->lse2; p.out = a->out;
   p.nkt = nkt; p.nbx = nbx; p.mask_radius = a->mask_radius;
+  { const char* e = getenv("CRAFT_PV_NOSTORE"); p.nostore = (e && atoi(e) != 0) ? 1 : 0; }
 
-  auto kern = cb::attn_pv_kernel<D, F, BK, KS, VS, POLY, MASKED, TRACE, SPLIT>;
+  auto kern = cb::attn_pv_kernel<D, F, BK, KS, VS, POLY, MASKED, TRACE, SPLIT, BULK>;
   static std::atomic<unsigned long long> set{0};
   if (ensure_smem(kern, S::kTotal, set, "attn_pv")) return -1;
   dim3 grid(pv_grid(nqt, a->M, nkt));
@@ -643,9 +645,19 @@ int craft_attn_pv(const craft_pv_args* a, void* stream) {
       case 3: return launch_pv<32, 128, 128, 3, 4, 3>(a, g, st);
       case 4: return launch_pv<32, 128, 128, 3, 4, 4>(a, g, st);
       case 8: return launch_pv<32, 128, 128, 3, 4, 8>(a, g, st);
-      default:
-        if (getenv("CRAFT_PV_TRACE")) return launch_pv<32, 128, 128, 3, 4, 0, false, true>(a, g, st);   // instrumented build
+      default: {
+        // CRAFT_PV_BULK=1 (experiment, default off): O write-back through a 32 KB staging buffer + cp.async.bulk,
+        // paid for by three V stages instead of four.  Measured slower (86.7 vs 83.3 us alone, 236.1 vs 238.9
+        // pairs/s: profiles/r02_pv_bulk_writeback.txt) -- the fourth V stage is worth more than the store drain.
+        static int bulk = -1;
+        if (bulk < 0) { const char* e = getenv("CRAFT_PV_BULK"); bulk = e ? (atoi(e) != 0) : 0; }
+        if (getenv("CRAFT_PV_TRACE")) {      // instrumented builds
+          if (bulk) return launch_pv<32, 128, 128, 3, 3, 0, false, true, false, true>(a, g, st);
+          return launch_pv<32, 128, 128, 3, 4, 0, false, true>(a, g, st);
+        }
+        if (bulk) return launch_pv<32, 128, 128, 3, 3, 0, false, false, false, true>(a, g, st);
         return launch_pv<32, 128, 128, 3, 4>(a, g, st);
+      }
     }
   }
   if (a->mask_radius > 0) {
@@ -838,6 +850,78 @@ int craft_nhwc_instnorm_stats(const void* x, int is_half, int N, int HW, int C, 
   if (check_launch("nhwc_stats")) return -1;
   launch_k(cb::instnorm_finalize_kernel, dim3((N * C + 7) / 8), dim3(256), 0, st, part, chunks, N * C, 1.0f / static_cast<float>(HW), eps, ab);
   return check_launch("instnorm_finalize");
+}
+
+}  // extern "C" (pause)
+template <typename T>
+static int launch_instnorm_fused(const void* x, int N, int HW, int C, float eps, const void* res, const float* rab,
+                                 int rab_nstride, int relu_in, int relu_out, float* part, long long part_capacity,
+                                 float* ab_out, void* out, cudaStream_t st) {
+  constexpr int V = cb::ActVec<T>::N;
+  const int cq = C / V;
+  cb::InFusedParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.HW = HW; p.C = C;
+  p.cqp = 1;
+  while (p.cqp < cq) p.cqp <<= 1;
+  const int sms = sm_count();
+  p.cpi = sms / N;
+  const int rowbytes = C * static_cast<int>(sizeof(T));
+  // small tensors: at least 32 rows per CTA, so that a CTA's 16 warps have something to add up
+  if (p.cpi > (HW + 31) / 32) p.cpi = (HW + 31) / 32;
+  if (p.cpi < 1) p.cpi = 1;
+  p.rows_per_cta = (HW + p.cpi - 1) / p.cpi;
+  const int overhead = (cb::kInThreads / 32 + 1) * 2 * C * 4 + cb::kInMaxPieces * 8 + 128;
+  const int cap_rows = std::min((227 * 1024 - overhead) / rowbytes, cb::kInMaxPieces * std::max(1, cb::kInPieceBytes / rowbytes));
+  p.smem_rows = std::min(p.rows_per_cta, cap_rows);
+  p.inv_hw = 1.0f / static_cast<float>(HW); p.eps = eps;
+  p.relu_in = relu_in; p.relu_out = relu_out; p.rab_nstride = rab_nstride;
+  const int grid = p.cpi * N;
+  // part: [0, 64) floats = the manual barrier's state (zero at first use), partial sums from float 64 on
+  if (static_cast<long long>(grid) * 2 * C + 64 > part_capacity)
+    return fail("instnorm_fused: partial buffer holds %lld floats, needs %lld", part_capacity, static_cast<long long>(grid) * 2 * C + 64);
+  static int coop = -1;
+  if (coop < 0) { const char* e = getenv("CRAFT_B200_IN_COOP"); coop = e ? (atoi(e) != 0) : 1; }
+  p.coop = coop;
+  const int smem = p.smem_rows * rowbytes + overhead;
+  auto kern = cb::instnorm_fused_kernel<T>;
+  static std::atomic<unsigned long long> set{0};
+  if (ensure_smem(kern, 227 * 1024, set, "instnorm_fused")) return -1;
+  // a cooperative launch: the grid barrier needs every CTA resident, and the driver -- not a spin loop of ours --
+  // is what guarantees it when other streams hold SMs (the context encoder runs next to this one)
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(cb::kInThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (coop) {
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.numAttrs = 1;
+  } else {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  }
+  cfg.attrs = attr;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<const T*>(x), static_cast<const T*>(res), rab, part + 64,
+                                     reinterpret_cast<unsigned*>(part), ab_out, static_cast<T*>(out), p);
+  if (e != cudaSuccess) return fail("instnorm_fused: launch failed: %s", cudaGetErrorString(e));
+  return check_launch("instnorm_fused");
+}
+
+extern "C" {
+int craft_nhwc_instnorm_apply(const void* x, int is_half, int N, int HW, int C, float eps, const void* res,
+                              const float* rab, int rab_nstride, int relu_in, int relu_out, float* part,
+                              long long part_capacity, float* ab_out, void* out, void* stream) {
+  if (!x || !out || !part) return fail("instnorm_apply: null operand");
+  const int V = is_half ? 8 : 4;
+  if (C % V || C < V || C > 256 || C / V > 32) return fail("instnorm_apply: C=%d must be a multiple of %d, at most %d", C, V, std::min(256, 32 * V));
+  if (N < 1 || N > sm_count()) return fail("instnorm_apply: N=%d images (at most one per SM)", N);
+  if (HW < 1) return fail("instnorm_apply: empty image");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_half)
+    return launch_instnorm_fused<__half>(x, N, HW, C, eps, res, rab, rab_nstride, relu_in, relu_out, part, part_capacity, ab_out, out, st);
+  return launch_instnorm_fused<float>(x, N, HW, C, eps, res, rab, rab_nstride, relu_in, relu_out, part, part_capacity, ab_out, out, st);
 }
 
 int craft_nhwc_affine(const void* v, int is_half, const float* ab, int ab_nstride, const void* res, const float* rab,

@@ -12,6 +12,7 @@
 // b = beta - mean*a.  Activations are channels-last fp32 or fp16 (statistics and the affine arithmetic are
 // always fp32): lanes run over channels, so every access is a coalesced 16-byte vector.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_fp16.h>
 #include "common.cuh"
 
@@ -209,6 +210,272 @@ __global__ void __launch_bounds__(256) nhwc_affine_kernel(const T* __restrict__ 
     for (int k = 0; k < V; ++k) r[k] = fmaxf(r[k], 0.f);
   }
   ActVec<T>::store(out + e, r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// instnorm_fused_kernel: InstanceNorm2d + ReLU (+ residual) of one channels-last tensor in ONE launch
+//     out = relu_out( res_term + relu_in( (x - mean) * rstd ) ),   res_term = 0 | res | ra*res + rb
+// replacing nhwc_stats + instnorm_finalize + nhwc_affine (three launches, x read twice from memory).
+// A cooperative grid of at most one CTA per SM; CTA j of image n owns a contiguous slab of rows:
+//   phase 1  the slab is pulled into shared memory with cp.async.bulk (16 KB pieces, one mbarrier each; the
+//            whole slab -- 198 KB for the 64-channel layers at 448x1024 -- is in flight at once) and the
+//            per-channel sum / sum of squares are accumulated from shared memory as the pieces land; one
+//            (sum, sumsq) pair per channel and CTA goes to `part`;
+//   grid.sync()
+//   phase 2  every CTA adds the partials of its image in a fixed order (bit-reproducible, no atomics), forms
+//            (rstd, -mean*rstd) and applies them to the slab still sitting in shared memory: x is read from
+//            memory ONCE, the only other traffic is the residual and the output.
+// Rows of a slab beyond the shared-memory capacity (larger images) are read from global memory in both phases.
+// Thread layout: a warp covers 32/CQP rows x CQP 16-byte channel groups (CQP = C/V rounded up to a power of
+// two), so a lane's channels are fixed and the cross-row reduction is a shuffle tree.
+// ---------------------------------------------------------------------------------------------
+constexpr int kInThreads = 512;
+constexpr int kInMaxPieces = 16;
+constexpr int kInPieceBytes = 16384;
+
+struct InFusedParams {
+  int N, HW, C;
+  int cpi;             // CTAs per image; grid = cpi * N
+  int rows_per_cta;
+  int smem_rows;       // rows of a slab held in shared memory
+  int cqp;             // vector columns rounded up to a power of two (<= 32)
+  float inv_hw, eps;
+  int relu_in, relu_out, rab_nstride;
+  int coop;            // 1: cooperative launch, cooperative_groups grid barrier; 0: plain launch, the barrier below
+};
+
+// Grid barrier of a NON-cooperative launch (CRAFT_B200_IN_COOP=0 experiment): sense-reversing, state = {count, sense}
+// in global memory, zero at first use and left as {0, sense+1}.  Only safe while every CTA of the grid can become
+// resident without another spinning grid holding its SM -- hence the cooperative launch is the default.
+__device__ __forceinline__ void grid_barrier_manual(unsigned* state, unsigned nctas, unsigned sense0) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned old = atomicAdd(state, 1u);
+    if (old == nctas - 1) {
+      state[0] = 0u;
+      __threadfence();
+      atomicAdd(state + 1, 1u);
+    } else {
+      unsigned v, spins = 0;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(state + 1) : "memory");
+        if (++spins > (1u << 26)) __trap();
+      } while (v == sense0);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <typename T> struct InSmemVec;
+template <> struct InSmemVec<float> {
+  __device__ static void load(const float* p, float (&v)[4]) {
+    const float4 x = *reinterpret_cast<const float4*>(p);
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+  }
+};
+template <> struct InSmemVec<__half> {
+  __device__ static void load(const __half* p, float (&v)[8]) {
+    const uint4 x = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&x);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(h[k]);
+      v[2 * k] = f.x; v[2 * k + 1] = f.y;
+    }
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kInThreads, 1) instnorm_fused_kernel(
+    const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ rab, float* part, unsigned* sync_state,
+    float* __restrict__ ab_out, T* __restrict__ out, const InFusedParams p) {
+  constexpr int V = ActVec<T>::N;
+  constexpr int NW = kInThreads / 32;
+  extern __shared__ __align__(128) uint8_t in_smem[];
+  const int C = p.C, C2 = 2 * p.C;
+  const int rowbytes = C * static_cast<int>(sizeof(T));
+  T* slab = reinterpret_cast<T*>(in_smem);
+  float* red = reinterpret_cast<float*>(in_smem + static_cast<size_t>(p.smem_rows) * rowbytes);   // [NW][C2]; later [nsub][C2]
+  float* s_ab = red + NW * C2;                                                                     // [C2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ab + C2);                                         // [kInMaxPieces]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cq = C / V, cqp = p.cqp;
+  const int rw = 32 / cqp;                         // rows per warp and pass
+  const int tc = lane & (cqp - 1), trw = lane / cqp;
+  const bool col_ok = tc < cq;
+  const int n = blockIdx.x / p.cpi, j = blockIdx.x - n * p.cpi;
+  const int r0 = j * p.rows_per_cta;
+  const int my_rows = max(0, min(p.HW, r0 + p.rows_per_cta) - r0);
+  const int in_smem_rows = min(my_rows, p.smem_rows);
+  const int piece_rows = max(1, kInPieceBytes / rowbytes);
+  const int npieces = (in_smem_rows + piece_rows - 1) / piece_rows;
+  const T* xg = x + (static_cast<size_t>(n) * p.HW + r0) * C;
+
+  unsigned sense0 = 0;
+  if (tid == 0) {
+    for (int k = 0; k < npieces; ++k) mbar_init(&bars[k], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  if (tid == 0) {
+    if (!p.coop) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(sense0) : "l"(sync_state + 1) : "memory");
+    for (int k = 0; k < npieces; ++k) {
+      const int rk = min(piece_rows, in_smem_rows - k * piece_rows);
+      const uint32_t bytes = static_cast<uint32_t>(rk) * rowbytes;
+      mbar_arrive_expect_tx(&bars[k], bytes);
+      bulk_load_1d(in_smem + static_cast<size_t>(k) * piece_rows * rowbytes, xg + static_cast<size_t>(k) * piece_rows * C, bytes,
+                   &bars[k]);
+    }
+  }
+
+  // ---- phase 1: per-channel sums over the slab
+  float s[V], q[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { s[k] = 0.f; q[k] = 0.f; }
+  const int rstep = NW * rw;
+  const int rfirst = warp * rw + trw;
+  if (col_ok) {
+    int waited = -1;
+    int r = rfirst;
+    for (; r < in_smem_rows; r += rstep) {
+      const int pc = r / piece_rows;
+      if (pc > waited) { mbar_wait(&bars[pc], 0u); waited = pc; }
+      float v[V];
+      InSmemVec<T>::load(slab + static_cast<size_t>(r) * C + tc * V, v);
+#pragma unroll
+      for (int k = 0; k < V; ++k) { s[k] += v[k]; q[k] = fmaf(v[k], v[k], q[k]); }
+    }
+    for (; r < my_rows; r += 4 * rstep) {            // overflow rows: straight from global, four loads in flight
+      float v[4][V];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int ru = min(r + u * rstep, my_rows - 1);
+        ActVec<T>::load(xg + static_cast<size_t>(ru) * C + tc * V, v[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (r + u * rstep < my_rows) {
+#pragma unroll
+          for (int k = 0; k < V; ++k) { s[k] += v[u][k]; q[k] = fmaf(v[u][k], v[u][k], q[k]); }
+        }
+      }
+    }
+  }
+  for (int o = cqp; o < 32; o <<= 1) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+      q[k] += __shfl_xor_sync(0xffffffffu, q[k], o);
+    }
+  }
+  if (trw == 0 && col_ok) {
+    float* dst = red + warp * C2 + 2 * V * tc;
+#pragma unroll
+    for (int k = 0; k < V; ++k) { dst[2 * k] = s[k]; dst[2 * k + 1] = q[k]; }
+  }
+  __syncthreads();
+  if (tid < C2) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) acc += red[w * C2 + tid];
+    part[static_cast<size_t>(blockIdx.x) * C2 + tid] = acc;
+  }
+  if (p.coop) {
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+  } else {
+    grid_barrier_manual(sync_state, gridDim.x, sense0);
+  }
+  pdl_launch_dependents();
+
+  // ---- totals of this image (fixed order), scale / shift.  16-byte loads: C2/4 vector columns x nsub row groups;
+  // a thread's partials (cpi / nsub of them, 5 for the 64-channel layers) are all requested before the first add
+  const int vcols = C2 / 4;
+  const int nsub = min(kInThreads / vcols, NW);       // red holds NW rows of C2 floats
+  {
+    const int vc = tid % vcols, sub = tid / vcols;
+    if (sub < nsub) {
+      const float4* src = reinterpret_cast<const float4*>(part + static_cast<size_t>(n) * p.cpi * C2) + vc;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = sub; c < p.cpi; c += 8 * nsub) {
+        float4 t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          t[u] = (c + u * nsub < p.cpi) ? __ldcg(src + static_cast<size_t>(c + u * nsub) * vcols) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { acc.x += t[u].x; acc.y += t[u].y; acc.z += t[u].z; acc.w += t[u].w; }
+      }
+      *reinterpret_cast<float4*>(red + sub * C2 + 4 * vc) = acc;
+    }
+  }
+  __syncthreads();
+  if (tid < C) {
+    float sm = 0.f, sq = 0.f;
+    for (int sub = 0; sub < nsub; ++sub) { sm += red[sub * C2 + 2 * tid]; sq += red[sub * C2 + 2 * tid + 1]; }
+    const float mean = sm * p.inv_hw;
+    const float var = fmaxf(sq * p.inv_hw - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + p.eps);
+    s_ab[2 * tid] = rstd;
+    s_ab[2 * tid + 1] = -mean * rstd;
+    if (j == 0 && ab_out) {
+      ab_out[(static_cast<size_t>(n) * C + tid) * 2] = rstd;
+      ab_out[(static_cast<size_t>(n) * C + tid) * 2 + 1] = -mean * rstd;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: apply
+  if (!col_ok) return;
+  float a[V], b[V], ra[V], rb[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    a[k] = s_ab[2 * (tc * V + k)];
+    b[k] = s_ab[2 * (tc * V + k) + 1];
+    ra[k] = 1.f; rb[k] = 0.f;
+  }
+  if (res && rab) {
+    const float* pr = rab + static_cast<size_t>(n) * p.rab_nstride + 2 * tc * V;
+#pragma unroll
+    for (int k = 0; k < V; ++k) { ra[k] = __ldg(pr + 2 * k); rb[k] = __ldg(pr + 2 * k + 1); }
+  }
+  const T* rg = res ? res + (static_cast<size_t>(n) * p.HW + r0) * C + tc * V : nullptr;
+  T* og = out + (static_cast<size_t>(n) * p.HW + r0) * C + tc * V;
+  for (int r = rfirst; r < my_rows; r += 4 * rstep) {
+    float v[4][V], z[4][V];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int ru = min(r + u * rstep, my_rows - 1);
+      if (rg) ActVec<T>::load(rg + static_cast<size_t>(ru) * C, z[u]);
+      if (ru < in_smem_rows) InSmemVec<T>::load(slab + static_cast<size_t>(ru) * C + tc * V, v[u]);
+      else ActVec<T>::load(xg + static_cast<size_t>(ru) * C + tc * V, v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int ru = r + u * rstep;
+      if (ru < my_rows) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          float y = fmaf(v[u][k], a[k], b[k]);
+          if (p.relu_in) y = fmaxf(y, 0.f);
+          if (rg) y += fmaf(z[u][k], ra[k], rb[k]);
+          if (p.relu_out) y = fmaxf(y, 0.f);
+          v[u][k] = y;
+        }
+        ActVec<T>::store(og + static_cast<size_t>(ru) * C, v[u]);
+      }
+    }
+  }
 }
 
 }  // namespace cb

@@ -682,35 +682,52 @@ __global__ void __launch_bounds__(256) modes_finalize_kernel(
   if (p >= g.Mp) return;
   const int y = p / g.Wp, x = p - y * g.Wp;
   if (x >= g.W) return;
+  // The kernel is bound by its instruction count (ncu: 685 warp instructions per token, issue slots the busiest
+  // unit), so everything that does not depend on the mode is hoisted and every access is a vector.
   float o[4][PER];
   float sc[4];
+  float wsc[PER];                          // this lane's score weights: the same for every mode
+#pragma unroll
+  for (int j = 0; j < PER / 4; ++j) {
+    const float4 w4 = gma ? make_float4(0.f, 0.f, 0.f, 0.f)
+                          : __ldg(reinterpret_cast<const float4*>(w_score + 8 * ((lane >> 1) + 16 * j) + 4 * (lane & 1)));
+    wsc[4 * j] = w4.x; wsc[4 * j + 1] = w4.y; wsc[4 * j + 2] = w4.z; wsc[4 * j + 3] = w4.w;
+  }
+  const float* src0 = O + (static_cast<long long>(lane >> 1) * g.Mp + p) * 8 + 4 * (lane & 1);
+  float part_s[4];                         // per-mode partial dot products, reduced over the warp together below
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
     sc[m] = -INFINITY;
+    part_s[m] = 0.f;
 #pragma unroll
     for (int e = 0; e < PER; ++e) o[m][e] = 0.f;
     if (m < M) {
-      const int nvalid = s_nvalid[m];
-      float s = 0.f;
+      const int nvalid = s_nvalid[m];      // warp-uniform: 1 or 2, rarely more (nsum <= 4, checked by the host)
 #pragma unroll
       for (int j = 0; j < PER / 4; ++j) {
-        // up to 4 partial slots, loaded as independent 16-byte requests (nsum <= 4, checked by the host)
-        const int chunk = (lane >> 1) + 16 * j;
-        const float* src = O + m * mode_stride + (static_cast<long long>(chunk) * g.Mp + p) * 8 + 4 * (lane & 1);
-        float4 part[4];
-#pragma unroll
-        for (int sp = 0; sp < 4; ++sp)
-          part[sp] = (sp < nvalid) ? __ldg(reinterpret_cast<const float4*>(src + sp * part_stride)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float acc[4] = {(part[0].x + part[1].x) + (part[2].x + part[3].x), (part[0].y + part[1].y) + (part[2].y + part[3].y),
-                              (part[0].z + part[1].z) + (part[2].z + part[3].z), (part[0].w + part[1].w) + (part[2].w + part[3].w)};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          o[m][4 * j + k] = acc[k];
-          if (!gma) s += acc[k] * __ldg(w_score + 8 * chunk + 4 * (lane & 1) + k);
+        const float* src = src0 + m * mode_stride + static_cast<long long>(16 * j) * g.Mp * 8;
+        float4 acc = __ldg(reinterpret_cast<const float4*>(src));
+        for (int sp = 1; sp < nvalid; ++sp) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(src + sp * part_stride));
+          acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
         }
+        o[m][4 * j] = acc.x; o[m][4 * j + 1] = acc.y; o[m][4 * j + 2] = acc.z; o[m][4 * j + 3] = acc.w;
+        part_s[m] += acc.x * wsc[4 * j] + acc.y * wsc[4 * j + 1] + acc.z * wsc[4 * j + 2] + acc.w * wsc[4 * j + 3];
       }
-      sc[m] = gma ? 0.f : warp_sum(s) + b_score[0];
     }
+  }
+  if (!gma) {
+    const float bsc = b_score[0];
+#pragma unroll
+    for (int o_ = 16; o_ > 0; o_ >>= 1) {      // the four reductions share one shuffle ladder
+#pragma unroll
+      for (int m = 0; m < 4; ++m) part_s[m] += __shfl_xor_sync(0xffffffffu, part_s[m], o_);
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) if (m < M) sc[m] = part_s[m] + bsc;
+  } else {
+#pragma unroll
+    for (int m = 0; m < 4; ++m) if (m < M) sc[m] = 0.f;
   }
   const float mx = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
   float den = 0.f;
@@ -720,19 +737,31 @@ __global__ void __launch_bounds__(256) modes_finalize_kernel(
     den += sc[m];
   }
   const float c = coeff[0];
+  const float rden = 1.0f / den;
   float yv[PER];
   float s1 = 0.f;
 #pragma unroll
-  for (int e = 0; e < PER; ++e) {
-    const int f = 8 * ((lane >> 1) + 16 * (e >> 2)) + 4 * (lane & 1) + (e & 3);
-    float agg = 0.f;
+  for (int j = 0; j < PER / 4; ++j) {
+    const int f0 = 8 * ((lane >> 1) + 16 * j) + 4 * (lane & 1);      // four consecutive channels: one vector access
+    float xin[4];
+    if (xf) {
+      const float4 x4 = *reinterpret_cast<const float4*>(xf + static_cast<size_t>(p) * ldxf + colxf + f0);
+      xin[0] = x4.x; xin[1] = x4.y; xin[2] = x4.z; xin[3] = x4.w;
+    } else {
+      const uint2 x2 = *reinterpret_cast<const uint2*>(xb + static_cast<size_t>(p) * ldx + colx + f0);
+      const float2 lo = unpack_act2(x2.x), hi = unpack_act2(x2.y);
+      xin[0] = lo.x; xin[1] = lo.y; xin[2] = hi.x; xin[3] = hi.y;
+    }
 #pragma unroll
-    for (int m = 0; m < 4; ++m) agg += sc[m] * o[m][e];
-    agg /= den;
-    const float xin = xf ? xf[static_cast<size_t>(p) * ldxf + colxf + f]
-                         : act2f(xb[static_cast<size_t>(p) * ldx + colx + f]);
-    yv[e] = gma ? (xin + c * agg) : (c * xin + agg);
-    s1 += yv[e];
+    for (int k = 0; k < 4; ++k) {
+      const int e = 4 * j + k;
+      float agg = 0.f;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) agg += sc[m] * o[m][e];
+      agg *= rden;
+      yv[e] = gma ? (xin[k] + c * agg) : (c * xin[k] + agg);
+      s1 += yv[e];
+    }
   }
   if (!gma) {
     const float mean = warp_sum(s1) * (1.0f / F);
@@ -747,10 +776,14 @@ __global__ void __launch_bounds__(256) modes_finalize_kernel(
     for (int e = 0; e < PER; ++e) yv[e] = (yv[e] - mean) * rstd;
   }
 #pragma unroll
-  for (int e = 0; e < PER; ++e) {
-    const int f = 8 * ((lane >> 1) + 16 * (e >> 2)) + 4 * (lane & 1) + (e & 3);
-    if (out_b) out_b[static_cast<size_t>(p) * ldb + colb + f] = f2act(yv[e]);
-    if (out_f) out_f[static_cast<size_t>(p) * ldf + colf + f] = yv[e];
+  for (int j = 0; j < PER / 4; ++j) {
+    const int f0 = 8 * ((lane >> 1) + 16 * j) + 4 * (lane & 1);
+    if (out_b)
+      *reinterpret_cast<uint2*>(out_b + static_cast<size_t>(p) * ldb + colb + f0) =
+          make_uint2(pack_act2(yv[4 * j], yv[4 * j + 1]), pack_act2(yv[4 * j + 2], yv[4 * j + 3]));
+    if (out_f)
+      *reinterpret_cast<float4*>(out_f + static_cast<size_t>(p) * ldf + colf + f0) =
+          make_float4(yv[4 * j], yv[4 * j + 1], yv[4 * j + 2], yv[4 * j + 3]);
   }
 }
 

@@ -2,6 +2,8 @@
 they stay stock PyTorch (cuDNN) and exist here only so that `CRAFT(args)` is self-contained and the
 reference checkpoints load key for key (conv1, norm1, layer{1,2,3}.{0,1}.{conv1,conv2,norm1,norm2,
 norm3,downsample.{0,1}}, conv2)."""
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -44,6 +46,10 @@ class ResidualBlock(nn.Module):
         y = fz.conv(self.conv1, x)
         y = fz.norm_act(self.norm1, y, self.conv1, relu=True)
         y2 = fz.conv(self.conv2, y)
+        if fz.one_launch_in:      # instance norm: statistics + transform + residual in one cooperative launch each
+            if self.downsample is not None:
+                x = fz.instnorm(fz.conv(self.downsample[0], x), self.norm3)
+            return fz.instnorm(y2, self.norm2, res=x, relu_in=True, relu_out=True)
         ab2 = fz.scale_shift(self.norm2, y2, self.conv2)
         if self.downsample is not None:
             xd = fz.conv(self.downsample[0], x)
@@ -62,6 +68,11 @@ class _Fused:
         self.kind, self.ops, self.half = kind, ops, half
         self.dtype = torch.float16 if half else torch.float32     # activation / conv operand type (stats stay fp32)
         self.cache = hotpath.PackedWeights()
+        # CRAFT_B200_FUSED_IN=1: InstanceNorm2d as ONE cooperative kernel per tensor (ops.instnorm_apply) instead of
+        # stats + finalize + affine.  Default off: 28 launches fewer and -0.2 ms of summed kernel time, but the same
+        # 4.19-4.21 ms per pair -- with the context encoder on the second stream the encoder phase is bound by SM
+        # time, not by its launch chain (profiles/r02_instnorm_one_launch.txt)
+        self.one_launch_in = kind == "instance" and os.environ.get("CRAFT_B200_FUSED_IN", "0") == "1"
 
     def conv(self, m, x, bias=False):
         """cuDNN convolution WITHOUT its bias: a conv bias in front of a normalisation is either a no-op
@@ -91,7 +102,15 @@ class _Fused:
         return out
 
     def norm_act(self, norm, y, conv, relu=True):
+        if self.one_launch_in:
+            return self.instnorm(y, norm, relu_in=relu)
         return self.affine(y, self.scale_shift(norm, y, conv), relu_in=relu)
+
+    def instnorm(self, y, norm, res=None, relu_in=False, relu_out=False):
+        out = torch.empty_like(y)     # keeps the channels-last strides
+        self.ops.instnorm_apply(y.permute(0, 2, 3, 1), res.permute(0, 2, 3, 1) if res is not None else None, None,
+                                relu_in, relu_out, eps=norm.eps, out=out.permute(0, 2, 3, 1))
+        return out
 
     def conv1_s2d(self, m, s):
         """The 7x7 stride-2 first convolution (core/extractor.py:129) on the space-to-depth input of

@@ -357,6 +357,28 @@ def instnorm_stats(x_nhwc, eps=1e-5):
     return ab
 
 
+_IN_PART = {}
+
+
+def instnorm_apply(x, res=None, rab=None, relu_in=False, relu_out=False, eps=1e-5, out=None, return_ab=False):
+    """out = relu_out([ra*res+rb | res] + relu_in(instance_norm(x))) in one cooperative launch that reads x once
+    (include/craft_b200.h craft_nhwc_instnorm_apply).  x/res/out [N,H,W,C] contiguous f32 or f16; rab f32 [N or 1,C,2]."""
+    _act_dtype(x, "x")
+    _chk(res, x.dtype, "res")
+    N, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _chk(out, x.dtype, "out")
+    key = (str(x.device), torch.cuda.current_stream(x.device).cuda_stream)
+    part = _IN_PART.get(key)          # per-CTA partial sums; every launch overwrites what it reads, stream-ordered
+    if part is None:
+        part = _IN_PART[key] = torch.zeros((1024 * 512,), dtype=torch.float32, device=x.device)
+    ab = torch.empty((N, Cc, 2), dtype=torch.float32, device=x.device) if return_ab else None
+    st = 0 if (rab is None or rab.shape[0] == 1) else 2 * Cc
+    OPS.nhwc_instnorm_apply(x, res, rab, st, bool(relu_in), bool(relu_out), N, H * W, Cc, float(eps), part, ab, out)
+    return (out, ab) if return_ab else out
+
+
 def image_s2d(img, dtype=torch.float16):
     """[N,3,H,W] f32 frames (0..255) -> normalised, 2x2 space-to-depth, channels-last, zero-bordered input of the
     encoders' first convolution: [N, H/2+3, W/2+3, 16] (include/craft_b200.h craft_image_s2d)."""

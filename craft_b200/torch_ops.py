@@ -321,6 +321,14 @@ def nhwc_affine(v, ab, ab_stride, res, rab, rab_stride, relu_in, relu_out, N, HW
               int(relu_out), N, HW, Cc, _ptr(out), _stream())
 
 
+@_op("nhwc_instnorm_apply(Tensor x, Tensor? res, Tensor? rab, int rab_stride, bool relu_in, bool relu_out, int N, int HW, int C, "
+     "float eps, Tensor(a!) part, Tensor(b!)? ab_out, Tensor(c!) out) -> ()")
+def nhwc_instnorm_apply(x, res, rab, rab_stride, relu_in, relu_out, N, HW, Cc, eps, part, ab_out, out):
+    half = 1 if x.dtype == torch.float16 else 0
+    _lib.call("craft_nhwc_instnorm_apply", _ptr(x), half, N, HW, Cc, float(eps), _ptr(res), _ptr(rab), rab_stride,
+              int(relu_in), int(relu_out), _ptr(part), part.numel(), _ptr(ab_out), _ptr(out), _stream())
+
+
 @_op("forward_interpolate(Tensor flow, int H, int W, Tensor(a!) out) -> ()")
 def forward_interpolate(flow, H, W, out):
     _chk(flow, f32, "flow"); _chk(out, f32, "out")

@@ -221,6 +221,16 @@ int craft_flow_encode(const float* flow, int H, int W, int mode, void* out, void
  * enough); the partials are reduced in a fixed order, so the result is run-to-run deterministic. */
 int craft_nhwc_instnorm_stats(const void* x, int is_half, int N, int HW, int C, float eps, float* part,
                               long long part_capacity, float* ab, void* stream);
+/* InstanceNorm2d + ReLU (+ residual) of a channels-last tensor in ONE cooperative launch (extractor.py:55-64 with
+ * norm_fn='instance'):  out = relu_out( [ra*res+rb | res] + relu_in( (x-mean)*rstd ) ).  Every CTA keeps its slab
+ * of x in shared memory across a grid barrier, so x is read from memory once (craft_nhwc_instnorm_stats +
+ * craft_nhwc_affine read it twice, in three launches).  x/res/out: [N,HW,C] f32 or f16 (is_half); rab: f32
+ * [N or 1][C][2] or NULL; part: f32 scratch, >= 64 + 2*C floats per SM, ZERO before its first use (the first 64
+ * floats are barrier state the kernel leaves reusable); ab_out: optional [N,C,2] (rstd, -mean*rstd).
+ * N <= number of SMs, C <= 256 (f16) / 128 (f32).  Deterministic (fixed reduction order).                        */
+int craft_nhwc_instnorm_apply(const void* x, int is_half, int N, int HW, int C, float eps, const void* res,
+                              const float* rab, int rab_nstride, int relu_in, int relu_out, float* part,
+                              long long part_capacity, float* ab_out, void* out, void* stream);
 /* Input transform of both encoders: f32 frames [N,3,H,W] in 0..255 -> 2*(x/255)-1 (core/network.py:170-171), 2x2
  * space-to-depth, channels-last, zero border (2 cells before, 1 after): out [N][H/2+3][W/2+3][16] (f16 if
  * out_is_half else f32), channel (py*2+px)*3 + c, channels 12..15 zero.  The 7x7 stride-2 convolution

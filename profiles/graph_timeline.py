@@ -47,6 +47,11 @@ def main(tag):
     print(out)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     open(os.path.join(ROOT, "gpurun_out", "graph_timeline_%s.txt" % tag), "w").write(out + "\n")
+    # the raw timeline (start relative to the first kernel, duration, name), for reading overlap and gaps
+    t0 = ks[0][0]
+    with open(os.path.join(ROOT, "gpurun_out", "graph_timeline_raw_%s.txt" % tag), "w") as f:
+        for s, e, n in ks:
+            f.write("%9.1f %8.1f  %s\n" % (s - t0, e - s, n.replace("void ", "").split("(")[0][:90]))
 
 
 if __name__ == "__main__":

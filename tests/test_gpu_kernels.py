@@ -393,6 +393,43 @@ def test_encoder_norm_kernels(Cc):
     assert outh.dtype == torch.float16 and torch.allclose(outh.float(), refh, atol=4e-3, rtol=2e-3), (outh.float() - refh).abs().max()
 
 
+@pytest.mark.parametrize("N,Cc,H,W", [(2, 64, 37, 50), (2, 96, 28, 64), (1, 128, 56, 128), (3, 64, 5, 7), (2, 256, 17, 9),
+                                      (2, 64, 224, 512), (1, 64, 400, 640)])
+def test_instnorm_one_launch(N, Cc, H, W):
+    """craft_nhwc_instnorm_apply (cooperative: slab in shared memory across a grid barrier) against
+    F.instance_norm (core/extractor.py:55-64 with norm_fn='instance') and against the three-launch kernels.
+    (2,64,224,512) is the 448x1024 layer-1 tensor (198 KB slab per CTA); (1,64,400,640) overflows shared memory."""
+    g = torch.Generator(device=DEV).manual_seed(Cc + H)
+    cl = torch.channels_last
+    x = (torch.randn((N, Cc, H, W), device=DEV, generator=g) * 2 + 0.3).contiguous(memory_format=cl)
+    r = torch.randn((N, Cc, H, W), device=DEV, generator=g).contiguous(memory_format=cl)
+    nhwc = lambda t: t.permute(0, 2, 3, 1)
+    for dt, atol, rtol in ((torch.float32, 2e-4, 1e-4), (torch.float16, 4e-3, 2e-3)):
+        if dt == torch.float32 and Cc > 128:
+            continue
+        xx, rr = x.to(dt), r.to(dt)
+        ref_n = F.instance_norm(xx.float(), eps=1e-5)
+        # norm + relu
+        out = torch.empty_like(xx)
+        _, ab = ops.instnorm_apply(nhwc(xx), relu_in=True, out=nhwc(out), return_ab=True)
+        torch.cuda.synchronize()
+        assert torch.allclose(out.float(), torch.relu(ref_n), atol=atol, rtol=rtol), (out.float() - torch.relu(ref_n)).abs().max()
+        ab3 = ops.instnorm_stats(nhwc(xx))
+        assert torch.allclose(ab, ab3, atol=1e-5, rtol=1e-4)
+        # norm + relu + residual + relu, and an affine on the residual branch
+        out2 = ops.instnorm_apply(nhwc(xx), res=nhwc(rr), relu_in=True, relu_out=True)
+        ref2 = torch.relu(rr.float() + torch.relu(ref_n))
+        assert torch.allclose(nhwc(ref2), out2.float(), atol=atol, rtol=rtol), (nhwc(ref2) - out2.float()).abs().max()
+        sab = torch.randn((1, Cc, 2), device=DEV, generator=g)
+        out3 = ops.instnorm_apply(nhwc(xx), res=nhwc(rr), rab=sab, relu_in=False, relu_out=False)
+        a, b = sab[0, :, 0].view(1, Cc, 1, 1), sab[0, :, 1].view(1, Cc, 1, 1)
+        ref3 = (a * rr.float() + b) + ref_n
+        assert torch.allclose(nhwc(ref3), out3.float(), atol=2 * atol, rtol=2 * rtol)
+        # fixed reduction order: bit-identical run to run
+        out4 = ops.instnorm_apply(nhwc(xx), res=nhwc(rr), relu_in=True, relu_out=True)
+        assert torch.equal(out2, out4)
+
+
 @pytest.mark.parametrize("kind", ["instance", "batch"])
 def test_fused_encoder_matches_module_path(kind):
     from craft_b200.extractor import BasicEncoder
