@@ -20,7 +20,8 @@
 // leaves one partial (max, sum) per CTA in consecutive slots of lse_part, the CTA that finishes
 // the query tile fills the unused slots with the neutral element.
 //
-// Warps (576 threads): 0 = TMA, 1 = MMA issuer (+TMEM alloc), 2..17 = epilogue:
+// Warps (640 threads): 0 = TMA, 1 = MMA issuer (+TMEM alloc), 2..3 idle (they complete the producer warpgroup, whose
+// registers setmaxnreg hands to the epilogue), 4..19 = epilogue:
 // group eg = tile parity (TMEM buffer), half ch = key-block rows 0-3 / 4-7 (columns 0-31 / 32-63 of
 // every mode), TMEM lane quadrant = warp & 3.  Thread = one query x 32 keys x M modes per tile.
 #pragma once
@@ -29,7 +30,9 @@
 
 namespace cb {
 
-constexpr int kScThreads = 64 + 512;   // 576 threads -> 112 registers each
+constexpr int kScThreads = 128 + 512;  // producer warpgroup (TMA, MMA, two idle warps) + 16 epilogue warps; 640 threads are
+                                       // launched with 96 registers each, setmaxnreg then moves 64 per producer thread to
+                                       // the epilogue warpgroups (32 / 112)
 constexpr int kScKStages = 3;
 constexpr int kScTailBytes = 512 /*barriers*/ + 2560 /*bias table*/ + 2048 /*level-3 exchange*/ + 16384 /*lse merge*/;
 
@@ -72,6 +75,86 @@ struct ScoreParams {
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
   else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+// SC_CORR, unclamped, M = 4 or 1: one key ROW (8 keys) of a thread's 4 x 8 window, raw accumulators of the modes ->
+// soft-aggregated score.  The generic epilogue below (any M, clamp) spent 58 instructions per key, a third of them
+// local-memory traffic and per-key branches on runtime constants; this form is 22 per key for M = 4, registers only:
+//   softmax over modes of w*s in the exp2 domain on the UNSCALED accumulators: exponent a_m*c - ext*c (c = w*scale*
+//   log2e; ext = max or, for c < 0, min of the a_m: NEG) is one FFMA per mode, the denominator is in [1, 4] (no
+//   range fix-up around the reciprocal) and the 1/sqrt(d) scale is applied once to the quotient.
+template <int MT, bool NEG>
+__device__ __forceinline__ void corr_row_fast(uint32_t taddr, float wc2, float scale, float& rawmax, float* __restrict__ out8,
+                                              bool release, uint64_t* acc_empty) {
+  uint32_t r0[8], r1[8], r2[8], r3[8];
+  tmem_ld8(taddr, r0);
+  if (MT == 4) {
+    tmem_ld8(taddr + 64, r1);
+    tmem_ld8(taddr + 128, r2);
+    tmem_ld8(taddr + 192, r3);
+  }
+  tmem_ld_wait();
+  if (release) {       // last row: the TMEM buffer is drained -> back to the MMA warp before the math
+    tc_fence_before();
+    mbar_arrive_warp(acc_empty);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float a0 = __uint_as_float(r0[j]);
+    if (MT == 1) {
+      rawmax = fmaxf(rawmax, a0);
+      out8[j] = a0 * scale;
+    } else {
+      const float a1 = __uint_as_float(r1[j]), a2 = __uint_as_float(r2[j]), a3 = __uint_as_float(r3[j]);
+      const float amax = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+      rawmax = fmaxf(rawmax, amax);
+      const float ext = NEG ? fminf(fminf(a0, a1), fminf(a2, a3)) : amax;
+      const float ntm = -ext * wc2;
+      const float e0 = fast_ex2(fmaf(a0, wc2, ntm)), e1 = fast_ex2(fmaf(a1, wc2, ntm));
+      const float e2 = fast_ex2(fmaf(a2, wc2, ntm)), e3 = fast_ex2(fmaf(a3, wc2, ntm));
+      const float num = fmaf(e3, a3, fmaf(e2, a2, fmaf(e1, a1, e0 * a0)));
+      const float den = (e0 + e1) + (e2 + e3);
+      out8[j] = (num * fast_rcp(den)) * scale;
+    }
+  }
+}
+
+// Any M (1, 2, 4), with or without the clamp (core/setrans.py:520-529): the rare configurations and the clamped
+// re-pass.  Same row-at-a-time shape as corr_row_fast (8 accumulator columns per mode in flight).
+__device__ __forceinline__ void corr_row_generic(uint32_t taddr, int M, float wl2, float scale, bool clamped, float clipv,
+                                              float& rawmax, float* __restrict__ out8, bool release, uint64_t* acc_empty) {
+  uint32_t r0[8], r1[8], r2[8], r3[8];
+  tmem_ld8(taddr, r0);
+  if (M > 1) tmem_ld8(taddr + 64, r1);
+  if (M > 2) {
+    tmem_ld8(taddr + 128, r2);
+    tmem_ld8(taddr + 192, r3);
+  }
+  tmem_ld_wait();
+  if (release) {
+    tc_fence_before();
+    mbar_arrive_warp(acc_empty);
+  }
+  const float lim = clamped ? clipv : INFINITY;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float a0 = __uint_as_float(r0[j]);
+    // M == 2: the unused modes duplicate mode 0/1, so that neither the max nor the (signed!) soft-aggregation
+    // weight ever sees an infinity; M == 1: all four are mode 0 and the aggregate is s0 itself
+    const float a1 = (M > 1) ? __uint_as_float(r1[j]) : a0;
+    const float a2 = (M > 2) ? __uint_as_float(r2[j]) : a0;
+    const float a3 = (M > 2) ? __uint_as_float(r3[j]) : a1;
+    rawmax = fmaxf(rawmax, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));
+    const float s0 = fminf(fmaxf(a0 * scale, -lim), lim), s1 = fminf(fmaxf(a1 * scale, -lim), lim);
+    const float s2 = fminf(fmaxf(a2 * scale, -lim), lim), s3 = fminf(fmaxf(a3 * scale, -lim), lim);
+    // softmax over modes of w*s (the Linear(1,1) bias cancels), exp2 domain
+    const float t0 = s0 * wl2, t1 = s1 * wl2, t2 = s2 * wl2, t3 = s3 * wl2;
+    const float tm = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
+    const float e0 = fast_ex2(t0 - tm), e1 = fast_ex2(t1 - tm), e2 = fast_ex2(t2 - tm), e3 = fast_ex2(t3 - tm);
+    const float num = (e0 * s0 + e1 * s1) + (e2 * s2 + e3 * s3);
+    const float den = (e0 + e1) + (e2 + e3);
+    out8[j] = (M == 1) ? s0 : num * fast_rcp(den);
+  }
 }
 
 // smem: Q tile (C/64 atoms x 16 KB) + K stages (C/64 atoms x 8 KB each) + tail
@@ -163,6 +246,8 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
     if (elect_one()) {
@@ -236,10 +321,12 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       lin += sg.nt;
     }
     __syncwarp();
+  }
   } else {
     // ------------------------------------ epilogue ----------------------------------------
-    const int eg = ((warp - 2) >> 2) & 1;           // epilogue group <-> TMEM buffer / tile parity
-    const int ch = (warp - 2) >> 3;                 // key-block rows ch*4 .. ch*4+3
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    const int eg = ((warp - 4) >> 2) & 1;           // epilogue group <-> TMEM buffer / tile parity
+    const int ch = (warp - 4) >> 3;                 // key-block rows ch*4 .. ch*4+3
     const int lane_grp = warp & 3;
     const int row = lane_grp * 32 + (threadIdx.x & 31);
     const float clipv = *p.clip;
@@ -253,6 +340,7 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const float wl2 = p.w_agg * kLog2e;
     const float sc2 = p.scale * kLog2e;
     const float wc2 = p.scale * wl2;             // exponent per unit of raw accumulator
+    const bool fast_corr = (MODE == SC_CORR) && !clamped && (p.M == 4 || p.M == 1);
 
     int seg = 0, g0 = 0;
     for (long long lin = lin_begin; lin < lin_end; ++seg) {
@@ -284,70 +372,22 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 
         if constexpr (MODE == SC_CORR) {
           float agg[32];
+          if (fast_corr) {
+            // warp-uniform choice of one specialised row routine (runtime constants of the launch)
+            if (p.M == 1) {
 #pragma unroll
-          for (int c = 0; c < 32; c += 16) {
-            uint32_t r0[16], r1[16], r2[16], r3[16];
-            tmem_ld16(trow + c, r0);
-            if (p.M > 1) tmem_ld16(trow + 64 + c, r1);
-            if (p.M > 2) {
-              tmem_ld16(trow + 128 + c, r2);
-              tmem_ld16(trow + 192 + c, r3);
-            }
-            tmem_ld_wait();
-            if (c == 16) {
-              // TMEM buffer drained -> hand it back to the MMA warp before the math
-              tc_fence_before();
-              mbar_arrive_warp(&acc_empty[eg]);
-            }
+              for (int r = 0; r < 4; ++r) corr_row_fast<1, false>(trow + 8 * r, wc2, p.scale, seg_rawmax, agg + 8 * r, r == 3, &acc_empty[eg]);
+            } else if (wc2 >= 0.f) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float a0 = __uint_as_float(r0[j]);
-              float v;
-              if (p.M == 1) {
-                seg_rawmax = fmaxf(seg_rawmax, a0);
-                const float s0 = a0 * p.scale;
-                v = clamped ? fminf(fmaxf(s0, -clipv), clipv) : s0;
-              } else {
-                const float a1 = __uint_as_float(r1[j]);
-                // M == 2: the unused modes duplicate mode 0/1, so that neither the max nor the (signed!)
-                // soft-aggregation weight ever sees an infinity
-                const float a2 = (p.M > 2) ? __uint_as_float(r2[j]) : a0;
-                const float a3 = (p.M > 2) ? __uint_as_float(r3[j]) : a1;
-                const float amax = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
-                seg_rawmax = fmaxf(seg_rawmax, amax);
-                if (!clamped) {
-                  // softmax over modes of w*s (the Linear(1,1) bias cancels) in the exp2 domain, on the UNSCALED
-                  // accumulators: exponent a_m*c - max_m(a_m*c) is one FFMA per mode, the raw maximum doubles as
-                  // the softmax maximum (c >= 0) and the 1/sqrt(d) scale is applied once to the quotient.  The
-                  // epilogue is bound by issue slots as much as by the MUFU unit: ~10 fewer instructions per key.
-                  const float tm = (wc2 >= 0.f ? amax : fminf(fminf(a0, a1), fminf(a2, a3))) * wc2;
-                  const float e0 = fast_ex2(fmaf(a0, wc2, -tm)), e1 = fast_ex2(fmaf(a1, wc2, -tm));
-                  float num = e0 * a0 + e1 * a1, den = e0 + e1;
-                  if (p.M > 2) {
-                    const float e2 = fast_ex2(fmaf(a2, wc2, -tm)), e3 = fast_ex2(fmaf(a3, wc2, -tm));
-                    num += e2 * a2 + e3 * a3;
-                    den += e2 + e3;
-                  }
-                  v = __fdividef(num * p.scale, den);
-                } else {
-                  const float s0 = fminf(fmaxf(a0 * p.scale, -clipv), clipv);
-                  const float s1 = fminf(fmaxf(a1 * p.scale, -clipv), clipv);
-                  const float s2 = fminf(fmaxf(a2 * p.scale, -clipv), clipv);
-                  const float s3 = fminf(fmaxf(a3 * p.scale, -clipv), clipv);
-                  const float t0 = s0 * wl2, t1 = s1 * wl2, t2 = s2 * wl2, t3 = s3 * wl2;
-                  const float tm = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
-                  const float e0 = fast_ex2(t0 - tm), e1 = fast_ex2(t1 - tm);
-                  float num = e0 * s0 + e1 * s1, den = e0 + e1;
-                  if (p.M > 2) {
-                    const float e2 = fast_ex2(t2 - tm), e3 = fast_ex2(t3 - tm);
-                    num += e2 * s2 + e3 * s3;
-                    den += e2 + e3;
-                  }
-                  v = __fdividef(num, den);
-                }
-              }
-              agg[c + j] = v;
+              for (int r = 0; r < 4; ++r) corr_row_fast<4, false>(trow + 8 * r, wc2, p.scale, seg_rawmax, agg + 8 * r, r == 3, &acc_empty[eg]);
+            } else {
+#pragma unroll
+              for (int r = 0; r < 4; ++r) corr_row_fast<4, true>(trow + 8 * r, wc2, p.scale, seg_rawmax, agg + 8 * r, r == 3, &acc_empty[eg]);
             }
+          } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+              corr_row_generic(trow + 8 * r, p.M, wl2, p.scale, clamped, clipv, seg_rawmax, agg + 8 * r, r == 3, &acc_empty[eg]);
           }
 
           if (qvalid) {
