@@ -456,6 +456,19 @@ def run_ours(args, cfg):
         a, b = pairs[i % len(pairs)]
         return model(a, b, iters=ITERS, test_mode=1)
 
+    # --lanes L: L independent pairs in flight per GPU (craft_b200.pipeline.PairStream / CRAFT.on_lane): every pair is
+    # still one batch-1 forward of the whole path; the kernels of different pairs overlap on the device
+    from craft_b200.pipeline import PairStream
+    lanes = max(1, args.lanes)
+    ps_val = PairStream(model, iters=ITERS, lanes=lanes)
+
+    def run_steps(n):
+        if lanes == 1:
+            for i in range(n):
+                step(i)
+        else:
+            ps_val.run_resident(pairs[i % len(pairs)] for i in range(n))
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -473,16 +486,25 @@ def run_ours(args, cfg):
         return
     sampler = ClockSampler(local) if rank == 0 else None
     with torch.no_grad():
-        for i in range(args.warmup):
+        # single-lane reference point (one pair at a time on one stream): the latency of a pair
+        for i in range(max(args.warmup, 1)):
             step(i)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(args.steps):
+            step(i)
+        s1.record()
+        barrier()
+        ms_single = s0.elapsed_time(s1)
+        run_steps(max(args.warmup, lanes))          # every lane captures its graph outside the timed region
         barrier()
         if sampler:
             sampler.start()
         n0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(args.steps):
-            step(i)
+        run_steps(args.steps)
         e1.record()
         barrier()
         launches = _lib.launch_count() - n0
@@ -507,8 +529,7 @@ def run_ours(args, cfg):
         else:
             # craft_b200.pipeline.PairStream: the same per-pair traffic (every pair's frames H2D, its flow D2H, all
             # inside the timed region) with the copies of neighbouring pairs on a second stream under the forward
-            from craft_b200.pipeline import PairStream
-            ps = PairStream(model, iters=ITERS)
+            ps = PairStream(model, iters=ITERS, lanes=lanes)
 
             def e2e_run(n):
                 got = 0
@@ -516,7 +537,7 @@ def run_ours(args, cfg):
                     got += 1
                 assert got == n
 
-        e2e_run(2)
+        e2e_run(max(2, lanes))
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
@@ -525,10 +546,10 @@ def run_ours(args, cfg):
         barrier()
         ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms, ms_e2e, ms_single], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
+    ms, ms_e2e, ms_single = t.tolist()
 
     roof, gpu_ref, cpu = None, None, None
     if rank == 0:
@@ -575,14 +596,20 @@ def run_ours(args, cfg):
                                          "+ craft_b200 norm/relu/residual kernels",
                                 launch="whole forward replayed as one CUDA graph; craft_b200 kernels use programmatic "
                                        "dependent launch",
+                                lanes=lanes,
+                                lanes_note="%d independent pairs in flight per GPU, one CUDA stream + workspace + graph each "
+                                           "(craft_b200.pipeline.PairStream); every pair is a batch-1 forward of the whole "
+                                           "path; `single_lane` is one pair at a time on one stream" % lanes,
+                                single_lane=dict(value=total / (ms_single * 1e-3), unit="pairs/s",
+                                                 ms_per_pair=ms_single / args.steps),
                                 dead_work="test_mode=1 returns only the last upsampled flow: the mask head + convex "
                                           "upsampling of iterations 1..%d (discarded by the reference) are elided, "
                                           "outputs bit-identical (tests/test_gpu_e2e.py)" % (ITERS - 1)),
                     e2e=dict(value=total / (ms_e2e * 1e-3), unit="pairs/s", h2d_bytes_per_step=2 * 3 * H * W,
                              d2h_bytes_per_step=2 * H * W * 4,
                              mode=("serial: H2D -> CRAFT.forward -> D2H on one stream" if args.e2e_serial else
-                                   "craft_b200.pipeline.PairStream: every pair's uint8 frames H2D and its flow D2H inside the "
-                                   "timed region, the copies of neighbouring pairs on a second stream under the forward")),
+                                   "craft_b200.pipeline.PairStream(lanes=%d): every pair's uint8 frames H2D and its flow D2H "
+                                   "inside the timed region, the copies on their own streams under the forwards" % lanes)),
                     gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu)
         if gpu_ref is not None:
             line["gpu_reference"] = gpu_ref
@@ -687,6 +714,8 @@ def main():
                     help="sintel = BASELINE configs[1] (default, the metric's configuration); kitti = configs[4] shape; "
                          "gma = configs[2] variant")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("CRAFT_B200_LANES", "3")),
+                    help="independent pairs in flight per GPU (1 = one pair at a time on one stream)")
     ap.add_argument("--e2e-serial", action="store_true", help="e2e leg: one pair at a time on one stream (no PairStream overlap)")
     ap.add_argument("--dropout-prob", type=float, default=None,
                     help="--config train only: override the transformers' dropout (reference training default 0.1/0.2)")

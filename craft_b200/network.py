@@ -20,6 +20,7 @@ from .extractor import BasicEncoder
 from .gma import Attention
 from .ops import TokenGrid
 import collections
+import contextlib
 
 from .setrans import SETransConfig, SelfAttVisPosTrans, WorkspaceCache, _require_inference
 from .update import GMAUpdateBlock
@@ -133,8 +134,9 @@ class CRAFT(nn.Module):
         #   "fp32-parity"     float16 operands + strict-fp32 cuDNN encoders: 1.35e-4 px, 2.6x slower (encoders).
         self.set_precision(os.environ.get("CRAFT_B200_PRECISION", "fp16"))
         self._graphs = collections.OrderedDict()   # LRU, bounded by max_cached_graphs
-        self.max_cached_graphs = 8
-        self._workspaces = WorkspaceCache(capacity=6)   # this model's own device buffers
+        self.max_cached_graphs = 12
+        self._workspaces = WorkspaceCache(capacity=12)  # this model's own device buffers
+        self._lane = 0                                  # see on_lane()
 
     def set_precision(self, tier):
         if tier not in ("bf16", "fp16", "fp32-parity"):
@@ -148,12 +150,31 @@ class CRAFT(nn.Module):
             self.encoder_tf32 = True
         return self
 
+    @contextlib.contextmanager
+    def on_lane(self, k):
+        """Several independent pairs in flight on one GPU: inside `with model.on_lane(k):` a forward uses lane k's own
+        workspace, CUDA graph and static input/output buffers (the parameters are shared), so forwards issued on
+        different CUDA streams under different lanes may overlap on the device.  The refinement loop is a serial chain
+        of kernels that each leave SMs idle (114 of 148 CTAs, prologue / epilogue bubbles); a second and third pair
+        fill them: 242 -> 274 -> 284 pairs/s at 448x1024 (profiles/r02_lanes.txt).  craft_b200.pipeline.PairStream
+        drives this; a plain `model(...)` call is lane 0.  (The attention diagnostics max_attn / clamp_count are
+        shared by the lanes and updated without atomics.)"""
+        prev, self._lane = self._lane, int(k)
+        try:
+            yield self
+        finally:
+            self._lane = prev
+
+    def _ws_slot(self):
+        return ("lane", self._lane) if self._lane else 0
+
     def workspace_for(self, H, W, device=None):
         """The device buffers this model uses for H x W images (token grid H/8 x W/8) at its precision tier --
         what tests and profiling scripts inspect after a forward."""
         device = device or next(self.parameters()).device
         with torch.cuda.device(device), ops.precision(self.act_dtype):
-            return self._workspaces.get(TokenGrid(H // 8, W // 8), device, self.materialize_level0 or self.level0)
+            return self._workspaces.get(TokenGrid(H // 8, W // 8), device, self.materialize_level0 or self.level0,
+                                        slot=self._ws_slot())
 
     def freeze_bn(self):
         for m in self.modules():
@@ -300,7 +321,8 @@ class CRAFT(nn.Module):
 
     def _forward_graphed(self, image1, image2, iters, flow_init, test_mode):
         key = (image1.device.index, tuple(image1.shape), int(iters), int(test_mode), flow_init is not None,
-               self.materialize_level0, hp.level0_mode(self.level0), self.encoder_tf32, self.encoder_half, self.elide_dead_upsample, self.precision)
+               self.materialize_level0, hp.level0_mode(self.level0), self.encoder_tf32, self.encoder_half, self.elide_dead_upsample, self.precision,
+               self._lane)
         sig = self._weights_signature()
         ent = self._graphs.get(key)
         if ent is not None:
@@ -339,7 +361,7 @@ class CRAFT(nn.Module):
             ent["launches"] = _lib.launch_count() - n0   # craft_b200 kernels per replay
             # the graph bakes in the workspace's addresses: keep the buffers alive as long as the graph is
             g8 = TokenGrid(image1.shape[2] // 8, image1.shape[3] // 8)
-            ent["ws"] = self._workspaces.get(g8, image1.device, self.materialize_level0 or self.level0)
+            ent["ws"] = self._workspaces.get(g8, image1.device, self.materialize_level0 or self.level0, slot=self._ws_slot())
             self._graphs[key] = ent
             while len(self._graphs) > self.max_cached_graphs:
                 self._graphs.popitem(last=False)
@@ -359,7 +381,7 @@ class CRAFT(nn.Module):
         B, _, H, W = image1.shape
         fmap1, fmap2, cnet_feat = self._encoders(image1.float(), image2.float())
         g = TokenGrid(H // 8, W // 8)
-        ws = self._workspaces.get(g, image1.device, self.materialize_level0 or savecorr or self.level0)
+        ws = self._workspaces.get(g, image1.device, self.materialize_level0 or savecorr or self.level0, slot=self._ws_slot())
         dev = image1.device
         flow_lo = torch.empty((B, 2, g.H, g.W), dtype=torch.float32, device=dev)
         n_up = iters if test_mode != 1 else 1
