@@ -548,14 +548,31 @@ __global__ void __launch_bounds__(128) convf1_kernel(const float* __restrict__ f
 
   constexpr int TX = 8;     // tokens per thread; block covers 16 tokens x 64 couts (gridDim.y = 2)
   __shared__ float in[2][7][16 + 6];
-  __shared__ float ws[98 * 64];
+  __shared__ __align__(16) float ws[98 * 64];
   const int tiles_per_row = (g.W + 15) / 16;
   const int y = blockIdx.x / tiles_per_row;
   const int xb = (blockIdx.x - y * tiles_per_row) * 16;
   const int co = blockIdx.y * 64 + (threadIdx.x & 63);
   const int tg = threadIdx.x >> 6;
   const int x0 = xb + tg * TX;
-  for (int i = threadIdx.x; i < 98 * 64; i += 128) ws[i] = wt[(i >> 6) * 128 + blockIdx.y * 64 + (i & 63)];
+  {
+    // this block's half of the weights: 98 rows of 64 contiguous floats.  All 16-byte requests of a thread are
+    // issued before the first store (13 per thread): the scalar copy loop this replaces ran its 49 L2 round trips
+    // nearly back to back and was most of the kernel's 16 us.
+    const float4* src = reinterpret_cast<const float4*>(wt) + blockIdx.y * 16;
+    float4* dst = reinterpret_cast<float4*>(ws);
+    float4 t[13];
+#pragma unroll
+    for (int u = 0; u < 13; ++u) {
+      const int i = threadIdx.x + u * 128;             // float4 index: row i >> 4, column group i & 15
+      t[u] = (i < 98 * 16) ? __ldg(src + (i >> 4) * 32 + (i & 15)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 13; ++u) {
+      const int i = threadIdx.x + u * 128;
+      if (i < 98 * 16) dst[i] = t[u];
+    }
+  }
   for (int i = threadIdx.x; i < 2 * 7 * 22; i += 128) {
     const int c = i / (7 * 22);
     const int r = (i / 22) % 7;

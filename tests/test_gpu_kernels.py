@@ -248,14 +248,17 @@ def _scores_ref(q, k, M, table, w_pos, clipv):
     return s, gmax
 
 
-@pytest.mark.parametrize("H,W,M,d,clipv", [(16, 24, 4, 64, float("inf")), (13, 22, 4, 64, 2.0), (8, 16, 1, 256, float("inf")),
-                                           (16, 16, 2, 64, float("inf"))])
-def test_corr_build(H, W, M, d, clipv):
+@pytest.mark.parametrize("H,W,M,d,clipv,w_agg", [(16, 24, 4, 64, float("inf"), 0.13), (13, 22, 4, 64, 2.0, 0.13),
+                                                 (8, 16, 1, 256, float("inf"), 0.13), (16, 16, 2, 64, float("inf"), 0.13),
+                                                 # a NEGATIVE soft-aggregation weight (feat2score.weight is signed): the
+                                                 # specialised epilogue then takes the mode MINIMUM as its softmax pivot
+                                                 (16, 24, 4, 64, float("inf"), -0.21), (13, 22, 2, 64, 2.0, -0.21)])
+def test_corr_build(H, W, M, d, clipv, w_agg):
     grid = TokenGrid(H, W)
     g = torch.Generator(device=DEV).manual_seed(11)
     q, k = _rand_qk(grid, M * d, g, 0.6)
     table = torch.randn((15, 15), device=DEV, generator=g) if M > 1 else None
-    w_agg, w_pos = 0.13, 0.5
+    w_pos = 0.5
     s, gmax = _scores_ref(q, k, M, table, w_pos, clipv)
     if M > 1:
         # soft aggregation is shift-invariant to the shared bias, so this matches the reference order
