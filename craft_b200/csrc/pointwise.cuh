@@ -706,9 +706,11 @@ __global__ void __launch_bounds__(256) modes_finalize_kernel(
   float wsc[PER];                          // this lane's score weights: the same for every mode
 #pragma unroll
   for (int j = 0; j < PER / 4; ++j) {
-    const float4 w4 = gma ? make_float4(0.f, 0.f, 0.f, 0.f)
-                          : __ldg(reinterpret_cast<const float4*>(w_score + 8 * ((lane >> 1) + 16 * j) + 4 * (lane & 1)));
-    wsc[4 * j] = w4.x; wsc[4 * j + 1] = w4.y; wsc[4 * j + 2] = w4.z; wsc[4 * j + 3] = w4.w;
+    // scalar loads: w_score is a module parameter, and nn.DataParallel replicas hold their parameters as views into
+    // one flat broadcast buffer -- aligned to 4 bytes only (a float4 load here trapped on the second GPU)
+    const float* wp = w_score + 8 * ((lane >> 1) + 16 * j) + 4 * (lane & 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wsc[4 * j + k] = gma ? 0.f : __ldg(wp + k);
   }
   const float* src0 = O + (static_cast<long long>(lane >> 1) * g.Mp + p) * 8 + 4 * (lane & 1);
   float part_s[4];                         // per-mode partial dot products, reduced over the warp together below

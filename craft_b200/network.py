@@ -205,7 +205,8 @@ class CRAFT(nn.Module):
         amp = bool(getattr(self.args, "mixed_precision", False))
         self.fnet.fused_half = self.cnet.fused_half = bool(self.encoder_half)
         if self.encoder_nhwc and not amp and self.fnet._can_fuse(image1) and self.cnet._can_fuse(image1):
-            return self._encoders_fused(image1, image2)
+            # nn.DataParallel replicas already run side by side (one thread per device): one stream each
+            return self._encoders_fused(image1, image2, one_stream=getattr(self, "_is_replica", False))
         image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
         image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
         # fnet (two frames) and cnet (frame 1) are independent: run cnet on a side stream so their
@@ -223,7 +224,7 @@ class CRAFT(nn.Module):
         cnet_feat.record_stream(main)
         return fmap1.float().contiguous(), fmap2.float().contiguous(), cnet_feat
 
-    def _encoders_fused(self, image1, image2):
+    def _encoders_fused(self, image1, image2, one_stream=False):
         """Inference fast path of both encoders: ONE input kernel (normalisation, 2x2
         space-to-depth, channels-last, the first convolution's zero border) for all three encoder inputs; cuDNN
         convolutions on channels-last tensors (the 7x7/2 one as a 4x4/1 over 16 channels); craft_b200 norm / ReLU /
@@ -231,7 +232,7 @@ class CRAFT(nn.Module):
         B = image1.shape[0]
         s = ops.image_s2d(torch.cat([image1, image2], dim=0), dtype=self.fnet.fused_dtype())
         main = torch.cuda.current_stream()
-        side = self._side_stream(image1.device)
+        side = main if one_stream else self._side_stream(image1.device)
         side.wait_stream(main)
         with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark,
                                         deterministic=False, allow_tf32=self.encoder_tf32):

@@ -364,6 +364,16 @@ def test_attn_lse_pv_finalize(H, W, M, d, F_):
         ops.modes_finalize(out2, kp, M, F_, grid, w_score=w_sc, b_score=b_sc, coeff=coeff, x_b=xb, out_f=yf2, pv_bk=BK)
         torch.cuda.synchronize()
         assert torch.equal(yf2, yf)
+        # parameters that are 4-byte-aligned views into a flat buffer (nn.DataParallel replicas: broadcast_coalesced)
+        flat = torch.zeros(1 + F_ + 1 + 1, device=DEV)
+        flat[1:1 + F_] = w_sc[0]
+        flat[1 + F_:2 + F_] = b_sc.reshape(-1)
+        flat[2 + F_:] = coeff.reshape(-1)
+        yf3 = grid.zeros(F_, dtype=torch.float32)
+        ops.modes_finalize(out2, kp, M, F_, grid, w_score=flat[1:1 + F_].view(1, F_), b_score=flat[1 + F_:2 + F_],
+                           coeff=flat[2 + F_:], x_b=xb, out_f=yf3, pv_bk=BK)
+        torch.cuda.synchronize()
+        assert torch.equal(yf3, yf)
 
 
 @pytest.mark.parametrize("Cc", [64, 96, 128, 256])
