@@ -43,6 +43,12 @@ class ResidualBlock(nn.Module):
 
     def forward_fused(self, x, fz):
         """Inference on channels-last activations: cuDNN convs + craft_b200 norm/relu/residual kernels."""
+        if fz.fold_bn:      # eval BatchNorm folded into the convolutions, bias + ReLU in cuDNN's epilogue
+            y = fz.conv_bn(self.conv1, self.norm1, x, relu=True)
+            y2 = fz.conv_bn(self.conv2, self.norm2, y, relu=True)
+            if self.downsample is not None:
+                x = fz.conv_bn(self.downsample[0], self.norm3, x, relu=False)
+            return fz.affine(y2, None, res=x, relu_out=True)
         y = fz.conv(self.conv1, x)
         y = fz.norm_act(self.norm1, y, self.conv1, relu=True)
         y2 = fz.conv(self.conv2, y)
@@ -73,6 +79,10 @@ class _Fused:
         # 4.19-4.21 ms per pair -- with the context encoder on the second stream the encoder phase is bound by SM
         # time, not by its launch chain (profiles/r02_instnorm_one_launch.txt)
         self.one_launch_in = kind == "instance" and os.environ.get("CRAFT_B200_FUSED_IN", "0") == "1"
+        # eval-mode BatchNorm (the context encoder) folded into the convolution weights, its shift and the ReLU applied
+        # by cuDNN's fused conv-bias-activation: no norm pass at all behind those convolutions.  CRAFT_B200_FOLD_BN=0:
+        # the separate scale/shift pass of nhwc_affine
+        self.fold_bn = kind == "batch" and os.environ.get("CRAFT_B200_FOLD_BN", "1") != "0"
 
     def conv(self, m, x, bias=False):
         """cuDNN convolution WITHOUT its bias: a conv bias in front of a normalisation is either a no-op
@@ -83,6 +93,21 @@ class _Fused:
         b = None
         if bias:
             b = self.cache.get(("b", id(m)), [m.bias], lambda: m.bias.detach().to(self.dtype))
+        return F.conv2d(x, w, b, m.stride, m.padding)
+
+    def _folded(self, m, norm, weight_of=None, key="wbn"):
+        """(w', b') with w' = w * gamma/sqrt(var+eps) per output channel and b' = beta + (bias - mean) * that scale."""
+        def build():
+            a = norm.weight.detach().float() * torch.rsqrt(norm.running_var.detach().float() + norm.eps)
+            b = norm.bias.detach().float() + (m.bias.detach().float() - norm.running_mean.detach().float()) * a
+            w = (weight_of() if weight_of is not None else m.weight.detach().float()) * a.view(-1, 1, 1, 1)
+            return w.to(self.dtype).contiguous(memory_format=torch.channels_last), b.to(self.dtype).contiguous()
+        return self.cache.get((key, id(m)), [m.weight, m.bias, norm.weight, norm.bias, norm.running_mean, norm.running_var], build)
+
+    def conv_bn(self, m, norm, x, relu):
+        w, b = self._folded(m, norm)
+        if relu:
+            return torch.cudnn_convolution_relu(x, w, b, m.stride, m.padding, (1, 1), 1)
         return F.conv2d(x, w, b, m.stride, m.padding)
 
     def scale_shift(self, norm, y, conv):
@@ -112,11 +137,11 @@ class _Fused:
                                 relu_in, relu_out, eps=norm.eps, out=out.permute(0, 2, 3, 1))
         return out
 
-    def conv1_s2d(self, m, s):
+    def conv1_s2d(self, m, s, norm=None):
         """The 7x7 stride-2 first convolution (core/extractor.py:129) on the space-to-depth input of
         ops.image_s2d: a 4x4 stride-1 convolution over 16 channels, no padding.  Row 2y + ky - 3 of the image is
         row y + a of the s2d grid with parity py, ky = 2a + py + 3, a in [-2, 1]; the same along x."""
-        def build():
+        def build32():
             w = m.weight.detach().float()                       # [O, 3, 7, 7]
             O = w.shape[0]
             w4 = torch.zeros((O, 16, 4, 4), dtype=torch.float32, device=w.device)
@@ -131,7 +156,13 @@ class _Fused:
                             if 0 <= kx <= 6:
                                 c0 = (py * 2 + px) * 3
                                 w4[:, c0:c0 + 3, a + 2, b + 2] = w[:, :, ky, kx]
-            return w4.to(self.dtype).contiguous(memory_format=torch.channels_last)
+            return w4
+
+        def build():
+            return build32().to(self.dtype).contiguous(memory_format=torch.channels_last)
+        if norm is not None:        # folded eval BatchNorm + ReLU (see conv_bn)
+            w4, b4 = self._folded(m, norm, weight_of=build32, key="wbn_s2d")
+            return torch.cudnn_convolution_relu(s.permute(0, 3, 1, 2), w4, b4, (1, 1), (0, 0), (1, 1), 1)
         w4 = self.cache.get(("w_s2d", id(m)), [m.weight], build)
         return F.conv2d(s.permute(0, 3, 1, 2), w4)              # NCHW view of the channels-last buffer
 
@@ -175,11 +206,17 @@ class BasicEncoder(nn.Module):
         if getattr(self, "_fz", None) is None or self._fz.kind != self.norm_fn or self._fz.half != half:
             self._fz = _Fused(self.norm_fn, half)
         fz = self._fz
-        if s2d is not None:
-            x = fz.conv1_s2d(self.conv1, s2d)
+        if fz.fold_bn:
+            if s2d is not None:
+                x = fz.conv1_s2d(self.conv1, s2d, norm=self.norm1)
+            else:
+                x = fz.conv_bn(self.conv1, self.norm1, x.to(fz.dtype).contiguous(memory_format=torch.channels_last), relu=True)
         else:
-            x = fz.conv(self.conv1, x.to(fz.dtype).contiguous(memory_format=torch.channels_last))
-        x = fz.norm_act(self.norm1, x, self.conv1, relu=True)
+            if s2d is not None:
+                x = fz.conv1_s2d(self.conv1, s2d)
+            else:
+                x = fz.conv(self.conv1, x.to(fz.dtype).contiguous(memory_format=torch.channels_last))
+            x = fz.norm_act(self.norm1, x, self.conv1, relu=True)
         for layer in (self.layer1, self.layer2, self.layer3):
             for blk in layer:
                 x = blk.forward_fused(x, fz)
