@@ -114,6 +114,8 @@ SIGNATURES = {
     "craft_nhwc_instnorm_stats": (_i, [_vp, _i, _i, _i, _i, _f, _vp, C.c_longlong, _vp, _vp]),
     "craft_image_s2d": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
     "craft_nhwc_instnorm_apply": (_i, [_vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _i, _i, _vp, C.c_longlong, _vp, _vp, _vp]),
+    "craft_conv3x3_c64": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, C.c_longlong, _vp, _f, _vp]),
+    "craft_nhwc_affine_pad": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "craft_nhwc_affine": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 

@@ -12,6 +12,7 @@
 #include "attn_pv.cuh"
 #include "common.cuh"
 #include "encoder.cuh"
+#include "conv_enc.cuh"
 #include "gemm.cuh"
 #include "hostio.cuh"
 #include "pointwise.cuh"
@@ -922,6 +923,65 @@ int craft_nhwc_instnorm_apply(const void* x, int is_half, int N, int HW, int C, 
   if (is_half)
     return launch_instnorm_fused<__half>(x, N, HW, C, eps, res, rab, rab_nstride, relu_in, relu_out, part, part_capacity, ab_out, out, st);
   return launch_instnorm_fused<float>(x, N, HW, C, eps, res, rab, rab_nstride, relu_in, relu_out, part, part_capacity, ab_out, out, st);
+}
+
+int craft_conv3x3_c64(const void* x, const void* w, const float* bias, int relu, int N, int H, int W, void* out,
+                      float* part, long long part_capacity, float* ab, float eps, void* stream) {
+  if (!x || !w || !out) return fail("conv3x3_c64: null operand");
+  if (N < 1 || H < 1 || W < 1) return fail("conv3x3_c64: empty input");
+  if ((ab != nullptr) != (part != nullptr)) return fail("conv3x3_c64: statistics need both `part` and `ab`");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cb::ConvEncParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.H = H; p.W = W; p.Wp = W + 2;
+  const long long rpi = static_cast<long long>(H + 1) * p.Wp;
+  if (rpi * N > 0x7fffffffLL - 4096) return fail("conv3x3_c64: %lld rows do not fit 32-bit row coordinates", rpi * N);
+  p.rpi = static_cast<int>(rpi);
+  p.tiles_per_image = (p.rpi + 127) / 128;
+  p.ctas_per_image = std::max(1, std::min(p.tiles_per_image, sm_count() / N));
+  p.bias = bias; p.relu = relu; p.out = static_cast<__half*>(out); p.part = part;
+  if (part && static_cast<long long>(p.ctas_per_image) * N * 64 * 2 > part_capacity)
+    return fail("conv3x3_c64: partial buffer holds %lld floats, needs %lld", part_capacity,
+                static_cast<long long>(p.ctas_per_image) * N * 64 * 2);
+  CUtensorMap tx, tw;
+  if (make_map_2d(&tx, x, rpi * N, 64, 64, 136)) return -1;
+  if (make_map_2d(&tw, w, 9 * 64, 64, 64, 64)) return -1;
+  const dim3 grid(p.ctas_per_image * N);
+  if (part) {
+    auto kern = cb::conv3x3_c64_kernel<true>;
+    static std::atomic<unsigned long long> set{0};
+    if (ensure_smem(kern, cb::kCvSmem, set, "conv3x3_c64")) return -1;
+    launch_k(kern, grid, dim3(cb::kCvThreads), cb::kCvSmem, st, tx, tw, p);
+    if (check_launch("conv3x3_c64")) return -1;
+    // InstanceNorm2d scale / shift from the per-CTA partial sums (fixed order)
+    launch_k(cb::instnorm_finalize_kernel, dim3((N * 64 + 7) / 8), dim3(256), 0, st, part, p.ctas_per_image, N * 64,
+             1.0f / (static_cast<float>(H) * static_cast<float>(W)), eps, ab);
+    return check_launch("instnorm_finalize");
+  }
+  auto kern = cb::conv3x3_c64_kernel<false>;
+  static std::atomic<unsigned long long> set{0};
+  if (ensure_smem(kern, cb::kCvSmem, set, "conv3x3_c64")) return -1;
+  launch_k(kern, grid, dim3(cb::kCvThreads), cb::kCvSmem, st, tx, tw, p);
+  return check_launch("conv3x3_c64");
+}
+
+int craft_nhwc_affine_pad(const void* v, int is_half, int v_pad, const float* ab, int ab_nstride, const void* res, int res_pad,
+                          const float* rab, int rab_nstride, int relu_in, int relu_out, int N, int H, int W, int C, void* out,
+                          int out_pad, void* stream) {
+  const int V = is_half ? 8 : 4;
+  if (!v || !out) return fail("nhwc_affine_pad: null operand");
+  if (C % V) return fail("nhwc_affine_pad: C must be a multiple of %d", V);
+  const long long rows = out_pad ? static_cast<long long>(N) * (H + 1) * (W + 2) : static_cast<long long>(N) * H * W;
+  const long long totalv = rows * (C / V);
+  const dim3 grid(static_cast<unsigned>((totalv + 255) / 256));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_half)
+    launch_k(cb::nhwc_affine_pad_kernel<__half>, grid, dim3(256), 0, st, static_cast<const __half*>(v), v_pad, ab, ab_nstride,
+             static_cast<const __half*>(res), res_pad, rab, rab_nstride, relu_in, relu_out, N, H, W, C, static_cast<__half*>(out), out_pad);
+  else
+    launch_k(cb::nhwc_affine_pad_kernel<float>, grid, dim3(256), 0, st, static_cast<const float*>(v), v_pad, ab, ab_nstride,
+             static_cast<const float*>(res), res_pad, rab, rab_nstride, relu_in, relu_out, N, H, W, C, static_cast<float*>(out), out_pad);
+  return check_launch("nhwc_affine_pad");
 }
 
 int craft_nhwc_affine(const void* v, int is_half, const float* ab, int ab_nstride, const void* res, const float* rab,

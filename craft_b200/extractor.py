@@ -41,6 +41,27 @@ class ResidualBlock(nn.Module):
             x = self.downsample(x)
         return self.relu(x + y)
 
+    def can_conv64(self, fz):
+        c1, c2 = self.conv1, self.conv2
+        return (fz.own_conv64 and self.downsample is None
+                and all(c.in_channels == 64 and c.out_channels == 64 and c.kernel_size == (3, 3) and c.stride == (1, 1)
+                        and c.padding == (1, 1) and c.dilation == (1, 1) and c.groups == 1 for c in (c1, c2)))
+
+    def forward_pad(self, x, fz, out_pad=True):
+        """The same block on a padded-flat activation (ops.PadAct) with both convolutions on the persistent tcgen05
+        kernel (csrc/conv_enc.cuh); the InstanceNorm statistics come out of the convolution's epilogue."""
+        ops = fz.ops
+        if fz.fold_bn:
+            w1, b1 = fz.folded64(self.conv1, self.norm1)
+            w2, b2 = fz.folded64(self.conv2, self.norm2)
+            y = ops.conv3x3_c64(x, w1, bias=b1, relu=True)
+            y2 = ops.conv3x3_c64(y, w2, bias=b2, relu=True)
+            return ops.nhwc_affine_pad(y2, None, res=x, relu_out=True, out_pad=out_pad)
+        t, ab1 = ops.conv3x3_c64(x, fz.w64(self.conv1), stats_eps=self.norm1.eps)
+        y = ops.nhwc_affine_pad(t, ab1, relu_in=True)
+        t2, ab2 = ops.conv3x3_c64(y, fz.w64(self.conv2), stats_eps=self.norm2.eps)
+        return ops.nhwc_affine_pad(t2, ab2, res=x, relu_in=True, relu_out=True, out_pad=out_pad)
+
     def forward_fused(self, x, fz):
         """Inference on channels-last activations: cuDNN convs + craft_b200 norm/relu/residual kernels."""
         if fz.fold_bn:      # eval BatchNorm folded into the convolutions, bias + ReLU in cuDNN's epilogue
@@ -83,6 +104,14 @@ class _Fused:
         # by cuDNN's fused conv-bias-activation: no norm pass at all behind those convolutions.  CRAFT_B200_FOLD_BN=0:
         # the separate scale/shift pass of nhwc_affine
         self.fold_bn = kind == "batch" and os.environ.get("CRAFT_B200_FOLD_BN", "1") != "0"
+        # the 64 -> 64 3x3 convolutions of layer1 on the persistent tcgen05 kernel of csrc/conv_enc.cuh (fp16
+        # activations in the padded-flat layout) instead of cuDNN; CRAFT_B200_CONV64=0: cuDNN
+        # Measured (profiles/r02_conv64.txt): 19.8 us against cuDNN's 23.2 us for two 224x512 images, 26.8 us with the
+        # InstanceNorm statistics in its epilogue against 33.4 us for cuDNN + the statistics kernels.  For the
+        # context encoder (one image, folded BatchNorm, no statistics) the gain is smaller than the layout-change
+        # pass it needs, so only CRAFT_B200_CONV64=2 turns it on there.
+        c64 = os.environ.get("CRAFT_B200_CONV64", "1")
+        self.own_conv64 = half and ((kind == "instance" and c64 != "0") or (self.fold_bn and c64 == "2"))
 
     def conv(self, m, x, bias=False):
         """cuDNN convolution WITHOUT its bias: a conv bias in front of a normalisation is either a no-op
@@ -103,6 +132,16 @@ class _Fused:
             w = (weight_of() if weight_of is not None else m.weight.detach().float()) * a.view(-1, 1, 1, 1)
             return w.to(self.dtype).contiguous(memory_format=torch.channels_last), b.to(self.dtype).contiguous()
         return self.cache.get((key, id(m)), [m.weight, m.bias, norm.weight, norm.bias, norm.running_mean, norm.running_var], build)
+
+    def w64(self, m):
+        return self.cache.get(("w64", id(m)), [m.weight], lambda: self.ops.pack_conv64_weight(m.weight))
+
+    def folded64(self, m, norm):
+        def build():
+            a = norm.weight.detach().float() * torch.rsqrt(norm.running_var.detach().float() + norm.eps)
+            b = norm.bias.detach().float() + (m.bias.detach().float() - norm.running_mean.detach().float()) * a
+            return self.ops.pack_conv64_weight(m.weight, scale=a), b.contiguous()
+        return self.cache.get(("wbn64", id(m)), [m.weight, m.bias, norm.weight, norm.bias, norm.running_mean, norm.running_var], build)
 
     def conv_bn(self, m, norm, x, relu):
         w, b = self._folded(m, norm)
@@ -206,18 +245,30 @@ class BasicEncoder(nn.Module):
         if getattr(self, "_fz", None) is None or self._fz.kind != self.norm_fn or self._fz.half != half:
             self._fz = _Fused(self.norm_fn, half)
         fz = self._fz
+        own = all(blk.can_conv64(fz) for blk in self.layer1)      # layer1 on the persistent tcgen05 convolution
         if fz.fold_bn:
             if s2d is not None:
                 x = fz.conv1_s2d(self.conv1, s2d, norm=self.norm1)
             else:
                 x = fz.conv_bn(self.conv1, self.norm1, x.to(fz.dtype).contiguous(memory_format=torch.channels_last), relu=True)
+            if own:
+                x = fz.ops.nhwc_affine_pad(x.permute(0, 2, 3, 1), None)          # layout change only
         else:
             if s2d is not None:
                 x = fz.conv1_s2d(self.conv1, s2d)
             else:
                 x = fz.conv(self.conv1, x.to(fz.dtype).contiguous(memory_format=torch.channels_last))
-            x = fz.norm_act(self.norm1, x, self.conv1, relu=True)
-        for layer in (self.layer1, self.layer2, self.layer3):
+            if own:     # norm1 + ReLU, written straight into the padded-flat layout
+                x = fz.ops.nhwc_affine_pad(x.permute(0, 2, 3, 1), fz.scale_shift(self.norm1, x, self.conv1), relu_in=True)
+            else:
+                x = fz.norm_act(self.norm1, x, self.conv1, relu=True)
+        layers = (self.layer1, self.layer2, self.layer3)
+        if own:
+            for i, blk in enumerate(self.layer1):
+                x = blk.forward_pad(x, fz, out_pad=(i + 1 < len(self.layer1)))
+            x = x.permute(0, 3, 1, 2)               # dense [N,H,W,64] -> the NCHW view of channels-last memory cuDNN takes
+            layers = layers[1:]
+        for layer in layers:
             for blk in layer:
                 x = blk.forward_fused(x, fz)
         return fz.conv(self.conv2, x, bias=True)

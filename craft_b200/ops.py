@@ -379,6 +379,72 @@ def instnorm_apply(x, res=None, rab=None, relu_in=False, relu_out=False, eps=1e-
     return (out, ab) if return_ab else out
 
 
+class PadAct:
+    """A channels-last activation in the padded-flat layout of craft_conv3x3_c64: t [N*(H+1)*(W+2), C], row
+    (n*(H+1)+y)*(W+2)+x, zeros in the cells x >= W and in the row y = H of every image."""
+
+    def __init__(self, t, N, H, W):
+        self.t, self.N, self.H, self.W = t, N, H, W
+
+    @staticmethod
+    def rows(N, H, W):
+        return N * (H + 1) * (W + 2)
+
+    def dense(self):
+        """[N,H,W,C] copy (tests)."""
+        C_ = self.t.shape[1]
+        return self.t.view(self.N, self.H + 1, self.W + 2, C_)[:, :self.H, :self.W].contiguous()
+
+
+_CONV_PART = {}
+
+
+def conv3x3_c64(x, w, bias=None, relu=False, stats_eps=None):
+    """3x3 'same' convolution 64 -> 64 on a PadAct (f16); w from pack_conv64_weight.  stats_eps: also return the
+    InstanceNorm2d (rstd, -mean*rstd) [N,64,2] of the fp32 result (accumulated in the convolution's epilogue)."""
+    assert isinstance(x, PadAct) and x.t.dtype == torch.float16 and x.t.shape[1] == 64
+    out = torch.empty_like(x.t)
+    part = ab = None
+    if stats_eps is not None:
+        key = (str(x.t.device), torch.cuda.current_stream(x.t.device).cuda_stream)
+        part = _CONV_PART.get(key)
+        if part is None:
+            part = _CONV_PART[key] = torch.empty((1024 * 128,), dtype=torch.float32, device=x.t.device)
+        ab = torch.empty((x.N, 64, 2), dtype=torch.float32, device=x.t.device)
+    OPS.conv3x3_c64(x.t, w, bias, bool(relu), x.N, x.H, x.W, out, part, ab, float(stats_eps or 0.0))
+    o = PadAct(out, x.N, x.H, x.W)
+    return (o, ab) if stats_eps is not None else o
+
+
+def pack_conv64_weight(w, scale=None):
+    """[64,64,3,3] -> f16 [576, 64]: tap-major (ky,kx row-major) blocks of [cout][cin]; scale: per-cout factor (folded norm)."""
+    ww = w.detach().float()
+    if scale is not None:
+        ww = ww * scale.view(-1, 1, 1, 1)
+    return ww.permute(2, 3, 0, 1).reshape(9 * 64, 64).to(torch.float16).contiguous()
+
+
+def nhwc_affine_pad(v, ab=None, res=None, rab=None, relu_in=False, relu_out=False, out_pad=True):
+    """nhwc_affine between dense [N,H,W,C] tensors and PadAct operands (any combination).  Returns a PadAct when
+    out_pad else a dense [N,H,W,C] tensor."""
+    vp, rp = isinstance(v, PadAct), isinstance(res, PadAct)
+    src = v.t if vp else v
+    _act_dtype(src, "v")
+    if vp:
+        N, H, W, Cc = v.N, v.H, v.W, v.t.shape[1]
+    else:
+        N, H, W, Cc = v.shape
+    rsrc = (res.t if rp else res) if res is not None else None
+    _chk(rsrc, src.dtype, "res")
+    if out_pad:
+        out = torch.empty((PadAct.rows(N, H, W), Cc), dtype=src.dtype, device=src.device)
+    else:
+        out = torch.empty((N, H, W, Cc), dtype=src.dtype, device=src.device)
+    st = lambda t: 0 if (t is None or t.shape[0] == 1) else 2 * Cc
+    OPS.nhwc_affine_pad(src, vp, ab, st(ab), rsrc, rp, rab, st(rab), bool(relu_in), bool(relu_out), N, H, W, Cc, out, bool(out_pad))
+    return PadAct(out, N, H, W) if out_pad else out
+
+
 def image_s2d(img, dtype=torch.float16):
     """[N,3,H,W] f32 frames (0..255) -> normalised, 2x2 space-to-depth, channels-last, zero-bordered input of the
     encoders' first convolution: [N, H/2+3, W/2+3, 16] (include/craft_b200.h craft_image_s2d)."""

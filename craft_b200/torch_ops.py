@@ -329,6 +329,27 @@ def nhwc_instnorm_apply(x, res, rab, rab_stride, relu_in, relu_out, N, HW, Cc, e
               int(relu_in), int(relu_out), _ptr(part), part.numel(), _ptr(ab_out), _ptr(out), _stream())
 
 
+@_op("conv3x3_c64(Tensor x, Tensor w, Tensor? bias, bool relu, int N, int H, int W, Tensor(a!) out, Tensor(b!)? part, "
+     "Tensor(c!)? ab, float eps) -> ()")
+def conv3x3_c64(x, w, bias, relu, N, H, W, out, part, ab, eps):
+    """x / out: padded-flat f16 [N*(H+1)*(W+2), 64]; w: f16 [576, 64] tap-major (include/craft_b200.h)."""
+    for t, nm in ((x, "x"), (w, "w"), (out, "out")):
+        _chk(t, f16, nm)
+    _chk(bias, f32, "bias"); _chk(part, f32, "part"); _chk(ab, f32, "ab")
+    rows = N * (H + 1) * (W + 2)
+    assert tuple(x.shape) == (rows, 64) and tuple(out.shape) == (rows, 64) and tuple(w.shape) == (576, 64)
+    _lib.call("craft_conv3x3_c64", _ptr(x), _ptr(w), _ptr(bias), int(relu), N, H, W, _ptr(out), _ptr(part),
+              part.numel() if part is not None else 0, _ptr(ab), float(eps), _stream(), fp16=True)
+
+
+@_op("nhwc_affine_pad(Tensor v, bool v_pad, Tensor? ab, int ab_stride, Tensor? res, bool res_pad, Tensor? rab, int rab_stride, "
+     "bool relu_in, bool relu_out, int N, int H, int W, int C, Tensor(a!) out, bool out_pad) -> ()")
+def nhwc_affine_pad(v, v_pad, ab, ab_stride, res, res_pad, rab, rab_stride, relu_in, relu_out, N, H, W, Cc, out, out_pad):
+    half = 1 if v.dtype == torch.float16 else 0
+    _lib.call("craft_nhwc_affine_pad", _ptr(v), half, int(v_pad), _ptr(ab), ab_stride, _ptr(res), int(res_pad), _ptr(rab),
+              rab_stride, int(relu_in), int(relu_out), N, H, W, Cc, _ptr(out), int(out_pad), _stream(), fp16=True)
+
+
 @_op("forward_interpolate(Tensor flow, int H, int W, Tensor(a!) out) -> ()")
 def forward_interpolate(flow, H, W, out):
     _chk(flow, f32, "flow"); _chk(out, f32, "out")

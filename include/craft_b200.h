@@ -231,6 +231,20 @@ int craft_nhwc_instnorm_stats(const void* x, int is_half, int N, int HW, int C, 
 int craft_nhwc_instnorm_apply(const void* x, int is_half, int N, int HW, int C, float eps, const void* res,
                               const float* rab, int rab_nstride, int relu_in, int relu_out, float* part,
                               long long part_capacity, float* ab_out, void* out, void* stream);
+/* 3x3 stride-1 convolution, 64 -> 64 channels, fp16, of the encoders' first residual layer (extractor.py:24-26,
+ * 142-146) as a persistent tcgen05 implicit GEMM.  x / out: "padded-flat" activations [N*(H+1)*(W+2)][64] f16 (row
+ * (n*(H+1)+y)*(W+2)+x; the cells x >= W and the row y = H of every image hold zeros: they are the padding); w: the
+ * weights as [9*64][64] f16, tap-major (ky,kx row-major) blocks of [cout][cin]; bias: f32 [64] or NULL, relu: the
+ * folded eval BatchNorm + ReLU of the context encoder.  With part/ab non-NULL the kernel also accumulates the
+ * InstanceNorm2d statistics of its fp32 output over the valid cells and ab[N][64][2] = (rstd, -mean*rstd) is
+ * written (part: f32 scratch, >= 128 floats per SM; deterministic).                                              */
+int craft_conv3x3_c64(const void* x, const void* w, const float* bias, int relu, int N, int H, int W, void* out,
+                      float* part, long long part_capacity, float* ab, float eps, void* stream);
+/* craft_nhwc_affine between the dense channels-last layout [N][H][W][C] and the padded-flat one of
+ * craft_conv3x3_c64 (*_pad != 0), in any combination; halo cells / gap rows of a padded output are set to zero. */
+int craft_nhwc_affine_pad(const void* v, int is_half, int v_pad, const float* ab, int ab_nstride, const void* res,
+                          int res_pad, const float* rab, int rab_nstride, int relu_in, int relu_out, int N, int H,
+                          int W, int C, void* out, int out_pad, void* stream);
 /* Input transform of both encoders: f32 frames [N,3,H,W] in 0..255 -> 2*(x/255)-1 (core/network.py:170-171), 2x2
  * space-to-depth, channels-last, zero border (2 cells before, 1 after): out [N][H/2+3][W/2+3][16] (f16 if
  * out_is_half else f32), channel (py*2+px)*3 + c, channels 12..15 zero.  The 7x7 stride-2 convolution

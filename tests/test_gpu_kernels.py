@@ -443,6 +443,54 @@ def test_instnorm_one_launch(N, Cc, H, W):
         assert torch.equal(out2, out4)
 
 
+def _to_pad(x_nhwc):
+    """dense [N,H,W,C] -> ops.PadAct with zero halo cells / gap rows (test helper; the model uses nhwc_affine_pad)."""
+    N, H, W, C_ = x_nhwc.shape
+    t = torch.zeros((N, H + 1, W + 2, C_), dtype=x_nhwc.dtype, device=x_nhwc.device)
+    t[:, :H, :W] = x_nhwc
+    return ops.PadAct(t.reshape(-1, C_), N, H, W)
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 37, 50), (1, 16, 16), (3, 9, 130), (2, 224, 512), (1, 192, 624)])
+def test_conv3x3_c64_persistent(N, H, W):
+    """craft_conv3x3_c64 (persistent tcgen05 implicit GEMM on the padded-flat layout; core/extractor.py:24-26 layer1
+    convolutions) against F.conv2d on the same fp16 operands; halo cells stay zero; bias + ReLU epilogue; the
+    InstanceNorm statistics of its epilogue against the statistics kernels on the dense result."""
+    g = torch.Generator(device=DEV).manual_seed(N * 1000 + H)
+    x = torch.randn((N, H, W, 64), device=DEV, generator=g).half()
+    w = (torch.randn((64, 64, 3, 3), device=DEV, generator=g) * 0.06)
+    b = torch.randn((64,), device=DEV, generator=g)
+    wp = ops.pack_conv64_weight(w)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.half().float(), None, padding=1).permute(0, 2, 3, 1)   # [N,H,W,64] fp32
+    xp = _to_pad(x)
+    y, ab = ops.conv3x3_c64(xp, wp, stats_eps=1e-5)
+    torch.cuda.synchronize()
+    got = y.dense().float()
+    assert torch.allclose(got, ref, atol=2e-2, rtol=1e-2), (got - ref).abs().max()
+    full = y.t.view(N, H + 1, W + 2, 64)
+    assert float(full[:, H].abs().max()) == 0.0 and float(full[:, :, W:].abs().max()) == 0.0      # padding stays zero
+    ab_ref = ops.instnorm_stats(ref.contiguous())                   # statistics of the fp32 result
+    assert torch.allclose(ab, ab_ref, atol=2e-3, rtol=2e-3), (ab - ab_ref).abs().max()
+    # bias + ReLU (folded eval BatchNorm), no statistics; bit-reproducible
+    y2 = ops.conv3x3_c64(xp, wp, bias=b, relu=True)
+    ref2 = torch.relu(ref + b.view(1, 1, 1, 64))
+    assert torch.allclose(y2.dense().float(), ref2, atol=2e-2, rtol=1e-2)
+    full2 = y2.t.view(N, H + 1, W + 2, 64)
+    assert float(full2[:, H].abs().max()) == 0.0 and float(full2[:, :, W:].abs().max()) == 0.0
+    y3, ab3 = ops.conv3x3_c64(xp, wp, stats_eps=1e-5)
+    assert torch.equal(y3.t, y.t) and torch.equal(ab3, ab)
+    # layout-converting affine: dense -> padded -> (residual, relu) -> dense
+    sab = torch.randn((N, 64, 2), device=DEV, generator=g)
+    a_, b_ = sab[:, :, 0].view(N, 1, 1, 64), sab[:, :, 1].view(N, 1, 1, 64)
+    p1 = ops.nhwc_affine_pad(x, sab, relu_in=True, out_pad=True)
+    assert torch.allclose(p1.dense().float(), torch.relu(a_ * x.float() + b_), atol=4e-3, rtol=2e-3)
+    f1 = p1.t.view(N, H + 1, W + 2, 64)
+    assert float(f1[:, H].abs().max()) == 0.0 and float(f1[:, :, W:].abs().max()) == 0.0
+    d1 = ops.nhwc_affine_pad(y, ab, res=p1, relu_in=True, relu_out=True, out_pad=False)
+    refd = torch.relu(p1.dense().float() + torch.relu(ab[:, :, 0].view(N, 1, 1, 64) * got + ab[:, :, 1].view(N, 1, 1, 64)))
+    assert d1.shape == (N, H, W, 64) and torch.allclose(d1.float(), refd, atol=8e-3, rtol=4e-3)
+
+
 @pytest.mark.parametrize("kind", ["instance", "batch"])
 def test_fused_encoder_matches_module_path(kind):
     from craft_b200.extractor import BasicEncoder
