@@ -357,9 +357,6 @@ def instnorm_stats(x_nhwc, eps=1e-5):
     return ab
 
 
-_IN_PART = {}
-
-
 def instnorm_apply(x, res=None, rab=None, relu_in=False, relu_out=False, eps=1e-5, out=None, return_ab=False):
     """out = relu_out([ra*res+rb | res] + relu_in(instance_norm(x))) in one cooperative launch that reads x once
     (include/craft_b200.h craft_nhwc_instnorm_apply).  x/res/out [N,H,W,C] contiguous f32 or f16; rab f32 [N or 1,C,2]."""
@@ -369,10 +366,9 @@ def instnorm_apply(x, res=None, rab=None, relu_in=False, relu_out=False, eps=1e-
     if out is None:
         out = torch.empty_like(x)
     _chk(out, x.dtype, "out")
-    key = (str(x.device), torch.cuda.current_stream(x.device).cuda_stream)
-    part = _IN_PART.get(key)          # per-CTA partial sums; every launch overwrites what it reads, stream-ordered
-    if part is None:
-        part = _IN_PART[key] = torch.zeros((1024 * 512,), dtype=torch.float32, device=x.device)
+    # per-call scratch (barrier state in the first 64 floats, zero before use; then per-CTA partial sums): never shared
+    # between CUDA graphs / lanes
+    part = torch.zeros((64 + 256 * 512,), dtype=torch.float32, device=x.device)
     ab = torch.empty((N, Cc, 2), dtype=torch.float32, device=x.device) if return_ab else None
     st = 0 if (rab is None or rab.shape[0] == 1) else 2 * Cc
     OPS.nhwc_instnorm_apply(x, res, rab, st, bool(relu_in), bool(relu_out), N, H * W, Cc, float(eps), part, ab, out)
@@ -396,9 +392,6 @@ class PadAct:
         return self.t.view(self.N, self.H + 1, self.W + 2, C_)[:, :self.H, :self.W].contiguous()
 
 
-_CONV_PART = {}
-
-
 def conv3x3_c64(x, w, bias=None, relu=False, stats_eps=None):
     """3x3 'same' convolution 64 -> 64 on a PadAct (f16); w from pack_conv64_weight.  stats_eps: also return the
     InstanceNorm2d (rstd, -mean*rstd) [N,64,2] of the fp32 result (accumulated in the convolution's epilogue)."""
@@ -406,10 +399,9 @@ def conv3x3_c64(x, w, bias=None, relu=False, stats_eps=None):
     out = torch.empty_like(x.t)
     part = ab = None
     if stats_eps is not None:
-        key = (str(x.t.device), torch.cuda.current_stream(x.t.device).cuda_stream)
-        part = _CONV_PART.get(key)
-        if part is None:
-            part = _CONV_PART[key] = torch.empty((1024 * 128,), dtype=torch.float32, device=x.t.device)
+        # per-call scratch (one (sum, sumsq) pair per channel and CTA): a buffer cached per stream would be shared by
+        # CUDA graphs captured on recycled stream handles and raced on by lanes replaying them side by side
+        part = torch.empty((256 * 128,), dtype=torch.float32, device=x.t.device)
         ab = torch.empty((x.N, 64, 2), dtype=torch.float32, device=x.t.device)
     OPS.conv3x3_c64(x.t, w, bias, bool(relu), x.N, x.H, x.W, out, part, ab, float(stats_eps or 0.0))
     o = PadAct(out, x.N, x.H, x.W)
