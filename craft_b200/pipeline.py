@@ -104,18 +104,25 @@ class PairStream:
                 yield s["out"]
             self._join()
 
-    def run_resident(self, pairs):
+    def run_resident(self, pairs, keep=True):
         """Forward every (image1, image2) pair of DEVICE tensors, round-robin over the lanes; returns the list of
-        full-resolution flows (device tensors).  Work issued on the caller's stream before the call is waited for by
-        every lane, and the caller's stream waits for every lane at the end, so CUDA events recorded around the call
-        on the caller's stream bracket all of it."""
+        full-resolution flows (device tensors; keep=False: only the last flow of every lane -- throughput runs).
+        Work issued on the caller's stream before the call is waited for by every lane, and the caller's stream waits
+        for every lane at the end, so CUDA events recorded around the call on the caller's stream bracket all of it."""
         outs = []
+        last = [None] * self.lanes
         with torch.cuda.device(self.device):
             self._fork()
             for i, (a, b) in enumerate(pairs):
                 k = i % self.lanes
                 with torch.cuda.stream(self._lane_stream(k)):
-                    outs.append(self._forward(k, a, b))
+                    o = self._forward(k, a, b)     # (a dropped result's memory is reused in the order of its own lane's stream)
+                if keep:
+                    outs.append(o)
+                else:
+                    last[k] = o
+            if not keep:
+                outs = [o for o in last if o is not None]
             self._join()
             if self.lanes > 1:      # allocated on a lane's stream, consumed on the caller's
                 cur = torch.cuda.current_stream(self.device)
