@@ -514,6 +514,7 @@ static int scores_common(const craft_scores_args* a, int mode, void* stream) {
   p.pos_table = a->pos_table; p.R = a->R; p.clip = a->clip; p.run_flag = a->run_flag;
   p.nkt_y = (a->H + 7) / 8; p.nkt_x = (a->W + 7) / 8;
   p.nqt = (g.Mp + 127) / 128;
+  if (static_cast<long long>(p.nqt) * p.nkt_y * p.nkt_x > 0x7fffffffLL) return fail("scores: %d x %d tiles exceed 32-bit tile indices", p.nqt, p.nkt_y * p.nkt_x);
   const int need = sc_slots(p.nqt, p.nkt_y * p.nkt_x);
   p.nslots = a->ksplit > 0 ? a->ksplit : need;
   p.mask_radius = (mode == cb::SC_LSE) ? a->mask_radius : 0;

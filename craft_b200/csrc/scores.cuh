@@ -196,22 +196,24 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   const int warp = threadIdx.x >> 5;
   const int nkt = p.nkt_y * p.nkt_x;
   // this CTA's contiguous range of the (query tile, key tile) list
-  const long long NT = static_cast<long long>(p.nqt) * nkt;
-  const long long lin_begin = NT * blockIdx.x / gridDim.x;
-  const long long lin_end = NT * (blockIdx.x + 1) / gridDim.x;
-  auto cta_of = [&](long long x) {
-    long long c = x * gridDim.x / NT;
-    while (c + 1 < static_cast<long long>(gridDim.x) && NT * (c + 1) / gridDim.x <= x) ++c;
-    while (c > 0 && NT * c / gridDim.x > x) --c;
+  // 32-bit tile indices (the host rejects grids with more than 2^31 / gridDim tiles): the 64-bit range variables
+  // cost the epilogue warps four registers and two spills in the tile loop
+  const int NT = p.nqt * nkt;
+  const int lin_begin = static_cast<int>(static_cast<long long>(NT) * blockIdx.x / gridDim.x);
+  const int lin_end = static_cast<int>(static_cast<long long>(NT) * (blockIdx.x + 1) / gridDim.x);
+  auto cta_of = [&](int x) {
+    long long c = static_cast<long long>(x) * gridDim.x / NT;
+    while (c + 1 < static_cast<long long>(gridDim.x) && static_cast<long long>(NT) * (c + 1) / gridDim.x <= x) ++c;
+    while (c > 0 && static_cast<long long>(NT) * c / gridDim.x > x) --c;
     return static_cast<int>(c);
   };
   struct Seg { int qt, t0, nt; };
-  auto seg_at = [&](long long lin) {
+  auto seg_at = [&](int lin) {
     Seg s;
-    s.qt = static_cast<int>(lin / nkt);
-    s.t0 = static_cast<int>(lin - static_cast<long long>(s.qt) * nkt);
-    const long long left = lin_end - lin;
-    s.nt = static_cast<int>(left < nkt - s.t0 ? left : nkt - s.t0);
+    s.qt = lin / nkt;
+    s.t0 = lin - s.qt * nkt;
+    const int left = lin_end - lin;
+    s.nt = left < nkt - s.t0 ? left : nkt - s.t0;
     return s;
   };
 
@@ -253,7 +255,7 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     if (elect_one()) {
       int stage = 0, seg = 0;
       uint32_t phase = 0;
-      for (long long lin = lin_begin; lin < lin_end; ++seg) {
+      for (int lin = lin_begin; lin < lin_end; ++seg) {
         const Seg sg = seg_at(lin);
         mbar_wait(q_free, (static_cast<uint32_t>(seg) & 1u) ^ 1u);       // previous segment's MMAs retired
         mbar_arrive_expect_tx(q_full, q_bytes);
@@ -284,7 +286,7 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const int ksteps = p.d / 16;
     int stage = 0, seg = 0, g = 0;
     uint32_t phase = 0;
-    for (long long lin = lin_begin; lin < lin_end; ++seg) {
+    for (int lin = lin_begin; lin < lin_end; ++seg) {
       const Seg sg = seg_at(lin);
       mbar_wait(q_full, static_cast<uint32_t>(seg) & 1u);
       for (int i = 0; i < sg.nt; ++i, ++g) {
@@ -334,6 +336,7 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + eg * 256 + ch * 32;
     const int R = p.R;
     const bool has_bias = p.pos_table != nullptr;
+    const uint32_t s_table_u32 = smem_u32(s_table);
     constexpr float kLog2e = 1.4426950408889634f;
 
     float st_sum = 0.f, st_sq = 0.f, st_rawmax = -INFINITY;   // st_rawmax: max of the UNSCALED accumulators
@@ -343,7 +346,7 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const bool fast_corr = (MODE == SC_CORR) && !clamped && (p.M == 4 || p.M == 1);
 
     int seg = 0, g0 = 0;
-    for (long long lin = lin_begin; lin < lin_end; ++seg) {
+    for (int lin = lin_begin; lin < lin_end; ++seg) {
       const Seg sgm = seg_at(lin);
       const int q = sgm.qt * 128 + row;
       const int qy = q / p.g.Wp, qx = q - qy * p.g.Wp;
@@ -365,7 +368,14 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const bool full = (ky0 + 4 <= p.g.H) && (kx0 + 8 <= p.g.W);
         // lanes outside the bias range read the all-zero rows, so the window path can be taken by the
         // whole warp at once (no divergence between the plain and the window path)
-        const float* trow_tab = near ? s_table + (iy0 + 4) * TW + (ix0 + 7) : s_table;
+        // 32-bit shared-memory address + ld.shared: a generic pointer derived from the aligned smem base costs two
+        // registers (it was one of the values spilled in this loop) and a generic LD per table read
+        const uint32_t tab_addr = s_table_u32 + 4u * static_cast<uint32_t>(near ? (iy0 + 4) * TW + (ix0 + 7) : 0);
+        auto trow_tab = [&](int idx) {
+          float v;
+          asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(tab_addr + 4u * static_cast<uint32_t>(idx)));
+          return v;
+        };
         const bool near_w = __any_sync(0xffffffffu, near);
         mbar_wait(&acc_full[eg], par);
         tc_fence_after();
@@ -393,7 +403,7 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           if (qvalid) {
             if (near_w) {      // warp-uniform: lanes outside the range add the zero rows
 #pragma unroll
-              for (int e = 0; e < 32; ++e) agg[e] += trow_tab[(e >> 3) * TW + (e & 7)];
+              for (int e = 0; e < 32; ++e) agg[e] += trow_tab((e >> 3) * TW + (e & 7));
             }
             if (full) {
 #pragma unroll
@@ -517,7 +527,7 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 // near the query: the positional bias enters the max; values are built in place
                 float x[32];
 #pragma unroll
-                for (int e = 0; e < 32; ++e) x[e] = fmaf(__uint_as_float(raw[e]), p.scale, trow_tab[(e >> 3) * TW + (e & 7)]);
+                for (int e = 0; e < 32; ++e) x[e] = fmaf(__uint_as_float(raw[e]), p.scale, trow_tab((e >> 3) * TW + (e & 7)));
                 float tmax = x[0];
 #pragma unroll
                 for (int e = 1; e < 32; ++e) tmax = fmaxf(tmax, x[e]);
@@ -536,7 +546,7 @@ scores_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 // recomputed in both passes instead of being kept in a second 32-register array
                 auto val = [&](int e) {
                   float s = fminf(fmaxf(__uint_as_float(raw[e]) * p.scale, -clipv), clipv);
-                  if (near) s += trow_tab[(e >> 3) * TW + (e & 7)];
+                  if (near) s += trow_tab((e >> 3) * TW + (e & 7));
                   if (!full && !((ky0 + (e >> 3) < p.g.H) && (kx0 + (e & 7) < p.g.W))) s = -INFINITY;
                   // --f2radius: the reference adds -1e9 (core/setrans.py:583), whose exp is exactly 0 in fp32
                   if (masking && (abs(ky0 + (e >> 3) - qy) > p.mask_radius || abs(kx0 + (e & 7) - qx) > p.mask_radius)) s = -INFINITY;
