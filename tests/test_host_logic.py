@@ -88,3 +88,35 @@ def test_geometry_and_weight_packing():
     p2 = ops.pack_conv_weight(w, Npad=32, cin_perm=perm).float().reshape(9, 32, 64)
     assert torch.equal(p2[0, :2, :3], w[:, perm, 0, 0])
     assert ops.blocked_keys(g, 128) == 7 * 8 * 128 and ops.blocked_keys(g, 64) == 7 * 16 * 64
+
+
+def test_padded_flat_layout_and_conv64_weight_packing():
+    """Host side of craft_conv3x3_c64 (include/craft_b200.h): the padded-flat row index, the tap-major weight layout
+    (identical to the update block's pack_conv_weight), the folded-norm scale, and CRAFT.on_lane bookkeeping."""
+    N, H, W = 2, 5, 7
+    assert ops.PadAct.rows(N, H, W) == N * (H + 1) * (W + 2)
+    x = torch.arange(N * H * W * 64, dtype=torch.float32).reshape(N, H, W, 64)
+    t = torch.zeros((N, H + 1, W + 2, 64))
+    t[:, :H, :W] = x
+    pa = ops.PadAct(t.reshape(-1, 64), N, H, W)
+    assert torch.equal(pa.dense(), x)
+    n, y, xx = 1, 3, 6
+    assert torch.equal(pa.t[(n * (H + 1) + y) * (W + 2) + xx], x[n, y, xx])          # row (n*(H+1)+y)*(W+2)+x
+    w = torch.randn(64, 64, 3, 3)
+    wp = ops.pack_conv64_weight(w)
+    assert wp.shape == (576, 64) and wp.dtype == torch.float16
+    with ops.precision(torch.float16):
+        assert torch.equal(wp, ops.pack_conv_weight(w))                                # same layout as the shift-GEMM weights
+    ky, kx, co, ci = 2, 0, 17, 40
+    assert wp[(ky * 3 + kx) * 64 + co, ci] == w[co, ci, ky, kx].half()
+    a = torch.rand(64) + 0.5
+    assert torch.equal(ops.pack_conv64_weight(w, scale=a), ops.pack_conv64_weight(w * a.view(-1, 1, 1, 1)))
+    # lanes: a context manager that only selects which workspace / graph a forward uses
+    m = CRAFT(craft_args())
+    assert m._lane == 0 and m._ws_slot() == 0
+    with m.on_lane(2):
+        assert m._lane == 2 and m._ws_slot() == ("lane", 2)
+        with m.on_lane(0):
+            assert m._ws_slot() == 0
+        assert m._lane == 2
+    assert m._lane == 0
